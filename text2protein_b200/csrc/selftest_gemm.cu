@@ -1,0 +1,245 @@
+// Stand-alone device self-test for the implicit-GEMM kernels (no torch, no oracle): compares the
+// tcgen05 path and the SIMT path against a one-thread-per-output naive kernel on random inputs.
+// Build: see __graft_entry__.build();  run on a B200:  build/selftest_gemm
+#include <cmath>
+#include <cstdlib>
+#include <vector>
+
+#include "kernels.h"
+
+using namespace t2p;
+
+static void fail_if(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) {
+    fprintf(stderr, "CUDA error at %s: %s\n", what, cudaGetErrorString(e));
+    exit(2);
+  }
+}
+
+__global__ void naive_conv(const __nv_bfloat16* a0, int c0, const __nv_bfloat16* a1, int c1, int B, int H,
+                           int W, int ks, const __nv_bfloat16* w, int N, const float* bias,
+                           const float* rowbias, int rps, const __nv_bfloat16* res, int res_up, float alpha,
+                           float* out) {
+  const long long M = 1ll * B * H * W;
+  const long long idx = blockIdx.x * 1ll * blockDim.x + threadIdx.x;
+  if (idx >= M * N) return;
+  const int n = idx % N;
+  const long long m = idx / N;
+  const int hw = H * W;
+  const int b = m / hw, rem = m % hw, h = rem / W, x = rem % W;
+  const int ctot = c0 + c1, pad = ks / 2;
+  double acc = 0.0;
+  for (int kh = 0; kh < ks; ++kh)
+    for (int kw = 0; kw < ks; ++kw) {
+      const int ih = h + kh - pad, iw = x + kw - pad;
+      if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
+      const long long pix = (1ll * b * H + ih) * W + iw;
+      const __nv_bfloat16* wr = w + (1ll * n * ks * ks + kh * ks + kw) * ctot;
+      for (int c = 0; c < c0; ++c) acc += double(__bfloat162float(a0[pix * c0 + c])) * double(__bfloat162float(wr[c]));
+      for (int c = 0; c < c1; ++c)
+        acc += double(__bfloat162float(a1[pix * c1 + c])) * double(__bfloat162float(wr[c0 + c]));
+    }
+  float v = float(acc);
+  if (bias) v += bias[n];
+  if (rowbias) v += rowbias[(m / rps) * N + n];
+  if (res) {
+    long long rr = m;
+    if (res_up) rr = (1ll * b * (H / 2) + h / 2) * (W / 2) + x / 2;
+    v += __bfloat162float(res[rr * N + n]);
+  }
+  out[idx] = v * alpha;
+}
+
+static float frand() { return (rand() / float(RAND_MAX)) * 2.f - 1.f; }
+
+template <typename T>
+static T* dev_upload(const std::vector<T>& h) {
+  T* d;
+  fail_if(cudaMalloc(&d, h.size() * sizeof(T) + 256), "malloc");
+  fail_if(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice), "h2d");
+  return d;
+}
+
+static std::vector<__nv_bfloat16> rand_bf16(size_t n, float scale) {
+  std::vector<__nv_bfloat16> v(n);
+  for (auto& x : v) x = __float2bfloat16(frand() * scale);
+  return v;
+}
+
+struct Case {
+  const char* name;
+  int B, H, W, c0, c1, ks, N;
+  bool bias, rowbias, res, res_up, out_fp32, stats;
+};
+
+static int run_case(const Case& c) {
+  const long long M = 1ll * c.B * c.H * c.W;
+  const int ctot = c.c0 + c.c1, K = c.ks * c.ks * ctot;
+  auto ha0 = rand_bf16(M * c.c0, 1.f);
+  auto ha1 = rand_bf16(c.c1 ? M * c.c1 : 1, 1.f);
+  auto hw = rand_bf16(1ll * c.N * K, 1.f / sqrtf(float(K)));
+  std::vector<float> hb(c.N), hrb(1ll * c.B * c.N);
+  for (auto& x : hb) x = frand();
+  for (auto& x : hrb) x = frand();
+  const long long res_rows = c.res_up ? M / 4 : M;
+  auto hres = rand_bf16(res_rows * c.N, 1.f);
+  std::vector<float> hres32(hres.size());
+  for (size_t i = 0; i < hres.size(); ++i) hres32[i] = __bfloat162float(hres[i]);
+
+  auto* a0 = dev_upload(ha0);
+  auto* a1 = dev_upload(ha1);
+  auto* w = dev_upload(hw);
+  auto* bias = dev_upload(hb);
+  auto* rb = dev_upload(hrb);
+  auto* res = dev_upload(hres);
+  auto* res32 = dev_upload(hres32);
+  float *ref, *out32, *ssum, *ssq;
+  __nv_bfloat16* out16;
+  fail_if(cudaMalloc(&ref, M * c.N * 4), "malloc");
+  fail_if(cudaMalloc(&out32, M * c.N * 4), "malloc");
+  fail_if(cudaMalloc(&out16, M * c.N * 2), "malloc");
+  fail_if(cudaMalloc(&ssum, c.B * c.N * 4), "malloc");
+  fail_if(cudaMalloc(&ssq, c.B * c.N * 4), "malloc");
+  cudaMemset(ssum, 0, c.B * c.N * 4);
+  cudaMemset(ssq, 0, c.B * c.N * 4);
+  cudaMemset(out32, 0xff, M * c.N * 4);
+  cudaMemset(out16, 0xff, M * c.N * 2);
+
+  const float alpha = c.res ? 0.70710678f : 1.f;
+  const int rps = c.H * c.W;
+  naive_conv<<<(unsigned)((M * c.N + 255) / 256), 256>>>(a0, c.c0, c.c1 ? a1 : nullptr, c.c1, c.B, c.H, c.W, c.ks, w,
+                                                        c.N, c.bias ? bias : nullptr, c.rowbias ? rb : nullptr, rps,
+                                                        c.res ? res : nullptr, c.res_up, alpha, ref);
+  fail_if(cudaGetLastError(), "naive launch");
+
+  ConvGemmArgs g;
+  g.a0 = a0; g.c0 = c.c0; g.a1 = c.c1 ? a1 : nullptr; g.c1 = c.c1;
+  g.B = c.B; g.H = c.H; g.W = c.W; g.ksize = c.ks; g.w = w; g.N = c.N;
+  g.bias = c.bias ? bias : nullptr;
+  g.rowbias = c.rowbias ? rb : nullptr;
+  g.rows_per_sample = rps;
+  g.res_up = c.res_up;
+  g.alpha = alpha;
+  if (c.out_fp32) { g.out = out32; g.out_dtype = kF32; g.residual = c.res ? (const void*)res32 : nullptr; }
+  else { g.out = out16; g.out_dtype = kBF16; g.residual = c.res ? (const void*)res : nullptr; }
+  if (c.stats) { g.stat_sum = ssum; g.stat_sq = ssq; }
+
+  int rc = 0;
+  std::vector<float> href(M * c.N), hout(M * c.N);
+  for (int pass = 0; pass < 2; ++pass) {  // 0: tcgen05, 1: SIMT
+    if (pass == 1) { g.stat_sum = nullptr; g.stat_sq = nullptr; }
+    try {
+      if (pass == 0) conv_gemm_tc(g, 0);
+      else conv_gemm_simt(g, kBF16, 0);
+    } catch (const std::exception& e) {
+      printf("  [%s] %s: EXCEPTION %s\n", pass ? "simt" : "tc", c.name, e.what());
+      return 1;
+    }
+    fail_if(cudaDeviceSynchronize(), pass ? "simt kernel" : "tc kernel");
+    fail_if(cudaMemcpy(href.data(), ref, M * c.N * 4, cudaMemcpyDeviceToHost), "d2h");
+    if (c.out_fp32) fail_if(cudaMemcpy(hout.data(), out32, M * c.N * 4, cudaMemcpyDeviceToHost), "d2h");
+    else {
+      std::vector<__nv_bfloat16> t(M * c.N);
+      fail_if(cudaMemcpy(t.data(), out16, M * c.N * 2, cudaMemcpyDeviceToHost), "d2h");
+      for (long long i = 0; i < M * c.N; ++i) hout[i] = __bfloat162float(t[i]);
+    }
+    double maxerr = 0, maxref = 0;
+    for (long long i = 0; i < M * c.N; ++i) {
+      double e = fabs(double(hout[i]) - double(href[i]));
+      if (!(e == e)) e = 1e30;
+      if (e > maxerr) maxerr = e;
+      if (fabs(href[i]) > maxref) maxref = fabs(href[i]);
+    }
+    const double tol = (c.out_fp32 ? 2e-4 : 1.2e-2) * (maxref > 1 ? maxref : 1);
+    const bool ok = maxerr <= tol;
+    printf("  [%s] %-28s M=%lld N=%d K=%d  maxerr=%.3e (max|ref|=%.2f) %s\n", pass ? "simt" : "tc  ", c.name, M, c.N,
+           K, maxerr, maxref, ok ? "PASS" : "FAIL");
+    if (!ok) rc = 1;
+    if (pass == 0 && c.stats) {
+      std::vector<float> hs(c.B * c.N), hq(c.B * c.N);
+      cudaMemcpy(hs.data(), ssum, c.B * c.N * 4, cudaMemcpyDeviceToHost);
+      cudaMemcpy(hq.data(), ssq, c.B * c.N * 4, cudaMemcpyDeviceToHost);
+      double es = 0, eq = 0;
+      for (int b = 0; b < c.B; ++b)
+        for (int n = 0; n < c.N; ++n) {
+          double s = 0, q = 0;
+          for (int r = 0; r < rps; ++r) {
+            const double v = hout[(1ll * b * rps + r) * c.N + n];
+            s += v; q += v * v;
+          }
+          es = fmax(es, fabs(s - hs[b * c.N + n]) / (1 + fabs(s)));
+          eq = fmax(eq, fabs(q - hq[b * c.N + n]) / (1 + fabs(q)));
+        }
+      const bool sok = es < 1e-3 && eq < 1e-3;
+      printf("  [tc  ] %-28s stats rel err sum=%.2e sq=%.2e %s\n", c.name, es, eq, sok ? "PASS" : "FAIL");
+      if (!sok) rc = 1;
+    }
+    cudaMemset(out32, 0xff, M * c.N * 4);
+    cudaMemset(out16, 0xff, M * c.N * 2);
+  }
+  cudaFree(a0); cudaFree(a1); cudaFree(w); cudaFree(bias); cudaFree(rb); cudaFree(res); cudaFree(res32);
+  cudaFree(ref); cudaFree(out32); cudaFree(out16); cudaFree(ssum); cudaFree(ssq);
+  return rc;
+}
+
+static void bench_case(int B, int H, int W, int cin, int N, int ks) {
+  const long long M = 1ll * B * H * W;
+  const int K = ks * ks * cin;
+  __nv_bfloat16 *a, *w, *o;
+  fail_if(cudaMalloc(&a, M * cin * 2), "malloc");
+  fail_if(cudaMalloc(&w, 1ll * N * K * 2), "malloc");
+  fail_if(cudaMalloc(&o, M * N * 2), "malloc");
+  cudaMemset(a, 0, M * cin * 2);
+  cudaMemset(w, 0, 1ll * N * K * 2);
+  ConvGemmArgs g;
+  g.a0 = a; g.c0 = cin; g.B = B; g.H = H; g.W = W; g.ksize = ks; g.w = w; g.N = N; g.out = o;
+  g.rows_per_sample = H * W;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int i = 0; i < 3; ++i) conv_gemm_tc(g, 0);
+  cudaEventRecord(e0);
+  const int iters = 10;
+  for (int i = 0; i < iters; ++i) conv_gemm_tc(g, 0);
+  cudaEventRecord(e1);
+  fail_if(cudaDeviceSynchronize(), "bench");
+  float ms;
+  cudaEventElapsedTime(&ms, e0, e1);
+  ms /= iters;
+  printf("  bench B=%d %dx%d cin=%d N=%d k=%d: %.3f ms  %.1f TFLOP/s\n", B, H, W, cin, N, ks, ms,
+         2.0 * M * N * K / (ms * 1e-3) / 1e12);
+  cudaFree(a); cudaFree(w); cudaFree(o);
+}
+
+int main(int argc, char** argv) {
+  srand(1234);
+  const Case cases[] = {
+      {"gemm 256x128x128", 1, 1, 256, 128, 0, 1, 128, false, false, false, false, false, false},
+      {"gemm M=200 ragged", 1, 1, 200, 128, 0, 1, 128, true, false, false, false, false, false},
+      {"gemm 1024x2048x256 fp32", 1, 1, 1024, 256, 0, 1, 2048, true, false, false, false, true, false},
+      {"conv3 128x128 c128->128", 2, 128, 128, 128, 0, 3, 128, true, true, false, false, false, true},
+      {"conv3 64x64 c128+128->128", 2, 64, 64, 128, 128, 3, 128, true, true, true, false, false, true},
+      {"conv3 32x32 c256->256", 3, 32, 32, 256, 0, 3, 256, true, false, true, false, false, true},
+      {"conv3 16x16 c256+256->256", 3, 16, 16, 256, 256, 3, 256, true, true, true, false, false, true},
+      {"conv3 8x8 c256->256", 3, 8, 8, 256, 0, 3, 256, true, true, false, false, false, true},
+      {"conv3 4x4 c256->256", 5, 4, 4, 256, 0, 3, 256, true, true, true, false, false, true},
+      {"conv3 2x2 c512->512", 5, 2, 2, 512, 0, 3, 512, true, true, true, false, false, false},
+      {"conv3 128x128 c128->5 fp32", 2, 128, 128, 128, 0, 3, 5, true, false, false, false, true, false},
+      {"conv3 32x32 res_up", 2, 32, 32, 256, 0, 3, 256, true, false, true, true, false, false},
+      {"conv1 64x64 c384->128", 2, 64, 64, 256, 128, 1, 128, true, false, false, false, false, false},
+      {"conv3 256x256 c256->256", 1, 256, 256, 256, 0, 3, 256, true, true, true, false, false, true},
+  };
+  int rc = 0;
+  for (const auto& c : cases) rc |= run_case(c);
+  if (argc > 1) {
+    bench_case(64, 128, 128, 128, 128, 3);
+    bench_case(64, 128, 128, 256, 128, 3);
+    bench_case(64, 64, 64, 128, 128, 3);
+    bench_case(64, 32, 32, 256, 256, 3);
+    bench_case(64, 16, 16, 256, 256, 3);
+    bench_case(64, 8, 8, 256, 256, 3);
+    bench_case(64, 4, 4, 256, 256, 3);
+    bench_case(64, 128, 128, 256, 128, 1);
+  }
+  printf(rc ? "SELFTEST FAILED\n" : "SELFTEST OK\n");
+  return rc;
+}
