@@ -11,6 +11,7 @@
 // NHWC bf16 / fp32.  Replaces the cuDNN / cuBLAS calls behind nn.Conv2d, NIN and nn.Linear on the
 // reference hot path (score_sde_pytorch/models/layers.py:82-95,128-137; model/attention.py:161-166).
 #include <cuda.h>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -46,6 +47,7 @@ struct TcParams {
   int out_fp32;
   float* stat_sum;
   float* stat_sq;
+  int debug_mode;  // 0 = normal; 1..3 = bring-up bisection (see T2P_TC_DEBUG)
 };
 
 template <int BN>
@@ -101,7 +103,9 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_gemm_tc_kernel(const __grid_
   ptx::tc_fence_after();
   const uint32_t tmem_acc = tmem_base_slot;
 
-  if (warp == 0) {
+  if (p.debug_mode == 1) {
+    // alloc / dealloc only
+  } else if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       ptx::prefetch_tmap(&p.tm_a0);
@@ -133,7 +137,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_gemm_tc_kernel(const __grid_
             ptx::tma_load_4d(sa, &p.tm_a0, fb, ch, w0 + kw - pad, h0 + kh - pad, b0);
           else
             ptx::tma_load_4d(sa, &p.tm_a1, fb, ch - p.c0, w0 + kw - pad, h0 + kh - pad, b0);
-          ptx::tma_load_2d(sb, &p.tm_w, fb, kb * BK, n0);
+          ptx::tma_load_4d(sb, &p.tm_w, fb, kb * BK, n0, 0, 0);  // all maps are encoded rank-4
         }
       }
     }
@@ -150,6 +154,10 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_gemm_tc_kernel(const __grid_
         const uint32_t sb = sa + C::A_BYTES;
         const uint64_t da = ptx::umma_desc_k_sw128(sa);
         const uint64_t db = ptx::umma_desc_k_sw128(sb);
+        if (p.debug_mode == 2) {
+          ptx::mbar_arrive(ptx::smem_u32(&empty_bar[s]));
+          continue;
+        }
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
           // advancing 16 bf16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
@@ -157,7 +165,8 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_gemm_tc_kernel(const __grid_
         }
         ptx::umma_commit(ptx::smem_u32(&empty_bar[s]));  // frees the smem slot when the MMAs retire
       }
-      ptx::umma_commit(ptx::smem_u32(&accum_bar));       // accumulator complete
+      if (p.debug_mode == 2) ptx::mbar_arrive(ptx::smem_u32(&accum_bar));
+      else ptx::umma_commit(ptx::smem_u32(&accum_bar));  // accumulator complete
     }
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..5)
@@ -177,8 +186,9 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_gemm_tc_kernel(const __grid_
       res_row = (static_cast<long long>(b) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
     }
     constexpr int CH = (BN >= 32) ? 32 : 16;
+    const int nchunks = (p.debug_mode >= 2) ? 0 : BN / CH;
 #pragma unroll 1
-    for (int c = 0; c < BN / CH; ++c) {
+    for (int c = 0; c < nchunks; ++c) {
       uint32_t r[32];
       const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + c * CH;
       if constexpr (CH == 32) {
@@ -411,6 +421,10 @@ void conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
   p.out_fp32 = (a.out_dtype == kF32);
   p.stat_sum = a.stat_sum;
   p.stat_sq = a.stat_sq;
+  {
+    static const int dbg = [] { const char* e = getenv("T2P_TC_DEBUG"); return e ? atoi(e) : 0; }();
+    p.debug_mode = dbg;
+  }
   if (a.rowbias || a.stat_sum) T2P_CHECK(a.rows_per_sample > 0, "rows_per_sample required");
   if (a.res_up) T2P_CHECK(a.ksize == 3 && (a.H % 2 == 0) && (a.W % 2 == 0), "res_up needs an even image");
 

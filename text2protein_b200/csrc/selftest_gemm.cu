@@ -229,7 +229,12 @@ int main(int argc, char** argv) {
       {"conv3 256x256 c256->256", 1, 256, 256, 256, 0, 3, 256, true, true, true, false, false, true},
   };
   int rc = 0;
-  for (const auto& c : cases) rc |= run_case(c);
+  const char* only = getenv("T2P_SELFTEST_CASE");
+  int ci = 0;
+  for (const auto& c : cases) {
+    if (!only || atoi(only) == ci) rc |= run_case(c);
+    ++ci;
+  }
   if (argc > 1) {
     bench_case(64, 128, 128, 128, 128, 3);
     bench_case(64, 128, 128, 256, 128, 3);
