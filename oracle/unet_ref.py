@@ -252,3 +252,14 @@ def rerandomize_(named_tensors, seed):
                 p.copy_(1.0 + 0.1 * torch.randn(p.shape, generator=g))
             else:
                 p.copy_(0.1 * torch.randn(p.shape, generator=g))
+
+
+def state_dict_from_tree(tree, cfg, seed):
+    """Builds a re-randomised state_dict from a committed ``param_tree_*.json`` (names, shapes and order of the
+    reference module), so the oracle can run without the reference or the product module."""
+    shapes = {k: s for k, s, _ in tree["state_dict"]}
+    params = [(k, torch.empty(shapes[k])) for k in tree["parameters"]]
+    rerandomize_(params, seed)
+    sd = {"sigmas": torch.tensor(get_sigmas(cfg))}
+    sd.update(dict(params))
+    return sd

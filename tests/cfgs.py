@@ -1,0 +1,73 @@
+"""Shared test configurations and synthetic-input builders (used by the golden generator and the tests)."""
+import copy
+
+import torch
+
+from oracle.unet_ref import AttrDict
+
+
+def tiny_cfg(channels=5, num_scales=4, max_res=32, nf=64, ch_mult=(1, 1, 2), attn=(16,), n_heads=4,
+             context_dim=64, num_res_blocks=1):
+    """A few-hundred-thousand-parameter UNet with every module kind of the real one: down/up ResBlocks, skip
+    concat with a channel change, AttnBlockpp + SpatialTransformer on a level and in the mid block."""
+    return AttrDict({
+        "training": {"sde": "vesde"},
+        "sampling": {"n_steps_each": 1, "noise_removal": True, "probability_flow": False, "snr": 0.17,
+                     "method": "pc", "predictor": "reverse_diffusion", "corrector": "langevin"},
+        "data": {"max_res_num": max_res, "min_res_num": 8, "num_channels": channels},
+        "model": {"condition": [], "sigma_max": 100.0, "sigma_min": 0.01, "num_scales": num_scales,
+                  "beta_min": 0.1, "beta_max": 20.0, "dropout": 0.1, "embedding_type": "positional",
+                  "name": "ncsnpp", "scale_by_sigma": True, "ema_rate": 0.999, "normalization": "GroupNorm",
+                  "nonlinearity": "swish", "nf": nf, "ch_mult": list(ch_mult), "num_res_blocks": num_res_blocks,
+                  "attn_resolutions": list(attn), "resamp_with_conv": True, "skip_rescale": True,
+                  "resblock_type": "biggan", "attention_type": "ddpm", "init_scale": 0.0, "fourier_scale": 16,
+                  "conv_size": 3, "n_heads": n_heads, "context_dim": context_dim},
+        "seed": 42,
+        "device": "cpu",
+    })
+
+
+def with_device(cfg, device):
+    c = copy.deepcopy(cfg)
+    c.device = device
+    return c
+
+
+def synthetic_inputs(cfg, batch, ctx_len, seed=1234, ctx_scale=0.02):
+    g = torch.Generator().manual_seed(seed)
+    C, N = cfg.data.num_channels, cfg.data.max_res_num
+    x = torch.randn(batch, C, N, N, generator=g) * 3.0
+    labels = torch.randint(0, cfg.model.num_scales, (batch,), generator=g)
+    ctx = torch.randn(batch, ctx_len, cfg.model.context_dim, generator=g) * ctx_scale
+    return x, labels, ctx
+
+
+def synthetic_condition(cfg, batch, kinds, seed=77):
+    """Self-consistent condition dict: coords_6d[:, -1] == length mask, coords_6d[:, 4:7] == ss."""
+    g = torch.Generator().manual_seed(seed)
+    C, N = cfg.data.num_channels, cfg.data.max_res_num
+    cond = {}
+    lengths = torch.randint(max(4, N // 3), N + 1, (batch,), generator=g)
+    ar = torch.arange(N)
+    lmask = (ar[None, :, None] < lengths[:, None, None]) & (ar[None, None, :] < lengths[:, None, None])
+    if "length" in kinds:
+        cond["length"] = lmask
+    ss = None
+    if "ss" in kinds:
+        assert C >= 8
+        blk = (torch.rand(batch, 3, N, generator=g) > 0.5).float()
+        ss = blk[:, :, :, None] * blk[:, :, None, :] * lmask[:, None].float()
+        cond["ss"] = ss
+    if "inpainting" in kinds:
+        coords = torch.rand(batch, C, N, N, generator=g) * 2 - 1
+        coords[:, 0] = 0.5 * (coords[:, 0] + coords[:, 0].transpose(1, 2))
+        coords[:, 1] = 0.5 * (coords[:, 1] + coords[:, 1].transpose(1, 2))
+        coords = coords * lmask[:, None].float()
+        if ss is not None:
+            coords[:, 4:7] = ss
+        coords[:, -1] = lmask.float()
+        start = (lengths.float() * 0.2).long()
+        stop = (lengths.float() * 0.7).long()
+        r = (ar[None, :] >= start[:, None]) & (ar[None, :] < stop[:, None])
+        cond["inpainting"] = {"coords_6d": coords, "mask_inpaint": r[:, :, None] | r[:, None, :]}
+    return cond
