@@ -1,0 +1,173 @@
+/* t2p.h -- C ABI of the B200-native Text2Protein sampling path (libt2p.so).
+ *
+ * The reference (szhan227/text2protein) has no FFI layer: its boundary is the Python API of
+ * score_sde_pytorch/{sampling,sde_lib,utils}.py and score_sde_pytorch/models/{ncsnpp,utils}.py.  The Python
+ * mirror in text2protein_b200/ keeps those names and signatures and forwards to the entry points below through
+ * ctypes.  Every entry point cites the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions: plain C types only; all tensor pointers are DEVICE pointers owned by the caller; `stream` is a
+ * cudaStream_t passed as void*; no entry point synchronises the host except where stated; return value 0 = ok,
+ * non-zero = failure with the message available from t2p_last_error() (thread-local).
+ */
+#ifndef T2P_H_
+#define T2P_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define T2P_ABI_VERSION 1
+
+enum t2p_dtype { T2P_F32 = 0, T2P_BF16 = 1, T2P_F64 = 2, T2P_I64 = 3, T2P_U8 = 4 };
+
+const char* t2p_last_error(void);
+int t2p_abi_version(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Score network.  Replaces score_sde_pytorch/utils.py:4-9 get_model + models/ncsnpp.py:74-263 UNetModel. */
+typedef struct t2p_unet t2p_unet;
+
+typedef struct t2p_unet_cfg {
+  int32_t num_channels;        /* data.num_channels                 ncsnpp.py:137 */
+  int32_t max_res_num;         /* data.max_res_num                  ncsnpp.py:87  */
+  int32_t nf;                  /* model.nf                          ncsnpp.py:80  */
+  int32_t n_ch_mult;
+  int32_t ch_mult[16];         /* model.ch_mult                     ncsnpp.py:81  */
+  int32_t num_res_blocks;      /* model.num_res_blocks              ncsnpp.py:82  */
+  int32_t n_attn_resolutions;
+  int32_t attn_resolutions[16];/* model.attn_resolutions            ncsnpp.py:83  */
+  int32_t n_heads;             /* model.n_heads                     ncsnpp.py:94  */
+  int32_t context_dim;         /* model.context_dim                 ncsnpp.py:95  */
+  int32_t num_scales;          /* model.num_scales (sigmas buffer)  ncsnpp.py:78  */
+  int32_t scale_by_sigma;      /* model.scale_by_sigma              ncsnpp.py:259 */
+  int32_t compute_dtype;       /* T2P_BF16: tcgen05 path; T2P_F32: CUDA-core verification path */
+} t2p_unet_cfg;
+
+int t2p_unet_create(const t2p_unet_cfg* cfg, t2p_unet** out);
+void t2p_unet_destroy(t2p_unet* u);
+
+/* Parameter tree introspection, in the reference's state_dict order (705 entries for cond_length.yml). */
+int t2p_unet_num_params(const t2p_unet* u);
+int t2p_unet_param_info(const t2p_unet* u, int index, char* name_buf, int name_cap, int64_t* shape4, int* ndim,
+                        int* dtype);
+
+/* Copies one state_dict tensor (fp32, or fp64 for "sigmas"; a leading "module." is ignored, as produced by
+ * DataParallel, score_sde_pytorch/utils.py:8) into the engine.  Replaces nn.Module.load_state_dict /
+ * ExponentialMovingAverage.copy_to (models/ema.py:51-61) on the device side. */
+int t2p_unet_load(t2p_unet* u, const char* name, const void* dev_ptr, const int64_t* shape, int ndim, int dtype,
+                  void* stream);
+/* Repacks all weights into kernel layout ([Cout][kh][kw][Cin], fused QKV, stacked Dense_0).  Call after loads. */
+int t2p_unet_finalize(t2p_unet* u, void* stream);
+
+/* Text context, fp32 [B][L][context_dim].  Projects to_k / to_v of every cross-attention ONCE per run
+ * (model/attention.py:174-175 recomputes them in each of the 2*num_scales forwards).  Synchronises `stream`. */
+int t2p_unet_set_context(t2p_unet* u, const float* ctx, int B, int L, void* stream);
+
+/* UNetModel.forward(x, time_cond, text_emb), ncsnpp.py:220-263.  x fp32 [B][C][N][N]; labels int64 [B];
+ * out [B][C][N][N] in `out_dtype` (T2P_F64 reproduces the reference's promoted dtype). */
+int t2p_unet_forward(t2p_unet* u, const float* x, const int64_t* labels, void* out, int out_dtype, int B,
+                     void* stream);
+
+/* Debug taps: with debug on, every top-level block's output is kept as fp32 NCHW ("pre_conv",
+ * "input_blocks.<i>", "mid_blocks", "out_blocks.<i>", "out"). */
+int t2p_unet_set_debug(t2p_unet* u, int enable);
+int t2p_unet_tap(t2p_unet* u, const char* name, float* dst, int64_t capacity, int64_t* shape4, void* stream);
+int64_t t2p_unet_workspace_bytes(const t2p_unet* u);
+int64_t t2p_unet_launches_per_forward(const t2p_unet* u);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Fused predictor / corrector half-steps.  Replace ReverseDiffusionPredictor.update_fn (sampling.py:162-167,
+ * with sde_lib.py:96-101 RSDE.discretize and :237-245 VESDE.discretize / :149-157 VPSDE.discretize),
+ * LangevinCorrector.update_fn (sampling.py:179-199) and the mask + .float() lines (sampling.py:283-287). */
+typedef struct t2p_step_args {
+  float* x;                 /* [B][C][N*N] fp32 state, updated in place */
+  const void* score;        /* model output: fp32 or fp64, NCHW or NHWC */
+  int32_t score_dtype;      /* T2P_F32 | T2P_F64 */
+  int32_t score_nhwc;
+  const double* sigmas;     /* optional: score = raw / sigmas[labels[b]] (ncsnpp.py:259-261) */
+  const int64_t* labels;
+  const float* G;           /* [B] predictor: discretised diffusion coefficient */
+  const float* sqrt_alpha;  /* [B] predictor, VP only: f = sqrt_alpha * x - x; NULL for VE (f = 0) */
+  const float* alpha;       /* [B] corrector, VP only; NULL = 1 */
+  int32_t probability_flow;
+  float snr;
+  const uint8_t* mask;      /* [B][C][N*N] conditional_mask (1 = free), or NULL */
+  const float* x_init;      /* x_initial, required with mask */
+  float* x_mean_out;        /* optional: masked x_mean as float */
+  uint64_t seed;
+  int64_t stream_id;        /* Philox stream of this half-step */
+  int64_t sample_offset;    /* global index of local sample 0 (batch sharding) */
+  int32_t B, C, HW;
+  double* workspace;        /* corrector: >= t2p_corrector_workspace_bytes(B, C*HW) bytes */
+} t2p_step_args;
+
+int64_t t2p_corrector_workspace_bytes(int B, int64_t elems_per_sample);
+int t2p_predictor_step(const t2p_step_args* a, void* stream);
+int t2p_corrector_step(const t2p_step_args* a, void* stream);
+
+/* Philox4x32-10 + Box-Muller normals of stream `stream_id`, global elements [first, first+count), times scale.
+ * Replaces torch.randn_like / VESDE.prior_sampling (sde_lib.py:229-230).  first, count multiples of 4. */
+int t2p_philox_normal(uint64_t seed, int64_t stream_id, int64_t first, int64_t count, float scale, float* out,
+                      void* stream);
+int t2p_philox_bits(uint64_t seed, int64_t stream_id, int64_t first_quad, int64_t quads, uint32_t* out,
+                    void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Whole sampling loop.  Replaces the body of pc_sampler (sampling.py:279-289) for the native score network and
+ * the VE SDE: K iterations of corrector (n_steps inner steps) then predictor, graph-captured once and replayed. */
+typedef struct t2p_run_args {
+  float* x;                  /* [B][C][N][N] fp32: in = masked prior sample, out = final x */
+  float* x_mean;             /* [B][C][N][N] fp32 out: masked x_mean of the last predictor step */
+  const uint8_t* mask;       /* or NULL */
+  const float* x_init;
+  const int64_t* label_table;/* [num_iters] host: labels per iteration (models/utils.py:166-169) */
+  const float* g_table;      /* [num_iters] host: G per iteration (sde_lib.py:237-245) */
+  int32_t num_iters;
+  int32_t n_steps;           /* corrector steps per iteration (sampling.n_steps_each) */
+  float snr;
+  int32_t probability_flow;
+  uint64_t seed;
+  int64_t sample_offset;
+  int32_t B;
+  int32_t use_graph;         /* 1: capture one iteration into a CUDA graph and replay it */
+} t2p_run_args;
+
+int t2p_pc_run(t2p_unet* u, const t2p_run_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Per-kernel entry points (unit-testable against their torch counterparts).  NHWC / token-major tensors. */
+typedef struct t2p_conv_args {
+  const void* a0; int32_t c0;      /* NHWC source 0 */
+  const void* a1; int32_t c1;      /* optional NHWC source 1 (channel concat), c1 = 0 if unused */
+  int32_t B, H, W, ksize;          /* ksize 1 or 3, stride 1, zero padding ksize/2 */
+  const void* w; int32_t N;        /* [N][ksize*ksize*(c0+c1)] (taps outer, channels inner) */
+  const float* bias;               /* [N] or NULL */
+  const float* rowbias;            /* [B][rowbias_ld] per-sample bias or NULL */
+  int32_t rowbias_ld;
+  const void* residual;            /* [M][N] in out dtype or NULL */
+  int32_t res_up;
+  float alpha;
+  void* out; int32_t out_dtype;
+  int32_t in_dtype;                /* T2P_BF16 -> tcgen05 kernel (needs c % 64 == 0); T2P_F32 -> CUDA-core kernel */
+  float* stat_sum; float* stat_sq; /* optional fused GroupNorm statistics (tcgen05 kernel only) */
+} t2p_conv_args;
+int t2p_conv2d(const t2p_conv_args* a, void* stream);        /* nn.Conv2d / NIN / nn.Linear: layers.py:82-95,128-137 */
+
+/* nn.GroupNorm(G, C, eps) [+ SiLU] [+ 2x2 mean | nearest x2] over the concat of a0|a1: layers.py:282-311 */
+int t2p_groupnorm(const void* a0, int c0, const void* a1, int c1, int B, int H, int W, int dtype, int groups,
+                  float eps, const float* gamma, const float* beta, int silu, int resample_mode, void* out,
+                  void* raw_out, void* stream);
+int t2p_layernorm(const void* x, const float* gamma, const float* beta, int64_t M, int C, float eps, int dtype,
+                  void* y, void* stream);                     /* attention.py:203-205 */
+int t2p_geglu(const void* z, int64_t M, int D, int dtype, void* out, void* stream); /* attention.py:42-44 */
+/* softmax(scale * q k^T) v on strided token-major views: layers.py:160-176, attention.py:170-193 */
+int t2p_attention(const void* q, const void* k, const void* v, void* out, int B, int heads, int Tq, int Tk, int d,
+                  int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, float scale, int dtype, int use_tensor_cores,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* T2P_H_ */

@@ -1,0 +1,364 @@
+// extern "C" surface of libt2p.so (include/t2p.h): argument marshalling, error plumbing and the
+// graph-captured sampling loop.
+#include <cstring>
+#include <memory>
+
+#include "../../include/t2p.h"
+#include "unet.h"
+
+namespace t2p {
+namespace {
+thread_local std::string g_last_error;
+}
+void set_last_error(const std::string& m) { g_last_error = m; }
+}  // namespace t2p
+
+struct t2p_unet {
+  std::unique_ptr<t2p::UNet> net;
+  // sampling-loop state (device), sized lazily
+  int run_B = 0, run_K = 0;
+  long long* labels = nullptr;
+  float* G = nullptr;
+  long long* state = nullptr;
+  long long* label_table = nullptr;
+  float* g_table = nullptr;
+  float* h = nullptr;
+  double* partial = nullptr;
+  ~t2p_unet() {
+    for (void* p : {static_cast<void*>(labels), static_cast<void*>(G), static_cast<void*>(state),
+                    static_cast<void*>(label_table), static_cast<void*>(g_table), static_cast<void*>(h),
+                    static_cast<void*>(partial)})
+      if (p) cudaFree(p);
+  }
+};
+
+#define T2P_API_BEGIN try {
+#define T2P_API_END                         \
+  return 0;                                 \
+  }                                         \
+  catch (const std::exception& e) {         \
+    t2p::set_last_error(e.what());          \
+    return -1;                              \
+  }                                         \
+  catch (...) {                             \
+    t2p::set_last_error("unknown error");   \
+    return -1;                              \
+  }
+
+using namespace t2p;
+
+static cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+const char* t2p_last_error(void) { return g_last_error.c_str(); }
+int t2p_abi_version(void) { return T2P_ABI_VERSION; }
+
+int t2p_unet_create(const t2p_unet_cfg* c, t2p_unet** out) {
+  T2P_API_BEGIN
+  T2P_CHECK(c && out, "null argument");
+  UNetConfig cfg;
+  cfg.num_channels = c->num_channels;
+  cfg.max_res_num = c->max_res_num;
+  cfg.nf = c->nf;
+  T2P_CHECK(c->n_ch_mult > 0 && c->n_ch_mult <= 16 && c->n_attn_resolutions >= 0 && c->n_attn_resolutions <= 16,
+            "bad ch_mult / attn_resolutions length");
+  cfg.ch_mult.assign(c->ch_mult, c->ch_mult + c->n_ch_mult);
+  cfg.attn_resolutions.assign(c->attn_resolutions, c->attn_resolutions + c->n_attn_resolutions);
+  cfg.num_res_blocks = c->num_res_blocks;
+  cfg.n_heads = c->n_heads;
+  cfg.context_dim = c->context_dim;
+  cfg.num_scales = c->num_scales;
+  cfg.scale_by_sigma = c->scale_by_sigma;
+  cfg.compute_dtype = c->compute_dtype;
+  auto u = std::make_unique<t2p_unet>();
+  u->net = std::make_unique<UNet>(cfg);
+  *out = u.release();
+  T2P_API_END
+}
+
+void t2p_unet_destroy(t2p_unet* u) { delete u; }
+
+int t2p_unet_num_params(const t2p_unet* u) { return u ? static_cast<int>(u->net->params().size()) : -1; }
+
+int t2p_unet_param_info(const t2p_unet* u, int index, char* name_buf, int name_cap, int64_t* shape4, int* ndim,
+                        int* dtype) {
+  T2P_API_BEGIN
+  T2P_CHECK(u && index >= 0 && index < static_cast<int>(u->net->params().size()), "bad parameter index");
+  const Param& p = *u->net->params()[index];
+  T2P_CHECK(static_cast<int>(p.name.size()) < name_cap, "name buffer too small");
+  std::strcpy(name_buf, p.name.c_str());
+  *ndim = static_cast<int>(p.shape.size());
+  for (size_t i = 0; i < p.shape.size() && i < 4; ++i) shape4[i] = p.shape[i];
+  *dtype = p.dtype;
+  T2P_API_END
+}
+
+int t2p_unet_load(t2p_unet* u, const char* name, const void* dev_ptr, const int64_t* shape, int ndim, int dtype,
+                  void* stream) {
+  T2P_API_BEGIN
+  T2P_CHECK(u && name && dev_ptr, "null argument");
+  u->net->load(name, dev_ptr, std::vector<int64_t>(shape, shape + ndim), dtype, S(stream));
+  T2P_API_END
+}
+
+int t2p_unet_finalize(t2p_unet* u, void* stream) {
+  T2P_API_BEGIN
+  u->net->finalize(S(stream));
+  T2P_API_END
+}
+
+int t2p_unet_set_context(t2p_unet* u, const float* ctx, int B, int L, void* stream) {
+  T2P_API_BEGIN
+  T2P_CHECK(u && ctx && B > 0 && L > 0, "bad context");
+  u->net->set_context(ctx, B, L, S(stream));
+  T2P_API_END
+}
+
+int t2p_unet_forward(t2p_unet* u, const float* x, const int64_t* labels, void* out, int out_dtype, int B,
+                     void* stream) {
+  T2P_API_BEGIN
+  T2P_CHECK(u && x && labels && out && B > 0, "bad forward arguments");
+  u->net->forward(x, reinterpret_cast<const long long*>(labels), out, out_dtype, B, S(stream));
+  T2P_API_END
+}
+
+int t2p_unet_set_debug(t2p_unet* u, int enable) {
+  T2P_API_BEGIN
+  u->net->set_debug(enable != 0);
+  T2P_API_END
+}
+
+int t2p_unet_tap(t2p_unet* u, const char* name, float* dst, int64_t capacity, int64_t* shape4, void* stream) {
+  T2P_API_BEGIN
+  T2P_CHECK(u->net->tap(name, dst, capacity, shape4, S(stream)), std::string("no tap named '") + name + "'");
+  T2P_API_END
+}
+
+int64_t t2p_unet_workspace_bytes(const t2p_unet* u) { return static_cast<int64_t>(u->net->workspace_bytes()); }
+int64_t t2p_unet_launches_per_forward(const t2p_unet* u) { return u->net->launches_per_forward(); }
+
+// ---------------------------------------------------------------------------------------------- steps
+static PcStepArgs step_args(const t2p_step_args* a) {
+  PcStepArgs p;
+  p.x = a->x; p.score = a->score; p.score_dtype = a->score_dtype; p.score_nhwc = a->score_nhwc;
+  p.sigmas = a->sigmas; p.labels = reinterpret_cast<const long long*>(a->labels);
+  p.G = a->G; p.sqrt_alpha = a->sqrt_alpha; p.alpha = a->alpha;
+  p.probability_flow = a->probability_flow; p.snr = a->snr;
+  p.mask = a->mask; p.x_init = a->x_init; p.x_mean_out = a->x_mean_out;
+  p.seed = a->seed; p.stream_base = a->stream_id; p.stream_mul = 0; p.iter_ptr = nullptr;
+  p.sample_offset = a->sample_offset;
+  p.B = a->B; p.C = a->C; p.HW = a->HW;
+  return p;
+}
+
+int64_t t2p_corrector_workspace_bytes(int B, int64_t elems_per_sample) {
+  return static_cast<int64_t>(sizeof(double)) * 2 * B * pc_corrector_chunks(B, elems_per_sample);
+}
+
+int t2p_predictor_step(const t2p_step_args* a, void* stream) {
+  T2P_API_BEGIN
+  T2P_CHECK(a && a->x && a->score, "null argument");
+  pc_predictor_step(step_args(a), S(stream));
+  T2P_API_END
+}
+
+int t2p_corrector_step(const t2p_step_args* a, void* stream) {
+  T2P_API_BEGIN
+  T2P_CHECK(a && a->x && a->score && a->workspace, "null argument");
+  PcStepArgs p = step_args(a);
+  p.chunks = pc_corrector_chunks(a->B, static_cast<long long>(a->C) * a->HW);
+  p.partial = a->workspace;
+  pc_corrector_step(p, S(stream));
+  T2P_API_END
+}
+
+int t2p_philox_normal(uint64_t seed, int64_t stream_id, int64_t first, int64_t count, float scale, float* out,
+                      void* stream) {
+  T2P_API_BEGIN
+  philox_normal_fill(seed, static_cast<unsigned long long>(stream_id), first, count, scale, out, S(stream));
+  T2P_API_END
+}
+
+int t2p_philox_bits(uint64_t seed, int64_t stream_id, int64_t first_quad, int64_t quads, uint32_t* out,
+                    void* stream) {
+  T2P_API_BEGIN
+  philox_bits_fill(seed, static_cast<unsigned long long>(stream_id), first_quad, quads, out, S(stream));
+  T2P_API_END
+}
+
+// ---------------------------------------------------------------------------------------------- run
+static void ensure_run_buffers(t2p_unet* u, int B, int K) {
+  const UNetConfig& c = u->net->cfg();
+  const long long E = static_cast<long long>(c.num_channels) * c.max_res_num * c.max_res_num;
+  if (u->run_B != B) {
+    for (void** p : {reinterpret_cast<void**>(&u->labels), reinterpret_cast<void**>(&u->G),
+                     reinterpret_cast<void**>(&u->state), reinterpret_cast<void**>(&u->h),
+                     reinterpret_cast<void**>(&u->partial)}) {
+      if (*p) T2P_CUDA(cudaFree(*p));
+      *p = nullptr;
+    }
+    T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->labels), sizeof(long long) * B));
+    T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->G), sizeof(float) * B));
+    T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->state), sizeof(long long) * 2));
+    T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->h), sizeof(float) * B * E));
+    T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->partial), sizeof(double) * 2 * B * pc_corrector_chunks(B, E)));
+    u->run_B = B;
+  }
+  if (u->run_K < K) {
+    if (u->label_table) T2P_CUDA(cudaFree(u->label_table));
+    if (u->g_table) T2P_CUDA(cudaFree(u->g_table));
+    T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->label_table), sizeof(long long) * K));
+    T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->g_table), sizeof(float) * K));
+    u->run_K = K;
+  }
+}
+
+int t2p_pc_run(t2p_unet* u, const t2p_run_args* a, void* stream) {
+  T2P_API_BEGIN
+  T2P_CHECK(u && a && a->x && a->x_mean && a->label_table && a->g_table, "null argument");
+  T2P_CHECK(a->num_iters > 0 && a->n_steps >= 0 && a->B > 0, "bad run arguments");
+  cudaStream_t st = S(stream);
+  UNet& net = *u->net;
+  const UNetConfig& c = net.cfg();
+  const int B = a->B, K = a->num_iters;
+  const int HW = c.max_res_num * c.max_res_num;
+  ensure_run_buffers(u, B, K);
+  T2P_CUDA(cudaMemcpyAsync(u->label_table, a->label_table, sizeof(long long) * K, cudaMemcpyHostToDevice, st));
+  T2P_CUDA(cudaMemcpyAsync(u->g_table, a->g_table, sizeof(float) * K, cudaMemcpyHostToDevice, st));
+  T2P_CUDA(cudaMemsetAsync(u->state, 0, sizeof(long long) * 2, st));
+
+  PcStepArgs base;
+  base.x = a->x; base.score = u->h; base.score_dtype = kF32; base.score_nhwc = 1;
+  base.sigmas = c.scale_by_sigma ? net.sigmas() : nullptr;
+  base.labels = u->labels; base.G = u->G;
+  base.probability_flow = a->probability_flow; base.snr = a->snr;
+  base.mask = a->mask; base.x_init = a->x_init;
+  base.seed = a->seed; base.stream_mul = a->n_steps + 1; base.iter_ptr = u->state;
+  base.sample_offset = a->sample_offset;
+  base.B = B; base.C = c.num_channels; base.HW = HW;
+  base.chunks = pc_corrector_chunks(B, static_cast<long long>(c.num_channels) * HW);
+  base.partial = u->partial;
+
+  auto iteration = [&]() {
+    run_prep(u->state, u->label_table, u->g_table, B, u->labels, u->G, st);
+    for (int j = 0; j < a->n_steps; ++j) {  // Langevin corrector, sampling.py:188-197
+      net.forward_raw(a->x, u->labels, u->h, B, st);
+      PcStepArgs s = base;
+      s.stream_base = 1 + j;
+      pc_corrector_step(s, st);
+    }
+    net.forward_raw(a->x, u->labels, u->h, B, st);  // reverse-diffusion predictor, sampling.py:162-167
+    PcStepArgs s = base;
+    s.stream_base = 1 + a->n_steps;
+    s.x_mean_out = a->x_mean;
+    pc_predictor_step(s, st);
+  };
+
+  if (!a->use_graph) {
+    for (int i = 0; i < K; ++i) iteration();
+  } else {
+    // one eager iteration sizes the workspace, builds TMA descriptors and sets kernel attributes
+    // outside the capture; the remaining K-1 iterations replay the captured graph.
+    iteration();
+    if (K > 1) {
+      cudaGraph_t graph = nullptr;
+      cudaGraphExec_t exec = nullptr;
+      T2P_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      try {
+        iteration();
+      } catch (...) {
+        cudaStreamEndCapture(st, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+      }
+      T2P_CUDA(cudaStreamEndCapture(st, &graph));
+      cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+      if (e != cudaSuccess) {
+        cudaGraphDestroy(graph);
+        T2P_CUDA(e);
+      }
+      for (int i = 1; i < K; ++i) {
+        e = cudaGraphLaunch(exec, st);
+        if (e != cudaSuccess) break;
+      }
+      cudaGraphExecDestroy(exec);
+      cudaGraphDestroy(graph);
+      T2P_CUDA(e);
+    }
+  }
+  T2P_API_END
+}
+
+// ---------------------------------------------------------------------------------------------- per-op
+int t2p_conv2d(const t2p_conv_args* a, void* stream) {
+  T2P_API_BEGIN
+  T2P_CHECK(a && a->a0 && a->w && a->out, "null argument");
+  ConvGemmArgs g;
+  g.a0 = a->a0; g.c0 = a->c0; g.a1 = a->a1; g.c1 = a->c1;
+  g.B = a->B; g.H = a->H; g.W = a->W; g.ksize = a->ksize; g.w = a->w; g.N = a->N;
+  g.bias = a->bias; g.rowbias = a->rowbias; g.rowbias_ld = a->rowbias_ld; g.rows_per_sample = a->H * a->W;
+  g.residual = a->residual; g.res_up = a->res_up; g.alpha = a->alpha;
+  g.out = a->out; g.out_dtype = a->out_dtype;
+  g.stat_sum = a->stat_sum; g.stat_sq = a->stat_sq;
+  if (a->in_dtype == T2P_BF16 && a->c0 % 64 == 0 && a->c1 % 64 == 0) conv_gemm_tc(g, S(stream));
+  else conv_gemm_simt(g, a->in_dtype, S(stream));
+  T2P_API_END
+}
+
+int t2p_groupnorm(const void* a0, int c0, const void* a1, int c1, int B, int H, int W, int dtype, int groups,
+                  float eps, const float* gamma, const float* beta, int silu, int resample_mode, void* out,
+                  void* raw_out, void* stream) {
+  T2P_API_BEGIN
+  const int C = c0 + c1;
+  double* sums = nullptr;
+  float* affine = nullptr;
+  T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&sums), sizeof(double) * 2 * B * C));
+  T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&affine), sizeof(float) * 2 * B * C));
+  try {
+    gn_stats(a0, c0, a1, c1, B, H * W, dtype, sums, S(stream));
+    gn_finalize(sums, gamma, beta, B, C, groups, H * W, eps, affine, affine + static_cast<size_t>(B) * C, S(stream));
+    gn_apply(a0, c0, a1, c1, B, H, W, dtype, affine, affine + static_cast<size_t>(B) * C, silu, resample_mode, out,
+             raw_out, S(stream));
+    T2P_CUDA(cudaStreamSynchronize(S(stream)));
+  } catch (...) {
+    cudaFree(sums);
+    cudaFree(affine);
+    throw;
+  }
+  cudaFree(sums);
+  cudaFree(affine);
+  T2P_API_END
+}
+
+int t2p_layernorm(const void* x, const float* gamma, const float* beta, int64_t M, int C, float eps, int dtype,
+                  void* y, void* stream) {
+  T2P_API_BEGIN
+  layernorm(x, gamma, beta, M, C, eps, dtype, y, S(stream));
+  T2P_API_END
+}
+
+int t2p_geglu(const void* z, int64_t M, int D, int dtype, void* out, void* stream) {
+  T2P_API_BEGIN
+  geglu(z, M, D, dtype, out, S(stream));
+  T2P_API_END
+}
+
+int t2p_attention(const void* q, const void* k, const void* v, void* out, int B, int heads, int Tq, int Tk, int d,
+                  int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, float scale, int dtype, int use_tensor_cores,
+                  void* stream) {
+  T2P_API_BEGIN
+  AttnArgs a;
+  a.q = q; a.k = k; a.v = v; a.out = out;
+  a.B = B; a.heads = heads; a.Tq = Tq; a.Tk = Tk; a.d = d;
+  a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo; a.scale = scale;
+  if (use_tensor_cores) {
+    T2P_CHECK(dtype == T2P_BF16 && attention_mma_supported(a), "tensor-core attention needs bf16 and a supported head dim");
+    attention_mma(a, S(stream));
+  } else {
+    attention_simt(a, dtype, S(stream));
+  }
+  T2P_API_END
+}
+
+}  // extern "C"

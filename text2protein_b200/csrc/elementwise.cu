@@ -1,0 +1,194 @@
+// Small helper kernels: timestep-embedding MLP, weight repacking, layout / dtype conversion.
+#include <cmath>
+
+#include "kernels.h"
+
+namespace t2p {
+namespace {
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
+
+// One block per sample: sinusoidal embedding (layers.py:97-111) -> Linear(nf,4nf) -> Linear(4nf,4nf)
+// (no activation in between, ncsnpp.py:227-228) -> SiLU (every consumer applies act(temb) first,
+// layers.py:316).  fp32 throughout; output [B][4nf].
+__global__ void temb_mlp_kernel(const long long* __restrict__ labels, int nf, float neg_coef,
+                                const float* __restrict__ w0,
+                                const float* __restrict__ b0, const float* __restrict__ w1,
+                                const float* __restrict__ b1, float* __restrict__ out) {
+  extern __shared__ float sm[];  // emb[nf] | h0[4nf]
+  float* emb = sm;
+  float* h0 = sm + nf;
+  const int b = blockIdx.x;
+  const int half = nf / 2;
+  const float t = static_cast<float>(labels[b]);
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const float f = expf(static_cast<float>(i) * neg_coef);
+    const float a = t * f;
+    emb[i] = sinf(a);
+    emb[half + i] = cosf(a);
+  }
+  if ((nf & 1) && threadIdx.x == 0) emb[nf - 1] = 0.f;
+  __syncthreads();
+  const int d = 4 * nf;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int n = warp; n < d; n += nw) {
+    float acc = 0.f;
+    for (int k = lane; k < nf; k += 32) acc = fmaf(emb[k], w0[static_cast<long long>(n) * nf + k], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) h0[n] = acc + b0[n];
+  }
+  __syncthreads();
+  for (int n = warp; n < d; n += nw) {
+    float acc = 0.f;
+    for (int k = lane; k < d; k += 32) acc = fmaf(h0[k], w1[static_cast<long long>(n) * d + k], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[static_cast<long long>(b) * d + n] = silu_f(acc + b1[n]);
+  }
+}
+
+template <typename TO>
+__device__ __forceinline__ void stv(TO* p, float v);
+template <>
+__device__ __forceinline__ void stv<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void stv<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+
+// conv weight [Cout][Cin][k][k] fp32 -> [Cout][k*k][cin_pad] (channels innermost, zero padded)
+template <typename TO>
+__global__ void pack_conv_kernel(const float* __restrict__ w, int cout, int cin, int kk, int cin_pad,
+                                 TO* __restrict__ out) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(cout) * kk * cin_pad;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % cin_pad);
+  const int t = static_cast<int>((idx / cin_pad) % kk);
+  const int o = static_cast<int>(idx / (static_cast<long long>(cin_pad) * kk));
+  const float v = (c < cin) ? w[(static_cast<long long>(o) * cin + c) * kk + t] : 0.f;
+  stv(out + idx, v);
+}
+
+// out[r][c] = in[c][r] (NIN.W is [in, out]; GEMM wants [out][in]); or plain copy when !transpose.
+template <typename TO>
+__global__ void pack_matrix_kernel(const float* __restrict__ w, int rows, int cols, int transpose,
+                                   TO* __restrict__ out) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(rows) * cols) return;
+  const int c = static_cast<int>(idx % cols);
+  const int r = static_cast<int>(idx / cols);
+  const float v = transpose ? w[static_cast<long long>(c) * rows + r] : w[idx];
+  stv(out + idx, v);
+}
+
+template <typename TO>
+__global__ void convert_kernel(const float* __restrict__ in, long long n, TO* __restrict__ out) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx < n) stv(out + idx, in[idx]);
+}
+
+template <typename T>
+__device__ __forceinline__ float ldv(const T* p);
+template <>
+__device__ __forceinline__ float ldv<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float ldv<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+// NHWC (any dtype) -> NCHW fp32, for debug taps and per-op tests
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, int B, int HW, int C, float* __restrict__ out) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(B) * HW * C) return;
+  const int p = static_cast<int>(idx % HW);
+  const int c = static_cast<int>((idx / HW) % C);
+  const int b = static_cast<int>(idx / (static_cast<long long>(HW) * C));
+  out[idx] = ldv(in + (static_cast<long long>(b) * HW + p) * C + c);
+}
+
+// NCHW fp32 -> NHWC dtype T with channel padding (zero)
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, int B, int HW, int C, int cpad,
+                                    T* __restrict__ out) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(B) * HW * cpad) return;
+  const int c = static_cast<int>(idx % cpad);
+  const int p = static_cast<int>((idx / cpad) % HW);
+  const int b = static_cast<int>(idx / (static_cast<long long>(HW) * cpad));
+  stv(out + idx, c < C ? in[(static_cast<long long>(b) * C + c) * HW + p] : 0.f);
+}
+
+// out[b,c,h,w] = h_nhwc[b,h,w,c] / sigma[label[b]]  in float64 (ncsnpp.py:259-261)
+template <typename TO>
+__global__ void scale_by_sigma_kernel(const float* __restrict__ h, const long long* __restrict__ labels,
+                                      const double* __restrict__ sigmas, int B, int HW, int C, int do_scale,
+                                      TO* __restrict__ out) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(B) * HW * C) return;
+  const int p = static_cast<int>(idx % HW);
+  const int c = static_cast<int>((idx / HW) % C);
+  const int b = static_cast<int>(idx / (static_cast<long long>(HW) * C));
+  double v = static_cast<double>(h[(static_cast<long long>(b) * HW + p) * C + c]);
+  if (do_scale) v = v / sigmas[labels[b]];
+  out[idx] = static_cast<TO>(v);
+}
+
+}  // namespace
+
+void temb_mlp(const long long* labels, int B, int nf, const float* w0, const float* b0, const float* w1,
+              const float* b1, float* out, cudaStream_t st) {
+  const size_t smem = sizeof(float) * (nf + 4 * nf);
+  // -(ln 10000 / (half - 1)) evaluated in double then rounded once, as Python does (layers.py:101-103)
+  const float neg_coef = static_cast<float>(-(log(10000.0) / static_cast<double>(nf / 2 - 1)));
+  temb_mlp_kernel<<<B, 256, smem, st>>>(labels, nf, neg_coef, w0, b0, w1, b1, out);
+  T2P_LAUNCH_CHECK();
+}
+
+void pack_conv_weight(const float* w, int cout, int cin, int k, int cin_pad, int out_dtype, void* out,
+                      cudaStream_t st) {
+  const long long total = static_cast<long long>(cout) * k * k * cin_pad;
+  const unsigned blocks = static_cast<unsigned>(cdiv64(total, 256));
+  if (out_dtype == kF32) pack_conv_kernel<float><<<blocks, 256, 0, st>>>(w, cout, cin, k * k, cin_pad, static_cast<float*>(out));
+  else pack_conv_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w, cout, cin, k * k, cin_pad, static_cast<__nv_bfloat16*>(out));
+  T2P_LAUNCH_CHECK();
+}
+
+void pack_matrix(const float* w, int rows, int cols, int transpose, int out_dtype, void* out, cudaStream_t st) {
+  const unsigned blocks = static_cast<unsigned>(cdiv64(static_cast<long long>(rows) * cols, 256));
+  if (out_dtype == kF32) pack_matrix_kernel<float><<<blocks, 256, 0, st>>>(w, rows, cols, transpose, static_cast<float*>(out));
+  else pack_matrix_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w, rows, cols, transpose, static_cast<__nv_bfloat16*>(out));
+  T2P_LAUNCH_CHECK();
+}
+
+void convert_f32(const float* in, long long n, int out_dtype, void* out, cudaStream_t st) {
+  const unsigned blocks = static_cast<unsigned>(cdiv64(n, 256));
+  if (out_dtype == kF32) convert_kernel<float><<<blocks, 256, 0, st>>>(in, n, static_cast<float*>(out));
+  else convert_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(in, n, static_cast<__nv_bfloat16*>(out));
+  T2P_LAUNCH_CHECK();
+}
+
+void nhwc_to_nchw_f32(const void* in, int dtype, int B, int HW, int C, float* out, cudaStream_t st) {
+  const unsigned blocks = static_cast<unsigned>(cdiv64(static_cast<long long>(B) * HW * C, 256));
+  if (dtype == kF32) nhwc_to_nchw_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(in), B, HW, C, out);
+  else nhwc_to_nchw_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), B, HW, C, out);
+  T2P_LAUNCH_CHECK();
+}
+
+void nchw_f32_to_nhwc(const float* in, int B, int HW, int C, int cpad, int out_dtype, void* out, cudaStream_t st) {
+  const unsigned blocks = static_cast<unsigned>(cdiv64(static_cast<long long>(B) * HW * cpad, 256));
+  if (out_dtype == kF32) nchw_to_nhwc_kernel<float><<<blocks, 256, 0, st>>>(in, B, HW, C, cpad, static_cast<float*>(out));
+  else nchw_to_nhwc_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(in, B, HW, C, cpad, static_cast<__nv_bfloat16*>(out));
+  T2P_LAUNCH_CHECK();
+}
+
+void scale_by_sigma(const float* h_nhwc, const long long* labels, const double* sigmas, int B, int HW, int C,
+                    int do_scale, int out_dtype, void* out, cudaStream_t st) {
+  const unsigned blocks = static_cast<unsigned>(cdiv64(static_cast<long long>(B) * HW * C, 256));
+  if (out_dtype == kF64)
+    scale_by_sigma_kernel<double><<<blocks, 256, 0, st>>>(h_nhwc, labels, sigmas, B, HW, C, do_scale, static_cast<double*>(out));
+  else if (out_dtype == kF32)
+    scale_by_sigma_kernel<float><<<blocks, 256, 0, st>>>(h_nhwc, labels, sigmas, B, HW, C, do_scale, static_cast<float*>(out));
+  else T2P_CHECK(false, "score output must be fp64 or fp32");
+  T2P_LAUNCH_CHECK();
+}
+
+}  // namespace t2p

@@ -25,6 +25,7 @@ struct SimtParams {
   const float* bias; const float* rowbias; int rows_per_sample;
   const void* residual; int res_up; float alpha;
   void* out; int out_fp32;
+  int rowbias_ld; int out_nchw;
 };
 
 template <typename T>
@@ -108,13 +109,16 @@ __global__ void __launch_bounds__(256) conv_gemm_simt_kernel(SimtParams p) {
       if (n >= p.N) continue;
       float v = acc[i][j];
       if (p.bias) v += p.bias[n];
-      if (p.rowbias) v += p.rowbias[static_cast<long long>(sample) * p.N + n];
+      if (p.rowbias) v += p.rowbias[static_cast<long long>(sample) * p.rowbias_ld + n];
       if (p.residual) {
         if (p.out_fp32) v += static_cast<const float*>(p.residual)[rrow * p.N + n];
         else v += __bfloat162float(static_cast<const __nv_bfloat16*>(p.residual)[rrow * p.N + n]);
       }
       v *= p.alpha;
-      if (p.out_fp32) static_cast<float*>(p.out)[static_cast<long long>(m) * p.N + n] = v;
+      if (p.out_nchw) {
+        const int b = m / hw;
+        static_cast<float*>(p.out)[(static_cast<long long>(b) * p.N + n) * hw + (m - b * hw)] = v;
+      } else if (p.out_fp32) static_cast<float*>(p.out)[static_cast<long long>(m) * p.N + n] = v;
       else static_cast<__nv_bfloat16*>(p.out)[static_cast<long long>(m) * p.N + n] = __float2bfloat16(v);
     }
   }
@@ -135,6 +139,9 @@ void conv_gemm_simt(const ConvGemmArgs& a, int in_dtype, cudaStream_t st) {
   p.bias = a.bias; p.rowbias = a.rowbias; p.rows_per_sample = a.rows_per_sample;
   p.residual = a.residual; p.res_up = a.res_up; p.alpha = a.alpha;
   p.out = a.out; p.out_fp32 = (a.out_dtype == kF32);
+  p.rowbias_ld = a.rowbias_ld > 0 ? a.rowbias_ld : a.N;
+  p.out_nchw = a.out_nchw;
+  if (a.out_nchw) T2P_CHECK(a.out_dtype == kF32 && a.residual == nullptr, "out_nchw is fp32-only, without residual");
   dim3 grid(cdiv(p.M, TM), cdiv(p.N, TN));
   if (in_dtype == kF32) conv_gemm_simt_kernel<float><<<grid, 256, 0, st>>>(p);
   else if (in_dtype == kBF16) conv_gemm_simt_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p);

@@ -47,6 +47,8 @@ struct TcParams {
   int out_fp32;
   float* stat_sum;
   float* stat_sq;
+  int rowbias_ld;
+  int out_nchw;
   int debug_mode;  // 0 = normal; 1..3 = bring-up bisection (see T2P_TC_DEBUG)
 };
 
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_gemm_tc_kernel(const __grid_
             if (nb + i < p.N) v[i] += __ldg(p.bias + nb + i);
         }
         if (p.rowbias) {
-          const float* rb = p.rowbias + static_cast<long long>(sample) * p.N + nb;
+          const float* rb = p.rowbias + static_cast<long long>(sample) * p.rowbias_ld + nb;
 #pragma unroll
           for (int i = 0; i < CH; ++i)
             if (nb + i < p.N) v[i] += __ldg(rb + i);
@@ -245,7 +247,14 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_gemm_tc_kernel(const __grid_
         for (int i = 0; i < CH; ++i) v[i] *= p.alpha;
         if (p.out_fp32) {
           float* o = static_cast<float*>(p.out) + static_cast<long long>(m) * p.N + nb;
-          if (full) {
+          if (p.out_nchw) {
+            const int hw = p.H * p.W;
+            const int b = m / hw;
+            const int pix = m - b * hw;
+#pragma unroll
+            for (int i = 0; i < CH; ++i)
+              if (nb + i < p.N) static_cast<float*>(p.out)[(static_cast<long long>(b) * p.N + nb + i) * hw + pix] = v[i];
+          } else if (full) {
 #pragma unroll
             for (int i = 0; i < CH / 4; ++i)
               reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -421,6 +430,9 @@ void conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
   p.out_fp32 = (a.out_dtype == kF32);
   p.stat_sum = a.stat_sum;
   p.stat_sq = a.stat_sq;
+  p.rowbias_ld = a.rowbias_ld > 0 ? a.rowbias_ld : a.N;
+  p.out_nchw = a.out_nchw;
+  if (a.out_nchw) T2P_CHECK(a.out_dtype == kF32 && a.residual == nullptr, "out_nchw is fp32-only, without residual");
   {
     static const int dbg = [] { const char* e = getenv("T2P_TC_DEBUG"); return e ? atoi(e) : 0; }();
     p.debug_mode = dbg;

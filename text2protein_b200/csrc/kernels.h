@@ -31,11 +31,92 @@ struct ConvGemmArgs {
   // optional per-(sample, channel) sum / sum-of-squares of the stored output (GroupNorm stats)
   float* stat_sum = nullptr;  // [M / rows_per_sample][N]
   float* stat_sq = nullptr;
+  int rowbias_ld = 0;  // row pitch of rowbias (0 -> N)
+  int out_nchw = 0;    // 1: store out as [B][N][H*W] (fp32 only; used by the final conv)
 };
 
 // bf16 tcgen05 / TMEM / TMA path (sm_100a).  A, W are bf16.
 void conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st);
 // fp32 or bf16 SIMT path (verification mode and tiny-channel edge layers). dtype of A and W.
 void conv_gemm_simt(const ConvGemmArgs& a, int in_dtype, cudaStream_t st);
+
+// ----------------------------------------------------------------------------- normalisation
+// GroupNorm statistics: per-(sample, channel) {sum, sum of squares} as interleaved doubles [B][C][2].
+void gn_stats(const void* a0, int c0, const void* a1, int c1, int B, int HW, int dtype, double* sums,
+              cudaStream_t st);
+// float [B][c] sums from a GEMM epilogue -> channels [coff, coff+c) of the interleaved double layout
+void gn_stats_from_f32(const float* s, const float* q, int B, int c, int ctot, int coff, double* sums,
+                       cudaStream_t st);
+// -> per-(sample, channel) affine  y = x * scale + shift  (fp32 [B][C] each)
+void gn_finalize(const double* sums, const float* gamma, const float* beta, int B, int C, int G, int HW, float eps,
+                 float* scale, float* shift, cudaStream_t st);
+// y = act(x * scale + shift) over the (virtual) channel concat of a0|a1; mode 0 same size, 1 = 2x2 mean
+// after the activation (raw_out, optional, receives the 2x2 mean of the raw input), 2 = nearest x2 upsample.
+void gn_apply(const void* a0, int c0, const void* a1, int c1, int B, int H, int W, int dtype, const float* scale,
+              const float* shift, int act, int mode, void* out, void* raw_out, cudaStream_t st);
+void layernorm(const void* x, const float* gamma, const float* beta, long long M, int C, float eps, int dtype,
+               void* y, cudaStream_t st);
+void geglu(const void* z, long long M, int D, int dtype, void* out, cudaStream_t st);
+
+// ----------------------------------------------------------------------------- attention
+struct AttnArgs {
+  const void* q = nullptr;
+  const void* k = nullptr;
+  const void* v = nullptr;
+  void* out = nullptr;
+  int B = 0, heads = 1, Tq = 0, Tk = 0, d = 0;
+  long long ldq = 0, ldk = 0, ldv = 0, ldo = 0;  // row pitches in elements
+  float scale = 1.f;
+};
+void attention_simt(const AttnArgs& a, int dtype, cudaStream_t st);
+void attention_mma(const AttnArgs& a, cudaStream_t st);  // bf16 tensor cores
+bool attention_mma_supported(const AttnArgs& a);
+
+// ----------------------------------------------------------------------------- helpers
+void temb_mlp(const long long* labels, int B, int nf, const float* w0, const float* b0, const float* w1,
+              const float* b1, float* out, cudaStream_t st);
+void pack_conv_weight(const float* w, int cout, int cin, int k, int cin_pad, int out_dtype, void* out,
+                      cudaStream_t st);
+void pack_matrix(const float* w, int rows, int cols, int transpose, int out_dtype, void* out, cudaStream_t st);
+void convert_f32(const float* in, long long n, int out_dtype, void* out, cudaStream_t st);
+void nhwc_to_nchw_f32(const void* in, int dtype, int B, int HW, int C, float* out, cudaStream_t st);
+void nchw_f32_to_nhwc(const float* in, int B, int HW, int C, int cpad, int out_dtype, void* out, cudaStream_t st);
+void scale_by_sigma(const float* h_nhwc, const long long* labels, const double* sigmas, int B, int HW, int C,
+                    int do_scale, int out_dtype, void* out, cudaStream_t st);
+
+// ----------------------------------------------------------------------------- PC sampler steps
+struct PcStepArgs {
+  float* x = nullptr;           // [B][C][HW] fp32 state, updated in place
+  const void* score = nullptr;  // fp32 or fp64; NCHW or NHWC
+  int score_dtype = kF32;
+  int score_nhwc = 0;
+  const double* sigmas = nullptr;   // optional: score = raw / sigmas[labels[b]]
+  const long long* labels = nullptr;
+  const float* G = nullptr;         // [B]
+  const float* sqrt_alpha = nullptr;
+  const float* alpha = nullptr;
+  int probability_flow = 0;
+  float snr = 0.f;
+  const unsigned char* mask = nullptr;
+  const float* x_init = nullptr;
+  float* x_mean_out = nullptr;
+  unsigned long long seed = 0;
+  long long stream_base = 0, stream_mul = 0;
+  const long long* iter_ptr = nullptr;
+  long long sample_offset = 0;
+  int B = 0, C = 0, HW = 0;
+  int chunks = 0;            // corrector only: pc_corrector_chunks(B, C*HW)
+  double* partial = nullptr; // corrector only: [B*chunks*2]
+};
+void pc_predictor_step(const PcStepArgs& a, cudaStream_t st);
+void pc_corrector_step(const PcStepArgs& a, cudaStream_t st);
+int pc_corrector_chunks(int B, long long E);
+void philox_normal_fill(unsigned long long seed, unsigned long long stream, long long first_element, long long count,
+                        float scale, float* out, cudaStream_t st);
+void philox_bits_fill(unsigned long long seed, unsigned long long stream, long long first_quad, long long quads,
+                      unsigned int* out, cudaStream_t st);
+void run_prep(long long* state, const long long* label_table, const float* g_table, int B, long long* labels, float* G,
+              cudaStream_t st);
+void apply_mask(float* x, const unsigned char* mask, const float* fixed, long long n, cudaStream_t st);
 
 }  // namespace t2p

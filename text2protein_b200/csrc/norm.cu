@@ -1,0 +1,385 @@
+// GroupNorm (+SiLU, +2x resampling, +skip concat), LayerNorm and GEGLU for NHWC / token-major tensors.
+//
+// All three are HBM-bound: one coalesced 16-byte-per-thread read and one write per element, with the
+// statistics kept per (sample, channel) so that the producer GEMM's epilogue can accumulate them and the
+// skip concat of the UNet up path (channels of two tensors, group boundaries straddling both) needs no copy.
+// Replaces nn.GroupNorm + nn.SiLU + naive_up/downsample_2d + torch.cat (score_sde_pytorch/models/layers.py:
+// 179-188,282-311; ncsnpp.py:250), nn.LayerNorm and GEGLU (model/attention.py:37-44,203-205).
+#include "kernels.h"
+
+namespace t2p {
+namespace {
+
+template <typename T>
+struct Vec8;
+template <>
+struct Vec8<float> {
+  float v[8];
+  __device__ static Vec8 load(const float* p) {
+    Vec8 r;
+    const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+  }
+  __device__ void store(float* p) const {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <>
+struct Vec8<__nv_bfloat16> {
+  float v[8];
+  __device__ static Vec8 load(const __nv_bfloat16* p) {
+    Vec8 r;
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      r.v[2 * i] = __uint_as_float(w[i] << 16);
+      r.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+    return r;
+  }
+  __device__ void store(__nv_bfloat16* p) const {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+
+// ------------------------------------------------------------------ statistics: per (sample, channel) sums
+template <typename T>
+__global__ void gn_stats_kernel(const T* __restrict__ a0, int c0, const T* __restrict__ a1, int c1, int HW,
+                                int pix_per_block, double* __restrict__ sums) {
+  extern __shared__ float sm[];  // [ctot][2]
+  const int ctot = c0 + c1;
+  const int slots = ctot >> 3;
+  const int rows = blockDim.x / slots;
+  const int slot = threadIdx.x % slots;
+  const int row = threadIdx.x / slots;
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < 2 * ctot; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  float s[8] = {}, q[8] = {};
+  if (row < rows) {
+    const int ch = slot << 3;
+    const T* src;
+    int cs, co;
+    if (ch < c0) { src = a0; cs = c0; co = ch; }
+    else { src = a1; cs = c1; co = ch - c0; }
+    const int p0 = blockIdx.x * pix_per_block;
+    const int p1 = min(HW, p0 + pix_per_block);
+    for (int p = p0 + row; p < p1; p += rows) {
+      const Vec8<T> v = Vec8<T>::load(src + (static_cast<long long>(b) * HW + p) * cs + co);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += v.v[i]; q[i] += v.v[i] * v.v[i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&sm[2 * (ch + i)], s[i]);
+      atomicAdd(&sm[2 * (ch + i) + 1], q[i]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * ctot; i += blockDim.x)
+    atomicAdd(&sums[static_cast<long long>(b) * 2 * ctot + i], static_cast<double>(sm[i]));
+}
+
+// float sums produced by the GEMM epilogue -> interleaved double layout used by finalize
+__global__ void gn_stats_from_f32_kernel(const float* __restrict__ s, const float* __restrict__ q, int B, int c,
+                                         int ctot, int coff, double* __restrict__ sums) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * c) return;
+  const int b = i / c, ch = i - b * c;
+  const long long o = (static_cast<long long>(b) * ctot + coff + ch) * 2;
+  sums[o] = s[i];
+  sums[o + 1] = q[i];
+}
+
+// per (sample, group): mean / rstd -> per (sample, channel) affine  y = x * scale + shift
+__global__ void gn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, int C, int G, int HW, float eps,
+                                   float* __restrict__ scale, float* __restrict__ shift, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int g = i % G, b = i / G;
+  const int cpg = C / G;
+  double s = 0, q = 0;
+  for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+    s += sums[(static_cast<long long>(b) * C + c) * 2];
+    q += sums[(static_cast<long long>(b) * C + c) * 2 + 1];
+  }
+  const double n = static_cast<double>(cpg) * HW;
+  const double mean = s / n;
+  double var = q / n - mean * mean;
+  if (var < 0) var = 0;
+  const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+    const float a = gamma[c] * rstd;
+    scale[static_cast<long long>(b) * C + c] = a;
+    shift[static_cast<long long>(b) * C + c] = beta[c] - static_cast<float>(mean) * a;
+  }
+}
+
+// ------------------------------------------------------------------ apply
+// MODE 0: same resolution; 1: 2x2 mean AFTER the activation (also emits the 2x2 mean of the raw input);
+// 2: nearest x2 upsample of the activated tensor.
+template <typename T, int MODE>
+__global__ void gn_apply_kernel(const T* __restrict__ a0, int c0, const T* __restrict__ a1, int c1, int B, int H,
+                                int W, const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                                T* __restrict__ out, T* __restrict__ raw_out) {
+  const int ctot = c0 + c1;
+  const int slots = ctot >> 3;
+  const int OH = (MODE == 1) ? H >> 1 : H, OW = (MODE == 1) ? W >> 1 : W;  // iteration space
+  const long long total = static_cast<long long>(B) * OH * OW * slots;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int slot = static_cast<int>(idx % slots);
+  long long pix = idx / slots;
+  const int ow = static_cast<int>(pix % OW);
+  pix /= OW;
+  const int oh = static_cast<int>(pix % OH);
+  const int b = static_cast<int>(pix / OH);
+  const int ch = slot << 3;
+  const T* src;
+  int cs, co;
+  if (ch < c0) { src = a0; cs = c0; co = ch; }
+  else { src = a1; cs = c1; co = ch - c0; }
+  float sc[8], sh[8];
+  {
+    const float4* ps = reinterpret_cast<const float4*>(scale + static_cast<long long>(b) * ctot + ch);
+    const float4* ph = reinterpret_cast<const float4*>(shift + static_cast<long long>(b) * ctot + ch);
+    const float4 s0 = ps[0], s1 = ps[1], h0 = ph[0], h1 = ph[1];
+    sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+    sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
+  }
+  if (MODE == 1) {
+    Vec8<T> acc, raw;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc.v[i] = 0.f; raw.v[i] = 0.f; }
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const long long ip = (static_cast<long long>(b) * H + (2 * oh + dy)) * W + (2 * ow + dx);
+        const Vec8<T> v = Vec8<T>::load(src + ip * cs + co);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float y = fmaf(v.v[i], sc[i], sh[i]);
+          if (act) y = silu_f(y);
+          acc.v[i] += y;
+          raw.v[i] += v.v[i];
+        }
+      }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc.v[i] *= 0.25f; raw.v[i] *= 0.25f; }
+    const long long op = (static_cast<long long>(b) * OH + oh) * OW + ow;
+    acc.store(out + op * ctot + ch);
+    if (raw_out) raw.store(raw_out + op * ctot + ch);
+  } else {
+    const long long ip = (static_cast<long long>(b) * H + oh) * W + ow;
+    Vec8<T> v = Vec8<T>::load(src + ip * cs + co);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float y = fmaf(v.v[i], sc[i], sh[i]);
+      v.v[i] = act ? silu_f(y) : y;
+    }
+    if (MODE == 0) {
+      v.store(out + ip * ctot + ch);
+    } else {
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const long long op = (static_cast<long long>(b) * (2 * H) + (2 * oh + dy)) * (2 * W) + (2 * ow + dx);
+          v.store(out + op * ctot + ch);
+        }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm over the last dim (one warp/row)
+template <typename T, int MAXV>
+__global__ void layernorm_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, int M, int C, float eps, T* __restrict__ y) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const int nv = C >> 8;  // 8-element vectors per lane (C % 256 == 0) -- else handled by the scalar kernel
+  float v[MAXV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j)
+    if (j < nv) {
+      const Vec8<T> t = Vec8<T>::load(x + static_cast<long long>(warp) * C + (j * 32 + lane) * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { v[j][i] = t.v[i]; s += t.v[i]; }
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j)
+    if (j < nv) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = v[j][i] - mean; q += d * d; }
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / C + eps);
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j)
+    if (j < nv) {
+      const int c = (j * 32 + lane) * 8;
+      Vec8<T> t;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t.v[i] = (v[j][i] - mean) * rstd * gamma[c + i] + beta[c + i];
+      t.store(y + static_cast<long long>(warp) * C + c);
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ float ld1(const T* p);
+template <>
+__device__ __forceinline__ float ld1<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float ld1<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void st1(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st1(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+
+// generic (any C): one warp per row, two passes over global memory
+template <typename T>
+__global__ void layernorm_generic_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, int M, int C, float eps,
+                                         T* __restrict__ y) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const T* r = x + static_cast<long long>(warp) * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += ld1(r + c);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+  for (int c = lane; c < C; c += 32) { const float d = ld1(r + c) - mean; q += d * d; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / C + eps);
+  for (int c = lane; c < C; c += 32)
+    st1(y + static_cast<long long>(warp) * C + c, (ld1(r + c) - mean) * rstd * gamma[c] + beta[c]);
+}
+
+// ------------------------------------------------------------------ GEGLU: out = a * gelu_erf(gate)
+template <typename T>
+__global__ void geglu_kernel(const T* __restrict__ z, long long M, int D, T* __restrict__ out) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const int slots = D >> 3;
+  if (idx >= M * slots) return;
+  const int slot = static_cast<int>(idx % slots);
+  const long long m = idx / slots;
+  const Vec8<T> a = Vec8<T>::load(z + m * 2 * D + slot * 8);
+  const Vec8<T> g = Vec8<T>::load(z + m * 2 * D + D + slot * 8);
+  Vec8<T> o;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o.v[i] = a.v[i] * (0.5f * g.v[i] * (1.f + erff(g.v[i] * 0.70710678118654752f)));
+  o.store(out + m * D + slot * 8);
+}
+
+}  // namespace
+
+// ===================================================================================== host launchers
+void gn_stats(const void* a0, int c0, const void* a1, int c1, int B, int HW, int dtype, double* sums,
+              cudaStream_t st) {
+  const int ctot = c0 + c1;
+  T2P_CHECK(c0 % 8 == 0 && c1 % 8 == 0 && ctot > 0, "GroupNorm channels must be multiples of 8");
+  const int slots = ctot / 8;
+  T2P_CHECK(slots <= 256, "too many channels for gn_stats");
+  const int threads = slots * (256 / slots);
+  // enough blocks to fill the machine, each with a contiguous run of pixels
+  int blocks = std::max(1, std::min(cdiv(HW, 64), cdiv(148 * 8, B)));
+  const int ppb = cdiv(HW, blocks);
+  blocks = cdiv(HW, ppb);
+  T2P_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * B * ctot, st));
+  dim3 grid(blocks, B);
+  const size_t smem = sizeof(float) * 2 * ctot;
+  if (dtype == kF32)
+    gn_stats_kernel<float><<<grid, threads, smem, st>>>(static_cast<const float*>(a0), c0,
+                                                        static_cast<const float*>(a1), c1, HW, ppb, sums);
+  else
+    gn_stats_kernel<__nv_bfloat16><<<grid, threads, smem, st>>>(static_cast<const __nv_bfloat16*>(a0), c0,
+                                                                static_cast<const __nv_bfloat16*>(a1), c1, HW, ppb,
+                                                                sums);
+  T2P_LAUNCH_CHECK();
+}
+
+void gn_stats_from_f32(const float* s, const float* q, int B, int c, int ctot, int coff, double* sums,
+                       cudaStream_t st) {
+  gn_stats_from_f32_kernel<<<cdiv(B * c, 256), 256, 0, st>>>(s, q, B, c, ctot, coff, sums);
+  T2P_LAUNCH_CHECK();
+}
+
+void gn_finalize(const double* sums, const float* gamma, const float* beta, int B, int C, int G, int HW, float eps,
+                 float* scale, float* shift, cudaStream_t st) {
+  T2P_CHECK(C % G == 0, "channels not divisible by groups");
+  const int total = B * G;
+  gn_finalize_kernel<<<cdiv(total, 128), 128, 0, st>>>(sums, gamma, beta, C, G, HW, eps, scale, shift, total);
+  T2P_LAUNCH_CHECK();
+}
+
+template <typename T>
+static void gn_apply_t(const void* a0, int c0, const void* a1, int c1, int B, int H, int W, const float* scale,
+                       const float* shift, int act, int mode, void* out, void* raw_out, cudaStream_t st) {
+  const int slots = (c0 + c1) / 8;
+  const int OH = mode == 1 ? H / 2 : H, OW = mode == 1 ? W / 2 : W;
+  const long long total = static_cast<long long>(B) * OH * OW * slots;
+  const unsigned blocks = static_cast<unsigned>(cdiv64(total, 256));
+  const T* p0 = static_cast<const T*>(a0);
+  const T* p1 = static_cast<const T*>(a1);
+  T* o = static_cast<T*>(out);
+  T* r = static_cast<T*>(raw_out);
+  if (mode == 0) gn_apply_kernel<T, 0><<<blocks, 256, 0, st>>>(p0, c0, p1, c1, B, H, W, scale, shift, act, o, r);
+  else if (mode == 1) gn_apply_kernel<T, 1><<<blocks, 256, 0, st>>>(p0, c0, p1, c1, B, H, W, scale, shift, act, o, r);
+  else gn_apply_kernel<T, 2><<<blocks, 256, 0, st>>>(p0, c0, p1, c1, B, H, W, scale, shift, act, o, r);
+  T2P_LAUNCH_CHECK();
+}
+
+void gn_apply(const void* a0, int c0, const void* a1, int c1, int B, int H, int W, int dtype, const float* scale,
+              const float* shift, int act, int mode, void* out, void* raw_out, cudaStream_t st) {
+  T2P_CHECK(mode >= 0 && mode <= 2, "bad resample mode");
+  if (mode == 1) T2P_CHECK(H % 2 == 0 && W % 2 == 0, "downsample needs even H, W");
+  if (dtype == kF32) gn_apply_t<float>(a0, c0, a1, c1, B, H, W, scale, shift, act, mode, out, raw_out, st);
+  else gn_apply_t<__nv_bfloat16>(a0, c0, a1, c1, B, H, W, scale, shift, act, mode, out, raw_out, st);
+}
+
+void layernorm(const void* x, const float* gamma, const float* beta, long long M, int C, float eps, int dtype,
+               void* y, cudaStream_t st) {
+  const unsigned blocks = static_cast<unsigned>(cdiv64(M, 8));
+  const bool fast = (C % 256 == 0) && C <= 1024;
+  if (dtype == kF32) {
+    if (fast) layernorm_kernel<float, 4><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), gamma, beta, (int)M, C, eps, static_cast<float*>(y));
+    else layernorm_generic_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), gamma, beta, (int)M, C, eps, static_cast<float*>(y));
+  } else {
+    if (fast) layernorm_kernel<__nv_bfloat16, 4><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), gamma, beta, (int)M, C, eps, static_cast<__nv_bfloat16*>(y));
+    else layernorm_generic_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), gamma, beta, (int)M, C, eps, static_cast<__nv_bfloat16*>(y));
+  }
+  T2P_LAUNCH_CHECK();
+}
+
+void geglu(const void* z, long long M, int D, int dtype, void* out, cudaStream_t st) {
+  T2P_CHECK(D % 8 == 0, "GEGLU width must be a multiple of 8");
+  const unsigned blocks = static_cast<unsigned>(cdiv64(M * (D / 8), 256));
+  if (dtype == kF32) geglu_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(z), M, D, static_cast<float*>(out));
+  else geglu_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(z), M, D, static_cast<__nv_bfloat16*>(out));
+  T2P_LAUNCH_CHECK();
+}
+
+}  // namespace t2p

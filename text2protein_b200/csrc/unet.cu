@@ -1,0 +1,743 @@
+// Score-network engine (see unet.h).  Module layout and forward order follow the reference
+// score_sde_pytorch/models/ncsnpp.py:74-263, layers.py:147-176,276-327 and model/attention.py:152-263;
+// what differs is the data layout (NHWC, compute dtype bf16 or fp32), the fusion boundaries and the
+// hoisted work (text K|V projections once per run, Dense_0 of every ResBlock as one stacked GEMM).
+#include "unet.h"
+
+#include <algorithm>
+#include <cmath>
+
+namespace t2p {
+
+// ======================================================================================= Workspace
+Workspace::~Workspace() {
+  if (base_) cudaFree(base_);
+}
+void Workspace::begin(bool dry) {
+  blocks_.clear();
+  top_ = 0;
+  dry_ = dry;
+  if (dry) peak_ = 0;
+}
+void Workspace::reserve(size_t bytes) {
+  if (bytes <= cap_) return;
+  if (base_) T2P_CUDA(cudaFree(base_));
+  base_ = nullptr;
+  cap_ = 0;
+  T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&base_), bytes));
+  cap_ = bytes;
+}
+void* Workspace::alloc(size_t bytes) {
+  bytes = (std::max<size_t>(bytes, 1) + 255) & ~static_cast<size_t>(255);
+  int best = -1;
+  for (int i = 0; i < static_cast<int>(blocks_.size()); ++i)
+    if (!blocks_[i].used && blocks_[i].size >= bytes && (best < 0 || blocks_[i].size < blocks_[best].size)) best = i;
+  size_t off;
+  if (best >= 0) {
+    Block& b = blocks_[best];
+    off = b.off;
+    if (b.size > bytes) {
+      Block rest{b.off + bytes, b.size - bytes, false};
+      b.size = bytes;
+      b.used = true;
+      blocks_.insert(blocks_.begin() + best + 1, rest);
+    } else {
+      b.used = true;
+    }
+  } else {
+    if (!blocks_.empty() && !blocks_.back().used) {  // grow the trailing free block
+      Block& b = blocks_.back();
+      off = b.off;
+      top_ = b.off + bytes;
+      b.size = bytes;
+      b.used = true;
+    } else {
+      off = top_;
+      blocks_.push_back(Block{off, bytes, true});
+      top_ += bytes;
+    }
+    peak_ = std::max(peak_, top_);
+    if (!dry_) T2P_CHECK(top_ <= cap_, "workspace overflow (plan and execution diverged)");
+  }
+  return reinterpret_cast<void*>(reinterpret_cast<uintptr_t>(dry_ ? reinterpret_cast<char*>(0x10000) : base_) + off);
+}
+void Workspace::free(void* p) {
+  if (!p) return;
+  const size_t off = reinterpret_cast<uintptr_t>(p) -
+                     reinterpret_cast<uintptr_t>(dry_ ? reinterpret_cast<char*>(0x10000) : base_);
+  for (int i = 0; i < static_cast<int>(blocks_.size()); ++i) {
+    if (blocks_[i].off != off) continue;
+    T2P_CHECK(blocks_[i].used, "double free in workspace");
+    blocks_[i].used = false;
+    if (i + 1 < static_cast<int>(blocks_.size()) && !blocks_[i + 1].used) {
+      blocks_[i].size += blocks_[i + 1].size;
+      blocks_.erase(blocks_.begin() + i + 1);
+    }
+    if (i > 0 && !blocks_[i - 1].used) {
+      blocks_[i - 1].size += blocks_[i].size;
+      blocks_.erase(blocks_.begin() + i);
+    }
+    return;
+  }
+  T2P_CHECK(false, "free of unknown workspace pointer");
+}
+
+// ======================================================================================= construction
+Param* UNet::add_param(const std::string& name, std::vector<int64_t> shape, int dtype) {
+  T2P_CHECK(!by_name_.count(name), "duplicate parameter " + name);
+  auto p = std::make_unique<Param>();
+  p->name = name;
+  p->shape = std::move(shape);
+  p->dtype = dtype;
+  Param* raw = p.get();
+  params_.push_back(std::move(p));
+  by_name_[name] = raw;
+  return raw;
+}
+
+GroupNormP UNet::make_gn(const std::string& key, int C, int G) {
+  GroupNormP g;
+  g.C = C;
+  g.G = G > 0 ? G : std::min(C / 4, 32);  // layers.py:282; attention.py:76-77 passes 32
+  g.w = add_param(key + ".weight", {C});
+  g.b = add_param(key + ".bias", {C});
+  return g;
+}
+LayerNormP UNet::make_ln(const std::string& key, int C) {
+  LayerNormP l;
+  l.C = C;
+  l.w = add_param(key + ".weight", {C});
+  l.b = add_param(key + ".bias", {C});
+  return l;
+}
+Linear UNet::make_conv(const std::string& key, int cin, int cout, int k) {
+  Linear l;
+  l.ksize = k;
+  l.cin = cin;
+  l.N = cout;
+  l.w = add_param(key + ".weight", {cout, cin, k, k});
+  l.b = add_param(key + ".bias", {cout});
+  return l;
+}
+Linear UNet::make_linear(const std::string& key, int cin, int cout, bool bias) {
+  Linear l;
+  l.cin = cin;
+  l.N = cout;
+  l.w = add_param(key + ".weight", {cout, cin});
+  if (bias) l.b = add_param(key + ".bias", {cout});
+  return l;
+}
+
+ModuleM UNet::make_res(const std::string& key, int in_ch, int out_ch, bool up, bool down) {
+  // ResnetBlockBigGANpp.__init__, layers.py:277-301 (registration order = state_dict order)
+  ModuleM m;
+  m.kind = 0;
+  m.res = std::make_unique<ResBlockM>();
+  ResBlockM& r = *m.res;
+  r.in_ch = in_ch; r.out_ch = out_ch; r.up = up; r.down = down;
+  r.gn0 = make_gn(key + ".GroupNorm_0", in_ch);
+  r.conv0 = make_conv(key + ".Conv_0", in_ch, out_ch, 3);
+  r.dense_w = add_param(key + ".Dense_0.weight", {out_ch, 4 * cfg_.nf});
+  r.dense_b = add_param(key + ".Dense_0.bias", {out_ch});
+  r.gn1 = make_gn(key + ".GroupNorm_1", out_ch);
+  r.conv1 = make_conv(key + ".Conv_1", out_ch, out_ch, 3);
+  r.has_skip_conv = (in_ch != out_ch) || up || down;
+  if (r.has_skip_conv) r.conv2 = make_conv(key + ".Conv_2", in_ch, out_ch, 1);
+  r.temb_off = temb_total_;
+  temb_total_ += out_ch;
+  return m;
+}
+
+ModuleM UNet::make_attn(const std::string& key, int C) {
+  // AttnBlockpp.__init__, layers.py:150-158
+  ModuleM m;
+  m.kind = 1;
+  m.attn = std::make_unique<AttnBlockM>();
+  AttnBlockM& a = *m.attn;
+  a.C = C;
+  a.gn = make_gn(key + ".GroupNorm_0", C);
+  a.qkv.nin = true; a.qkv.cin = C; a.qkv.N = 3 * C;
+  for (int i = 0; i < 3; ++i) {
+    a.qkv.w_cat.push_back(add_param(key + ".NIN_" + std::to_string(i) + ".W", {C, C}));
+    a.qkv.b_cat.push_back(add_param(key + ".NIN_" + std::to_string(i) + ".b", {C}));
+  }
+  a.proj.nin = true; a.proj.cin = C; a.proj.N = C;
+  a.proj.w_cat.push_back(add_param(key + ".NIN_3.W", {C, C}));
+  a.proj.b_cat.push_back(add_param(key + ".NIN_3.b", {C}));
+  return m;
+}
+
+ModuleM UNet::make_st(const std::string& key, int C) {
+  // SpatialTransformer / BasicTransformerBlock / CrossAttention / FeedForward __init__,
+  // model/attention.py:227-248,197-209,153-168,48-61
+  ModuleM m;
+  m.kind = 2;
+  m.st = std::make_unique<TransformerM>();
+  TransformerM& t = *m.st;
+  t.C = C;
+  t.heads = cfg_.n_heads;
+  T2P_CHECK(C % cfg_.n_heads == 0, "channels must be divisible by n_heads");
+  t.norm = make_gn(key + ".norm", C, 32);
+  t.proj_in = make_conv(key + ".proj_in", C, C, 1);
+  const std::string bk = key + ".transformer_blocks.0";
+  t.qkv1.cin = C; t.qkv1.N = 3 * C;
+  t.qkv1.w_cat.push_back(add_param(bk + ".attn1.to_q.weight", {C, C}));
+  t.qkv1.w_cat.push_back(add_param(bk + ".attn1.to_k.weight", {C, C}));
+  t.qkv1.w_cat.push_back(add_param(bk + ".attn1.to_v.weight", {C, C}));
+  t.out1 = make_linear(bk + ".attn1.to_out.0", C, C, true);
+  t.ff_in = make_linear(bk + ".ff.net.0.proj", C, 8 * C, true);
+  t.ff_out = make_linear(bk + ".ff.net.2", 4 * C, C, true);
+  t.q2 = make_linear(bk + ".attn2.to_q", C, C, false);
+  t.kv2.cin = cfg_.context_dim; t.kv2.N = 2 * C;
+  t.kv2.w_cat.push_back(add_param(bk + ".attn2.to_k.weight", {C, cfg_.context_dim}));
+  t.kv2.w_cat.push_back(add_param(bk + ".attn2.to_v.weight", {C, cfg_.context_dim}));
+  t.out2 = make_linear(bk + ".attn2.to_out.0", C, C, true);
+  t.ln1 = make_ln(bk + ".norm1", C);
+  t.ln2 = make_ln(bk + ".norm2", C);
+  t.ln3 = make_ln(bk + ".norm3", C);
+  t.proj_out = make_conv(key + ".proj_out", C, C, 1);
+  return m;
+}
+
+UNet::UNet(const UNetConfig& cfg) : cfg_(cfg) {
+  T2P_CHECK(cfg.compute_dtype == kBF16 || cfg.compute_dtype == kF32, "compute dtype must be bf16 or fp32");
+  T2P_CHECK(!cfg.ch_mult.empty(), "ch_mult empty");
+  const int nf = cfg.nf;
+  const int nres = static_cast<int>(cfg.ch_mult.size());
+  std::vector<int> res(nres);
+  for (int i = 0; i < nres; ++i) res[i] = cfg.max_res_num / (1 << i);
+  T2P_CHECK(res[nres - 1] >= 1 && (cfg.max_res_num % (1 << (nres - 1))) == 0, "max_res_num not divisible by 2^levels");
+  auto has_attn = [&](int r) {
+    return std::find(cfg.attn_resolutions.begin(), cfg.attn_resolutions.end(), r) != cfg.attn_resolutions.end();
+  };
+  // registration order == reference state_dict order (ncsnpp.py:78-217)
+  sigmas_ = add_param("sigmas", {cfg.num_scales}, kF64);
+  pre0_w_ = add_param("pre_blocks.0.weight", {4 * nf, nf});
+  pre0_b_ = add_param("pre_blocks.0.bias", {4 * nf});
+  pre1_w_ = add_param("pre_blocks.1.weight", {4 * nf, 4 * nf});
+  pre1_b_ = add_param("pre_blocks.1.bias", {4 * nf});
+  pre_conv_ = make_conv("pre_conv", cfg.num_channels, nf, 3);
+  pre_conv_.force_f32 = true;  // reads the fp32 sampler state directly (Cin = 5 / 8)
+
+  std::vector<int> in_channels{nf};
+  int in_ch = nf;
+  for (int lvl = 0; lvl < nres; ++lvl) {
+    for (int ib = 0; ib < cfg.num_res_blocks; ++ib) {
+      const int out_ch = nf * cfg.ch_mult[lvl];
+      const std::string key = "input_blocks." + std::to_string(input_blocks_.size());
+      BlockM blk;
+      blk.push_back(make_res(key + ".0", in_ch, out_ch, false, false));
+      in_ch = out_ch;
+      if (has_attn(res[lvl])) {
+        blk.push_back(make_attn(key + ".1", in_ch));
+        blk.push_back(make_st(key + ".2", in_ch));
+      }
+      input_blocks_.push_back(std::move(blk));
+      in_channels.push_back(in_ch);
+    }
+    if (lvl != nres - 1) {
+      const std::string key = "input_blocks." + std::to_string(input_blocks_.size());
+      BlockM blk;
+      blk.push_back(make_res(key + ".0", in_ch, in_ch, false, true));
+      input_blocks_.push_back(std::move(blk));
+      in_channels.push_back(in_ch);
+    }
+  }
+  const int mid = in_channels.back();
+  mid_block_.push_back(make_res("mid_blocks.0", mid, mid, false, false));
+  mid_block_.push_back(make_attn("mid_blocks.1", mid));
+  mid_block_.push_back(make_st("mid_blocks.2", in_ch));
+  mid_block_.push_back(make_res("mid_blocks.3", mid, mid, false, false));
+
+  for (int lvl = nres - 1; lvl >= 0; --lvl) {
+    for (int ib = 0; ib < cfg.num_res_blocks + 1; ++ib) {
+      const int out_ch = nf * cfg.ch_mult[lvl];
+      const std::string key = "out_blocks." + std::to_string(out_blocks_.size());
+      BlockM blk;
+      int j = 0;
+      const int skip = in_channels.back();
+      in_channels.pop_back();
+      blk.push_back(make_res(key + "." + std::to_string(j++), in_ch + skip, out_ch, false, false));
+      in_ch = out_ch;
+      if (has_attn(res[lvl])) {
+        blk.push_back(make_attn(key + "." + std::to_string(j++), in_ch));
+        blk.push_back(make_st(key + "." + std::to_string(j++), in_ch));
+      }
+      if (lvl != 0 && ib == cfg.num_res_blocks) blk.push_back(make_res(key + "." + std::to_string(j++), in_ch, in_ch, true, false));
+      out_blocks_.push_back(std::move(blk));
+    }
+  }
+  T2P_CHECK(in_channels.empty(), "skip bookkeeping broken");
+  out_gn_ = make_gn("out.0", in_ch);
+  out_conv_ = make_conv("out.2", in_ch, cfg.num_channels, 3);
+
+  auto collect = [&](BlockM& blk) {
+    for (auto& m : blk) {
+      if (m.kind == 0) {
+        all_res_.push_back(m.res.get());
+        all_linear_.push_back(&m.res->conv0);
+        all_linear_.push_back(&m.res->conv1);
+        if (m.res->has_skip_conv) all_linear_.push_back(&m.res->conv2);
+      } else if (m.kind == 1) {
+        all_linear_.push_back(&m.attn->qkv);
+        all_linear_.push_back(&m.attn->proj);
+      } else {
+        TransformerM& t = *m.st;
+        all_st_.push_back(&t);
+        for (Linear* l : {&t.proj_in, &t.proj_out, &t.qkv1, &t.out1, &t.q2, &t.kv2, &t.out2, &t.ff_in, &t.ff_out})
+          all_linear_.push_back(l);
+      }
+    }
+  };
+  for (auto& b : input_blocks_) collect(b);
+  collect(mid_block_);
+  for (auto& b : out_blocks_) collect(b);
+  all_linear_.push_back(&pre_conv_);
+  all_linear_.push_back(&out_conv_);
+  // every ResBlock's Dense_0 (temb -> per-channel bias) stacked into one [sum out_ch][4nf] fp32 GEMM
+  dense_all_.cin = 4 * nf;
+  dense_all_.N = temb_total_;
+  dense_all_.force_f32 = true;
+  for (auto* r : all_res_) {
+    dense_all_.w_cat.push_back(r->dense_w);
+    dense_all_.b_cat.push_back(r->dense_b);
+  }
+  all_linear_.push_back(&dense_all_);
+
+  // device storage is allocated lazily in load(), so the parameter tree can be built (and inspected
+  // through the C ABI) on a host without a GPU
+}
+
+UNet::~UNet() {
+  for (void* p : owned_) cudaFree(p);
+  for (auto& kv : taps_) cudaFree(kv.second.first);
+  if (h_scratch_) cudaFree(h_scratch_);
+}
+
+void UNet::load(const std::string& name, const void* dev_ptr, const std::vector<int64_t>& shape, int dtype,
+                cudaStream_t st) {
+  std::string key = name;
+  if (key.rfind("module.", 0) == 0) key = key.substr(7);  // DataParallel prefix (score_sde_pytorch/utils.py:8)
+  auto it = by_name_.find(key);
+  T2P_CHECK(it != by_name_.end(), "unknown parameter '" + name + "'");
+  Param* p = it->second;
+  T2P_CHECK(shape == p->shape, "shape mismatch for '" + name + "'");
+  T2P_CHECK(dtype == p->dtype, "dtype mismatch for '" + name + "'");
+  if (!p->data) {
+    T2P_CUDA(cudaMalloc(&p->data, std::max<size_t>(16, p->numel() * dtype_size(p->dtype))));
+    owned_.push_back(p->data);
+  }
+  T2P_CUDA(cudaMemcpyAsync(p->data, dev_ptr, p->numel() * dtype_size(p->dtype), cudaMemcpyDeviceToDevice, st));
+  p->loaded = true;
+  finalized_ = false;
+}
+
+void UNet::pack(Linear& l, cudaStream_t st) {
+  const int wdt = l.force_f32 ? kF32 : cfg_.compute_dtype;
+  const size_t wbytes = static_cast<size_t>(l.N) * l.K() * dtype_size(wdt);
+  if (!l.wp) {
+    T2P_CUDA(cudaMalloc(&l.wp, wbytes));
+    owned_.push_back(l.wp);
+  }
+  if (l.w) {
+    if (l.ksize == 1) pack_matrix(static_cast<const float*>(l.w->data), l.N, l.cin, 0, wdt, l.wp, st);
+    else pack_conv_weight(static_cast<const float*>(l.w->data), l.N, l.cin, l.ksize, l.cin, wdt, l.wp, st);
+    if (l.b) l.bp = static_cast<float*>(l.b->data);
+  } else {
+    int row = 0;
+    for (Param* w : l.w_cat) {
+      const int n = static_cast<int>(l.nin ? w->shape[1] : w->shape[0]);
+      char* dst = static_cast<char*>(l.wp) + static_cast<size_t>(row) * l.cin * dtype_size(wdt);
+      pack_matrix(static_cast<const float*>(w->data), n, l.cin, l.nin ? 1 : 0, wdt, dst, st);
+      row += n;
+    }
+    T2P_CHECK(row == l.N, "fused projection rows mismatch");
+    if (!l.b_cat.empty()) {
+      if (!l.bp) {
+        T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&l.bp), sizeof(float) * l.N));
+        owned_.push_back(l.bp);
+      }
+      int off = 0;
+      for (Param* b : l.b_cat) {
+        T2P_CUDA(cudaMemcpyAsync(l.bp + off, b->data, sizeof(float) * b->numel(), cudaMemcpyDeviceToDevice, st));
+        off += static_cast<int>(b->numel());
+      }
+    }
+  }
+}
+
+void UNet::finalize(cudaStream_t st) {
+  for (auto& p : params_) T2P_CHECK(p->loaded, "parameter '" + p->name + "' was never loaded");
+  for (Linear* l : all_linear_) pack(*l, st);
+  finalized_ = true;
+}
+
+// ======================================================================================= forward helpers
+Act UNet::new_act(int B, int H, int W, int C, bool with_stats) {
+  Act a;
+  a.B = B; a.H = H; a.W = W; a.C = C;
+  a.p = ws_.alloc(static_cast<size_t>(a.rows()) * C * dtype_size(cfg_.compute_dtype));
+  if (with_stats && cfg_.compute_dtype == kBF16 && C % 64 == 0) {
+    a.ssum = static_cast<float*>(ws_.alloc(sizeof(float) * 2 * B * C));
+    a.ssq = a.ssum + static_cast<size_t>(B) * C;
+    if (!dry_) T2P_CUDA(cudaMemsetAsync(a.ssum, 0, sizeof(float) * 2 * B * C, st_));
+  }
+  return a;
+}
+void UNet::free_act(Act& a) {
+  ws_.free(a.p);
+  if (a.ssum) ws_.free(a.ssum);
+  a = Act{};
+}
+
+void UNet::gemm(const Linear& l, const Act& a0, const Act* a1, Act& out, const float* rowbias, int rowbias_ld,
+                const void* residual, int res_up, float alpha, int out_dtype, int out_nchw) {
+  ConvGemmArgs g;
+  g.a0 = a0.p; g.c0 = a0.C;
+  if (a1) { g.a1 = a1->p; g.c1 = a1->C; }
+  T2P_CHECK(g.c0 + g.c1 == l.cin, "GEMM input channels do not match the weight");
+  g.B = a0.B; g.H = a0.H; g.W = a0.W;
+  g.ksize = l.ksize;
+  g.w = l.wp; g.N = l.N;
+  g.bias = l.bp;
+  g.rowbias = rowbias; g.rowbias_ld = rowbias_ld;
+  g.rows_per_sample = a0.H * a0.W;
+  g.residual = residual; g.res_up = res_up; g.alpha = alpha;
+  g.out = out.p;
+  g.out_dtype = out_dtype >= 0 ? out_dtype : cfg_.compute_dtype;
+  g.out_nchw = out_nchw;
+  const bool tc = cfg_.compute_dtype == kBF16 && !l.force_f32 && (g.c0 % 64 == 0) && (g.c1 % 64 == 0);
+  if (tc && out.ssum) { g.stat_sum = out.ssum; g.stat_sq = out.ssq; }
+  if (!tc && out.ssum) {  // only the tensor-core epilogue produces GroupNorm statistics
+    ws_.free(out.ssum);
+    out.ssum = out.ssq = nullptr;
+  }
+  ++launches_;
+  if (dry_) return;
+  if (tc) conv_gemm_tc(g, st_);
+  else conv_gemm_simt(g, l.force_f32 ? kF32 : cfg_.compute_dtype, st_);
+}
+
+void UNet::group_norm(const GroupNormP& gn, const Act& a0, const Act* a1, int act, int mode, Act& out, Act* raw_out) {
+  const int C = a0.C + (a1 ? a1->C : 0);
+  T2P_CHECK(C == gn.C, "GroupNorm channel mismatch");
+  const int B = a0.B, HW = a0.H * a0.W;
+  double* sums = static_cast<double*>(ws_.alloc(sizeof(double) * 2 * B * C));
+  float* scale = static_cast<float*>(ws_.alloc(sizeof(float) * 2 * B * C));
+  float* shift = scale + static_cast<size_t>(B) * C;
+  const bool fused = a0.ssum && (!a1 || a1->ssum);
+  launches_ += fused ? (a1 ? 2 : 1) : 2;  // stats (+memset) or conversion(s)
+  launches_ += 2;                          // finalize + apply
+  if (!dry_) {
+    if (fused) {
+      gn_stats_from_f32(a0.ssum, a0.ssq, B, a0.C, C, 0, sums, st_);
+      if (a1) gn_stats_from_f32(a1->ssum, a1->ssq, B, a1->C, C, a0.C, sums, st_);
+    } else {
+      gn_stats(a0.p, a0.C, a1 ? a1->p : nullptr, a1 ? a1->C : 0, B, HW, cfg_.compute_dtype, sums, st_);
+    }
+    gn_finalize(sums, static_cast<const float*>(gn.w->data), static_cast<const float*>(gn.b->data), B, C, gn.G, HW,
+                1e-6f, scale, shift, st_);
+    gn_apply(a0.p, a0.C, a1 ? a1->p : nullptr, a1 ? a1->C : 0, B, a0.H, a0.W, cfg_.compute_dtype, scale, shift, act,
+             mode, out.p, raw_out ? raw_out->p : nullptr, st_);
+  }
+  ws_.free(sums);
+  ws_.free(scale);
+}
+
+void UNet::attention(const void* q, const void* k, const void* v, void* out, int B, int heads, int Tq, int Tk, int d,
+                     long long ldq, long long ldk, long long ldv, long long ldo, float scale) {
+  AttnArgs a;
+  a.q = q; a.k = k; a.v = v; a.out = out;
+  a.B = B; a.heads = heads; a.Tq = Tq; a.Tk = Tk; a.d = d;
+  a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo; a.scale = scale;
+  ++launches_;
+  if (dry_) return;
+  if (cfg_.compute_dtype == kBF16 && attention_mma_supported(a)) attention_mma(a, st_);
+  else attention_simt(a, cfg_.compute_dtype, st_);
+}
+
+// ResnetBlockBigGANpp.forward, layers.py:303-327
+Act UNet::run_res(ResBlockM& m, const Act& a0, const Act* a1) {
+  const int B = a0.B, H = a0.H, W = a0.W;
+  const int OH = m.down ? H / 2 : (m.up ? H * 2 : H), OW = m.down ? W / 2 : (m.up ? W * 2 : W);
+  const int mode = m.down ? 1 : (m.up ? 2 : 0);
+  Act h = new_act(B, OH, OW, m.in_ch, false);
+  Act xr;  // 2x2 mean of the raw input (skip path of a down block)
+  if (m.down) xr = new_act(B, OH, OW, m.in_ch, false);
+  group_norm(m.gn0, a0, a1, 1, mode, h, m.down ? &xr : nullptr);
+  Act h1 = new_act(B, OH, OW, m.out_ch, true);
+  gemm(m.conv0, h, nullptr, h1, temb_all_ + m.temb_off, temb_total_, nullptr, 0, 1.f);
+  free_act(h);
+  Act h2 = new_act(B, OH, OW, m.out_ch, false);
+  group_norm(m.gn1, h1, nullptr, 1, 0, h2, nullptr);
+  free_act(h1);
+  // skip path.  A 1x1 conv commutes with nearest upsampling, so for up blocks it runs at the low
+  // resolution and the Conv_1 epilogue reads it through the 2x index map (res_up).
+  Act skip;
+  const void* residual;
+  int res_up = 0;
+  if (!m.has_skip_conv) {
+    T2P_CHECK(a1 == nullptr, "identity skip with a concat input");
+    residual = a0.p;
+  } else if (m.down) {
+    skip = new_act(B, OH, OW, m.out_ch, false);
+    gemm(m.conv2, xr, nullptr, skip, nullptr, 0, nullptr, 0, 1.f);
+    residual = skip.p;
+  } else {
+    skip = new_act(B, H, W, m.out_ch, false);
+    gemm(m.conv2, a0, a1, skip, nullptr, 0, nullptr, 0, 1.f);
+    residual = skip.p;
+    res_up = m.up ? 1 : 0;
+  }
+  if (m.down) free_act(xr);
+  Act out = new_act(B, OH, OW, m.out_ch, true);
+  gemm(m.conv1, h2, nullptr, out, nullptr, 0, residual, res_up, 0.70710678118654752f);
+  free_act(h2);
+  if (skip.p) free_act(skip);
+  return out;
+}
+
+// AttnBlockpp.forward, layers.py:160-176
+Act UNet::run_attn(AttnBlockM& m, const Act& x) {
+  const int B = x.B, T = x.H * x.W, C = m.C;
+  Act hn = new_act(B, x.H, x.W, C, false);
+  group_norm(m.gn, x, nullptr, 0, 0, hn, nullptr);
+  Act qkv = new_act(B, x.H, x.W, 3 * C, false);
+  gemm(m.qkv, hn, nullptr, qkv, nullptr, 0, nullptr, 0, 1.f);
+  free_act(hn);
+  Act ao = new_act(B, x.H, x.W, C, false);
+  const size_t es = dtype_size(cfg_.compute_dtype);
+  const char* base = static_cast<const char*>(qkv.p);
+  attention(base, base + C * es, base + 2 * C * es, ao.p, B, 1, T, T, C, 3 * C, 3 * C, 3 * C, C,
+            1.f / std::sqrt(static_cast<float>(C)));
+  free_act(qkv);
+  Act out = new_act(B, x.H, x.W, C, true);
+  gemm(m.proj, ao, nullptr, out, nullptr, 0, x.p, 0, 0.70710678118654752f);
+  free_act(ao);
+  return out;
+}
+
+// SpatialTransformer.forward / BasicTransformerBlock._forward, model/attention.py:250-263,211-215
+Act UNet::run_st(TransformerM& m, const Act& x) {
+  const int B = x.B, H = x.H, W = x.W, T = H * W, C = m.C, d = C / m.heads;
+  const size_t es = dtype_size(cfg_.compute_dtype);
+  const float scale = 1.f / std::sqrt(static_cast<float>(d));
+  T2P_CHECK(m.kv != nullptr && ctx_B_ == B, "set_context() must be called with the same batch before forward");
+  auto ln = [&](const LayerNormP& l, const Act& in, Act& out) {
+    ++launches_;
+    if (!dry_)
+      layernorm(in.p, static_cast<const float*>(l.w->data), static_cast<const float*>(l.b->data), in.rows(), C,
+                1e-5f, cfg_.compute_dtype, out.p, st_);
+  };
+  Act hn = new_act(B, H, W, C, false);
+  group_norm(m.norm, x, nullptr, 0, 0, hn, nullptr);
+  Act t = new_act(B, H, W, C, false);
+  gemm(m.proj_in, hn, nullptr, t, nullptr, 0, nullptr, 0, 1.f);
+  // --- self attention
+  ln(m.ln1, t, hn);
+  Act qkv = new_act(B, H, W, 3 * C, false);
+  gemm(m.qkv1, hn, nullptr, qkv, nullptr, 0, nullptr, 0, 1.f);
+  Act ao = new_act(B, H, W, C, false);
+  {
+    const char* base = static_cast<const char*>(qkv.p);
+    attention(base, base + C * es, base + 2 * C * es, ao.p, B, m.heads, T, T, d, 3 * C, 3 * C, 3 * C, C, scale);
+  }
+  free_act(qkv);
+  Act t2 = new_act(B, H, W, C, false);
+  gemm(m.out1, ao, nullptr, t2, nullptr, 0, t.p, 0, 1.f);
+  free_act(t);
+  // --- cross attention to the text context (K|V hoisted to set_context)
+  ln(m.ln2, t2, hn);
+  Act q = new_act(B, H, W, C, false);
+  gemm(m.q2, hn, nullptr, q, nullptr, 0, nullptr, 0, 1.f);
+  {
+    const char* kv = static_cast<const char*>(m.kv);
+    attention(q.p, kv, kv + C * es, ao.p, B, m.heads, T, ctx_L_, d, C, 2 * C, 2 * C, C, scale);
+  }
+  free_act(q);
+  Act t3 = new_act(B, H, W, C, false);
+  gemm(m.out2, ao, nullptr, t3, nullptr, 0, t2.p, 0, 1.f);
+  free_act(t2);
+  free_act(ao);
+  // --- GEGLU feed-forward
+  ln(m.ln3, t3, hn);
+  Act z = new_act(B, H, W, 8 * C, false);
+  gemm(m.ff_in, hn, nullptr, z, nullptr, 0, nullptr, 0, 1.f);
+  free_act(hn);
+  Act gz = new_act(B, H, W, 4 * C, false);
+  ++launches_;
+  if (!dry_) geglu(z.p, z.rows(), 4 * C, cfg_.compute_dtype, gz.p, st_);
+  free_act(z);
+  Act t4 = new_act(B, H, W, C, false);
+  gemm(m.ff_out, gz, nullptr, t4, nullptr, 0, t3.p, 0, 1.f);
+  free_act(gz);
+  free_act(t3);
+  Act out = new_act(B, H, W, C, true);
+  gemm(m.proj_out, t4, nullptr, out, nullptr, 0, x.p, 0, 1.f);
+  free_act(t4);
+  return out;
+}
+
+// TimestepEmbedSequential.forward, ncsnpp.py:54-69
+Act UNet::run_block(BlockM& blk, const Act& a0, const Act* a1, const std::string& tapname) {
+  Act cur;
+  for (size_t j = 0; j < blk.size(); ++j) {
+    ModuleM& m = blk[j];
+    Act next;
+    if (j == 0) {
+      T2P_CHECK(m.kind == 0, "blocks start with a ResBlock");
+      next = run_res(*m.res, a0, a1);
+    } else if (m.kind == 0) {
+      next = run_res(*m.res, cur, nullptr);
+    } else if (m.kind == 1) {
+      next = run_attn(*m.attn, cur);
+    } else {
+      next = run_st(*m.st, cur);
+    }
+    if (j > 0) free_act(cur);
+    cur = next;
+  }
+  record_tap(tapname, cur);
+  return cur;
+}
+
+void UNet::record_tap(const std::string& name, const Act& a, int dtype) {
+  if (dtype < 0) dtype = cfg_.compute_dtype;
+  if (!debug_ || dry_) return;
+  const int64_t n = a.rows() * a.C;
+  auto it = taps_.find(name);
+  if (it == taps_.end() || it->second.second != std::vector<int64_t>{a.B, a.C, a.H, a.W}) {
+    if (it != taps_.end()) cudaFree(it->second.first);
+    float* buf = nullptr;
+    T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&buf), sizeof(float) * n));
+    taps_[name] = {buf, {a.B, a.C, a.H, a.W}};
+    it = taps_.find(name);
+  }
+  nhwc_to_nchw_f32(a.p, dtype, a.B, a.H * a.W, a.C, it->second.first, st_);
+}
+
+bool UNet::tap(const std::string& name, float* dst, int64_t capacity, int64_t shape[4], cudaStream_t st) {
+  auto it = taps_.find(name);
+  if (it == taps_.end()) return false;
+  int64_t n = 1;
+  for (int i = 0; i < 4; ++i) { shape[i] = it->second.second[i]; n *= shape[i]; }
+  T2P_CHECK(capacity >= n, "tap destination too small");
+  T2P_CUDA(cudaMemcpyAsync(dst, it->second.first, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  return true;
+}
+
+void UNet::set_context(const float* ctx, int B, int L, cudaStream_t st) {
+  T2P_CHECK(finalized_, "finalize() before set_context()");
+  const int D = cfg_.context_dim;
+  const size_t es = dtype_size(cfg_.compute_dtype);
+  const long long rows = static_cast<long long>(B) * L;
+  void* cbuf = nullptr;
+  T2P_CUDA(cudaMalloc(&cbuf, std::max<size_t>(256, rows * D * es)));
+  convert_f32(ctx, rows * D, cfg_.compute_dtype, cbuf, st);
+  for (TransformerM* t : all_st_) {
+    if (t->kv) { T2P_CUDA(cudaFree(t->kv)); t->kv = nullptr; }
+    T2P_CUDA(cudaMalloc(&t->kv, std::max<size_t>(256, rows * 2 * t->C * es)));
+    ConvGemmArgs g;
+    g.a0 = cbuf; g.c0 = D; g.B = 1; g.H = 1; g.W = static_cast<int>(rows); g.ksize = 1;
+    g.w = t->kv2.wp; g.N = 2 * t->C; g.out = t->kv; g.out_dtype = cfg_.compute_dtype;
+    if (cfg_.compute_dtype == kBF16 && D % 64 == 0) conv_gemm_tc(g, st);
+    else conv_gemm_simt(g, cfg_.compute_dtype, st);
+  }
+  T2P_CUDA(cudaStreamSynchronize(st));
+  T2P_CUDA(cudaFree(cbuf));
+  ctx_B_ = B;
+  ctx_L_ = L;
+}
+
+// UNetModel.forward, ncsnpp.py:220-263
+void UNet::forward_impl(const float* x, const long long* labels, float* h_out, int B) {
+  const int N = cfg_.max_res_num, C = cfg_.num_channels, nf = cfg_.nf;
+  launches_ = 0;
+  temb_all_ = static_cast<float*>(ws_.alloc(sizeof(float) * static_cast<size_t>(B) * temb_total_));
+  {
+    float* temb = static_cast<float*>(ws_.alloc(sizeof(float) * static_cast<size_t>(B) * 4 * nf));
+    launches_ += 2;
+    if (!dry_) {
+      temb_mlp(labels, B, nf, static_cast<const float*>(pre0_w_->data), static_cast<const float*>(pre0_b_->data),
+               static_cast<const float*>(pre1_w_->data), static_cast<const float*>(pre1_b_->data), temb, st_);
+      ConvGemmArgs g;
+      g.a0 = temb; g.c0 = 4 * nf; g.B = 1; g.H = 1; g.W = B; g.ksize = 1;
+      g.w = dense_all_.wp; g.N = temb_total_; g.bias = dense_all_.bp; g.out = temb_all_; g.out_dtype = kF32;
+      conv_gemm_simt(g, kF32, st_);
+    }
+    ws_.free(temb);
+  }
+  // pre_conv on the fp32 state: NCHW -> NHWC fp32, then the edge-layer GEMM (K = 9*C)
+  Act h = new_act(B, N, N, nf, true);
+  {
+    float* xn = static_cast<float*>(ws_.alloc(sizeof(float) * static_cast<size_t>(B) * N * N * C));
+    launches_ += 1;
+    if (!dry_) nchw_f32_to_nhwc(x, B, N * N, C, C, kF32, xn, st_);
+    Act xa;
+    xa.p = xn; xa.B = B; xa.H = N; xa.W = N; xa.C = C;
+    gemm(pre_conv_, xa, nullptr, h, nullptr, 0, nullptr, 0, 1.f);
+    ws_.free(xn);
+  }
+  record_tap("pre_conv", h);
+  std::vector<Act> hs{h};
+  for (size_t i = 0; i < input_blocks_.size(); ++i) {
+    h = run_block(input_blocks_[i], hs.back(), nullptr, "input_blocks." + std::to_string(i));
+    hs.push_back(h);
+  }
+  h = run_block(mid_block_, hs.back(), nullptr, "mid_blocks");
+  bool h_owned = true;  // mid output is not in hs
+  for (size_t i = 0; i < out_blocks_.size(); ++i) {
+    Act skip = hs.back();
+    hs.pop_back();
+    Act next = run_block(out_blocks_[i], h, &skip, "out_blocks." + std::to_string(i));
+    if (h_owned) free_act(h);
+    free_act(skip);
+    h = next;
+    h_owned = true;
+  }
+  T2P_CHECK(hs.empty(), "skip stack not drained");
+  Act hn = new_act(B, N, N, h.C, false);
+  group_norm(out_gn_, h, nullptr, 1, 0, hn, nullptr);
+  free_act(h);
+  Act o;
+  o.p = h_out; o.B = B; o.H = N; o.W = N; o.C = C;
+  gemm(out_conv_, hn, nullptr, o, nullptr, 0, nullptr, 0, 1.f, kF32);
+  free_act(hn);
+  ws_.free(temb_all_);
+  temb_all_ = nullptr;
+}
+
+void UNet::forward_raw(const float* x, const long long* labels, float* h_out, int B, cudaStream_t st) {
+  T2P_CHECK(finalized_, "finalize() before forward()");
+  st_ = st;
+  if (planned_B_ != B) {
+    // dry pass: same code path, no launches; sizes the arena for this batch
+    dry_ = true;
+    ws_.begin(true);
+    forward_impl(x, labels, h_out, B);
+    dry_ = false;
+    ws_.reserve(ws_.peak());
+    planned_B_ = B;
+  }
+  ws_.begin(false);
+  forward_impl(x, labels, h_out, B);
+}
+
+void UNet::forward(const float* x, const long long* labels, void* out, int out_dtype, int B, cudaStream_t st) {
+  const int N = cfg_.max_res_num, C = cfg_.num_channels;
+  const size_t need = sizeof(float) * static_cast<size_t>(B) * N * N * C;
+  if (need > h_scratch_bytes_) {
+    if (h_scratch_) T2P_CUDA(cudaFree(h_scratch_));
+    T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&h_scratch_), need));
+    h_scratch_bytes_ = need;
+  }
+  forward_raw(x, labels, h_scratch_, B, st);
+  scale_by_sigma(h_scratch_, labels, sigmas(), B, N * N, C, cfg_.scale_by_sigma, out_dtype, out, st);
+  if (debug_) {
+    Act o;
+    o.p = h_scratch_; o.B = B; o.H = N; o.W = N; o.C = C;
+    record_tap("out", o, kF32);  // the final conv output is fp32 regardless of the compute dtype
+  }
+}
+
+}  // namespace t2p

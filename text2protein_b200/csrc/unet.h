@@ -1,0 +1,196 @@
+// Native score-network engine: builds the module tree of the reference UNetModel from the config
+// (score_sde_pytorch/models/ncsnpp.py:74-217), owns kernel-layout copies of the weights and runs the
+// forward pass (ncsnpp.py:220-263) as a fixed sequence of t2p kernels on one CUDA stream.
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "kernels.h"
+
+namespace t2p {
+
+struct UNetConfig {
+  int num_channels = 5;
+  int max_res_num = 128;
+  int nf = 128;
+  std::vector<int> ch_mult;
+  int num_res_blocks = 2;
+  std::vector<int> attn_resolutions;
+  int n_heads = 8;
+  int context_dim = 4096;
+  int num_scales = 2000;
+  int scale_by_sigma = 1;
+  int compute_dtype = kBF16;  // kBF16 (tcgen05 path) or kF32 (verification path)
+};
+
+struct Param {
+  std::string name;
+  std::vector<int64_t> shape;
+  int dtype = kF32;       // kF32 for parameters, kF64 for the sigmas buffer
+  void* data = nullptr;   // device master copy in `dtype`
+  bool loaded = false;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+// Deterministic first-fit pool over one device arena: the alloc / free sequence of a forward pass is a
+// pure function of the batch size, so replays (and CUDA-graph captures) see identical addresses.
+class Workspace {
+ public:
+  ~Workspace();
+  void begin(bool dry);
+  void* alloc(size_t bytes);
+  void free(void* p);
+  size_t peak() const { return peak_; }
+  void reserve(size_t bytes);
+  size_t capacity() const { return cap_; }
+
+ private:
+  struct Block { size_t off, size; bool used; };
+  std::vector<Block> blocks_;
+  char* base_ = nullptr;
+  size_t cap_ = 0, top_ = 0, peak_ = 0;
+  bool dry_ = false;
+};
+
+struct Act {  // NHWC activation in the compute dtype (+ optional producer-side GroupNorm statistics)
+  void* p = nullptr;
+  int B = 0, H = 0, W = 0, C = 0;
+  float* ssum = nullptr;
+  float* ssq = nullptr;
+  long long rows() const { return static_cast<long long>(B) * H * W; }
+};
+
+struct Linear {  // packed [N][K] weight in compute dtype (or fp32 when force_f32), fp32 bias
+  Param* w = nullptr;
+  Param* b = nullptr;
+  std::vector<Param*> w_cat;  // several source matrices concatenated along N (fused projections)
+  std::vector<Param*> b_cat;
+  bool nin = false;           // sources are NIN.W ([in, out]) and need a transpose
+  int ksize = 1, cin = 0, N = 0;
+  bool force_f32 = false;
+  void* wp = nullptr;
+  float* bp = nullptr;
+  int K() const { return ksize * ksize * cin; }
+};
+
+struct GroupNormP { Param* w = nullptr; Param* b = nullptr; int C = 0, G = 0; };
+struct LayerNormP { Param* w = nullptr; Param* b = nullptr; int C = 0; };
+
+struct ResBlockM {
+  int in_ch = 0, out_ch = 0;
+  bool up = false, down = false, has_skip_conv = false;
+  GroupNormP gn0, gn1;
+  Linear conv0, conv1, conv2;
+  Param* dense_w = nullptr;
+  Param* dense_b = nullptr;
+  int temb_off = 0;
+};
+struct AttnBlockM {
+  int C = 0;
+  GroupNormP gn;
+  Linear qkv, proj;
+};
+struct TransformerM {
+  int C = 0, heads = 0;
+  GroupNormP norm;
+  Linear proj_in, proj_out, qkv1, out1, q2, kv2, out2, ff_in, ff_out;
+  LayerNormP ln1, ln2, ln3;
+  void* kv = nullptr;  // hoisted K|V projection of the text context, [B*L][2C]
+};
+struct ModuleM {
+  int kind = 0;  // 0 ResBlock, 1 AttnBlock, 2 SpatialTransformer
+  std::unique_ptr<ResBlockM> res;
+  std::unique_ptr<AttnBlockM> attn;
+  std::unique_ptr<TransformerM> st;
+};
+using BlockM = std::vector<ModuleM>;
+
+class UNet {
+ public:
+  explicit UNet(const UNetConfig& cfg);
+  ~UNet();
+  const UNetConfig& cfg() const { return cfg_; }
+  const std::vector<std::unique_ptr<Param>>& params() const { return params_; }
+  void load(const std::string& name, const void* dev_ptr, const std::vector<int64_t>& shape, int dtype,
+            cudaStream_t st);
+  void finalize(cudaStream_t st);
+  // ctx: fp32 [B][L][context_dim] on the device.  Projects K|V of every cross-attention once (the
+  // reference recomputes them in all 2*num_scales forwards, attention.py:174-175).
+  void set_context(const float* ctx, int B, int L, cudaStream_t st);
+  // x: fp32 NCHW [B][C][N][N]; labels: int64 [B]; h_out: fp32 NHWC [B][N][N][C] un-scaled final conv
+  // (what the fused PC-step kernels consume).  Returns through `h_out` only.
+  void forward_raw(const float* x, const long long* labels, float* h_out, int B, cudaStream_t st);
+  // Reference-shaped output: NCHW, divided by sigmas[labels] in double (ncsnpp.py:259-261), fp64 or fp32.
+  void forward(const float* x, const long long* labels, void* out, int out_dtype, int B, cudaStream_t st);
+  const double* sigmas() const { return static_cast<const double*>(sigmas_->data); }
+  void set_debug(bool on) { debug_ = on; }
+  // copies a recorded block output (fp32 NCHW) to dst; returns its shape
+  bool tap(const std::string& name, float* dst, int64_t capacity, int64_t shape[4], cudaStream_t st);
+  size_t workspace_bytes() const { return ws_.capacity(); }
+  long long launches_per_forward() const { return launches_; }
+
+ private:
+  Param* add_param(const std::string& name, std::vector<int64_t> shape, int dtype = kF32);
+  GroupNormP make_gn(const std::string& key, int C, int G = 0);
+  LayerNormP make_ln(const std::string& key, int C);
+  Linear make_conv(const std::string& key, int cin, int cout, int k);
+  Linear make_linear(const std::string& key, int cin, int cout, bool bias);
+  ModuleM make_res(const std::string& key, int in_ch, int out_ch, bool up, bool down);
+  ModuleM make_attn(const std::string& key, int C);
+  ModuleM make_st(const std::string& key, int C);
+  void pack(Linear& l, cudaStream_t st);
+
+  // forward helpers (all honour dry_)
+  Act new_act(int B, int H, int W, int C, bool with_stats);
+  void free_act(Act& a);
+  void gemm(const Linear& l, const Act& a0, const Act* a1, Act& out, const float* rowbias, int rowbias_ld,
+            const void* residual, int res_up, float alpha, int out_dtype = -1, int out_nchw = 0);
+  void group_norm(const GroupNormP& g, const Act& a0, const Act* a1, int act, int mode, Act& out, Act* raw_out);
+  void attention(const void* q, const void* k, const void* v, void* out, int B, int heads, int Tq, int Tk, int d,
+                 long long ldq, long long ldk, long long ldv, long long ldo, float scale);
+  Act run_res(ResBlockM& m, const Act& a0, const Act* a1);
+  Act run_attn(AttnBlockM& m, const Act& x);
+  Act run_st(TransformerM& m, const Act& x);
+  Act run_block(BlockM& blk, const Act& a0, const Act* a1, const std::string& tapname);
+  void record_tap(const std::string& name, const Act& a, int dtype = -1);
+  void forward_impl(const float* x, const long long* labels, float* h_out, int B);
+
+  UNetConfig cfg_;
+  std::vector<std::unique_ptr<Param>> params_;
+  std::unordered_map<std::string, Param*> by_name_;
+  Param* sigmas_ = nullptr;
+  Param *pre0_w_, *pre0_b_, *pre1_w_, *pre1_b_;
+  Linear pre_conv_, out_conv_;
+  GroupNormP out_gn_;
+  std::vector<BlockM> input_blocks_, out_blocks_;
+  BlockM mid_block_;
+  std::vector<ResBlockM*> all_res_;
+  std::vector<TransformerM*> all_st_;
+  std::vector<Linear*> all_linear_;
+  Linear dense_all_;  // every ResBlock's Dense_0 stacked along N
+  int temb_total_ = 0;
+  bool finalized_ = false;
+  std::vector<void*> owned_;  // device allocations freed in the destructor
+
+  // per-forward state
+  Workspace ws_;
+  cudaStream_t st_ = nullptr;
+  bool dry_ = false;
+  bool debug_ = false;
+  int planned_B_ = -1;
+  long long launches_ = 0;
+  float* temb_all_ = nullptr;
+  int ctx_B_ = 0, ctx_L_ = 0;
+  std::map<std::string, std::pair<float*, std::vector<int64_t>>> taps_;
+  float* h_scratch_ = nullptr;
+  size_t h_scratch_bytes_ = 0;
+};
+
+}  // namespace t2p

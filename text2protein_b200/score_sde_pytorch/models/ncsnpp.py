@@ -1,0 +1,238 @@
+"""Score UNet -- drop-in for the reference ``score_sde_pytorch/models/ncsnpp.py::UNetModel``.
+
+The module is a *parameter container* with exactly the reference's state_dict names, shapes and order (so
+``.pth`` checkpoints, ``load_state_dict`` and the positional EMA list of models/ema.py keep working), and a
+``forward(x, time_cond, text_emb)`` that runs the native sm_100a engine (csrc/unet.cu) through the C ABI.
+The parameter tree itself comes from the engine (``t2p_unet_param_info``), which derives it from the config
+the way ``UNetModel.__init__`` does (reference :74-217); there is no PyTorch implementation of the forward
+pass and no CPU fallback.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from text2protein_b200 import _lib
+from . import utils as mutils
+
+
+def _engine_cfg(config, compute_dtype):
+    m = config.model
+    if m.resblock_type.lower() != "biggan":
+        raise NotImplementedError("only resblock_type 'biggan' is supported (every shipped config uses it)")
+    if m.embedding_type.lower() != "positional":
+        raise NotImplementedError("only embedding_type 'positional' is supported")
+    if m.nonlinearity.lower() != "swish":
+        raise NotImplementedError("only nonlinearity 'swish' is supported")
+    if not m.skip_rescale:
+        raise NotImplementedError("skip_rescale=False is not supported")
+    c = _lib.UnetCfg()
+    c.num_channels = config.data.num_channels
+    c.max_res_num = config.data.max_res_num
+    c.nf = m.nf
+    c.n_ch_mult = len(m.ch_mult)
+    for i, v in enumerate(m.ch_mult):
+        c.ch_mult[i] = v
+    c.num_res_blocks = m.num_res_blocks
+    c.n_attn_resolutions = len(m.attn_resolutions)
+    for i, v in enumerate(m.attn_resolutions):
+        c.attn_resolutions[i] = v
+    c.n_heads = m.n_heads          # AttributeError if absent, like the reference (ncsnpp.py:94-95)
+    c.context_dim = m.context_dim
+    c.num_scales = m.num_scales
+    c.scale_by_sigma = 1 if m.scale_by_sigma else 0
+    c.compute_dtype = compute_dtype
+    return c
+
+
+class _Node(nn.Module):
+    """Anonymous container; children / parameters are attached by dotted name."""
+
+
+def _fan_avg_uniform_(t, scale, in_axis, out_axis):
+    """DDPM 'fan_avg' uniform variance scaling (reference layers.py:44-80)."""
+    shape = t.shape
+    rf = np.prod(shape) / shape[in_axis] / shape[out_axis]
+    fan_in, fan_out = shape[in_axis] * rf, shape[out_axis] * rf
+    scale = 1e-10 if scale == 0 else scale
+    bound = math.sqrt(3 * scale / ((fan_in + fan_out) / 2))
+    with torch.no_grad():
+        t.uniform_(-bound, bound)
+
+
+class UNetModel(nn.Module):
+    """``UNetModel(config)``; ``config.model.compute_dtype`` (optional, default 'bf16') selects the tcgen05
+    path ('bf16') or the CUDA-core verification path ('fp32')."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        dt = str(config.model.get("compute_dtype", "bf16")).lower() if hasattr(config.model, "get") else "bf16"
+        self._compute_dtype = {"bf16": _lib.BF16, "bfloat16": _lib.BF16, "fp32": _lib.F32, "float32": _lib.F32}[dt]
+        self.nf = config.model.nf
+        self.n_heads = config.model.n_heads
+        self.context_dim = config.model.context_dim
+        self.register_buffer('sigmas', torch.tensor(mutils.get_sigmas(config)))
+        self._handle = C.c_void_p(0)
+        self._create_engine()
+        self._build_tree()
+        self._synced_version = None
+        self._ctx_key = None
+        self.reset_parameters()
+
+    # ------------------------------------------------------------------ engine lifetime
+    def _create_engine(self):
+        cfg = _engine_cfg(self.config, self._compute_dtype)
+        h = C.c_void_p(0)
+        _lib.check(_lib.lib().t2p_unet_create(C.byref(cfg), C.byref(h)))
+        self._handle = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) and self._handle.value:
+                _lib.lib().t2p_unet_destroy(self._handle)
+                self._handle = C.c_void_p(0)
+        except Exception:
+            pass
+
+    def _engine_params(self):
+        L = _lib.lib()
+        n = L.t2p_unet_num_params(self._handle)
+        out = []
+        buf = C.create_string_buffer(256)
+        shape = (C.c_int64 * 4)()
+        ndim, dtype = C.c_int(0), C.c_int(0)
+        for i in range(n):
+            _lib.check(L.t2p_unet_param_info(self._handle, i, buf, 256, shape, C.byref(ndim), C.byref(dtype)))
+            out.append((buf.value.decode(), tuple(shape[j] for j in range(ndim.value)), dtype.value))
+        return out
+
+    def _build_tree(self):
+        for name, shape, dtype in self._engine_params():
+            if name == "sigmas":
+                assert dtype == _lib.F64 and tuple(self.sigmas.shape) == shape
+                continue
+            parts = name.split(".")
+            node = self
+            for p in parts[:-1]:
+                if p not in node._modules:
+                    node.add_module(p, _Node())
+                node = node._modules[p]
+            node.register_parameter(parts[-1], nn.Parameter(torch.empty(shape, dtype=torch.float32)))
+
+    def reset_parameters(self):
+        """Random init in the spirit of the reference (DDPM fan_avg-uniform convs / dense, zero biases and
+        init_scale-0 output layers, zeroed proj_out, default torch init for the transformer linears)."""
+        init_scale = self.config.model.init_scale
+        for name, p in self.named_parameters():
+            parts = name.split(".")
+            leaf, parent = parts[-1], parts[-2] if len(parts) > 1 else ""
+            with torch.no_grad():
+                if parent.startswith("GroupNorm") or parent.startswith("norm") or name.startswith("out.0."):
+                    p.fill_(1.0 if leaf == "weight" else 0.0)
+                elif leaf in ("bias", "b"):
+                    p.zero_()
+                elif leaf == "W":  # NIN [in, out]
+                    _fan_avg_uniform_(p, init_scale if parent == "NIN_3" else 0.1, in_axis=0, out_axis=1)
+                elif parent == "proj_out":
+                    p.zero_()
+                elif parent == "Conv_1" or name.startswith("out.2."):
+                    _fan_avg_uniform_(p, init_scale, in_axis=1, out_axis=0)
+                elif parent in ("Conv_0", "Conv_2", "Dense_0") or parts[0] in ("pre_blocks", "pre_conv"):
+                    _fan_avg_uniform_(p, 1.0, in_axis=1, out_axis=0)
+                else:
+                    nn.init.kaiming_uniform_(p, a=math.sqrt(5))
+
+    # ------------------------------------------------------------------ weights -> engine
+    def _weights_version(self):
+        return tuple(t._version for t in self.state_dict(keep_vars=True).values()) + \
+            tuple(t.data_ptr() for t in self.state_dict(keep_vars=True).values())
+
+    def sync_weights(self, force=False):
+        """Pushes the current parameters (e.g. after load_state_dict / ema.copy_to) to the engine and repacks
+        them into kernel layout.  Called automatically by forward when a parameter changed."""
+        ver = self._weights_version()
+        if not force and ver == self._synced_version:
+            return
+        L = _lib.lib()
+        st = _lib.current_stream()
+        keep = []
+        for name, t in self.state_dict(keep_vars=True).items():
+            if not t.is_cuda:
+                raise _lib.NativeError("UNetModel parameters must live on a CUDA device (model.to('cuda')); "
+                                       "there is no CPU path")
+            want = torch.float64 if name == "sigmas" else torch.float32
+            src = t.detach().to(want).contiguous()
+            keep.append(src)
+            shape = (C.c_int64 * max(1, src.dim()))(*src.shape)
+            _lib.check(L.t2p_unet_load(self._handle, name.encode(), _lib.ptr(src), shape, src.dim(),
+                                       _lib.torch_dtype_code(want), st))
+        _lib.check(L.t2p_unet_finalize(self._handle, st))
+        torch.cuda.current_stream().synchronize()
+        self._synced_version = ver
+        self._ctx_key = None
+
+    def set_context(self, text_emb):
+        """Projects K|V of every cross-attention for this text context once (hoisted out of the loop)."""
+        if text_emb is None:
+            raise TypeError("context=None is not supported: the reference model crashes on it as well "
+                            "(to_k expects context_dim inputs, model/attention.py:161-175)")
+        key = (text_emb.data_ptr(), tuple(text_emb.shape), text_emb._version, text_emb.dtype)
+        if key == self._ctx_key:
+            return
+        ctx = text_emb.detach().to(torch.float32).contiguous()
+        if ctx.dim() != 3 or ctx.shape[2] != self.context_dim:
+            raise ValueError(f"context must be [B, L, {self.context_dim}], got {tuple(ctx.shape)}")
+        _lib.check(_lib.lib().t2p_unet_set_context(self._handle, _lib.ptr(ctx), ctx.shape[0], ctx.shape[1],
+                                                   _lib.current_stream()))
+        self._ctx_key = key
+
+    # ------------------------------------------------------------------ forward
+    def train(self, mode=True):
+        if mode:
+            raise NotImplementedError("the native score network is inference-only (sampling path)")
+        return super().train(False)
+
+    @torch.no_grad()
+    def forward(self, x, time_cond, text_emb=None):
+        """x [B,C,N,N] (any float dtype, cast to fp32 like ``x.float()``, reference :229), time_cond [B] integer
+        noise labels, text_emb [B,L,context_dim].  Returns float64 [B,C,N,N] = h / sigmas[time_cond]
+        (the reference's promoted dtype, :259-261)."""
+        if not x.is_cuda:
+            raise _lib.NativeError("UNetModel.forward needs CUDA tensors; there is no CPU path")
+        self.sync_weights()
+        self.set_context(text_emb)
+        xf = x.detach().to(torch.float32).contiguous()
+        labels = time_cond.detach().long().contiguous()
+        B = xf.shape[0]
+        if text_emb.shape[0] != B:
+            raise ValueError("context batch does not match x")
+        out = torch.empty(xf.shape, dtype=torch.float64, device=xf.device)
+        _lib.check(_lib.lib().t2p_unet_forward(self._handle, _lib.ptr(xf), _lib.ptr(labels), _lib.ptr(out),
+                                               _lib.F64, B, _lib.current_stream()))
+        return out
+
+    # ------------------------------------------------------------------ debugging aids
+    def set_debug(self, on=True):
+        _lib.check(_lib.lib().t2p_unet_set_debug(self._handle, 1 if on else 0))
+
+    def tap(self, name, max_elems=1 << 28):
+        shape = (C.c_int64 * 4)()
+        probe = torch.empty(max_elems if max_elems < (1 << 22) else (1 << 22), dtype=torch.float32, device="cuda")
+        L = _lib.lib()
+        rc = L.t2p_unet_tap(self._handle, name.encode(), _lib.ptr(probe), probe.numel(), shape, _lib.current_stream())
+        if rc != 0:
+            msg = L.t2p_last_error().decode()
+            if "too small" not in msg:
+                raise _lib.NativeError(msg)
+            probe = torch.empty(max_elems, dtype=torch.float32, device="cuda")
+            _lib.check(L.t2p_unet_tap(self._handle, name.encode(), _lib.ptr(probe), probe.numel(), shape,
+                                      _lib.current_stream()))
+        n = shape[0] * shape[1] * shape[2] * shape[3]
+        return probe[:n].reshape(shape[0], shape[1], shape[2], shape[3]).clone()
+
+    @property
+    def native_handle(self):
+        return self._handle
