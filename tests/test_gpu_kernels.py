@@ -1,0 +1,249 @@
+"""Per-kernel parity (through the C ABI) against torch fp32 / the oracle.  Needs a B200."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import philox_ref
+from tests.gpu_util import nchw, nhwc, rel_err
+from text2protein_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+# references are plain fp32 math: keep cuDNN / cuBLAS off their TF32 paths
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _st():
+    return _lib.current_stream()
+
+
+def _conv(a0, w, ksize, bias=None, a1=None, rowbias=None, residual=None, res_up=0, alpha=1.0, in_dtype=torch.float32,
+          out_dtype=None, stats=False):
+    """a0/a1 NCHW fp32 on cuda, w [Cout, Cin, k, k] fp32.  Returns NCHW fp32 (and stats)."""
+    out_dtype = out_dtype or in_dtype
+    B, c0, H, W = a0.shape
+    c1 = a1.shape[1] if a1 is not None else 0
+    N = w.shape[0]
+    wp = w.permute(0, 2, 3, 1).contiguous().reshape(N, -1).to(in_dtype).contiguous()
+    A0 = nhwc(a0, in_dtype)
+    A1 = nhwc(a1, in_dtype) if a1 is not None else None
+    out = torch.empty(B, H, W, N, dtype=out_dtype, device="cuda")
+    R = None
+    if residual is not None:
+        R = nhwc(residual, out_dtype)
+    a = _lib.ConvArgs()
+    a.a0, a.c0 = A0.data_ptr(), c0
+    a.a1, a.c1 = (A1.data_ptr() if A1 is not None else None), c1
+    a.B, a.H, a.W, a.ksize = B, H, W, ksize
+    a.w, a.N = wp.data_ptr(), N
+    a.bias = bias.data_ptr() if bias is not None else None
+    if rowbias is not None:
+        a.rowbias, a.rowbias_ld = rowbias.data_ptr(), rowbias.shape[1]
+    a.residual = R.data_ptr() if R is not None else None
+    a.res_up, a.alpha = res_up, alpha
+    a.out, a.out_dtype, a.in_dtype = out.data_ptr(), _lib.torch_dtype_code(out_dtype), _lib.torch_dtype_code(in_dtype)
+    ss = None
+    if stats:
+        ss = torch.zeros(2, B, N, dtype=torch.float32, device="cuda")
+        a.stat_sum, a.stat_sq = ss[0].data_ptr(), ss[1].data_ptr()
+    _lib.check(_lib.lib().t2p_conv2d(C.byref(a), _st()))
+    torch.cuda.synchronize()
+    return nchw(out.float()), ss
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 1.5e-2)])
+@pytest.mark.parametrize("H,cin,cin1,cout,k", [(32, 64, 0, 128, 3), (16, 128, 64, 64, 3), (8, 128, 0, 128, 3),
+                                               (4, 64, 0, 192, 3), (16, 64, 128, 64, 1), (64, 64, 0, 5, 3)])
+def test_conv2d_matches_torch(dtype, tol, H, cin, cin1, cout, k):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    B = 3
+    a0 = torch.randn(B, cin, H, H, device="cuda", generator=g)
+    a1 = torch.randn(B, cin1, H, H, device="cuda", generator=g) if cin1 else None
+    w = torch.randn(cout, cin + cin1, k, k, device="cuda", generator=g) / math.sqrt((cin + cin1) * k * k)
+    bias = torch.randn(cout, device="cuda", generator=g)
+    rowbias = torch.randn(B, cout + 7, device="cuda", generator=g)
+    res = torch.randn(B, cout, H, H, device="cuda", generator=g)
+    if dtype == torch.bfloat16:  # compare on identical (bf16-representable) operands
+        a0, w, res = a0.bfloat16().float(), w.bfloat16().float(), res.bfloat16().float()
+        a1 = a1.bfloat16().float() if a1 is not None else None
+    x = a0 if a1 is None else torch.cat([a0, a1], 1)
+    ref = (F.conv2d(x, w, bias, padding=k // 2) + rowbias[:, :cout, None, None] + res) * 0.70710678
+    out, _ = _conv(a0, w, k, bias=bias, a1=a1, rowbias=rowbias, residual=res, alpha=0.70710678, in_dtype=dtype)
+    assert rel_err(out, ref) < tol
+
+
+def test_conv2d_upsampled_residual_and_fused_stats():
+    g = torch.Generator(device="cuda").manual_seed(2)
+    B, H, cin, cout = 2, 16, 64, 64
+    a0 = torch.randn(B, cin, H, H, device="cuda", generator=g).bfloat16().float()
+    w = (torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / 24).bfloat16().float()
+    res = torch.randn(B, cout, H // 2, H // 2, device="cuda", generator=g).bfloat16().float()
+    ref = F.conv2d(a0, w, None, padding=1) + res.repeat_interleave(2, 2).repeat_interleave(2, 3)
+    out, ss = _conv(a0, w, 3, residual=res, res_up=1, in_dtype=torch.bfloat16, stats=True)
+    assert rel_err(out, ref) < 1.5e-2
+    # statistics describe the tensor exactly as stored
+    assert torch.allclose(ss[0], out.sum(dim=(2, 3)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(ss[1], (out * out).sum(dim=(2, 3)), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("c0,c1,groups", [(64, 0, 16), (128, 64, 32), (256, 128, 32)])
+def test_groupnorm_silu_resample_concat(dtype, tol, mode, c0, c1, groups):
+    g = torch.Generator(device="cuda").manual_seed(3)
+    B, H = 2, 16
+    a0 = (torch.randn(B, c0, H, H, device="cuda", generator=g) * 2 + 0.5).to(dtype).float()
+    a1 = (torch.randn(B, c1, H, H, device="cuda", generator=g) - 1.0).to(dtype).float() if c1 else None
+    C_ = c0 + c1
+    gamma = 1 + 0.1 * torch.randn(C_, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(C_, device="cuda", generator=g)
+    x = a0 if a1 is None else torch.cat([a0, a1], 1)
+    ref = F.silu(F.group_norm(x, groups, gamma, beta, eps=1e-6))
+    raw_ref = None
+    if mode == 1:
+        ref = F.avg_pool2d(ref, 2)
+        raw_ref = F.avg_pool2d(x, 2)
+    elif mode == 2:
+        ref = ref.repeat_interleave(2, 2).repeat_interleave(2, 3)
+    OH = H // 2 if mode == 1 else (H * 2 if mode == 2 else H)
+    A0, A1 = nhwc(a0, dtype), (nhwc(a1, dtype) if a1 is not None else None)
+    out = torch.empty(B, OH, OH, C_, dtype=dtype, device="cuda")
+    raw = torch.empty(B, OH, OH, C_, dtype=dtype, device="cuda") if mode == 1 else None
+    _lib.check(_lib.lib().t2p_groupnorm(_lib.ptr(A0), c0, _lib.ptr(A1), c1, B, H, H, _lib.torch_dtype_code(dtype),
+                                        groups, 1e-6, _lib.ptr(gamma), _lib.ptr(beta), 1, mode, _lib.ptr(out),
+                                        _lib.ptr(raw), _st()))
+    torch.cuda.synchronize()
+    assert rel_err(nchw(out.float()), ref) < tol
+    if raw is not None:
+        assert rel_err(nchw(raw.float()), raw_ref) < tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("Cdim", [64, 256, 512, 1024])
+def test_layernorm_and_geglu(dtype, tol, Cdim):
+    g = torch.Generator(device="cuda").manual_seed(4)
+    M = 77
+    x = (torch.randn(M, Cdim, device="cuda", generator=g) * 1.5 + 0.3).to(dtype)
+    gamma = 1 + 0.1 * torch.randn(Cdim, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(Cdim, device="cuda", generator=g)
+    y = torch.empty_like(x)
+    _lib.check(_lib.lib().t2p_layernorm(_lib.ptr(x), _lib.ptr(gamma), _lib.ptr(beta), M, Cdim, 1e-5,
+                                        _lib.torch_dtype_code(dtype), _lib.ptr(y), _st()))
+    assert rel_err(y.float(), F.layer_norm(x.float(), (Cdim,), gamma, beta)) < tol
+    z = torch.randn(M, 2 * Cdim, device="cuda", generator=g).to(dtype)
+    o = torch.empty(M, Cdim, dtype=dtype, device="cuda")
+    _lib.check(_lib.lib().t2p_geglu(_lib.ptr(z), M, Cdim, _lib.torch_dtype_code(dtype), _lib.ptr(o), _st()))
+    a, gate = z.float().chunk(2, dim=-1)
+    assert rel_err(o.float(), a * F.gelu(gate)) < tol
+
+
+@pytest.mark.parametrize("dtype,tc,tol", [(torch.float32, 0, 2e-5), (torch.bfloat16, 0, 2e-2), (torch.bfloat16, 1, 2e-2)])
+@pytest.mark.parametrize("heads,d,Tq,Tk", [(1, 256, 64, 64), (8, 32, 256, 256), (8, 32, 256, 77), (4, 16, 16, 8),
+                                           (8, 64, 100, 300), (1, 512, 32, 32), (8, 128, 64, 512)])
+def test_attention(dtype, tc, tol, heads, d, Tq, Tk):
+    if tc and d % 16:
+        pytest.skip("tensor-core kernel needs d % 16 == 0")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B = 2
+    inner = heads * d
+    # strided views, exactly like the fused QKV projection output
+    qkv = torch.randn(B, Tq, 3 * inner, device="cuda", generator=g).to(dtype)
+    kv = torch.randn(B, Tk, 2 * inner, device="cuda", generator=g).to(dtype)
+    q = qkv[..., :inner]
+    k, v = kv[..., :inner], kv[..., inner:]
+    out = torch.empty(B, Tq, inner, dtype=dtype, device="cuda")
+    scale = d ** -0.5
+    es = qkv.element_size()
+    _lib.check(_lib.lib().t2p_attention(C.c_void_p(qkv.data_ptr()), C.c_void_p(kv.data_ptr()),
+                                        C.c_void_p(kv.data_ptr() + inner * es), _lib.ptr(out), B, heads, Tq, Tk, d,
+                                        3 * inner, 2 * inner, 2 * inner, inner, scale, _lib.torch_dtype_code(dtype),
+                                        tc, _st()))
+
+    def split(t):
+        return t.float().reshape(B, -1, heads, d).permute(0, 2, 1, 3)
+
+    ref = torch.softmax(split(q) @ split(k).transpose(-1, -2) * scale, dim=-1) @ split(v)
+    ref = ref.permute(0, 2, 1, 3).reshape(B, Tq, inner)
+    assert rel_err(out.float(), ref) < tol
+
+
+def test_philox_bits_exact_and_normals_close():
+    seed, stream = 0x1234567ABCDEF, 7
+    bits = torch.empty(4096 * 4, dtype=torch.int32, device="cuda")
+    _lib.check(_lib.lib().t2p_philox_bits(C.c_uint64(seed), stream, 1000, 4096, _lib.ptr(bits), _st()))
+    got = bits.cpu().numpy().view(np.uint32).reshape(-1, 4)
+    want = philox_ref.philox_bits(seed, stream, 1000, 4096)
+    assert np.array_equal(got, want)  # integer path: bit-exact
+    n = torch.empty(1 << 16, dtype=torch.float32, device="cuda")
+    _lib.check(_lib.lib().t2p_philox_normal(C.c_uint64(seed), stream, 4000, n.numel(), C.c_float(1.0), _lib.ptr(n),
+                                            _st()))
+    ref = philox_ref.philox_normal(seed, stream, 4000, n.numel())
+    assert np.abs(n.cpu().numpy() - ref).max() < 2e-5
+
+
+def _ref_steps(x, score64, G, snr, noise_c, noise_p, mask, x_init):
+    """oracle restatement of one corrector + one predictor half-step (sampler_ref.pc_sampler_ref body)."""
+    B = x.shape[0]
+    grad = score64
+    grad_norm = torch.norm(grad.reshape(B, -1), dim=-1).mean()
+    noise_norm = torch.norm(noise_c.reshape(B, -1), dim=-1).mean()
+    step = (snr * noise_norm / grad_norm) ** 2 * 2 * torch.ones(B)
+    xm = x + step[:, None, None, None] * grad
+    xc = xm + torch.sqrt(step * 2)[:, None, None, None] * noise_c
+    xc = torch.where(mask, xc, x_init).float()
+    rev_f = torch.zeros_like(x) - G[:, None, None, None] ** 2 * score64
+    xm2 = x - rev_f
+    xp = xm2 + G[:, None, None, None] * noise_p
+    return xc, torch.where(mask, xp, x_init).float(), torch.where(mask, xm2, x_init).float()
+
+
+@pytest.mark.parametrize("B,Cc,N", [(2, 5, 32), (3, 8, 64), (64, 5, 16)])
+def test_pc_steps_match_oracle_math(B, Cc, N):
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(B, Cc, N, N, generator=g) * 10
+    h = torch.randn(B, N, N, Cc, generator=g)                     # raw NHWC fp32 network output
+    labels = torch.randint(0, 50, (B,), generator=g)
+    sigmas = torch.tensor(np.exp(np.linspace(np.log(100.0), np.log(0.01), 50)))
+    G = torch.rand(B, generator=g) + 0.1
+    mask = torch.rand(B, Cc, N, N, generator=g) > 0.3
+    x_init = torch.randn(B, Cc, N, N, generator=g)
+    score64 = h.permute(0, 3, 1, 2).double() / sigmas[labels][:, None, None, None]
+    seed = 99
+
+    def noise(stream):
+        n = torch.empty(B, Cc, N, N, dtype=torch.float32, device="cuda")
+        _lib.check(_lib.lib().t2p_philox_normal(C.c_uint64(seed), stream, 0, n.numel(), C.c_float(1.0), _lib.ptr(n),
+                                                _st()))
+        return n.cpu()
+
+    xc_ref, xp_ref, xm_ref = _ref_steps(x, score64, G, 0.17, noise(11), noise(12), mask, x_init)
+    dev = {k: v.cuda() for k, v in dict(h=h, labels=labels, sigmas=sigmas, G=G, x_init=x_init).items()}
+    mask_u8 = mask.cuda().contiguous().view(torch.uint8)
+    ws = torch.empty(_lib.lib().t2p_corrector_workspace_bytes(B, Cc * N * N) // 8, dtype=torch.float64, device="cuda")
+
+    def args(xbuf, stream):
+        a = _lib.StepArgs()
+        a.x, a.score, a.score_dtype, a.score_nhwc = xbuf.data_ptr(), dev["h"].data_ptr(), _lib.F32, 1
+        a.sigmas, a.labels, a.G = dev["sigmas"].data_ptr(), dev["labels"].data_ptr(), dev["G"].data_ptr()
+        a.snr, a.mask, a.x_init = 0.17, mask_u8.data_ptr(), dev["x_init"].data_ptr()
+        a.seed, a.stream_id, a.B, a.C, a.HW = seed, stream, B, Cc, N * N
+        a.workspace = ws.data_ptr()
+        return a
+
+    xc = x.cuda().clone()
+    _lib.check(_lib.lib().t2p_corrector_step(C.byref(args(xc, 11)), _st()))
+    xp = x.cuda().clone()
+    xm = torch.empty_like(xp)
+    a = args(xp, 12)
+    a.x_mean_out = xm.data_ptr()
+    _lib.check(_lib.lib().t2p_predictor_step(C.byref(a), _st()))
+    torch.cuda.synchronize()
+    for got, ref in ((xc, xc_ref), (xp, xp_ref), (xm, xm_ref)):
+        got = got.cpu()
+        assert torch.equal(got[~mask], x_init[~mask])            # mask handling is bit-exact
+        assert rel_err(got, ref) < 2e-6

@@ -24,7 +24,12 @@ struct t2p_unet {
   float* g_table = nullptr;
   float* h = nullptr;
   double* partial = nullptr;
+  cudaStream_t run_stream = nullptr;  // capture is illegal on the legacy default stream: the loop runs here
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   ~t2p_unet() {
+    if (run_stream) cudaStreamDestroy(run_stream);
+    if (ev_in) cudaEventDestroy(ev_in);
+    if (ev_out) cudaEventDestroy(ev_out);
     for (void* p : {static_cast<void*>(labels), static_cast<void*>(G), static_cast<void*>(state),
                     static_cast<void*>(label_table), static_cast<void*>(g_table), static_cast<void*>(h),
                     static_cast<void*>(partial)})
@@ -218,7 +223,20 @@ int t2p_pc_run(t2p_unet* u, const t2p_run_args* a, void* stream) {
   T2P_API_BEGIN
   T2P_CHECK(u && a && a->x && a->x_mean && a->label_table && a->g_table, "null argument");
   T2P_CHECK(a->num_iters > 0 && a->n_steps >= 0 && a->B > 0, "bad run arguments");
-  cudaStream_t st = S(stream);
+  cudaStream_t user = S(stream);
+  if (!u->run_stream) {
+    T2P_CUDA(cudaStreamCreateWithFlags(&u->run_stream, cudaStreamNonBlocking));
+    T2P_CUDA(cudaEventCreateWithFlags(&u->ev_in, cudaEventDisableTiming));
+    T2P_CUDA(cudaEventCreateWithFlags(&u->ev_out, cudaEventDisableTiming));
+  }
+  // order the loop after everything already queued on the caller's stream, and the caller after the loop
+  cudaStream_t st = u->run_stream;
+  T2P_CUDA(cudaEventRecord(u->ev_in, user));
+  T2P_CUDA(cudaStreamWaitEvent(st, u->ev_in, 0));
+  struct Rejoin {
+    t2p_unet* u; cudaStream_t user;
+    ~Rejoin() { if (cudaEventRecord(u->ev_out, u->run_stream) == cudaSuccess) cudaStreamWaitEvent(user, u->ev_out, 0); }
+  } rejoin{u, user};
   UNet& net = *u->net;
   const UNetConfig& c = net.cfg();
   const int B = a->B, K = a->num_iters;
@@ -311,13 +329,14 @@ int t2p_groupnorm(const void* a0, int c0, const void* a1, int c1, int B, int H, 
                   void* raw_out, void* stream) {
   T2P_API_BEGIN
   const int C = c0 + c1;
-  double* sums = nullptr;
+  float* sums = nullptr;
   float* affine = nullptr;
-  T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&sums), sizeof(double) * 2 * B * C));
+  const int nblk = gn_stats_blocks(B, H * W);
+  T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&sums), sizeof(float) * 2 * B * C * nblk));
   T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&affine), sizeof(float) * 2 * B * C));
   try {
     gn_stats(a0, c0, a1, c1, B, H * W, dtype, sums, S(stream));
-    gn_finalize(sums, gamma, beta, B, C, groups, H * W, eps, affine, affine + static_cast<size_t>(B) * C, S(stream));
+    gn_finalize(sums, nblk, gamma, beta, B, C, groups, H * W, eps, affine, affine + static_cast<size_t>(B) * C, S(stream));
     gn_apply(a0, c0, a1, c1, B, H, W, dtype, affine, affine + static_cast<size_t>(B) * C, silu, resample_mode, out,
              raw_out, S(stream));
     T2P_CUDA(cudaStreamSynchronize(S(stream)));

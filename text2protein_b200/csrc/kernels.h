@@ -41,15 +41,17 @@ void conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st);
 void conv_gemm_simt(const ConvGemmArgs& a, int in_dtype, cudaStream_t st);
 
 // ----------------------------------------------------------------------------- normalisation
-// GroupNorm statistics: per-(sample, channel) {sum, sum of squares} as interleaved doubles [B][C][2].
-void gn_stats(const void* a0, int c0, const void* a1, int c1, int B, int HW, int dtype, double* sums,
+// GroupNorm statistics: per-(sample, pixel block, channel) {sum, sum of squares}, part[B][nblk][C][2] floats,
+// nblk = gn_stats_blocks(B, HW); reduced without atomics so results are run-to-run deterministic.
+int gn_stats_blocks(int B, int HW);
+void gn_stats(const void* a0, int c0, const void* a1, int c1, int B, int HW, int dtype, float* part,
               cudaStream_t st);
-// float [B][c] sums from a GEMM epilogue -> channels [coff, coff+c) of the interleaved double layout
-void gn_stats_from_f32(const float* s, const float* q, int B, int c, int ctot, int coff, double* sums,
+// float [B][c] sums from a GEMM epilogue -> channels [coff, coff+c) of part[B][1][ctot][2]
+void gn_stats_from_f32(const float* s, const float* q, int B, int c, int ctot, int coff, float* part,
                        cudaStream_t st);
-// -> per-(sample, channel) affine  y = x * scale + shift  (fp32 [B][C] each)
-void gn_finalize(const double* sums, const float* gamma, const float* beta, int B, int C, int G, int HW, float eps,
-                 float* scale, float* shift, cudaStream_t st);
+// -> per-(sample, channel) affine  y = x * scale + shift  (fp32 [B][C] each); blocks are added in double
+void gn_finalize(const float* part, int nblk, const float* gamma, const float* beta, int B, int C, int G, int HW,
+                 float eps, float* scale, float* shift, cudaStream_t st);
 // y = act(x * scale + shift) over the (virtual) channel concat of a0|a1; mode 0 same size, 1 = 2x2 mean
 // after the activation (raw_out, optional, receives the 2x2 mean of the raw input), 2 = nearest x2 upsample.
 void gn_apply(const void* a0, int c0, const void* a1, int c1, int B, int H, int W, int dtype, const float* scale,

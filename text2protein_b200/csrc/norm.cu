@@ -55,21 +55,21 @@ struct Vec8<__nv_bfloat16> {
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
 
 // ------------------------------------------------------------------ statistics: per (sample, channel) sums
+// Deterministic two-level reduction (no atomics): each block reduces a contiguous run of pixels to
+// part[b][blk][c][{sum, sumsq}] in a fixed order; gn_finalize adds the blocks in order, in double.
 template <typename T>
 __global__ void gn_stats_kernel(const T* __restrict__ a0, int c0, const T* __restrict__ a1, int c1, int HW,
-                                int pix_per_block, double* __restrict__ sums) {
-  extern __shared__ float sm[];  // [ctot][2]
+                                int pix_per_block, float* __restrict__ part) {
+  extern __shared__ float sm[];  // [rows][2 * ctot]
   const int ctot = c0 + c1;
   const int slots = ctot >> 3;
   const int rows = blockDim.x / slots;
   const int slot = threadIdx.x % slots;
   const int row = threadIdx.x / slots;
   const int b = blockIdx.y;
-  for (int i = threadIdx.x; i < 2 * ctot; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
   float s[8] = {}, q[8] = {};
-  if (row < rows) {
-    const int ch = slot << 3;
+  const int ch = slot << 3;
+  {
     const T* src;
     int cs, co;
     if (ch < c0) { src = a0; cs = c0; co = ch; }
@@ -81,30 +81,35 @@ __global__ void gn_stats_kernel(const T* __restrict__ a0, int c0, const T* __res
 #pragma unroll
       for (int i = 0; i < 8; ++i) { s[i] += v.v[i]; q[i] += v.v[i] * v.v[i]; }
     }
+  }
+  float* mine = sm + static_cast<size_t>(row) * 2 * ctot;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      atomicAdd(&sm[2 * (ch + i)], s[i]);
-      atomicAdd(&sm[2 * (ch + i) + 1], q[i]);
-    }
+  for (int i = 0; i < 8; ++i) {
+    mine[2 * (ch + i)] = s[i];
+    mine[2 * (ch + i) + 1] = q[i];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * ctot; i += blockDim.x)
-    atomicAdd(&sums[static_cast<long long>(b) * 2 * ctot + i], static_cast<double>(sm[i]));
+  float* dst = part + (static_cast<long long>(b) * gridDim.x + blockIdx.x) * 2 * ctot;
+  for (int i = threadIdx.x; i < 2 * ctot; i += blockDim.x) {
+    float acc = 0.f;
+    for (int r = 0; r < rows; ++r) acc += sm[static_cast<size_t>(r) * 2 * ctot + i];
+    dst[i] = acc;
+  }
 }
 
-// float sums produced by the GEMM epilogue -> interleaved double layout used by finalize
+// float sums produced by the GEMM epilogue -> part layout with one block per sample
 __global__ void gn_stats_from_f32_kernel(const float* __restrict__ s, const float* __restrict__ q, int B, int c,
-                                         int ctot, int coff, double* __restrict__ sums) {
+                                         int ctot, int coff, float* __restrict__ part) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * c) return;
   const int b = i / c, ch = i - b * c;
   const long long o = (static_cast<long long>(b) * ctot + coff + ch) * 2;
-  sums[o] = s[i];
-  sums[o + 1] = q[i];
+  part[o] = s[i];
+  part[o + 1] = q[i];
 }
 
 // per (sample, group): mean / rstd -> per (sample, channel) affine  y = x * scale + shift
-__global__ void gn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
+__global__ void gn_finalize_kernel(const float* __restrict__ part, int nblk, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, int C, int G, int HW, float eps,
                                    float* __restrict__ scale, float* __restrict__ shift, int total) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -112,9 +117,12 @@ __global__ void gn_finalize_kernel(const double* __restrict__ sums, const float*
   const int g = i % G, b = i / G;
   const int cpg = C / G;
   double s = 0, q = 0;
-  for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-    s += sums[(static_cast<long long>(b) * C + c) * 2];
-    q += sums[(static_cast<long long>(b) * C + c) * 2 + 1];
+  for (int k = 0; k < nblk; ++k) {
+    const float* pb = part + (static_cast<long long>(b) * nblk + k) * 2 * C;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      s += static_cast<double>(pb[2 * c]);
+      q += static_cast<double>(pb[2 * c + 1]);
+    }
   }
   const double n = static_cast<double>(cpg) * HW;
   const double mean = s / n;
@@ -297,41 +305,50 @@ __global__ void geglu_kernel(const T* __restrict__ z, long long M, int D, T* __r
 }  // namespace
 
 // ===================================================================================== host launchers
-void gn_stats(const void* a0, int c0, const void* a1, int c1, int B, int HW, int dtype, double* sums,
+int gn_stats_blocks(int B, int HW) {
+  // enough blocks to fill the machine, each with a contiguous run of pixels
+  int blocks = std::max(1, std::min(cdiv(HW, 64), cdiv(148 * 8, B)));
+  const int ppb = cdiv(HW, blocks);
+  return cdiv(HW, ppb);
+}
+
+void gn_stats(const void* a0, int c0, const void* a1, int c1, int B, int HW, int dtype, float* part,
               cudaStream_t st) {
   const int ctot = c0 + c1;
   T2P_CHECK(c0 % 8 == 0 && c1 % 8 == 0 && ctot > 0, "GroupNorm channels must be multiples of 8");
   const int slots = ctot / 8;
   T2P_CHECK(slots <= 256, "too many channels for gn_stats");
   const int threads = slots * (256 / slots);
-  // enough blocks to fill the machine, each with a contiguous run of pixels
-  int blocks = std::max(1, std::min(cdiv(HW, 64), cdiv(148 * 8, B)));
+  const int blocks = gn_stats_blocks(B, HW);
   const int ppb = cdiv(HW, blocks);
-  blocks = cdiv(HW, ppb);
-  T2P_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * B * ctot, st));
   dim3 grid(blocks, B);
-  const size_t smem = sizeof(float) * 2 * ctot;
-  if (dtype == kF32)
+  const size_t smem = sizeof(float) * 2 * ctot * (threads / slots);
+  if (dtype == kF32) {
+    static bool cfgd = false;
+    if (!cfgd) { T2P_CUDA(cudaFuncSetAttribute(gn_stats_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); cfgd = true; }
     gn_stats_kernel<float><<<grid, threads, smem, st>>>(static_cast<const float*>(a0), c0,
-                                                        static_cast<const float*>(a1), c1, HW, ppb, sums);
-  else
+                                                        static_cast<const float*>(a1), c1, HW, ppb, part);
+  } else {
+    static bool cfgd = false;
+    if (!cfgd) { T2P_CUDA(cudaFuncSetAttribute(gn_stats_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); cfgd = true; }
     gn_stats_kernel<__nv_bfloat16><<<grid, threads, smem, st>>>(static_cast<const __nv_bfloat16*>(a0), c0,
                                                                 static_cast<const __nv_bfloat16*>(a1), c1, HW, ppb,
-                                                                sums);
+                                                                part);
+  }
   T2P_LAUNCH_CHECK();
 }
 
-void gn_stats_from_f32(const float* s, const float* q, int B, int c, int ctot, int coff, double* sums,
+void gn_stats_from_f32(const float* s, const float* q, int B, int c, int ctot, int coff, float* part,
                        cudaStream_t st) {
-  gn_stats_from_f32_kernel<<<cdiv(B * c, 256), 256, 0, st>>>(s, q, B, c, ctot, coff, sums);
+  gn_stats_from_f32_kernel<<<cdiv(B * c, 256), 256, 0, st>>>(s, q, B, c, ctot, coff, part);
   T2P_LAUNCH_CHECK();
 }
 
-void gn_finalize(const double* sums, const float* gamma, const float* beta, int B, int C, int G, int HW, float eps,
-                 float* scale, float* shift, cudaStream_t st) {
+void gn_finalize(const float* part, int nblk, const float* gamma, const float* beta, int B, int C, int G, int HW,
+                 float eps, float* scale, float* shift, cudaStream_t st) {
   T2P_CHECK(C % G == 0, "channels not divisible by groups");
   const int total = B * G;
-  gn_finalize_kernel<<<cdiv(total, 128), 128, 0, st>>>(sums, gamma, beta, C, G, HW, eps, scale, shift, total);
+  gn_finalize_kernel<<<cdiv(total, 128), 128, 0, st>>>(part, nblk, gamma, beta, C, G, HW, eps, scale, shift, total);
   T2P_LAUNCH_CHECK();
 }
 

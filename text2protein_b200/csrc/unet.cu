@@ -422,10 +422,11 @@ void UNet::group_norm(const GroupNormP& gn, const Act& a0, const Act* a1, int ac
   const int C = a0.C + (a1 ? a1->C : 0);
   T2P_CHECK(C == gn.C, "GroupNorm channel mismatch");
   const int B = a0.B, HW = a0.H * a0.W;
-  double* sums = static_cast<double*>(ws_.alloc(sizeof(double) * 2 * B * C));
+  const bool fused = a0.ssum && (!a1 || a1->ssum);
+  const int nblk = fused ? 1 : gn_stats_blocks(B, HW);
+  float* sums = static_cast<float*>(ws_.alloc(sizeof(float) * 2 * B * C * nblk));
   float* scale = static_cast<float*>(ws_.alloc(sizeof(float) * 2 * B * C));
   float* shift = scale + static_cast<size_t>(B) * C;
-  const bool fused = a0.ssum && (!a1 || a1->ssum);
   launches_ += fused ? (a1 ? 2 : 1) : 2;  // stats (+memset) or conversion(s)
   launches_ += 2;                          // finalize + apply
   if (!dry_) {
@@ -435,8 +436,8 @@ void UNet::group_norm(const GroupNormP& gn, const Act& a0, const Act* a1, int ac
     } else {
       gn_stats(a0.p, a0.C, a1 ? a1->p : nullptr, a1 ? a1->C : 0, B, HW, cfg_.compute_dtype, sums, st_);
     }
-    gn_finalize(sums, static_cast<const float*>(gn.w->data), static_cast<const float*>(gn.b->data), B, C, gn.G, HW,
-                1e-6f, scale, shift, st_);
+    gn_finalize(sums, nblk, static_cast<const float*>(gn.w->data), static_cast<const float*>(gn.b->data), B, C, gn.G,
+                HW, 1e-6f, scale, shift, st_);
     gn_apply(a0.p, a0.C, a1 ? a1->p : nullptr, a1 ? a1->C : 0, B, a0.H, a0.W, cfg_.compute_dtype, scale, shift, act,
              mode, out.p, raw_out ? raw_out->p : nullptr, st_);
   }

@@ -179,9 +179,11 @@ class UNetModel(nn.Module):
         if text_emb is None:
             raise TypeError("context=None is not supported: the reference model crashes on it as well "
                             "(to_k expects context_dim inputs, model/attention.py:161-175)")
-        key = (text_emb.data_ptr(), tuple(text_emb.shape), text_emb._version, text_emb.dtype)
-        if key == self._ctx_key:
+        # identity + version of the tensor OBJECT (kept alive here): a pointer-based key would be fooled by the
+        # caching allocator handing the same address to a new context tensor
+        if self._ctx_key is not None and self._ctx_key[0] is text_emb and self._ctx_key[1] == text_emb._version:
             return
+        key = (text_emb, text_emb._version)
         ctx = text_emb.detach().to(torch.float32).contiguous()
         if ctx.dim() != 3 or ctx.shape[2] != self.context_dim:
             raise ValueError(f"context must be [B, L, {self.context_dim}], got {tuple(ctx.shape)}")
