@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Headline benchmark: 6D maps/sec of the full predictor-corrector sampling loop (BASELINE.json).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (config.workload): BASELINE config 2, ``cond_length.yml`` -- N=128 6D maps, C=5, batch 64 per GPU,
+length-conditioned, text context L=256 x 4096, VESDE num_scales=2000, snr 0.17, random-init re-randomised
+weights, synthetic inputs.  A *step* is one PC iteration over the batch (Langevin corrector + reverse-diffusion
+predictor = 2 score-network forwards + 2 fused step kernels).  ``value`` = maps/s of a full 2000-iteration run
+extrapolated from the K timed iterations: n_gpus * B / (ms_per_step * num_scales).  Every rank runs the same
+per-GPU batch (weak scaling); chains are independent, so there is no collective inside the loop.
+
+The JSON line also carries: ``e2e`` (same metric through the public ``pc_sampler`` call with host buffers),
+``roofline`` (dominant kernel, CUDA-event timed), ``cpu_baseline`` (the oracle port on the host cores),
+``clocks`` (nvidia-smi during the timed region), ``gpu_launches``.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "6D maps/sec (N=128, full PC loop)"
+UNIT = "maps/s"
+WORKLOAD = "cond_length.yml N=128 C=5 B=64/GPU L=256 num_scales=2000 VESDE PC(langevin+reverse_diffusion)"
+CTX_LEN = 256
+BATCH = 64
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+def _inputs(cfg, batch, seed=1234, sample_offset=0):
+    g = torch.Generator().manual_seed(seed + sample_offset)
+    N = cfg.data.max_res_num
+    ctx = torch.randn(batch, CTX_LEN, cfg.model.context_dim, generator=g) * 0.02
+    lengths = torch.randint(40, N + 1, (batch,), generator=g)
+    ar = torch.arange(N)
+    lmask = (ar[None, :, None] < lengths[:, None, None]) & (ar[None, None, :] < lengths[:, None, None])
+    return ctx, {"length": lmask}
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def _oracle_setup(cfg, batch, seed_weights=42):
+    """Oracle port of the reference path on CPU with the same re-randomised weights recipe and inputs."""
+    import json as _json
+    from oracle import sampler_ref, unet_ref
+    tree = _json.load(open(os.path.join(ROOT, "tests", "golden", "param_tree_cond_length.json")))
+    sd = unet_ref.state_dict_from_tree(tree, cfg, seed_weights)
+    ctx, cond = _inputs(cfg, batch)
+    sde = sampler_ref.VESDERef(cfg.model.sigma_min, cfg.model.sigma_max, cfg.model.num_scales)
+    shape = (batch, cfg.data.num_channels, cfg.data.max_res_num, cfg.data.max_res_num)
+    model = lambda x, lab, cx: unet_ref.unet_forward(sd, cfg, x, lab, cx)  # noqa: E731
+    return sde, model, shape, ctx, cond
+
+
+def _oracle_iterations(cfg, batch, iters):
+    from oracle import sampler_ref
+    sde, model, shape, ctx, cond = _oracle_setup(cfg, batch)
+    t0 = time.perf_counter()
+    sampler_ref.pc_sampler_ref(sde, model, shape, cfg.sampling.snr, n_steps=cfg.sampling.n_steps_each, eps=1e-5,
+                               condition=cond, context=ctx, noise_fn=sampler_ref.philox_noise_fn(2024),
+                               num_iters=iters)
+    return time.perf_counter() - t0
+
+
+def run_reference(args, cfg):
+    """--impl reference: the reference's CPU path (oracle port; the reference itself is Python and cannot travel
+    to the GPU box) on all host cores, each step a bounded sample (1 map) of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    batch = 1
+    from oracle import sampler_ref
+    sde, model, shape, ctx, cond = _oracle_setup(cfg, batch)
+    noise = sampler_ref.philox_noise_fn(2024)
+
+    def one_iter_run(k):
+        t0 = time.perf_counter()
+        sampler_ref.pc_sampler_ref(sde, model, shape, cfg.sampling.snr, n_steps=1, eps=1e-5, condition=cond,
+                                   context=ctx, noise_fn=noise, num_iters=k)
+        return time.perf_counter() - t0
+
+    if args.warmup > 0:
+        one_iter_run(args.warmup)
+    dt = one_iter_run(args.steps)
+    ms = dt / args.steps * 1e3
+    value = batch / (ms * 1e-3 * cfg.model.num_scales)
+    sample = f"B={batch} map(s), {args.steps} PC iterations of {cfg.model.num_scales}, fp32, torch CPU"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ native arm
+def run_native(args, cfg):
+    import torch.distributed as dist
+    from oracle import unet_ref  # weight re-randomisation recipe only; not on the measured path
+    from text2protein_b200 import _lib
+    from text2protein_b200.score_sde_pytorch import sampling, sde_lib
+    from text2protein_b200.score_sde_pytorch.models.ncsnpp import UNetModel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg.device = f"cuda:{local}"
+    cfg.model.compute_dtype = "bf16"
+    B = BATCH
+    torch.manual_seed(cfg.seed)
+    model = UNetModel(cfg).to(dev)
+    unet_ref.rerandomize_(model.named_parameters(), 42)
+    model.sync_weights()
+
+    ctx_h, cond_h = _inputs(cfg, B, sample_offset=rank * B)
+    ctx_pin = ctx_h.pin_memory()
+    len_pin = cond_h["length"].pin_memory()
+    sde = sde_lib.VESDE(cfg.model.sigma_min, cfg.model.sigma_max, cfg.model.num_scales)
+    shape = (B, cfg.data.num_channels, cfg.data.max_res_num, cfg.data.max_res_num)
+    K, W = args.steps, args.warmup
+    L = _lib.lib()
+
+    # ---------------- device-resident loop (value): persistent buffers, graph-replayed iterations
+    ctx_d = ctx_pin.to(dev, non_blocking=True)
+    cond_d = {"length": len_pin.to(dev, non_blocking=True)}
+    x = sampling.philox_normal(shape, 2024, 0, dev, scale=float(sde.sigma_max), sample_offset=rank * B)
+    x, cmask = sampling.apply_condition(x, cond_d)
+    x = x.contiguous()
+    x_init = x.clone()
+    x_mean = torch.empty_like(x)
+    mask_u8 = cmask.contiguous().view(torch.uint8)
+    model.set_context(ctx_d)
+    labels, G = sampling.ve_tables(sde, 1e-5, max(K, W, 1))
+
+    def run(k):
+        a = _lib.RunArgs()
+        a.x, a.x_mean, a.mask, a.x_init = x.data_ptr(), x_mean.data_ptr(), mask_u8.data_ptr(), x_init.data_ptr()
+        a.label_table, a.g_table = labels.data_ptr(), G.data_ptr()
+        a.num_iters, a.n_steps, a.snr, a.probability_flow = k, 1, float(cfg.sampling.snr), 0
+        a.seed, a.sample_offset, a.B, a.use_graph = 2024, rank * B, B, 1
+        _lib.check(L.t2p_pc_run(model.native_handle, C.byref(a), _lib.current_stream()))
+
+    side = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(side):
+        run(max(W, 1))  # warm-up: first iteration eager, graph captured, the rest replayed
+        side.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clocks = ClockSampler(local)
+        if rank == 0:
+            clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(side)
+        run(K)
+        e1.record(side)
+        side.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        clk = clocks.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / K
+    num_scales = cfg.model.num_scales
+    value = world * B / (ms_step * 1e-3 * num_scales)
+    launches_fwd = int(L.t2p_unet_launches_per_forward(model.native_handle))
+    gpu_launches = K * (2 * launches_fwd + 3)
+
+    # ---------------- end to end through the public API (e2e): host buffers in, samples out, every run
+    sampler = sampling.get_pc_sampler(sde, shape, sampling.ReverseDiffusionPredictor, sampling.LangevinCorrector,
+                                      snr=cfg.sampling.snr, n_steps=1, eps=1e-5, device=cfg.device, seed=2024,
+                                      num_iters=K, sample_offset=rank * B)
+    out_pin = torch.empty(shape, dtype=torch.float32).pin_memory()
+
+    def e2e_once():
+        c = ctx_pin.to(dev, non_blocking=True)                       # H2D: text context
+        cd = {"length": len_pin.to(dev, non_blocking=True)}          # H2D: length mask
+        s, _ = sampler(model, cd, c)
+        if world > 1:                                                # final NCCL all-gather of the samples
+            parts = [torch.empty_like(s) for _ in range(world)]
+            dist.all_gather(parts, s)
+        out_pin.copy_(s, non_blocking=True)                          # D2H: this rank's maps
+        torch.cuda.synchronize()
+
+    e2e_once()  # warm-up (captures the graph for these buffers)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e_once()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms_step = t.item() * 1e3 / K
+    e2e_value = world * B / (e2e_ms_step * 1e-3 * num_scales)
+    h2d = (ctx_pin.numel() * 4 + len_pin.numel()) / K
+    d2h = out_pin.numel() * 4 / K
+
+    # ---------------- roofline of the dominant kernel: CUDA events around every implicit-GEMM launch of eager
+    # forward passes (the same launches the graph replays), aggregated per kernel shape
+    roof = None
+    fwd_flops = None
+    if rank == 0:
+        peak_burst, peak_sust, hbm, src = _peaks()
+        xs = x.clone()
+        lab = torch.full((B,), 7, dtype=torch.int64, device=dev)
+        model(xs, lab, ctx_d)  # warm
+        _lib.check(L.t2p_unet_set_profile(model.native_handle, 1))
+        reps = 3
+        for _ in range(reps):
+            model(xs, lab, ctx_d)
+        torch.cuda.synchronize()
+        recs = (_lib.GemmRecord * 4096)()
+        n = L.t2p_unet_profile_read(model.native_handle, recs, 4096)
+        _lib.check(L.t2p_unet_set_profile(model.native_handle, 0))
+        groups = {}
+        total_flops = 0.0
+        for r in recs[:n]:
+            fl = 2.0 * r.M * r.N * r.K
+            total_flops += fl
+            key = (r.tensor_core, r.ksize, r.M, r.N, r.K)
+            g = groups.setdefault(key, [0, 0.0, fl])
+            g[0] += 1
+            g[1] += r.ms
+        fwd_flops = total_flops / reps
+        key, (cnt, ms, fl) = max(groups.items(), key=lambda kv: kv[1][1])
+        avg_ms = ms / cnt
+        achieved = fl / (avg_ms * 1e-3) / 1e12
+        tc_ms = sum(v[1] for k, v in groups.items() if k[0]) / reps
+        all_ms = sum(v[1] for v in groups.values()) / reps
+        roof = {"bound": "tensor", "achieved": achieved, "peak": peak_sust, "unit": "TFLOP/s",
+                "frac": achieved / peak_sust, "traffic": None,
+                "kernel": f"conv_gemm_tc_kernel k={key[1]} M={key[2]} N={key[3]} K={key[4]}",
+                "launches_per_forward": cnt // reps, "avg_launch_ms": avg_ms,
+                "flops_per_launch": fl, "peak_source": f"{src} sustained (burst {peak_burst})",
+                "share_of_gemm_time": ms / reps / all_ms,
+                "gemm_ms_per_forward": all_ms, "tc_gemm_ms_per_forward": tc_ms,
+                "gemm_flops_per_forward": fwd_flops,
+                "forward_tflops_incl_everything": (2 * fwd_flops) / (ms_step * 1e-3) / 1e12}
+
+    # ---------------- CPU baseline: the oracle port on this box's host cores, bounded sample
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cores = os.cpu_count()
+        torch.set_num_threads(cores)
+        iters = 2
+        dt = _oracle_iterations(cfg, 1, iters)
+        cpu_ms = dt / iters * 1e3
+        cpu = {"value": 1 / (cpu_ms * 1e-3 * num_scales), "unit": UNIT, "cores": torch.get_num_threads(),
+               "kind": "port", "sample": f"B=1 map, {iters} PC iterations of {num_scales} (incl. setup), fp32 torch CPU"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "batch_per_gpu": B, "l2": "working set (GBs of activations per "
+                           "forward) exceeds the 126 MB L2; no explicit flush", "extrapolated_from_iterations": K,
+                           "num_scales": num_scales, "parallelism": f"dp{world} (independent chains, no collective in the loop)"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": e2e_ms_step},
+                "gpu_launches": gpu_launches, "launches_per_forward": launches_fwd,
+                "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
+                "workspace_gb": L.t2p_unet_workspace_bytes(model.native_handle) / 1e9}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    from text2protein_b200 import load_config
+    cfg = load_config("cond_length", device="cpu")
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for "
+                             "the CPU baseline)")
+        run_native(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

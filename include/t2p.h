@@ -74,6 +74,13 @@ int t2p_unet_forward(t2p_unet* u, const float* x, const int64_t* labels, void* o
  * "input_blocks.<i>", "mid_blocks", "out_blocks.<i>", "out"). */
 int t2p_unet_set_debug(t2p_unet* u, int enable);
 int t2p_unet_tap(t2p_unet* u, const char* name, float* dst, int64_t capacity, int64_t* shape4, void* stream);
+/* Profile mode: CUDA events around every implicit-GEMM launch of the following forward passes (eager only).
+ * t2p_unet_profile_read synchronises, fills up to `cap` records and returns the number recorded (or -1). */
+typedef struct t2p_gemm_record {
+  int64_t M; int32_t N; int32_t K; int32_t ksize; int32_t tensor_core; int32_t H; int32_t W; float ms;
+} t2p_gemm_record;
+int t2p_unet_set_profile(t2p_unet* u, int enable);
+int t2p_unet_profile_read(t2p_unet* u, t2p_gemm_record* out, int cap);
 int64_t t2p_unet_workspace_bytes(const t2p_unet* u);
 int64_t t2p_unet_launches_per_forward(const t2p_unet* u);
 

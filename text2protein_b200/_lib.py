@@ -44,6 +44,11 @@ class ConvArgs(C.Structure):
                 ("in_dtype", C.c_int32), ("stat_sum", C.c_void_p), ("stat_sq", C.c_void_p)]
 
 
+class GemmRecord(C.Structure):
+    _fields_ = [("M", C.c_int64), ("N", C.c_int32), ("K", C.c_int32), ("ksize", C.c_int32),
+                ("tensor_core", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("ms", C.c_float)]
+
+
 # name -> (restype, argtypes); must list every symbol include/t2p.h declares (tests/test_abi.py checks)
 SIGNATURES = {
     "t2p_last_error": (C.c_char_p, []),
@@ -60,6 +65,8 @@ SIGNATURES = {
     "t2p_unet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "t2p_unet_set_debug": (C.c_int, [C.c_void_p, C.c_int]),
     "t2p_unet_tap": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]),
+    "t2p_unet_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "t2p_unet_profile_read": (C.c_int, [C.c_void_p, C.POINTER(GemmRecord), C.c_int]),
     "t2p_unet_workspace_bytes": (C.c_int64, [C.c_void_p]),
     "t2p_unet_launches_per_forward": (C.c_int64, [C.c_void_p]),
     "t2p_corrector_workspace_bytes": (C.c_int64, [C.c_int, C.c_int64]),

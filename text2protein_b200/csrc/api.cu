@@ -13,8 +13,25 @@ thread_local std::string g_last_error;
 void set_last_error(const std::string& m) { g_last_error = m; }
 }  // namespace t2p
 
+struct RunKey {
+  const void *x, *x_mean, *mask, *x_init;
+  int B, n_steps;
+  float snr;
+  int pf;
+  unsigned long long seed;
+  long long sample_offset;
+  long long generation;
+  bool operator==(const RunKey& o) const {
+    return x == o.x && x_mean == o.x_mean && mask == o.mask && x_init == o.x_init && B == o.B &&
+           n_steps == o.n_steps && snr == o.snr && pf == o.pf && seed == o.seed && sample_offset == o.sample_offset &&
+           generation == o.generation;
+  }
+};
+
 struct t2p_unet {
   std::unique_ptr<t2p::UNet> net;
+  cudaGraphExec_t graph_exec = nullptr;
+  RunKey graph_key{};
   // sampling-loop state (device), sized lazily
   int run_B = 0, run_K = 0;
   long long* labels = nullptr;
@@ -27,6 +44,7 @@ struct t2p_unet {
   cudaStream_t run_stream = nullptr;  // capture is illegal on the legacy default stream: the loop runs here
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   ~t2p_unet() {
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
     if (run_stream) cudaStreamDestroy(run_stream);
     if (ev_in) cudaEventDestroy(ev_in);
     if (ev_out) cudaEventDestroy(ev_out);
@@ -138,6 +156,27 @@ int t2p_unet_tap(t2p_unet* u, const char* name, float* dst, int64_t capacity, in
   T2P_API_BEGIN
   T2P_CHECK(u->net->tap(name, dst, capacity, shape4, S(stream)), std::string("no tap named '") + name + "'");
   T2P_API_END
+}
+
+int t2p_unet_set_profile(t2p_unet* u, int enable) {
+  T2P_API_BEGIN
+  u->net->set_profile(enable != 0);
+  T2P_API_END
+}
+
+int t2p_unet_profile_read(t2p_unet* u, t2p_gemm_record* out, int cap) {
+  try {
+    std::vector<GemmRecord> tmp(cap > 0 ? cap : 0);
+    const int n = u->net->profile_records(tmp.data(), cap);
+    for (int i = 0; i < n && i < cap; ++i) {
+      out[i].M = tmp[i].M; out[i].N = tmp[i].N; out[i].K = tmp[i].K; out[i].ksize = tmp[i].ksize;
+      out[i].tensor_core = tmp[i].tc; out[i].H = tmp[i].H; out[i].W = tmp[i].W; out[i].ms = tmp[i].ms;
+    }
+    return n;
+  } catch (const std::exception& e) {
+    t2p::set_last_error(e.what());
+    return -1;
+  }
 }
 
 int64_t t2p_unet_workspace_bytes(const t2p_unet* u) { return static_cast<int64_t>(u->net->workspace_bytes()); }
@@ -276,34 +315,34 @@ int t2p_pc_run(t2p_unet* u, const t2p_run_args* a, void* stream) {
   if (!a->use_graph) {
     for (int i = 0; i < K; ++i) iteration();
   } else {
-    // one eager iteration sizes the workspace, builds TMA descriptors and sets kernel attributes
-    // outside the capture; the remaining K-1 iterations replay the captured graph.
-    iteration();
-    if (K > 1) {
-      cudaGraph_t graph = nullptr;
-      cudaGraphExec_t exec = nullptr;
-      T2P_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-      try {
-        iteration();
-      } catch (...) {
-        cudaStreamEndCapture(st, &graph);
-        if (graph) cudaGraphDestroy(graph);
-        throw;
-      }
-      T2P_CUDA(cudaStreamEndCapture(st, &graph));
-      cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
-      if (e != cudaSuccess) {
+    // The captured iteration is cached: a later run with the same buffers, batch, seed and weights replays
+    // it for all K iterations.  On a miss, iteration 0 runs eagerly (sizes the workspace, builds TMA
+    // descriptors, sets kernel attributes outside the capture), then iterations 1..K-1 replay the capture.
+    RunKey key{a->x, a->x_mean, a->mask, a->x_init, a->B, a->n_steps, a->snr, a->probability_flow, a->seed,
+               a->sample_offset, net.generation()};
+    int first = 0;
+    if (!u->graph_exec || !(key == u->graph_key)) {
+      if (u->graph_exec) { cudaGraphExecDestroy(u->graph_exec); u->graph_exec = nullptr; }
+      iteration();
+      first = 1;
+      if (K > 1) {
+        cudaGraph_t graph = nullptr;
+        T2P_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        try {
+          iteration();
+        } catch (...) {
+          cudaStreamEndCapture(st, &graph);
+          if (graph) cudaGraphDestroy(graph);
+          throw;
+        }
+        T2P_CUDA(cudaStreamEndCapture(st, &graph));
+        cudaError_t e = cudaGraphInstantiate(&u->graph_exec, graph, 0);
         cudaGraphDestroy(graph);
-        T2P_CUDA(e);
+        if (e != cudaSuccess) { u->graph_exec = nullptr; T2P_CUDA(e); }
+        u->graph_key = key;
       }
-      for (int i = 1; i < K; ++i) {
-        e = cudaGraphLaunch(exec, st);
-        if (e != cudaSuccess) break;
-      }
-      cudaGraphExecDestroy(exec);
-      cudaGraphDestroy(graph);
-      T2P_CUDA(e);
     }
+    for (int i = first; i < K; ++i) T2P_CUDA(cudaGraphLaunch(u->graph_exec, st));
   }
   T2P_API_END
 }

@@ -370,6 +370,7 @@ void UNet::finalize(cudaStream_t st) {
   for (auto& p : params_) T2P_CHECK(p->loaded, "parameter '" + p->name + "' was never loaded");
   for (Linear* l : all_linear_) pack(*l, st);
   finalized_ = true;
+  ++generation_;
 }
 
 // ======================================================================================= forward helpers
@@ -414,8 +415,44 @@ void UNet::gemm(const Linear& l, const Act& a0, const Act* a1, Act& out, const f
   }
   ++launches_;
   if (dry_) return;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (profile_) {
+    T2P_CUDA(cudaEventCreate(&e0));
+    T2P_CUDA(cudaEventCreate(&e1));
+    T2P_CUDA(cudaEventRecord(e0, st_));
+  }
   if (tc) conv_gemm_tc(g, st_);
   else conv_gemm_simt(g, l.force_f32 ? kF32 : cfg_.compute_dtype, st_);
+  if (profile_) {
+    T2P_CUDA(cudaEventRecord(e1, st_));
+    GemmRecord r;
+    r.M = a0.rows(); r.N = l.N; r.K = l.K(); r.ksize = l.ksize; r.tc = tc ? 1 : 0;
+    r.H = a0.H; r.W = a0.W;
+    r.e0 = e0; r.e1 = e1;
+    profile_log_.push_back(r);
+  }
+}
+
+void UNet::set_profile(bool on) {
+  profile_ = on;
+  for (auto& r : profile_log_) {
+    if (r.e0) cudaEventDestroy(r.e0);
+    if (r.e1) cudaEventDestroy(r.e1);
+  }
+  profile_log_.clear();
+}
+
+int UNet::profile_records(GemmRecord* out, int cap) {
+  int n = 0;
+  for (auto& r : profile_log_) {
+    if (r.e0 && r.e1) {
+      T2P_CUDA(cudaEventSynchronize(r.e1));
+      T2P_CUDA(cudaEventElapsedTime(&r.ms, r.e0, r.e1));
+    }
+    if (out && n < cap) out[n] = r;
+    ++n;
+  }
+  return n;
 }
 
 void UNet::group_norm(const GroupNormP& gn, const Act& a0, const Act* a1, int act, int mode, Act& out, Act* raw_out) {
@@ -427,7 +464,7 @@ void UNet::group_norm(const GroupNormP& gn, const Act& a0, const Act* a1, int ac
   float* sums = static_cast<float*>(ws_.alloc(sizeof(float) * 2 * B * C * nblk));
   float* scale = static_cast<float*>(ws_.alloc(sizeof(float) * 2 * B * C));
   float* shift = scale + static_cast<size_t>(B) * C;
-  launches_ += fused ? (a1 ? 2 : 1) : 2;  // stats (+memset) or conversion(s)
+  launches_ += fused ? (a1 ? 2 : 1) : 1;  // statistics kernel, or conversion(s) of epilogue sums
   launches_ += 2;                          // finalize + apply
   if (!dry_) {
     if (fused) {
@@ -648,6 +685,7 @@ void UNet::set_context(const float* ctx, int B, int L, cudaStream_t st) {
   T2P_CUDA(cudaFree(cbuf));
   ctx_B_ = B;
   ctx_L_ = L;
+  ++generation_;
 }
 
 // UNetModel.forward, ncsnpp.py:220-263

@@ -112,6 +112,13 @@ struct ModuleM {
 };
 using BlockM = std::vector<ModuleM>;
 
+struct GemmRecord {  // one implicit-GEMM launch of a profiled forward pass
+  long long M = 0;
+  int N = 0, K = 0, ksize = 1, tc = 0, H = 0, W = 0;
+  float ms = 0.f;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+
 class UNet {
  public:
   explicit UNet(const UNetConfig& cfg);
@@ -133,6 +140,10 @@ class UNet {
   void set_debug(bool on) { debug_ = on; }
   // copies a recorded block output (fp32 NCHW) to dst; returns its shape
   bool tap(const std::string& name, float* dst, int64_t capacity, int64_t shape[4], cudaStream_t st);
+  // profile mode: CUDA events around every implicit-GEMM launch of the following forward passes
+  void set_profile(bool on);
+  int profile_records(GemmRecord* out, int cap);
+  long long generation() const { return generation_; }  // bumped by finalize() / set_context()
   size_t workspace_bytes() const { return ws_.capacity(); }
   long long launches_per_forward() const { return launches_; }
 
@@ -184,6 +195,9 @@ class UNet {
   cudaStream_t st_ = nullptr;
   bool dry_ = false;
   bool debug_ = false;
+  bool profile_ = false;
+  long long generation_ = 0;
+  std::vector<GemmRecord> profile_log_;
   int planned_B_ = -1;
   long long launches_ = 0;
   float* temb_all_ = nullptr;
