@@ -158,7 +158,8 @@ typedef struct t2p_conv_args {
   float alpha;
   void* out; int32_t out_dtype;
   int32_t in_dtype;                /* T2P_BF16 -> tcgen05 kernel (needs c % 64 == 0); T2P_F32 -> CUDA-core kernel */
-  float* stat_sum; float* stat_sq; /* optional fused GroupNorm statistics (tcgen05 kernel only) */
+  float* stat_part;                /* optional fused GroupNorm statistics, [B*H*W/128][N][2] {sum, sumsq} per
+                                      128-row tile (tcgen05 kernel, bf16 out, H*W % 128 == 0) */
 } t2p_conv_args;
 int t2p_conv2d(const t2p_conv_args* a, void* stream);        /* nn.Conv2d / NIN / nn.Linear: layers.py:82-95,128-137 */
 

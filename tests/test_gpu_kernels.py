@@ -49,8 +49,8 @@ def _conv(a0, w, ksize, bias=None, a1=None, rowbias=None, residual=None, res_up=
     a.out, a.out_dtype, a.in_dtype = out.data_ptr(), _lib.torch_dtype_code(out_dtype), _lib.torch_dtype_code(in_dtype)
     ss = None
     if stats:
-        ss = torch.zeros(2, B, N, dtype=torch.float32, device="cuda")
-        a.stat_sum, a.stat_sq = ss[0].data_ptr(), ss[1].data_ptr()
+        ss = torch.full((B, H * W // 128, N, 2), float("nan"), dtype=torch.float32, device="cuda")
+        a.stat_part = ss.data_ptr()
     _lib.check(_lib.lib().t2p_conv2d(C.byref(a), _st()))
     torch.cuda.synchronize()
     return nchw(out.float()), ss
@@ -87,8 +87,9 @@ def test_conv2d_upsampled_residual_and_fused_stats():
     out, ss = _conv(a0, w, 3, residual=res, res_up=1, in_dtype=torch.bfloat16, stats=True)
     assert rel_err(out, ref) < 1.5e-2
     # statistics describe the tensor exactly as stored
-    assert torch.allclose(ss[0], out.sum(dim=(2, 3)), rtol=1e-4, atol=1e-2)
-    assert torch.allclose(ss[1], (out * out).sum(dim=(2, 3)), rtol=1e-4, atol=1e-2)
+    tot = ss.sum(dim=1)  # [B, N, 2] over the 128-row tiles of each sample
+    assert torch.allclose(tot[..., 0], out.sum(dim=(2, 3)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(tot[..., 1], (out * out).sum(dim=(2, 3)), rtol=1e-4, atol=1e-2)
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])

@@ -357,7 +357,7 @@ int t2p_conv2d(const t2p_conv_args* a, void* stream) {
   g.bias = a->bias; g.rowbias = a->rowbias; g.rowbias_ld = a->rowbias_ld; g.rows_per_sample = a->H * a->W;
   g.residual = a->residual; g.res_up = a->res_up; g.alpha = a->alpha;
   g.out = a->out; g.out_dtype = a->out_dtype;
-  g.stat_sum = a->stat_sum; g.stat_sq = a->stat_sq;
+  g.stat_part = a->stat_part;
   if (a->in_dtype == T2P_BF16 && a->c0 % 64 == 0 && a->c1 % 64 == 0) conv_gemm_tc(g, S(stream));
   else conv_gemm_simt(g, a->in_dtype, S(stream));
   T2P_API_END
@@ -375,7 +375,7 @@ int t2p_groupnorm(const void* a0, int c0, const void* a1, int c1, int B, int H, 
   T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&affine), sizeof(float) * 2 * B * C));
   try {
     gn_stats(a0, c0, a1, c1, B, H * W, dtype, sums, S(stream));
-    gn_finalize(sums, nblk, gamma, beta, B, C, groups, H * W, eps, affine, affine + static_cast<size_t>(B) * C, S(stream));
+    gn_finalize(sums, nblk, C, nullptr, 0, 0, gamma, beta, B, groups, H * W, eps, affine, affine + static_cast<size_t>(B) * C, S(stream));
     gn_apply(a0, c0, a1, c1, B, H, W, dtype, affine, affine + static_cast<size_t>(B) * C, silu, resample_mode, out,
              raw_out, S(stream));
     T2P_CUDA(cudaStreamSynchronize(S(stream)));

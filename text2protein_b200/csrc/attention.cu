@@ -95,9 +95,4 @@ void attention_simt(const AttnArgs& a, int dtype, cudaStream_t st) {
   T2P_LAUNCH_CHECK();
 }
 
-#ifndef T2P_HAVE_ATTENTION_MMA
-bool attention_mma_supported(const AttnArgs&) { return false; }
-void attention_mma(const AttnArgs&, cudaStream_t) { T2P_CHECK(false, "attention_mma not built"); }
-#endif
-
 }  // namespace t2p

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) conv_gemm_simt_kernel(SimtParams p) {
 
 void conv_gemm_simt(const ConvGemmArgs& a, int in_dtype, cudaStream_t st) {
   T2P_CHECK(a.ksize == 1 || a.ksize == 3, "ksize must be 1 or 3");
-  T2P_CHECK(a.stat_sum == nullptr, "SIMT path does not fuse GroupNorm statistics");
+  T2P_CHECK(a.stat_part == nullptr, "SIMT path does not fuse GroupNorm statistics");
   SimtParams p{};
   p.a0 = a.a0; p.a1 = a.a1; p.c0 = a.c0; p.c1 = a.c1;
   p.B = a.B; p.H = a.H; p.W = a.W; p.ksize = a.ksize;

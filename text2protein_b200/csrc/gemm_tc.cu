@@ -45,8 +45,7 @@ struct TcParams {
   float alpha;
   void* out;
   int out_fp32;
-  float* stat_sum;
-  float* stat_sq;
+  float* stat_part;  // [M tiles][N][2] per-tile column {sum, sum of squares} or null
   int rowbias_ld;
   int out_nchw;
   int debug_mode;  // 0 = normal; 1..3 = bring-up bisection (see T2P_TC_DEBUG)
@@ -77,6 +76,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_gemm_tc_kernel(const __grid_
   __shared__ __align__(8) uint64_t empty_bar[C::STAGES];
   __shared__ __align__(8) uint64_t accum_bar;
   __shared__ uint32_t tmem_base_slot;
+  __shared__ float2 stat_sm[4][BN >= 32 ? BN : 32];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -286,33 +286,45 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_gemm_tc_kernel(const __grid_
           for (int i = 0; i < CH; ++i) v[i] = __bfloat162float(__float2bfloat16(v[i]));
         }
       }
-      if (p.stat_sum) {
-        // Per-(sample, channel) partial sums over this warp's 32 rows.  All rows of a warp belong
-        // to one sample whenever rows_per_sample % 32 == 0; otherwise fall back to per-row atomics.
-        const bool uniform = (p.rows_per_sample % 32) == 0;
-        if (uniform) {
-          const int s0 = __shfl_sync(0xffffffffu, sample, 0);
+      if constexpr (CH == 32) {
+        if (p.stat_part) {
+          // column sums over this warp's 32 rows by a transposing butterfly: after the 5 exchange steps lane l
+          // holds the totals of column nb + l (31 shuffles per quantity instead of 32 x 5)
+          float sq[32];
 #pragma unroll
-          for (int i = 0; i < CH; ++i) {
-            float a = row_ok ? v[i] : 0.f;
-            float b = a * a;
+          for (int i = 0; i < 32; ++i) {
+            if (!row_ok) v[i] = 0.f;
+            sq[i] = v[i] * v[i];
+          }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              a += __shfl_xor_sync(0xffffffffu, a, o);
-              b += __shfl_xor_sync(0xffffffffu, b, o);
-            }
-            if (lane == (i & 31) && nb + i < p.N && (m0 + q * 32) < p.M) {
-              atomicAdd(p.stat_sum + static_cast<long long>(s0) * p.N + nb + i, a);
-              atomicAdd(p.stat_sq + static_cast<long long>(s0) * p.N + nb + i, b);
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+              const float send_v = upper ? v[i] : v[i + off];
+              const float keep_v = upper ? v[i + off] : v[i];
+              const float send_q = upper ? sq[i] : sq[i + off];
+              const float keep_q = upper ? sq[i + off] : sq[i];
+              v[i] = keep_v + __shfl_xor_sync(0xffffffffu, send_v, off);
+              sq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
             }
           }
-        } else if (row_ok) {
-#pragma unroll
-          for (int i = 0; i < CH; ++i)
-            if (nb + i < p.N) {
-              atomicAdd(p.stat_sum + static_cast<long long>(sample) * p.N + nb + i, v[i]);
-              atomicAdd(p.stat_sq + static_cast<long long>(sample) * p.N + nb + i, v[i] * v[i]);
-            }
+          stat_sm[q][c * 32 + lane] = make_float2(v[0], sq[0]);
+        }
+      }
+    }
+    if constexpr (CH == 32) {
+      if (p.stat_part) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+        const int e = (warp - 2) * 32 + lane;
+        for (int ch = e; ch < BN; ch += 128) {
+          if (n0 + ch < p.N) {
+            // fixed order -> run-to-run deterministic statistics
+            const float2 a0 = stat_sm[0][ch], a1 = stat_sm[1][ch], a2 = stat_sm[2][ch], a3 = stat_sm[3][ch];
+            float* dst = p.stat_part + (static_cast<long long>(blockIdx.x) * p.N + n0 + ch) * 2;
+            dst[0] = (a0.x + a1.x) + (a2.x + a3.x);
+            dst[1] = (a0.y + a1.y) + (a2.y + a3.y);
+          }
         }
       }
     }
@@ -428,8 +440,7 @@ void conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
   p.alpha = a.alpha;
   p.out = a.out;
   p.out_fp32 = (a.out_dtype == kF32);
-  p.stat_sum = a.stat_sum;
-  p.stat_sq = a.stat_sq;
+  p.stat_part = a.stat_part;
   p.rowbias_ld = a.rowbias_ld > 0 ? a.rowbias_ld : a.N;
   p.out_nchw = a.out_nchw;
   if (a.out_nchw) T2P_CHECK(a.out_dtype == kF32 && a.residual == nullptr, "out_nchw is fp32-only, without residual");
@@ -437,7 +448,10 @@ void conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
     static const int dbg = [] { const char* e = getenv("T2P_TC_DEBUG"); return e ? atoi(e) : 0; }();
     p.debug_mode = dbg;
   }
-  if (a.rowbias || a.stat_sum) T2P_CHECK(a.rows_per_sample > 0, "rows_per_sample required");
+  if (a.rowbias) T2P_CHECK(a.rows_per_sample > 0, "rows_per_sample required");
+  if (a.stat_part)
+    T2P_CHECK(a.rows_per_sample > 0 && a.rows_per_sample % BM == 0 && a.out_dtype == kBF16 && a.N >= 32,
+              "fused GroupNorm statistics need whole 128-row tiles per sample, bf16 output and N >= 32");
   if (a.res_up) T2P_CHECK(a.ksize == 3 && (a.H % 2 == 0) && (a.W % 2 == 0), "res_up needs an even image");
 
   // M-tile = box of 128 pixels in (b, h, w) raster order

@@ -28,9 +28,9 @@ struct ConvGemmArgs {
   float alpha = 1.f;
   void* out = nullptr;
   int out_dtype = kBF16;
-  // optional per-(sample, channel) sum / sum-of-squares of the stored output (GroupNorm stats)
-  float* stat_sum = nullptr;  // [M / rows_per_sample][N]
-  float* stat_sq = nullptr;
+  // optional fused GroupNorm statistics of the stored output: per 128-row tile and channel {sum, sum of squares},
+  // [M / 128][N][2] == part[B][rows_per_sample / 128][N][2] (tcgen05 kernel, rows_per_sample % 128 == 0)
+  float* stat_part = nullptr;
   int rowbias_ld = 0;  // row pitch of rowbias (0 -> N)
   int out_nchw = 0;    // 1: store out as [B][N][H*W] (fp32 only; used by the final conv)
 };
@@ -46,12 +46,10 @@ void conv_gemm_simt(const ConvGemmArgs& a, int in_dtype, cudaStream_t st);
 int gn_stats_blocks(int B, int HW);
 void gn_stats(const void* a0, int c0, const void* a1, int c1, int B, int HW, int dtype, float* part,
               cudaStream_t st);
-// float [B][c] sums from a GEMM epilogue -> channels [coff, coff+c) of part[B][1][ctot][2]
-void gn_stats_from_f32(const float* s, const float* q, int B, int c, int ctot, int coff, float* part,
-                       cudaStream_t st);
-// -> per-(sample, channel) affine  y = x * scale + shift  (fp32 [B][C] each); blocks are added in double
-void gn_finalize(const float* part, int nblk, const float* gamma, const float* beta, int B, int C, int G, int HW,
-                 float eps, float* scale, float* shift, cudaStream_t st);
+// -> per-(sample, channel) affine  y = x * scale + shift  (fp32 [B][C] each) over the channel concat of two
+// statistics sources (part0: channels [0, c0), part1: [c0, c0 + c1)); blocks are added in order, in double
+void gn_finalize(const float* part0, int nblk0, int c0, const float* part1, int nblk1, int c1, const float* gamma,
+                 const float* beta, int B, int G, int HW, float eps, float* scale, float* shift, cudaStream_t st);
 // y = act(x * scale + shift) over the (virtual) channel concat of a0|a1; mode 0 same size, 1 = 2x2 mean
 // after the activation (raw_out, optional, receives the 2x2 mean of the raw input), 2 = nearest x2 upsample.
 void gn_apply(const void* a0, int c0, const void* a1, int c1, int B, int H, int W, int dtype, const float* scale,

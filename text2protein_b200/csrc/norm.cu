@@ -97,31 +97,27 @@ __global__ void gn_stats_kernel(const T* __restrict__ a0, int c0, const T* __res
   }
 }
 
-// float sums produced by the GEMM epilogue -> part layout with one block per sample
-__global__ void gn_stats_from_f32_kernel(const float* __restrict__ s, const float* __restrict__ q, int B, int c,
-                                         int ctot, int coff, float* __restrict__ part) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * c) return;
-  const int b = i / c, ch = i - b * c;
-  const long long o = (static_cast<long long>(b) * ctot + coff + ch) * 2;
-  part[o] = s[i];
-  part[o + 1] = q[i];
-}
-
 // per (sample, group): mean / rstd -> per (sample, channel) affine  y = x * scale + shift
-__global__ void gn_finalize_kernel(const float* __restrict__ part, int nblk, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, int C, int G, int HW, float eps,
-                                   float* __restrict__ scale, float* __restrict__ shift, int total) {
+__global__ void gn_finalize_kernel(const float* __restrict__ part0, int nblk0, int c0,
+                                   const float* __restrict__ part1, int nblk1, int c1,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, int G, int HW,
+                                   float eps, float* __restrict__ scale, float* __restrict__ shift, int total) {
+  const int C = c0 + c1;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int g = i % G, b = i / G;
   const int cpg = C / G;
   double s = 0, q = 0;
-  for (int k = 0; k < nblk; ++k) {
-    const float* pb = part + (static_cast<long long>(b) * nblk + k) * 2 * C;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-      s += static_cast<double>(pb[2 * c]);
-      q += static_cast<double>(pb[2 * c + 1]);
+  for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+    const bool first = c < c0;
+    const float* part = first ? part0 : part1;
+    const int nblk = first ? nblk0 : nblk1;
+    const int cs = first ? c0 : c1;
+    const int cc = first ? c : c - c0;
+    for (int k = 0; k < nblk; ++k) {
+      const float* pb = part + ((static_cast<long long>(b) * nblk + k) * cs + cc) * 2;
+      s += static_cast<double>(pb[0]);
+      q += static_cast<double>(pb[1]);
     }
   }
   const double n = static_cast<double>(cpg) * HW;
@@ -338,17 +334,12 @@ void gn_stats(const void* a0, int c0, const void* a1, int c1, int B, int HW, int
   T2P_LAUNCH_CHECK();
 }
 
-void gn_stats_from_f32(const float* s, const float* q, int B, int c, int ctot, int coff, float* part,
-                       cudaStream_t st) {
-  gn_stats_from_f32_kernel<<<cdiv(B * c, 256), 256, 0, st>>>(s, q, B, c, ctot, coff, part);
-  T2P_LAUNCH_CHECK();
-}
-
-void gn_finalize(const float* part, int nblk, const float* gamma, const float* beta, int B, int C, int G, int HW,
-                 float eps, float* scale, float* shift, cudaStream_t st) {
-  T2P_CHECK(C % G == 0, "channels not divisible by groups");
+void gn_finalize(const float* part0, int nblk0, int c0, const float* part1, int nblk1, int c1, const float* gamma,
+                 const float* beta, int B, int G, int HW, float eps, float* scale, float* shift, cudaStream_t st) {
+  T2P_CHECK((c0 + c1) % G == 0, "channels not divisible by groups");
   const int total = B * G;
-  gn_finalize_kernel<<<cdiv(total, 128), 128, 0, st>>>(part, nblk, gamma, beta, C, G, HW, eps, scale, shift, total);
+  gn_finalize_kernel<<<cdiv(total, 128), 128, 0, st>>>(part0, nblk0, c0, part1, nblk1, c1, gamma, beta, G, HW, eps,
+                                                       scale, shift, total);
   T2P_LAUNCH_CHECK();
 }
 

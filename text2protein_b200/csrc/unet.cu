@@ -378,16 +378,16 @@ Act UNet::new_act(int B, int H, int W, int C, bool with_stats) {
   Act a;
   a.B = B; a.H = H; a.W = W; a.C = C;
   a.p = ws_.alloc(static_cast<size_t>(a.rows()) * C * dtype_size(cfg_.compute_dtype));
-  if (with_stats && cfg_.compute_dtype == kBF16 && C % 64 == 0) {
-    a.ssum = static_cast<float*>(ws_.alloc(sizeof(float) * 2 * B * C));
-    a.ssq = a.ssum + static_cast<size_t>(B) * C;
-    if (!dry_) T2P_CUDA(cudaMemsetAsync(a.ssum, 0, sizeof(float) * 2 * B * C, st_));
+  // the tensor-core epilogue can emit GroupNorm statistics when every 128-row tile lies inside one sample
+  if (with_stats && cfg_.compute_dtype == kBF16 && C >= 32 && (H * W) % 128 == 0) {
+    a.snblk = H * W / 128;
+    a.spart = static_cast<float*>(ws_.alloc(sizeof(float) * 2 * static_cast<size_t>(B) * a.snblk * C));
   }
   return a;
 }
 void UNet::free_act(Act& a) {
   ws_.free(a.p);
-  if (a.ssum) ws_.free(a.ssum);
+  if (a.spart) ws_.free(a.spart);
   a = Act{};
 }
 
@@ -408,10 +408,11 @@ void UNet::gemm(const Linear& l, const Act& a0, const Act* a1, Act& out, const f
   g.out_dtype = out_dtype >= 0 ? out_dtype : cfg_.compute_dtype;
   g.out_nchw = out_nchw;
   const bool tc = cfg_.compute_dtype == kBF16 && !l.force_f32 && (g.c0 % 64 == 0) && (g.c1 % 64 == 0);
-  if (tc && out.ssum) { g.stat_sum = out.ssum; g.stat_sq = out.ssq; }
-  if (!tc && out.ssum) {  // only the tensor-core epilogue produces GroupNorm statistics
-    ws_.free(out.ssum);
-    out.ssum = out.ssq = nullptr;
+  if (tc && out.spart) g.stat_part = out.spart;
+  if (!tc && out.spart) {  // only the tensor-core epilogue produces GroupNorm statistics
+    ws_.free(out.spart);
+    out.spart = nullptr;
+    out.snblk = 0;
   }
   ++launches_;
   if (dry_) return;
@@ -459,26 +460,35 @@ void UNet::group_norm(const GroupNormP& gn, const Act& a0, const Act* a1, int ac
   const int C = a0.C + (a1 ? a1->C : 0);
   T2P_CHECK(C == gn.C, "GroupNorm channel mismatch");
   const int B = a0.B, HW = a0.H * a0.W;
-  const bool fused = a0.ssum && (!a1 || a1->ssum);
-  const int nblk = fused ? 1 : gn_stats_blocks(B, HW);
-  float* sums = static_cast<float*>(ws_.alloc(sizeof(float) * 2 * B * C * nblk));
+  // statistics per source: taken from the producer's epilogue when it left them, else one reduction kernel
+  const Act* src[2] = {&a0, a1};
+  const float* part[2] = {nullptr, nullptr};
+  int nblk[2] = {0, 0};
+  float* owned[2] = {nullptr, nullptr};
+  for (int i = 0; i < 2; ++i) {
+    if (!src[i]) continue;
+    if (src[i]->spart) {
+      part[i] = src[i]->spart;
+      nblk[i] = src[i]->snblk;
+      continue;
+    }
+    nblk[i] = gn_stats_blocks(B, HW);
+    owned[i] = static_cast<float*>(ws_.alloc(sizeof(float) * 2 * static_cast<size_t>(B) * nblk[i] * src[i]->C));
+    part[i] = owned[i];
+    ++launches_;
+    if (!dry_) gn_stats(src[i]->p, src[i]->C, nullptr, 0, B, HW, cfg_.compute_dtype, owned[i], st_);
+  }
   float* scale = static_cast<float*>(ws_.alloc(sizeof(float) * 2 * B * C));
   float* shift = scale + static_cast<size_t>(B) * C;
-  launches_ += fused ? (a1 ? 2 : 1) : 1;  // statistics kernel, or conversion(s) of epilogue sums
-  launches_ += 2;                          // finalize + apply
+  launches_ += 2;  // finalize + apply
   if (!dry_) {
-    if (fused) {
-      gn_stats_from_f32(a0.ssum, a0.ssq, B, a0.C, C, 0, sums, st_);
-      if (a1) gn_stats_from_f32(a1->ssum, a1->ssq, B, a1->C, C, a0.C, sums, st_);
-    } else {
-      gn_stats(a0.p, a0.C, a1 ? a1->p : nullptr, a1 ? a1->C : 0, B, HW, cfg_.compute_dtype, sums, st_);
-    }
-    gn_finalize(sums, nblk, static_cast<const float*>(gn.w->data), static_cast<const float*>(gn.b->data), B, C, gn.G,
-                HW, 1e-6f, scale, shift, st_);
+    gn_finalize(part[0], nblk[0], a0.C, part[1], nblk[1], a1 ? a1->C : 0, static_cast<const float*>(gn.w->data),
+                static_cast<const float*>(gn.b->data), B, gn.G, HW, 1e-6f, scale, shift, st_);
     gn_apply(a0.p, a0.C, a1 ? a1->p : nullptr, a1 ? a1->C : 0, B, a0.H, a0.W, cfg_.compute_dtype, scale, shift, act,
              mode, out.p, raw_out ? raw_out->p : nullptr, st_);
   }
-  ws_.free(sums);
+  for (int i = 0; i < 2; ++i)
+    if (owned[i]) ws_.free(owned[i]);
   ws_.free(scale);
 }
 

@@ -62,8 +62,8 @@ class Workspace {
 struct Act {  // NHWC activation in the compute dtype (+ optional producer-side GroupNorm statistics)
   void* p = nullptr;
   int B = 0, H = 0, W = 0, C = 0;
-  float* ssum = nullptr;
-  float* ssq = nullptr;
+  float* spart = nullptr;  // [B][snblk][C][2] per-tile {sum, sum of squares} left by the producer GEMM
+  int snblk = 0;
   long long rows() const { return static_cast<long long>(B) * H * W; }
 };
 
