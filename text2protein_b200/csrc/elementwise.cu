@@ -117,6 +117,49 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, int B, int HW,
   stv(out + idx, c < C ? in[(static_cast<long long>(b) * C + c) * HW + p] : 0.f);
 }
 
+// First conv as a plain GEMM: A[m][k] with k = tap * C + c (zero padded to kpad), from the fp32 NCHW state.
+// 3x3, stride 1, zero padding 1.  One thread writes 8 consecutive k (16 bytes).
+__global__ void im2col3x3_nchw_kernel(const float* __restrict__ x, int B, int C, int H, int W, int kpad,
+                                      __nv_bfloat16* __restrict__ out) {
+  const int kv = kpad >> 3;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(B) * H * W * kv;
+  if (idx >= total) return;
+  const int v = static_cast<int>(idx % kv);
+  long long m = idx / kv;
+  const int w = static_cast<int>(m % W);
+  m /= W;
+  const int h = static_cast<int>(m % H);
+  const int b = static_cast<int>(m / H);
+  __nv_bfloat16 vals[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = v * 8 + j;
+    float f = 0.f;
+    if (k < 9 * C) {
+      const int tap = k / C, c = k - tap * C;
+      const int ih = h + tap / 3 - 1, iw = w + tap % 3 - 1;
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) f = x[((static_cast<long long>(b) * C + c) * H + ih) * W + iw];
+    }
+    vals[j] = __float2bfloat16(f);
+  }
+  *reinterpret_cast<uint4*>(out + idx * 8) = *reinterpret_cast<const uint4*>(vals);
+}
+
+// conv weight [Cout][C][3][3] fp32 -> [Cout][kpad] bf16 with k = tap * C + c
+__global__ void pack_first_conv_kernel(const float* __restrict__ w, int cout, int C, int kpad,
+                                       __nv_bfloat16* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= cout * kpad) return;
+  const int k = idx % kpad, o = idx / kpad;
+  float f = 0.f;
+  if (k < 9 * C) {
+    const int tap = k / C, c = k - tap * C;
+    f = w[(static_cast<long long>(o) * C + c) * 9 + tap];
+  }
+  out[idx] = __float2bfloat16(f);
+}
+
 // out[b,c,h,w] = h_nhwc[b,h,w,c] / sigma[label[b]]  in float64 (ncsnpp.py:259-261)
 template <typename TO>
 __global__ void scale_by_sigma_kernel(const float* __restrict__ h, const long long* __restrict__ labels,
@@ -177,6 +220,19 @@ void nchw_f32_to_nhwc(const float* in, int B, int HW, int C, int cpad, int out_d
   const unsigned blocks = static_cast<unsigned>(cdiv64(static_cast<long long>(B) * HW * cpad, 256));
   if (out_dtype == kF32) nchw_to_nhwc_kernel<float><<<blocks, 256, 0, st>>>(in, B, HW, C, cpad, static_cast<float*>(out));
   else nchw_to_nhwc_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(in, B, HW, C, cpad, static_cast<__nv_bfloat16*>(out));
+  T2P_LAUNCH_CHECK();
+}
+
+void im2col3x3_nchw(const float* x, int B, int C, int H, int W, int kpad, void* out, cudaStream_t st) {
+  T2P_CHECK(kpad % 8 == 0 && kpad >= 9 * C, "bad im2col padding");
+  const long long total = static_cast<long long>(B) * H * W * (kpad / 8);
+  im2col3x3_nchw_kernel<<<static_cast<unsigned>(cdiv64(total, 256)), 256, 0, st>>>(x, B, C, H, W, kpad,
+                                                                                   static_cast<__nv_bfloat16*>(out));
+  T2P_LAUNCH_CHECK();
+}
+
+void pack_first_conv(const float* w, int cout, int C, int kpad, void* out, cudaStream_t st) {
+  pack_first_conv_kernel<<<cdiv(cout * kpad, 256), 256, 0, st>>>(w, cout, C, kpad, static_cast<__nv_bfloat16*>(out));
   T2P_LAUNCH_CHECK();
 }
 

@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_gemm_tc_kernel(const __grid_
   __shared__ __align__(8) uint64_t accum_bar;
   __shared__ uint32_t tmem_base_slot;
   __shared__ float2 stat_sm[4][BN >= 32 ? BN : 32];
+  __shared__ float bias_sm[BN >= 32 ? BN : 32];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -173,11 +174,28 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_gemm_tc_kernel(const __grid_
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..5)
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    ptx::mbar_wait(ptx::smem_u32(&accum_bar), 0);
-    ptx::tc_fence_after();
     const int m = m0 + q * 32 + lane;
     const bool row_ok = m < p.M;
     const int sample = (p.rows_per_sample > 0) ? (m / p.rows_per_sample) : 0;
+    // While the main loop runs, stage the per-column bias (+ the per-sample time-embedding bias when the
+    // whole tile belongs to one sample) in shared memory: the epilogue then never waits on global loads.
+    const bool rb_uniform = p.rowbias != nullptr && (p.rows_per_sample % BM) == 0;
+    {
+      const int e = (warp - 2) * 32 + lane;
+      const float* rb0 = rb_uniform ? p.rowbias + static_cast<long long>(m0 / p.rows_per_sample) * p.rowbias_ld : nullptr;
+      for (int ch = e; ch < BN; ch += 128) {
+        const int n = n0 + ch;
+        float bv = 0.f;
+        if (n < p.N) {
+          if (p.bias) bv = __ldg(p.bias + n);
+          if (rb0) bv += __ldg(rb0 + n);
+        }
+        bias_sm[ch] = bv;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    ptx::mbar_wait(ptx::smem_u32(&accum_bar), 0);
+    ptx::tc_fence_after();
     long long res_row = m;
     if (p.res_up && row_ok) {
       const int hw = p.H * p.W;
@@ -208,12 +226,9 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_gemm_tc_kernel(const __grid_
       for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]);
       const bool full = (nb + CH <= p.N) && ((p.N & 7) == 0);
       if (row_ok) {
-        if (p.bias) {
 #pragma unroll
-          for (int i = 0; i < CH; ++i)
-            if (nb + i < p.N) v[i] += __ldg(p.bias + nb + i);
-        }
-        if (p.rowbias) {
+        for (int i = 0; i < CH; ++i) v[i] += bias_sm[c * CH + i];
+        if (p.rowbias && !rb_uniform) {
           const float* rb = p.rowbias + static_cast<long long>(sample) * p.rowbias_ld + nb;
 #pragma unroll
           for (int i = 0; i < CH; ++i)

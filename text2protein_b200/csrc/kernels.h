@@ -81,6 +81,9 @@ void pack_matrix(const float* w, int rows, int cols, int transpose, int out_dtyp
 void convert_f32(const float* in, long long n, int out_dtype, void* out, cudaStream_t st);
 void nhwc_to_nchw_f32(const void* in, int dtype, int B, int HW, int C, float* out, cudaStream_t st);
 void nchw_f32_to_nhwc(const float* in, int B, int HW, int C, int cpad, int out_dtype, void* out, cudaStream_t st);
+// first conv (Cin = 5 / 8) as a K = kpad GEMM on the tensor cores: im2col of the fp32 NCHW state + matching weights
+void im2col3x3_nchw(const float* x, int B, int C, int H, int W, int kpad, void* out, cudaStream_t st);
+void pack_first_conv(const float* w, int cout, int C, int kpad, void* out, cudaStream_t st);
 void scale_by_sigma(const float* h_nhwc, const long long* labels, const double* sigmas, int B, int HW, int C,
                     int do_scale, int out_dtype, void* out, cudaStream_t st);
 

@@ -97,35 +97,45 @@ __global__ void gn_stats_kernel(const T* __restrict__ a0, int c0, const T* __res
   }
 }
 
-// per (sample, group): mean / rstd -> per (sample, channel) affine  y = x * scale + shift
+// per (sample, group): mean / rstd -> per (sample, channel) affine  y = x * scale + shift.
+// One warp per (sample, group); lanes stride over (channel, block) pairs and combine in double in a fixed
+// order, so the result does not depend on scheduling.
 __global__ void gn_finalize_kernel(const float* __restrict__ part0, int nblk0, int c0,
                                    const float* __restrict__ part1, int nblk1, int c1,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, int G, int HW,
                                    float eps, float* __restrict__ scale, float* __restrict__ shift, int total) {
   const int C = c0 + c1;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int g = i % G, b = i / G;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= total) return;
+  const int g = wid % G, b = wid / G;
   const int cpg = C / G;
   double s = 0, q = 0;
-  for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+  for (int ci = 0; ci < cpg; ++ci) {
+    const int c = g * cpg + ci;
     const bool first = c < c0;
     const float* part = first ? part0 : part1;
     const int nblk = first ? nblk0 : nblk1;
     const int cs = first ? c0 : c1;
     const int cc = first ? c : c - c0;
-    for (int k = 0; k < nblk; ++k) {
-      const float* pb = part + ((static_cast<long long>(b) * nblk + k) * cs + cc) * 2;
-      s += static_cast<double>(pb[0]);
-      q += static_cast<double>(pb[1]);
+    for (int k = lane; k < nblk; k += 32) {
+      const float2 v = *reinterpret_cast<const float2*>(part + ((static_cast<long long>(b) * nblk + k) * cs + cc) * 2);
+      s += static_cast<double>(v.x);
+      q += static_cast<double>(v.y);
     }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
   }
   const double n = static_cast<double>(cpg) * HW;
   const double mean = s / n;
   double var = q / n - mean * mean;
   if (var < 0) var = 0;
   const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-  for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+  for (int ci = lane; ci < cpg; ci += 32) {
+    const int c = g * cpg + ci;
     const float a = gamma[c] * rstd;
     scale[static_cast<long long>(b) * C + c] = a;
     shift[static_cast<long long>(b) * C + c] = beta[c] - static_cast<float>(mean) * a;
@@ -338,7 +348,7 @@ void gn_finalize(const float* part0, int nblk0, int c0, const float* part1, int 
                  const float* beta, int B, int G, int HW, float eps, float* scale, float* shift, cudaStream_t st) {
   T2P_CHECK((c0 + c1) % G == 0, "channels not divisible by groups");
   const int total = B * G;
-  gn_finalize_kernel<<<cdiv(total, 128), 128, 0, st>>>(part0, nblk0, c0, part1, nblk1, c1, gamma, beta, G, HW, eps,
+  gn_finalize_kernel<<<cdiv(total, 4), 128, 0, st>>>(part0, nblk0, c0, part1, nblk1, c1, gamma, beta, G, HW, eps,
                                                        scale, shift, total);
   T2P_LAUNCH_CHECK();
 }

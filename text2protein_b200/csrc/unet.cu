@@ -369,6 +369,14 @@ void UNet::pack(Linear& l, cudaStream_t st) {
 void UNet::finalize(cudaStream_t st) {
   for (auto& p : params_) T2P_CHECK(p->loaded, "parameter '" + p->name + "' was never loaded");
   for (Linear* l : all_linear_) pack(*l, st);
+  if (cfg_.compute_dtype == kBF16) {
+    first_kpad_ = (9 * cfg_.num_channels + 63) / 64 * 64;
+    if (!first_wp_) {
+      T2P_CUDA(cudaMalloc(&first_wp_, static_cast<size_t>(cfg_.nf) * first_kpad_ * 2));
+      owned_.push_back(first_wp_);
+    }
+    pack_first_conv(static_cast<const float*>(pre_conv_.w->data), cfg_.nf, cfg_.num_channels, first_kpad_, first_wp_, st);
+  }
   finalized_ = true;
   ++generation_;
 }
@@ -716,9 +724,25 @@ void UNet::forward_impl(const float* x, const long long* labels, float* h_out, i
     }
     ws_.free(temb);
   }
-  // pre_conv on the fp32 state: NCHW -> NHWC fp32, then the edge-layer GEMM (K = 9*C)
   Act h = new_act(B, N, N, nf, true);
-  {
+  if (cfg_.compute_dtype == kBF16) {
+    // pre_conv (Cin = 5 / 8) as a tensor-core GEMM over the im2col of the fp32 state, K padded to 64
+    Act xa;
+    xa.B = 1; xa.H = 1; xa.W = B * N * N; xa.C = first_kpad_;
+    xa.p = ws_.alloc(static_cast<size_t>(xa.W) * first_kpad_ * 2);
+    launches_ += 2;
+    if (!dry_) {
+      im2col3x3_nchw(x, B, C, N, N, first_kpad_, xa.p, st_);
+      ConvGemmArgs g;
+      g.a0 = xa.p; g.c0 = first_kpad_; g.B = 1; g.H = 1; g.W = xa.W; g.ksize = 1;
+      g.w = first_wp_; g.N = nf; g.bias = pre_conv_.bp; g.out = h.p; g.out_dtype = kBF16;
+      g.rows_per_sample = N * N;
+      g.stat_part = h.spart;
+      conv_gemm_tc(g, st_);
+    }
+    ws_.free(xa.p);
+  } else {
+    // verification path: NCHW -> NHWC fp32, then the CUDA-core GEMM (K = 9*C)
     float* xn = static_cast<float*>(ws_.alloc(sizeof(float) * static_cast<size_t>(B) * N * N * C));
     launches_ += 1;
     if (!dry_) nchw_f32_to_nhwc(x, B, N * N, C, C, kF32, xn, st_);

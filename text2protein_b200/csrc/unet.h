@@ -186,6 +186,8 @@ class UNet {
   std::vector<TransformerM*> all_st_;
   std::vector<Linear*> all_linear_;
   Linear dense_all_;  // every ResBlock's Dense_0 stacked along N
+  void* first_wp_ = nullptr;  // pre_conv weights as [nf][first_kpad_] bf16 (k = tap * C + c)
+  int first_kpad_ = 0;
   int temb_total_ = 0;
   bool finalized_ = false;
   std::vector<void*> owned_;  // device allocations freed in the destructor
