@@ -164,6 +164,7 @@ def run_native(args, cfg):
     import torch.distributed as dist
     from oracle import unet_ref  # weight re-randomisation recipe only; not on the measured path
     from text2protein_b200 import _lib
+    from text2protein_b200.distributed import gather_samples
     from text2protein_b200.score_sde_pytorch import sampling, sde_lib
     from text2protein_b200.score_sde_pytorch.models.ncsnpp import UNetModel
 
@@ -251,8 +252,7 @@ def run_native(args, cfg):
         cd = {"length": len_pin.to(dev, non_blocking=True)}          # H2D: length mask
         s, _ = sampler(model, cd, c)
         if world > 1:                                                # final NCCL all-gather of the samples
-            parts = [torch.empty_like(s) for _ in range(world)]
-            dist.all_gather(parts, s)
+            gather_samples(s, world * B)
         out_pin.copy_(s, non_blocking=True)                          # D2H: this rank's maps
         torch.cuda.synchronize()
 
