@@ -162,7 +162,7 @@ def run_reference(args, cfg):
 # ------------------------------------------------------------------------------------------------ native arm
 def run_native(args, cfg):
     import torch.distributed as dist
-    from oracle import unet_ref  # weight re-randomisation recipe only; not on the measured path
+    from text2protein_b200.synthetic import rerandomize_
     from text2protein_b200 import _lib
     from text2protein_b200.distributed import gather_samples
     from text2protein_b200.score_sde_pytorch import sampling, sde_lib
@@ -181,7 +181,7 @@ def run_native(args, cfg):
     B = BATCH
     torch.manual_seed(cfg.seed)
     model = UNetModel(cfg).to(dev)
-    unet_ref.rerandomize_(model.named_parameters(), 42)
+    rerandomize_(model.named_parameters(), 42)
     model.sync_weights()
 
     ctx_h, cond_h = _inputs(cfg, B, sample_offset=rank * B)

@@ -116,3 +116,16 @@ def test_host_tables_match_reference(golden_dir, N):
     assert np.array_equal(sde.discrete_sigmas.numpy(), g[f"discrete_sigmas_{N}"])
     cfg = AttrDict({"model": {"sigma_max": 100.0, "sigma_min": 0.01, "num_scales": N}})
     assert np.array_equal(mutils.get_sigmas(cfg), g[f"model_sigmas_{N}"])
+
+
+def test_synthetic_weight_recipe_equals_oracle_copy():
+    from oracle.unet_ref import rerandomize_ as ref
+    from text2protein_b200.synthetic import rerandomize_ as ours
+    tree = _tree("tiny5")
+    shapes = {k: s for k, s, _ in tree["state_dict"]}
+    for prefix in ("", "module."):
+        a = [(prefix + k, torch.empty(shapes[k])) for k in tree["parameters"]]
+        b = [(prefix + k, torch.empty(shapes[k])) for k in tree["parameters"]]
+        ref(a, 42)
+        ours(b, 42)
+        assert all(torch.equal(x[1], y[1]) for x, y in zip(a, b))

@@ -6,7 +6,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
-from oracle import unet_ref  # noqa: E402  (weight re-randomisation recipe only)
+from text2protein_b200.synthetic import rerandomize_  # noqa: E402
 from text2protein_b200 import load_config  # noqa: E402
 from text2protein_b200.score_sde_pytorch.models.ncsnpp import UNetModel  # noqa: E402
 
@@ -14,7 +14,7 @@ B = int(os.environ.get("T2P_B", "64"))
 cfg = load_config("cond_length", device="cuda")
 cfg.model.compute_dtype = "bf16"
 model = UNetModel(cfg).cuda()
-unet_ref.rerandomize_(model.named_parameters(), 42)
+rerandomize_(model.named_parameters(), 42)
 g = torch.Generator().manual_seed(0)
 x = (torch.randn(B, 5, 128, 128, generator=g) * 10).cuda()
 ctx = (torch.randn(B, 256, 4096, generator=g) * 0.02).cuda()
