@@ -158,10 +158,13 @@ typedef struct t2p_conv_args {
   float alpha;
   void* out; int32_t out_dtype;
   int32_t in_dtype;                /* T2P_BF16 -> tcgen05 kernel (needs c % 64 == 0); T2P_F32 -> CUDA-core kernel */
-  float* stat_part;                /* optional fused GroupNorm statistics, [B*H*W/128][N][2] {sum, sumsq} per
-                                      128-row tile (tcgen05 kernel, bf16 out, H*W % 128 == 0) */
+  float* stat_part;                /* optional fused GroupNorm statistics, [B*H*W/T][N][2] {sum, sumsq} per
+                                      T-pixel tile, T = t2p_conv2d_stat_tile(args) (tcgen05 kernel, bf16 out) */
 } t2p_conv_args;
 int t2p_conv2d(const t2p_conv_args* a, void* stream);        /* nn.Conv2d / NIN / nn.Linear: layers.py:82-95,128-137 */
+/* Pixel-tile size T of the fused GroupNorm statistics t2p_conv2d would write for these arguments (H*W % T == 0),
+ * or 0 when this launch cannot produce them (then stat_part must be NULL).  Host-only, no GPU work. */
+int t2p_conv2d_stat_tile(const t2p_conv_args* a);
 
 /* nn.GroupNorm(G, C, eps) [+ SiLU] [+ 2x2 mean | nearest x2] over the concat of a0|a1: layers.py:282-311 */
 int t2p_groupnorm(const void* a0, int c0, const void* a1, int c1, int B, int H, int W, int dtype, int groups,

@@ -49,7 +49,9 @@ def _conv(a0, w, ksize, bias=None, a1=None, rowbias=None, residual=None, res_up=
     a.out, a.out_dtype, a.in_dtype = out.data_ptr(), _lib.torch_dtype_code(out_dtype), _lib.torch_dtype_code(in_dtype)
     ss = None
     if stats:
-        ss = torch.full((B, H * W // 128, N, 2), float("nan"), dtype=torch.float32, device="cuda")
+        tile = _lib.lib().t2p_conv2d_stat_tile(C.byref(a))
+        assert tile > 0 and (H * W) % tile == 0, tile
+        ss = torch.full((B, H * W // tile, N, 2), float("nan"), dtype=torch.float32, device="cuda")
         a.stat_part = ss.data_ptr()
     _lib.check(_lib.lib().t2p_conv2d(C.byref(a), _st()))
     torch.cuda.synchronize()
@@ -77,17 +79,18 @@ def test_conv2d_matches_torch(dtype, tol, H, cin, cin1, cout, k):
     assert rel_err(out, ref) < tol
 
 
-def test_conv2d_upsampled_residual_and_fused_stats():
+@pytest.mark.parametrize("H,cin,cout", [(16, 64, 64), (16, 64, 128), (32, 128, 256), (64, 64, 128)])
+def test_conv2d_upsampled_residual_and_fused_stats(H, cin, cout):
     g = torch.Generator(device="cuda").manual_seed(2)
-    B, H, cin, cout = 2, 16, 64, 64
+    B = 2
     a0 = torch.randn(B, cin, H, H, device="cuda", generator=g).bfloat16().float()
-    w = (torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / 24).bfloat16().float()
+    w = (torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / math.sqrt(9 * cin)).bfloat16().float()
     res = torch.randn(B, cout, H // 2, H // 2, device="cuda", generator=g).bfloat16().float()
     ref = F.conv2d(a0, w, None, padding=1) + res.repeat_interleave(2, 2).repeat_interleave(2, 3)
     out, ss = _conv(a0, w, 3, residual=res, res_up=1, in_dtype=torch.bfloat16, stats=True)
     assert rel_err(out, ref) < 1.5e-2
     # statistics describe the tensor exactly as stored
-    tot = ss.sum(dim=1)  # [B, N, 2] over the 128-row tiles of each sample
+    tot = ss.sum(dim=1)  # [B, N, 2] over the pixel tiles of each sample
     assert torch.allclose(tot[..., 0], out.sum(dim=(2, 3)), rtol=1e-4, atol=1e-2)
     assert torch.allclose(tot[..., 1], (out * out).sum(dim=(2, 3)), rtol=1e-4, atol=1e-2)
 

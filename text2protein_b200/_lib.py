@@ -77,6 +77,7 @@ SIGNATURES = {
     "t2p_philox_bits": (C.c_int, [C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "t2p_pc_run": (C.c_int, [C.c_void_p, C.POINTER(RunArgs), C.c_void_p]),
     "t2p_conv2d": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
+    "t2p_conv2d_stat_tile": (C.c_int, [C.POINTER(ConvArgs)]),
     "t2p_groupnorm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                 C.c_void_p]),

@@ -348,9 +348,7 @@ int t2p_pc_run(t2p_unet* u, const t2p_run_args* a, void* stream) {
 }
 
 // ---------------------------------------------------------------------------------------------- per-op
-int t2p_conv2d(const t2p_conv_args* a, void* stream) {
-  T2P_API_BEGIN
-  T2P_CHECK(a && a->a0 && a->w && a->out, "null argument");
+static ConvGemmArgs conv_args_from_abi(const t2p_conv_args* a) {
   ConvGemmArgs g;
   g.a0 = a->a0; g.c0 = a->c0; g.a1 = a->a1; g.c1 = a->c1;
   g.B = a->B; g.H = a->H; g.W = a->W; g.ksize = a->ksize; g.w = a->w; g.N = a->N;
@@ -358,6 +356,23 @@ int t2p_conv2d(const t2p_conv_args* a, void* stream) {
   g.residual = a->residual; g.res_up = a->res_up; g.alpha = a->alpha;
   g.out = a->out; g.out_dtype = a->out_dtype;
   g.stat_part = a->stat_part;
+  return g;
+}
+
+int t2p_conv2d_stat_tile(const t2p_conv_args* a) {
+  try {
+    if (!a || a->in_dtype != T2P_BF16 || a->c0 % 64 != 0 || a->c1 % 64 != 0) return 0;
+    return conv_gemm_tc_stat_tile(conv_args_from_abi(a));
+  } catch (const std::exception& e) {
+    set_last_error(e.what());
+    return 0;
+  }
+}
+
+int t2p_conv2d(const t2p_conv_args* a, void* stream) {
+  T2P_API_BEGIN
+  T2P_CHECK(a && a->a0 && a->w && a->out, "null argument");
+  ConvGemmArgs g = conv_args_from_abi(a);
   if (a->in_dtype == T2P_BF16 && a->c0 % 64 == 0 && a->c1 % 64 == 0) conv_gemm_tc(g, S(stream));
   else conv_gemm_simt(g, a->in_dtype, S(stream));
   T2P_API_END

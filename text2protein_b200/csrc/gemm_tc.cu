@@ -11,6 +11,7 @@
 // NHWC bf16 / fp32.  Replaces the cuDNN / cuBLAS calls behind nn.Conv2d, NIN and nn.Linear on the
 // reference hot path (score_sde_pytorch/models/layers.py:82-95,128-137; model/attention.py:161-166).
 #include <cuda.h>
+#include <algorithm>
 #include <cstdlib>
 #include <mutex>
 #include <unordered_map>
@@ -27,11 +28,15 @@ constexpr int BM = 128;      // rows (pixels) per tile == UMMA M
 constexpr int BK = 64;       // bf16 elements per 128-byte swizzled row
 constexpr int UMMA_K = 16;   // K per tcgen05.mma for 16-bit inputs
 constexpr int NUM_THREADS = 192;
+constexpr int SMEM_TILE_BUDGET = 192 * 1024;
 
 struct TcParams {
   CUtensorMap tm_a0;
   CUtensorMap tm_a1;
   CUtensorMap tm_w;
+  CUtensorMap tm_out;    // channel-major kernel: [M][N] bf16 output, box 32 channels x 32 pixels (TMA store)
+  CUtensorMap tm_res;    // channel-major kernel: residual tensor, same pixel box as A
+  CUtensorMap tm_ident;  // channel-major kernel: 128 x 128 bf16 identity (residual added by the tensor core)
   int M, N;
   int c0, c1;
   int taps;          // 1 or 9
@@ -48,17 +53,20 @@ struct TcParams {
   float* stat_part;  // [M tiles][N][2] per-tile column {sum, sum of squares} or null
   int rowbias_ld;
   int out_nchw;
-  int debug_mode;  // 0 = normal; 1..3 = bring-up bisection (see T2P_TC_DEBUG)
+  int n_tiles;       // tiles along N
+  int num_tiles;     // m_tiles * n_tiles
 };
 
 template <int BN>
 struct Cfg {
-  static constexpr int STAGES = (BN <= 128) ? 3 : 4;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (SMEM_TILE_BUDGET / STAGE_BYTES) < 8 ? (SMEM_TILE_BUDGET / STAGE_BYTES) : 8;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int ACC_COLS = BN < 32 ? 32 : BN;   // TMEM columns of one accumulator
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;        // two accumulators: epilogue(i) overlaps mainloop(i + 1)
+  static constexpr int CH = (BN >= 32) ? 32 : 16;       // accumulator columns per tcgen05.ld
 };
 
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
@@ -68,23 +76,153 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// Per-row state of one epilogue thread for the current tile.
+struct EpiRow {
+  int m;               // global output row
+  bool row_ok;
+  int sample;
+  long long res_row;   // row of the residual tensor (through the x2 nearest-upsample map when res_up)
+  int n0;
+  bool rb_uniform;
+};
+
+// Epilogue of CH accumulator columns [c * CH, (c + 1) * CH) of one row: + bias (+ time-embedding bias)
+// + residual, * alpha, store, and (CH == 32) the per-warp column statistics of the stored values.
+template <int CH>
+__device__ __forceinline__ void epilogue_chunk(const TcParams& p, const EpiRow& er, const uint32_t (&r)[32], int c,
+                                               const float* __restrict__ bsm, float2* __restrict__ stat_row, int lane) {
+  const int nb = er.n0 + c * CH;
+  float v[CH];
+#pragma unroll
+  for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]);
+  const bool full = (nb + CH <= p.N) && ((p.N & 7) == 0);
+  if (er.row_ok) {
+#pragma unroll
+    for (int i = 0; i < CH; ++i) v[i] += bsm[c * CH + i];
+    if (p.rowbias && !er.rb_uniform) {
+      const float* rb = p.rowbias + static_cast<long long>(er.sample) * p.rowbias_ld + nb;
+#pragma unroll
+      for (int i = 0; i < CH; ++i)
+        if (nb + i < p.N) v[i] += __ldg(rb + i);
+    }
+    if (p.residual) {
+      if (p.out_fp32) {
+        const float* rs = static_cast<const float*>(p.residual) + er.res_row * p.N + nb;
+#pragma unroll
+        for (int i = 0; i < CH; ++i)
+          if (nb + i < p.N) v[i] += rs[i];
+      } else if (full) {
+        const uint4* rs = reinterpret_cast<const uint4*>(
+            static_cast<const __nv_bfloat16*>(p.residual) + er.res_row * p.N + nb);
+        uint4 t[CH / 8];
+#pragma unroll
+        for (int i = 0; i < CH / 8; ++i) t[i] = rs[i];
+#pragma unroll
+        for (int i = 0; i < CH / 8; ++i) {
+          v[8 * i + 0] += bf16_lo(t[i].x); v[8 * i + 1] += bf16_hi(t[i].x);
+          v[8 * i + 2] += bf16_lo(t[i].y); v[8 * i + 3] += bf16_hi(t[i].y);
+          v[8 * i + 4] += bf16_lo(t[i].z); v[8 * i + 5] += bf16_hi(t[i].z);
+          v[8 * i + 6] += bf16_lo(t[i].w); v[8 * i + 7] += bf16_hi(t[i].w);
+        }
+      } else {
+        const __nv_bfloat16* rs = static_cast<const __nv_bfloat16*>(p.residual) + er.res_row * p.N + nb;
+#pragma unroll
+        for (int i = 0; i < CH; ++i)
+          if (nb + i < p.N) v[i] += __bfloat162float(rs[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < CH; ++i) v[i] *= p.alpha;
+    if (p.out_fp32) {
+      float* o = static_cast<float*>(p.out) + static_cast<long long>(er.m) * p.N + nb;
+      if (p.out_nchw) {
+        const int hw = p.H * p.W;
+        const int b = er.m / hw;
+        const int pix = er.m - b * hw;
+#pragma unroll
+        for (int i = 0; i < CH; ++i)
+          if (nb + i < p.N) static_cast<float*>(p.out)[(static_cast<long long>(b) * p.N + nb + i) * hw + pix] = v[i];
+      } else if (full) {
+#pragma unroll
+        for (int i = 0; i < CH / 4; ++i)
+          reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < CH; ++i)
+          if (nb + i < p.N) o[i] = v[i];
+      }
+    } else {
+      __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(er.m) * p.N + nb;
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < CH / 8; ++i) {
+          uint4 t;
+          t.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
+          t.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+          t.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
+          t.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+          reinterpret_cast<uint4*>(o)[i] = t;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < CH; ++i)
+          if (nb + i < p.N) o[i] = __float2bfloat16(v[i]);
+      }
+      // statistics are taken over the values as stored (bf16-rounded), matching what the
+      // GroupNorm consumer will read back
+#pragma unroll
+      for (int i = 0; i < CH; ++i) v[i] = __bfloat162float(__float2bfloat16(v[i]));
+    }
+  }
+  if constexpr (CH == 32) {
+    if (p.stat_part) {
+      // column sums over this warp's 32 rows by a transposing butterfly: after the 5 exchange steps lane l
+      // holds the totals of column nb + l (31 shuffles per quantity instead of 32 x 5)
+      float sq[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (!er.row_ok) v[i] = 0.f;
+        sq[i] = v[i] * v[i];
+      }
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+          const float send_v = upper ? v[i] : v[i + off];
+          const float keep_v = upper ? v[i + off] : v[i];
+          const float send_q = upper ? sq[i] : sq[i + off];
+          const float keep_q = upper ? sq[i + off] : sq[i];
+          v[i] = keep_v + __shfl_xor_sync(0xffffffffu, send_v, off);
+          sq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+        }
+      }
+      stat_row[c * 32 + lane] = make_float2(v[0], sq[0]);
+    }
+  }
+}
+
+// Persistent kernel: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...
+// (N-tile fastest, so that CTAs running side by side share the activation tile in L2).  The TMA ring runs
+// ahead across tile boundaries and the accumulator is double-buffered in TMEM, so the epilogue of tile i
+// overlaps the main loop of tile i + 1.
 template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS) conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
   using C = Cfg<BN>;
+  constexpr int CH = C::CH;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[C::STAGES];
   __shared__ __align__(8) uint64_t empty_bar[C::STAGES];
-  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ __align__(8) uint64_t tfull_bar[2];   // accumulator ready for the epilogue
+  __shared__ __align__(8) uint64_t tempty_bar[2];  // accumulator drained by the epilogue
   __shared__ uint32_t tmem_base_slot;
   __shared__ float2 stat_sm[4][BN >= 32 ? BN : 32];
-  __shared__ float bias_sm[BN >= 32 ? BN : 32];
+  __shared__ float bias_sm[2][BN >= 32 ? BN : 32];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t tiles = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
 
-  const int m0 = blockIdx.x * BM;
-  const int n0 = blockIdx.y * BN;
   const int ctot = p.c0 + p.c1;
   const int chunks_per_tap = ctot / BK;
   const int num_kb = p.taps * chunks_per_tap;
@@ -94,7 +232,10 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_gemm_tc_kernel(const __grid_
       ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1);
     }
-    ptx::mbar_init(ptx::smem_u32(&accum_bar), 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&tfull_bar[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&tempty_bar[s]), 4);  // one arrival per epilogue warp
+    }
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -104,43 +245,47 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_gemm_tc_kernel(const __grid_
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_acc = tmem_base_slot;
+  const uint32_t tmem_base = tmem_base_slot;
 
-  if (p.debug_mode == 1) {
-    // alloc / dealloc only
-  } else if (warp == 0) {
+  if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       ptx::prefetch_tmap(&p.tm_a0);
       ptx::prefetch_tmap(&p.tm_w);
       if (p.c1 > 0) ptx::prefetch_tmap(&p.tm_a1);
-      int b0 = 0, h0 = 0, w0 = m0;
-      if (!p.mode2d) {
-        const int hw = p.H * p.W;
-        b0 = m0 / hw;
-        const int rem = m0 - b0 * hw;
-        h0 = rem / p.W;
-        w0 = rem - h0 * p.W;
-      }
       const int pad = (p.taps == 9) ? 1 : 0;
-      int kb = 0;
-      for (int tap = 0; tap < p.taps; ++tap) {
-        const int kh = (p.taps == 9) ? tap / 3 : 0;
-        const int kw = (p.taps == 9) ? tap - kh * 3 : 0;
-        for (int cc = 0; cc < chunks_per_tap; ++cc, ++kb) {
-          const int s = kb % C::STAGES;
-          const uint32_t ph = (kb / C::STAGES) & 1;
-          ptx::mbar_wait(ptx::smem_u32(&empty_bar[s]), ph ^ 1);
-          const uint32_t fb = ptx::smem_u32(&full_bar[s]);
-          ptx::mbar_arrive_expect_tx(fb, C::STAGE_BYTES);
-          const uint32_t sa = tiles + s * C::STAGE_BYTES;
-          const uint32_t sb = sa + C::A_BYTES;
-          const int ch = cc * BK;
-          if (ch < p.c0)
-            ptx::tma_load_4d(sa, &p.tm_a0, fb, ch, w0 + kw - pad, h0 + kh - pad, b0);
-          else
-            ptx::tma_load_4d(sa, &p.tm_a1, fb, ch - p.c0, w0 + kw - pad, h0 + kh - pad, b0);
-          ptx::tma_load_4d(sb, &p.tm_w, fb, kb * BK, n0, 0, 0);  // all maps are encoded rank-4
+      const int hw = p.H * p.W;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int mt = t / p.n_tiles;
+        const int m0 = mt * BM;
+        const int n0 = (t - mt * p.n_tiles) * BN;
+        int b0 = 0, h0 = 0, w0 = m0;
+        if (!p.mode2d) {
+          b0 = m0 / hw;
+          const int rem = m0 - b0 * hw;
+          h0 = rem / p.W;
+          w0 = rem - h0 * p.W;
+        }
+        int kb = 0;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int kh = (p.taps == 9) ? tap / 3 : 0;
+          const int kw = (p.taps == 9) ? tap - kh * 3 : 0;
+          for (int cc = 0; cc < chunks_per_tap; ++cc, ++kb) {
+            ptx::mbar_wait(ptx::smem_u32(&empty_bar[s]), ph ^ 1);
+            const uint32_t fb = ptx::smem_u32(&full_bar[s]);
+            ptx::mbar_arrive_expect_tx(fb, C::STAGE_BYTES);
+            const uint32_t sa = tiles + s * C::STAGE_BYTES;
+            const uint32_t sb = sa + C::A_BYTES;
+            const int ch = cc * BK;
+            if (ch < p.c0)
+              ptx::tma_load_4d(sa, &p.tm_a0, fb, ch, w0 + kw - pad, h0 + kh - pad, b0);
+            else
+              ptx::tma_load_4d(sa, &p.tm_a1, fb, ch - p.c0, w0 + kw - pad, h0 + kh - pad, b0);
+            ptx::tma_load_4d(sb, &p.tm_w, fb, kb * BK, n0, 0, 0);  // all maps are encoded rank-4
+            if (++s == C::STAGES) { s = 0; ph ^= 1; }
+          }
         }
       }
     }
@@ -148,197 +293,120 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_gemm_tc_kernel(const __grid_
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % C::STAGES;
-        const uint32_t ph = (kb / C::STAGES) & 1;
-        ptx::mbar_wait(ptx::smem_u32(&full_bar[s]), ph);
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t tl = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tl) {
+        const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
+        ptx::mbar_wait(ptx::smem_u32(&tempty_bar[as]), aph ^ 1);  // epilogue has drained this accumulator
         ptx::tc_fence_after();
-        const uint32_t sa = tiles + s * C::STAGE_BYTES;
-        const uint32_t sb = sa + C::A_BYTES;
-        const uint64_t da = ptx::umma_desc_k_sw128(sa);
-        const uint64_t db = ptx::umma_desc_k_sw128(sb);
-        if (p.debug_mode == 2) {
-          ptx::mbar_arrive(ptx::smem_u32(&empty_bar[s]));
-          continue;
-        }
+        const uint32_t tmem_acc = tmem_base + as * C::ACC_COLS;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(ptx::smem_u32(&full_bar[s]), ph);
+          ptx::tc_fence_after();
+          const uint32_t sa = tiles + s * C::STAGE_BYTES;
+          const uint32_t sb = sa + C::A_BYTES;
+          const uint64_t da = ptx::umma_desc_k_sw128(sa);
+          const uint64_t db = ptx::umma_desc_k_sw128(sb);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // advancing 16 bf16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
-          ptx::umma_bf16(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advancing 16 bf16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
+            ptx::umma_bf16(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          ptx::umma_commit(ptx::smem_u32(&empty_bar[s]));  // frees the smem slot when the MMAs retire
+          if (++s == C::STAGES) { s = 0; ph ^= 1; }
         }
-        ptx::umma_commit(ptx::smem_u32(&empty_bar[s]));  // frees the smem slot when the MMAs retire
+        ptx::umma_commit(ptx::smem_u32(&tfull_bar[as]));  // accumulator complete
       }
-      if (p.debug_mode == 2) ptx::mbar_arrive(ptx::smem_u32(&accum_bar));
-      else ptx::umma_commit(ptx::smem_u32(&accum_bar));  // accumulator complete
     }
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..5)
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    const int m = m0 + q * 32 + lane;
-    const bool row_ok = m < p.M;
-    const int sample = (p.rows_per_sample > 0) ? (m / p.rows_per_sample) : 0;
-    // While the main loop runs, stage the per-column bias (+ the per-sample time-embedding bias when the
-    // whole tile belongs to one sample) in shared memory: the epilogue then never waits on global loads.
-    const bool rb_uniform = p.rowbias != nullptr && (p.rows_per_sample % BM) == 0;
-    {
-      const int e = (warp - 2) * 32 + lane;
-      const float* rb0 = rb_uniform ? p.rowbias + static_cast<long long>(m0 / p.rows_per_sample) * p.rowbias_ld : nullptr;
-      for (int ch = e; ch < BN; ch += 128) {
-        const int n = n0 + ch;
-        float bv = 0.f;
-        if (n < p.N) {
-          if (p.bias) bv = __ldg(p.bias + n);
-          if (rb0) bv += __ldg(rb0 + n);
-        }
-        bias_sm[ch] = bv;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-    }
-    ptx::mbar_wait(ptx::smem_u32(&accum_bar), 0);
-    ptx::tc_fence_after();
-    long long res_row = m;
-    if (p.res_up && row_ok) {
-      const int hw = p.H * p.W;
-      const int b = m / hw;
-      const int rem = m - b * hw;
-      const int h = rem / p.W;
-      const int w = rem - h * p.W;
-      res_row = (static_cast<long long>(b) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
-    }
-    constexpr int CH = (BN >= 32) ? 32 : 16;
-    const int nchunks = (p.debug_mode >= 2) ? 0 : BN / CH;
-#pragma unroll 1
-    for (int c = 0; c < nchunks; ++c) {
-      uint32_t r[32];
-      const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + c * CH;
-      if constexpr (CH == 32) {
-        ptx::tmem_ld_32x32(taddr, r);
-      } else {
-        uint32_t r16[16];
-        ptx::tmem_ld_32x16(taddr, r16);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) r[i] = r16[i];
-      }
-      ptx::tmem_ld_wait();
-      const int nb = n0 + c * CH;
-      float v[CH];
-#pragma unroll
-      for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]);
-      const bool full = (nb + CH <= p.N) && ((p.N & 7) == 0);
-      if (row_ok) {
-#pragma unroll
-        for (int i = 0; i < CH; ++i) v[i] += bias_sm[c * CH + i];
-        if (p.rowbias && !rb_uniform) {
-          const float* rb = p.rowbias + static_cast<long long>(sample) * p.rowbias_ld + nb;
-#pragma unroll
-          for (int i = 0; i < CH; ++i)
-            if (nb + i < p.N) v[i] += __ldg(rb + i);
-        }
-        if (p.residual) {
-          if (p.out_fp32) {
-            const float* rs = static_cast<const float*>(p.residual) + res_row * p.N + nb;
-#pragma unroll
-            for (int i = 0; i < CH; ++i)
-              if (nb + i < p.N) v[i] += rs[i];
-          } else if (full) {
-            const uint4* rs = reinterpret_cast<const uint4*>(
-                static_cast<const __nv_bfloat16*>(p.residual) + res_row * p.N + nb);
-#pragma unroll
-            for (int i = 0; i < CH / 8; ++i) {
-              const uint4 t = rs[i];
-              v[8 * i + 0] += bf16_lo(t.x); v[8 * i + 1] += bf16_hi(t.x);
-              v[8 * i + 2] += bf16_lo(t.y); v[8 * i + 3] += bf16_hi(t.y);
-              v[8 * i + 4] += bf16_lo(t.z); v[8 * i + 5] += bf16_hi(t.z);
-              v[8 * i + 6] += bf16_lo(t.w); v[8 * i + 7] += bf16_hi(t.w);
-            }
-          } else {
-            const __nv_bfloat16* rs = static_cast<const __nv_bfloat16*>(p.residual) + res_row * p.N + nb;
-#pragma unroll
-            for (int i = 0; i < CH; ++i)
-              if (nb + i < p.N) v[i] += __bfloat162float(rs[i]);
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < CH; ++i) v[i] *= p.alpha;
-        if (p.out_fp32) {
-          float* o = static_cast<float*>(p.out) + static_cast<long long>(m) * p.N + nb;
-          if (p.out_nchw) {
-            const int hw = p.H * p.W;
-            const int b = m / hw;
-            const int pix = m - b * hw;
-#pragma unroll
-            for (int i = 0; i < CH; ++i)
-              if (nb + i < p.N) static_cast<float*>(p.out)[(static_cast<long long>(b) * p.N + nb + i) * hw + pix] = v[i];
-          } else if (full) {
-#pragma unroll
-            for (int i = 0; i < CH / 4; ++i)
-              reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < CH; ++i)
-              if (nb + i < p.N) o[i] = v[i];
-          }
-        } else {
-          __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(m) * p.N + nb;
-          if (full) {
-#pragma unroll
-            for (int i = 0; i < CH / 8; ++i) {
-              uint4 t;
-              t.x = pack_bf16(v[8 * i + 0], v[8 * i + 1]);
-              t.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
-              t.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
-              t.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
-              reinterpret_cast<uint4*>(o)[i] = t;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < CH; ++i)
-              if (nb + i < p.N) o[i] = __float2bfloat16(v[i]);
-          }
-          // statistics are taken over the values as stored (bf16-rounded), matching what the
-          // GroupNorm consumer will read back
-#pragma unroll
-          for (int i = 0; i < CH; ++i) v[i] = __bfloat162float(__float2bfloat16(v[i]));
-        }
-      }
-      if constexpr (CH == 32) {
-        if (p.stat_part) {
-          // column sums over this warp's 32 rows by a transposing butterfly: after the 5 exchange steps lane l
-          // holds the totals of column nb + l (31 shuffles per quantity instead of 32 x 5)
-          float sq[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (!row_ok) v[i] = 0.f;
-            sq[i] = v[i] * v[i];
-          }
-#pragma unroll
-          for (int off = 16; off >= 1; off >>= 1) {
-            const bool upper = (lane & off) != 0;
-#pragma unroll
-            for (int i = 0; i < off; ++i) {
-              const float send_v = upper ? v[i] : v[i + off];
-              const float keep_v = upper ? v[i + off] : v[i];
-              const float send_q = upper ? sq[i] : sq[i + off];
-              const float keep_q = upper ? sq[i + off] : sq[i];
-              v[i] = keep_v + __shfl_xor_sync(0xffffffffu, send_v, off);
-              sq[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
-            }
-          }
-          stat_sm[q][c * 32 + lane] = make_float2(v[0], sq[0]);
-        }
-      }
-    }
-    if constexpr (CH == 32) {
-      if (p.stat_part) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
-        const int e = (warp - 2) * 32 + lane;
+    const int e = (warp - 2) * 32 + lane;
+    const int hw = p.H * p.W;
+    uint32_t tl = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tl) {
+      const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
+      const int mt = t / p.n_tiles;
+      const int m0 = mt * BM;
+      EpiRow er;
+      er.n0 = (t - mt * p.n_tiles) * BN;
+      er.m = m0 + q * 32 + lane;
+      er.row_ok = er.m < p.M;
+      er.sample = (p.rows_per_sample > 0) ? (er.m / p.rows_per_sample) : 0;
+      // While the main loop runs, stage the per-column bias (+ the per-sample time-embedding bias when the
+      // whole tile belongs to one sample) in shared memory: the epilogue then never waits on global loads.
+      er.rb_uniform = p.rowbias != nullptr && (p.rows_per_sample % BM) == 0;
+      float* bsm = bias_sm[as];
+      {
+        const float* rb0 =
+            er.rb_uniform ? p.rowbias + static_cast<long long>(m0 / p.rows_per_sample) * p.rowbias_ld : nullptr;
         for (int ch = e; ch < BN; ch += 128) {
-          if (n0 + ch < p.N) {
-            // fixed order -> run-to-run deterministic statistics
-            const float2 a0 = stat_sm[0][ch], a1 = stat_sm[1][ch], a2 = stat_sm[2][ch], a3 = stat_sm[3][ch];
-            float* dst = p.stat_part + (static_cast<long long>(blockIdx.x) * p.N + n0 + ch) * 2;
-            dst[0] = (a0.x + a1.x) + (a2.x + a3.x);
-            dst[1] = (a0.y + a1.y) + (a2.y + a3.y);
+          const int n = er.n0 + ch;
+          float bv = 0.f;
+          if (n < p.N) {
+            if (p.bias) bv = __ldg(p.bias + n);
+            if (rb0) bv += __ldg(rb0 + n);
+          }
+          bsm[ch] = bv;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      er.res_row = er.m;
+      if (p.res_up && er.row_ok) {
+        const int b = er.m / hw;
+        const int rem = er.m - b * hw;
+        const int h = rem / p.W;
+        const int w = rem - h * p.W;
+        er.res_row = (static_cast<long long>(b) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
+      }
+      ptx::mbar_wait(ptx::smem_u32(&tfull_bar[as]), aph);
+      ptx::tc_fence_after();
+      const uint32_t tbase = tmem_base + as * C::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
+      auto release_acc = [&]() {
+        // every tcgen05.ld of this warp has completed: hand the accumulator back to the MMA warp
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[as]));
+      };
+      if constexpr (CH == 16) {
+        uint32_t r[32];
+        {
+          uint32_t r16[16];
+          ptx::tmem_ld_32x16(tbase, r16);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = r16[i];
+        }
+        release_acc();
+        epilogue_chunk<16>(p, er, r, 0, bsm, stat_sm[q], lane);
+      } else {
+        constexpr int NCH = BN / 32;
+        uint32_t r0[32], r1[32];
+        ptx::tmem_ld_32x32(tbase, r0);
+#pragma unroll 1
+        for (int c = 0; c < NCH; c += 2) {
+          ptx::tmem_ld_wait();
+          if (c + 1 < NCH) ptx::tmem_ld_32x32(tbase + (c + 1) * 32, r1);
+          else release_acc();
+          epilogue_chunk<32>(p, er, r0, c, bsm, stat_sm[q], lane);
+          if (c + 1 < NCH) {
+            ptx::tmem_ld_wait();
+            if (c + 2 < NCH) ptx::tmem_ld_32x32(tbase + (c + 2) * 32, r0);
+            else release_acc();
+            epilogue_chunk<32>(p, er, r1, c + 1, bsm, stat_sm[q], lane);
+          }
+        }
+        if (p.stat_part) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+          for (int ch = e; ch < BN; ch += 128) {
+            if (er.n0 + ch < p.N) {
+              // fixed order -> run-to-run deterministic statistics
+              const float2 a0 = stat_sm[0][ch], a1 = stat_sm[1][ch], a2 = stat_sm[2][ch], a3 = stat_sm[3][ch];
+              float* dst = p.stat_part + (static_cast<long long>(mt) * p.N + er.n0 + ch) * 2;
+              dst[0] = (a0.x + a1.x) + (a2.x + a3.x);
+              dst[1] = (a0.y + a1.y) + (a2.y + a3.y);
+            }
           }
         }
       }
@@ -347,7 +415,281 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_gemm_tc_kernel(const __grid_
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_acc, C::TMEM_COLS);
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// =====================================================================================================
+// Channel-major variant:  out^T[N, M] = Wt[N, K] * im2col(A)[M, K]^T.
+//
+// The 128 UMMA rows (TMEM lanes) are OUTPUT CHANNELS and the UMMA N dimension is a tile of PX pixels, i.e. the
+// weight slice is the "A" operand and the shifted pixel window the "B" operand.  Against the pixel-major
+// kernel above this (i) halves the weight traffic per FLOP for the 128-channel layers (one 16 KB weight slice
+// feeds 256 pixels instead of 128: the L2 -> SMEM operand stream is what bounds these layers), (ii) makes the
+// epilogue channel-per-thread: bias and time-embedding bias are per-thread scalars, GroupNorm statistics are
+// per-thread running sums (no shuffles, no shared memory, no barriers), and every store / residual load of a
+// warp is one contiguous 64-byte run of the NHWC tensor.
+template <int PX>
+struct CfgT {
+  static constexpr int W_BYTES = 128 * BK * 2;
+  static constexpr int P_BYTES = PX * BK * 2;
+  static constexpr int STAGE_BYTES = W_BYTES + P_BYTES;
+  static constexpr int STAGES = (SMEM_TILE_BUDGET / STAGE_BYTES) < 8 ? (SMEM_TILE_BUDGET / STAGE_BYTES) : 8;
+  static constexpr int OUT_BYTES = 4 * 2 * 32 * 32 * 2;  // per epilogue warp: 2 buffers of 32 px x 32 ch bf16
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_BYTES + 1024;
+  static constexpr int TMEM_COLS = 2 * PX;
+};
+
+struct EpiT {
+  int n;            // output channel of this thread
+  bool ch_ok;
+  float bch;        // bias[n] (+ rowbias[sample][n] when the tile lies inside one sample)
+  bool rb_uniform;
+  int m0;
+};
+
+// 32 consecutive pixels [m0 + c * 32, +32) of this thread's channel -> bf16 in h[] (two pixels per word)
+__device__ __forceinline__ void epilogue_chunk_t(const TcParams& p, const EpiT& et, const uint32_t (&r)[32], int c,
+                                                 float& ssum, float& ssq, unsigned short (&h)[32]) {
+  const int mb = et.m0 + c * 32;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + et.bch;
+  if (p.rowbias && !et.rb_uniform && et.ch_ok) {
+    int cur = -1;
+    float rbv = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int sm = min(mb + j, p.M - 1) / p.rows_per_sample;
+      if (sm != cur) {
+        cur = sm;
+        rbv = __ldg(p.rowbias + static_cast<long long>(sm) * p.rowbias_ld + et.n);
+      }
+      v[j] += rbv;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const __nv_bfloat16 b = __float2bfloat16(v[j] * p.alpha);
+    h[j] = __bfloat16_as_ushort(b);
+    v[j] = __bfloat162float(b);  // statistics over the values as stored
+  }
+  if (p.stat_part && et.ch_ok) {
+    if (mb + 32 <= p.M) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        ssum += v[j];
+        ssq = fmaf(v[j], v[j], ssq);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (mb + j < p.M) {
+          ssum += v[j];
+          ssq = fmaf(v[j], v[j], ssq);
+        }
+      }
+    }
+  }
+}
+
+template <int PX>
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_tcT_kernel(const __grid_constant__ TcParams p) {
+  using C = CfgT<PX>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[C::STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[C::STAGES];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t tiles = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t out_stage = tiles + C::STAGES * C::STAGE_BYTES;  // 1024-aligned (stage sizes are multiples of 1 KB)
+
+  const int ctot = p.c0 + p.c1;
+  const int chunks_per_tap = ctot / BK;
+  const int num_kb_main = p.taps * chunks_per_tap;
+  const int num_kb = num_kb_main + (p.residual ? 2 : 0);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&tfull_bar[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&tempty_bar[s]), 4);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(ptx::smem_u32(&tmem_base_slot), C::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      ptx::prefetch_tmap(&p.tm_a0);
+      ptx::prefetch_tmap(&p.tm_w);
+      if (p.c1 > 0) ptx::prefetch_tmap(&p.tm_a1);
+      if (p.residual) {
+        ptx::prefetch_tmap(&p.tm_res);
+        ptx::prefetch_tmap(&p.tm_ident);
+      }
+      const int pad = (p.taps == 9) ? 1 : 0;
+      const int hw = p.H * p.W;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int pt = t / p.n_tiles;
+        const int m0 = pt * PX;
+        const int n0 = (t - pt * p.n_tiles) * 128;
+        int b0 = 0, h0 = 0, w0 = m0;
+        if (!p.mode2d) {
+          b0 = m0 / hw;
+          const int rem = m0 - b0 * hw;
+          h0 = rem / p.W;
+          w0 = rem - h0 * p.W;
+        }
+        int kb = 0;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int kh = (p.taps == 9) ? tap / 3 : 0;
+          const int kw = (p.taps == 9) ? tap - kh * 3 : 0;
+          for (int cc = 0; cc < chunks_per_tap; ++cc, ++kb) {
+            ptx::mbar_wait(ptx::smem_u32(&empty_bar[s]), ph ^ 1);
+            const uint32_t fb = ptx::smem_u32(&full_bar[s]);
+            ptx::mbar_arrive_expect_tx(fb, C::STAGE_BYTES);
+            const uint32_t sw = tiles + s * C::STAGE_BYTES;
+            const uint32_t sp = sw + C::W_BYTES;
+            const int ch = cc * BK;
+            ptx::tma_load_4d(sw, &p.tm_w, fb, kb * BK, n0, 0, 0);
+            if (ch < p.c0)
+              ptx::tma_load_4d(sp, &p.tm_a0, fb, ch, w0 + kw - pad, h0 + kh - pad, b0);
+            else
+              ptx::tma_load_4d(sp, &p.tm_a1, fb, ch - p.c0, w0 + kw - pad, h0 + kh - pad, b0);
+            if (++s == C::STAGES) { s = 0; ph ^= 1; }
+          }
+        }
+        if (p.residual) {
+          // residual[m][n0 .. n0 + 128) enters the accumulator through two identity k-blocks: exact in fp32,
+          // fetched by TMA like any operand, no epilogue loads
+          for (int j = 0; j < 2; ++j) {
+            ptx::mbar_wait(ptx::smem_u32(&empty_bar[s]), ph ^ 1);
+            const uint32_t fb = ptx::smem_u32(&full_bar[s]);
+            ptx::mbar_arrive_expect_tx(fb, C::STAGE_BYTES);
+            const uint32_t sw = tiles + s * C::STAGE_BYTES;
+            const uint32_t sp = sw + C::W_BYTES;
+            ptx::tma_load_4d(sw, &p.tm_ident, fb, j * BK, 0, 0, 0);
+            ptx::tma_load_4d(sp, &p.tm_res, fb, n0 + j * BK, w0, h0, b0);
+            if (++s == C::STAGES) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(PX);  // M = 128 channels, N = PX pixels
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t tl = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tl) {
+        const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
+        ptx::mbar_wait(ptx::smem_u32(&tempty_bar[as]), aph ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + as * PX;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(ptx::smem_u32(&full_bar[s]), ph);
+          ptx::tc_fence_after();
+          const uint32_t sw = tiles + s * C::STAGE_BYTES;
+          const uint64_t dw = ptx::umma_desc_k_sw128(sw);
+          const uint64_t dp = ptx::umma_desc_k_sw128(sw + C::W_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) ptx::umma_bf16(tmem_acc, dw + 2 * k, dp + 2 * k, idesc, (kb | k) != 0);
+          ptx::umma_commit(ptx::smem_u32(&empty_bar[s]));
+          if (++s == C::STAGES) { s = 0; ph ^= 1; }
+        }
+        ptx::umma_commit(ptx::smem_u32(&tfull_bar[as]));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5): thread = channel
+    const int q = warp & 3;
+    EpiT et;
+    et.rb_uniform = p.rowbias != nullptr && (p.rows_per_sample % PX) == 0;
+    const uint32_t obuf = out_stage + q * (2 * 32 * 32 * 2);  // this warp's two [32 px][32 ch] bf16 buffers
+    uint32_t tl = 0;
+    uint32_t nstore = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tl) {
+      const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
+      const int pt = t / p.n_tiles;
+      const int nw0 = (t - pt * p.n_tiles) * 128 + q * 32;  // first channel of this warp
+      et.m0 = pt * PX;
+      et.n = nw0 + lane;
+      et.ch_ok = et.n < p.N;
+      et.bch = 0.f;
+      if (et.ch_ok) {
+        if (p.bias) et.bch = __ldg(p.bias + et.n);
+        if (et.rb_uniform)
+          et.bch += __ldg(p.rowbias + static_cast<long long>(et.m0 / p.rows_per_sample) * p.rowbias_ld + et.n);
+      }
+      ptx::mbar_wait(ptx::smem_u32(&tfull_bar[as]), aph);
+      ptx::tc_fence_after();
+      const uint32_t tbase = tmem_base + as * PX + (static_cast<uint32_t>(q * 32) << 16);
+      auto release_acc = [&]() {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[as]));
+      };
+      // bf16 values -> this warp's staging buffer ([pixel][channel], 64-byte rows) -> one TMA store per chunk.
+      // TMA clips rows >= M and channels >= N, so ragged edges need no masks here.
+      auto store_chunk = [&](const unsigned short (&h)[32], int c) {
+        const uint32_t buf = obuf + (nstore & 1) * (32 * 32 * 2);
+        __syncwarp();  // lane 0 has waited for the store that last read this buffer
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(buf + j * 64 + lane * 2), "h"(h[j]) : "memory");
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && nw0 < p.N && et.m0 + c * 32 < p.M) {
+          ptx::tma_store_4d(&p.tm_out, buf, nw0, et.m0 + c * 32, 0, 0);
+          ptx::tma_store_commit();
+          ptx::tma_store_wait_read<1>();  // the previous store (other buffer) has finished reading smem
+        }
+        ++nstore;
+      };
+      constexpr int NCH = PX / 32;
+      float ssum = 0.f, ssq = 0.f;
+      uint32_t r0[32], r1[32];
+      unsigned short h[32];
+      ptx::tmem_ld_32x32(tbase, r0);
+#pragma unroll 1
+      for (int c = 0; c < NCH; c += 2) {
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld_32x32(tbase + (c + 1) * 32, r1);
+        epilogue_chunk_t(p, et, r0, c, ssum, ssq, h);
+        store_chunk(h, c);
+        ptx::tmem_ld_wait();
+        if (c + 2 < NCH) ptx::tmem_ld_32x32(tbase + (c + 2) * 32, r0);
+        else release_acc();
+        epilogue_chunk_t(p, et, r1, c + 1, ssum, ssq, h);
+        store_chunk(h, c + 1);
+      }
+      if (p.stat_part && et.ch_ok)
+        *reinterpret_cast<float2*>(p.stat_part + (static_cast<long long>(pt) * p.N + et.n) * 2) = make_float2(ssum, ssq);
+    }
+    if (lane == 0) ptx::tma_store_wait_read<0>();  // smem must stay valid until the last store has read it
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -371,8 +713,9 @@ struct TmapKey {
   const void* ptr;
   uint64_t d[4];
   uint32_t b[4];
+  int swizzle;
   bool operator==(const TmapKey& o) const {
-    if (ptr != o.ptr) return false;
+    if (ptr != o.ptr || swizzle != o.swizzle) return false;
     for (int i = 0; i < 4; ++i)
       if (d[i] != o.d[i] || b[i] != o.b[i]) return false;
     return true;
@@ -380,7 +723,7 @@ struct TmapKey {
 };
 struct TmapKeyHash {
   size_t operator()(const TmapKey& k) const {
-    uint64_t h = reinterpret_cast<uint64_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
+    uint64_t h = reinterpret_cast<uint64_t>(k.ptr) * 0x9E3779B97F4A7C15ull + k.swizzle;
     for (int i = 0; i < 4; ++i) {
       h ^= (k.d[i] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
       h ^= (k.b[i] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
@@ -389,11 +732,12 @@ struct TmapKeyHash {
   }
 };
 
-// bf16 tensor with dims d[0] (innermost, contiguous) .. d[3]; dense strides; box b[0..3].
-CUtensorMap make_tmap_bf16(const void* ptr, const uint64_t d[4], const uint32_t b[4]) {
+// bf16 tensor with dims d[0] (innermost, contiguous) .. d[3]; dense strides; box b[0..3]; 128-byte swizzle
+// (operand tiles) or none (the epilogue's store tiles).
+CUtensorMap make_tmap_bf16(const void* ptr, const uint64_t d[4], const uint32_t b[4], bool swizzle128 = true) {
   static std::mutex mu;
   static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
-  TmapKey key{ptr, {d[0], d[1], d[2], d[3]}, {b[0], b[1], b[2], b[3]}};
+  TmapKey key{ptr, {d[0], d[1], d[2], d[3]}, {b[0], b[1], b[2], b[3]}, swizzle128 ? 1 : 0};
   std::lock_guard<std::mutex> lk(mu);
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
@@ -406,16 +750,39 @@ CUtensorMap make_tmap_bf16(const void* ptr, const uint64_t d[4], const uint32_t 
   T2P_CHECK((strides[0] & 15) == 0, "TMA row pitch must be a multiple of 16 bytes");
   CUresult r = encode_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims,
                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   T2P_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string(int(r)));
   if (cache.size() > 65536) cache.clear();
   cache.emplace(key, tm);
   return tm;
 }
 
+// 128 x 128 bf16 identity: the channel-major kernel adds the residual through two identity k-blocks
+const void* identity128() {
+  static void* dev = [] {
+    std::vector<__nv_bfloat16> h(128 * 128, __float2bfloat16(0.f));
+    for (int i = 0; i < 128; ++i) h[i * 128 + i] = __float2bfloat16(1.f);
+    void* d = nullptr;
+    T2P_CUDA(cudaMalloc(&d, h.size() * 2));
+    T2P_CUDA(cudaMemcpy(d, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+    return d;
+  }();
+  return dev;
+}
+
+int sm_count() {
+  static int n = [] {
+    int dev = 0, v = 0;
+    T2P_CUDA(cudaGetDevice(&dev));
+    T2P_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    return v;
+  }();
+  return n;
+}
+
 template <int BN>
-void launch(const TcParams& p, cudaStream_t st) {
+void launch(TcParams& p, cudaStream_t st) {
   using C = Cfg<BN>;
   static bool configured = false;
   if (!configured) {
@@ -423,12 +790,97 @@ void launch(const TcParams& p, cudaStream_t st) {
                                   C::SMEM_BYTES));
     configured = true;
   }
-  dim3 grid(cdiv(p.M, BM), cdiv(p.N, BN));
+  p.n_tiles = cdiv(p.N, BN);
+  p.num_tiles = cdiv(p.M, BM) * p.n_tiles;
+  const int grid = std::min(p.num_tiles, sm_count());
   conv_gemm_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p);
   T2P_LAUNCH_CHECK();
 }
 
+template <int PX>
+void launch_t(TcParams& p, cudaStream_t st) {
+  using C = CfgT<PX>;
+  static bool configured = false;
+  if (!configured) {
+    T2P_CUDA(cudaFuncSetAttribute(conv_gemm_tcT_kernel<PX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  C::SMEM_BYTES));
+    configured = true;
+  }
+  p.n_tiles = cdiv(p.N, 128);
+  p.num_tiles = cdiv(p.M, PX) * p.n_tiles;
+  const int grid = std::min(p.num_tiles, sm_count());
+  conv_gemm_tcT_kernel<PX><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p);
+  T2P_LAUNCH_CHECK();
+}
+
+// `rows` consecutive pixels (b, h, w raster order) as one TMA box (tw, th, tb) of the NHWC tensor
+bool pixel_box(const ConvGemmArgs& a, int rows, uint32_t& tw, uint32_t& th, uint32_t& tb) {
+  if (a.ksize == 1) { tw = rows; th = 1; tb = 1; return true; }
+  if (a.W >= rows) {
+    if (a.W % rows) return false;
+    tw = rows; th = 1; tb = 1;
+    return true;
+  }
+  if (rows % a.W) return false;
+  tw = a.W;
+  th = std::min<uint32_t>(a.H, rows / a.W);
+  if (a.H % th) return false;
+  tb = rows / (tw * th);
+  return tb == 1 || th == static_cast<uint32_t>(a.H);  // a tile spanning samples must cover whole images
+}
+
+struct Plan {
+  bool channel_major = false;
+  int rows = BM;  // pixels per tile
+  int bn = 128;   // pixel-major kernel: channels per tile
+  uint32_t tw = 0, th = 0, tb = 0;
+  bool stats_ok = false;
+};
+
+Plan make_plan(const ConvGemmArgs& a) {
+  Plan pl;
+  const long long M = static_cast<long long>(a.B) * a.H * a.W;
+  const bool want_stats = a.stat_part != nullptr;
+  if (a.N >= 128 && a.N % 8 == 0 && a.out_dtype == kBF16 && !a.out_nchw && !a.res_up) {
+    // channel-major kernel: widest pixel tile that still spreads the problem over (most of) the SMs
+    int pick = 0;
+    for (int px : {256, 128, 64}) {
+      uint32_t tw, th, tb;
+      if (!pixel_box(a, px, tw, th, tb)) continue;
+      if (want_stats && (a.rows_per_sample % px) != 0) continue;
+      pick = px;
+      if (cdiv64(M, px) * cdiv(a.N, 128) >= 96) break;
+    }
+    if (pick) {
+      pl.channel_major = true;
+      pl.rows = pick;
+      pixel_box(a, pick, pl.tw, pl.th, pl.tb);
+      pl.stats_ok = want_stats && a.out_dtype == kBF16;
+      return pl;
+    }
+  }
+  T2P_CHECK(pixel_box(a, BM, pl.tw, pl.th, pl.tb), "unsupported image geometry for the 128-pixel tile");
+  pl.rows = BM;
+  const int m_tiles = static_cast<int>(cdiv64(M, BM));
+  if (a.N <= 16) pl.bn = 16;
+  else if (a.N <= 32) pl.bn = 32;
+  else if (a.N <= 64) pl.bn = 64;
+  else {
+    pl.bn = (a.N % 256 == 0) ? 256 : 128;
+    while (pl.bn > 32 && m_tiles * cdiv(a.N, pl.bn) < 96) pl.bn >>= 1;
+  }
+  pl.stats_ok = want_stats && a.rows_per_sample > 0 && a.rows_per_sample % BM == 0 && a.out_dtype == kBF16 && a.N >= 32;
+  return pl;
+}
+
 }  // namespace
+
+int conv_gemm_tc_stat_tile(const ConvGemmArgs& a) {
+  ConvGemmArgs q = a;
+  if (!q.stat_part) q.stat_part = reinterpret_cast<float*>(16);  // plan as if statistics were requested
+  const Plan pl = make_plan(q);
+  return pl.stats_ok ? pl.rows : 0;
+}
 
 void conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
   T2P_CHECK(a.ksize == 1 || a.ksize == 3, "ksize must be 1 or 3");
@@ -458,62 +910,54 @@ void conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
   p.stat_part = a.stat_part;
   p.rowbias_ld = a.rowbias_ld > 0 ? a.rowbias_ld : a.N;
   p.out_nchw = a.out_nchw;
+  p.mode2d = (a.ksize == 1) ? 1 : 0;
   if (a.out_nchw) T2P_CHECK(a.out_dtype == kF32 && a.residual == nullptr, "out_nchw is fp32-only, without residual");
-  {
-    static const int dbg = [] { const char* e = getenv("T2P_TC_DEBUG"); return e ? atoi(e) : 0; }();
-    p.debug_mode = dbg;
-  }
   if (a.rowbias) T2P_CHECK(a.rows_per_sample > 0, "rows_per_sample required");
-  if (a.stat_part)
-    T2P_CHECK(a.rows_per_sample > 0 && a.rows_per_sample % BM == 0 && a.out_dtype == kBF16 && a.N >= 32,
-              "fused GroupNorm statistics need whole 128-row tiles per sample, bf16 output and N >= 32");
   if (a.res_up) T2P_CHECK(a.ksize == 3 && (a.H % 2 == 0) && (a.W % 2 == 0), "res_up needs an even image");
 
-  // M-tile = box of 128 pixels in (b, h, w) raster order
-  uint32_t tw, th, tb;
-  if (a.ksize == 1) {
-    p.mode2d = 1;
-    tw = BM; th = 1; tb = 1;
-  } else {
-    p.mode2d = 0;
-    if (a.W >= BM) {
-      T2P_CHECK(a.W % BM == 0, "W must be a multiple of 128 when >= 128");
-      tw = BM; th = 1; tb = 1;
-    } else {
-      T2P_CHECK(BM % a.W == 0, "W must divide 128");
-      tw = a.W;
-      th = std::min<uint32_t>(a.H, BM / a.W);
-      T2P_CHECK(a.H % th == 0, "H must be a multiple of the tile height");
-      tb = BM / (tw * th);
-      T2P_CHECK(tb == 1 || th == static_cast<uint32_t>(a.H), "tile must cover whole images when spanning samples");
-    }
-  }
+  const Plan pl = make_plan(a);
+  if (a.stat_part)
+    T2P_CHECK(pl.stats_ok, "fused GroupNorm statistics need whole pixel tiles per sample and bf16 output "
+                           "(ask conv_gemm_tc_stat_tile first)");
+
   auto amap = [&](const void* ptr, int c) {
     if (p.mode2d) {
       uint64_t d[4] = {static_cast<uint64_t>(c), static_cast<uint64_t>(M), 1, 1};
-      uint32_t b[4] = {BK, BM, 1, 1};
+      uint32_t b[4] = {BK, static_cast<uint32_t>(pl.rows), 1, 1};
       return make_tmap_bf16(ptr, d, b);
     }
     uint64_t d[4] = {static_cast<uint64_t>(c), static_cast<uint64_t>(a.W), static_cast<uint64_t>(a.H),
                      static_cast<uint64_t>(a.B)};
-    uint32_t b[4] = {BK, tw, th, tb};
+    uint32_t b[4] = {BK, pl.tw, pl.th, pl.tb};
     return make_tmap_bf16(ptr, d, b);
   };
   p.tm_a0 = amap(a.a0, a.c0);
   p.tm_a1 = (a.c1 > 0) ? amap(a.a1, a.c1) : p.tm_a0;
-
-  int bn;
-  if (a.N <= 16) bn = 16;
-  else if (a.N <= 32) bn = 32;
-  else if (a.N <= 64) bn = 64;
-  else if (a.N % 256 == 0 && cdiv(p.M, BM) * (a.N / 256) >= 148) bn = 256;
-  else bn = 128;
   {
     uint64_t d[4] = {static_cast<uint64_t>(taps) * ctot, static_cast<uint64_t>(a.N), 1, 1};
-    uint32_t b[4] = {BK, static_cast<uint32_t>(bn), 1, 1};
+    uint32_t b[4] = {BK, static_cast<uint32_t>(pl.channel_major ? 128 : pl.bn), 1, 1};
     p.tm_w = make_tmap_bf16(a.w, d, b);
   }
-  switch (bn) {
+  if (pl.channel_major) {
+    {
+      uint64_t d[4] = {static_cast<uint64_t>(a.N), static_cast<uint64_t>(M), 1, 1};
+      uint32_t b[4] = {32, 32, 1, 1};
+      p.tm_out = make_tmap_bf16(a.out, d, b, false);
+    }
+    if (a.residual) {
+      p.tm_res = amap(a.residual, a.N);
+      uint64_t d[4] = {128, 128, 1, 1};
+      uint32_t b[4] = {BK, 128, 1, 1};
+      p.tm_ident = make_tmap_bf16(identity128(), d, b);
+    }
+    switch (pl.rows) {
+      case 256: launch_t<256>(p, st); break;
+      case 128: launch_t<128>(p, st); break;
+      default: launch_t<64>(p, st); break;
+    }
+    return;
+  }
+  switch (pl.bn) {
     case 16: launch<16>(p, st); break;
     case 32: launch<32>(p, st); break;
     case 64: launch<64>(p, st); break;

@@ -28,8 +28,8 @@ struct ConvGemmArgs {
   float alpha = 1.f;
   void* out = nullptr;
   int out_dtype = kBF16;
-  // optional fused GroupNorm statistics of the stored output: per 128-row tile and channel {sum, sum of squares},
-  // [M / 128][N][2] == part[B][rows_per_sample / 128][N][2] (tcgen05 kernel, rows_per_sample % 128 == 0)
+  // optional fused GroupNorm statistics of the stored output: per pixel tile and channel {sum, sum of squares},
+  // [M / T][N][2] == part[B][rows_per_sample / T][N][2], T = conv_gemm_tc_stat_tile(args) (tcgen05 kernels only)
   float* stat_part = nullptr;
   int rowbias_ld = 0;  // row pitch of rowbias (0 -> N)
   int out_nchw = 0;    // 1: store out as [B][N][H*W] (fp32 only; used by the final conv)
@@ -37,6 +37,9 @@ struct ConvGemmArgs {
 
 // bf16 tcgen05 / TMEM / TMA path (sm_100a).  A, W are bf16.
 void conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st);
+// pixel-tile size T the tcgen05 launch for these arguments uses for fused GroupNorm statistics
+// (rows_per_sample % T == 0), or 0 when it cannot produce them
+int conv_gemm_tc_stat_tile(const ConvGemmArgs& a);
 // fp32 or bf16 SIMT path (verification mode and tiny-channel edge layers). dtype of A and W.
 void conv_gemm_simt(const ConvGemmArgs& a, int in_dtype, cudaStream_t st);
 

@@ -98,7 +98,7 @@ static int run_case(const Case& c) {
   fail_if(cudaMalloc(&ref, M * c.N * 4), "malloc");
   fail_if(cudaMalloc(&out32, M * c.N * 4), "malloc");
   fail_if(cudaMalloc(&out16, M * c.N * 2), "malloc");
-  const long long tiles = (M + 127) / 128;
+  const long long tiles = (M + 63) / 64;  // upper bound on the number of statistics tiles
   fail_if(cudaMalloc(&ssum, tiles * c.N * 8), "malloc");
   ssq = nullptr;
   cudaMemset(out32, 0xff, M * c.N * 4);
@@ -121,7 +121,8 @@ static int run_case(const Case& c) {
   g.alpha = alpha;
   if (c.out_fp32) { g.out = out32; g.out_dtype = kF32; g.residual = c.res ? (const void*)res32 : nullptr; }
   else { g.out = out16; g.out_dtype = kBF16; g.residual = c.res ? (const void*)res : nullptr; }
-  const bool do_stats = c.stats && (rps % 128 == 0) && !c.out_fp32;
+  const int stile = (c.stats && !c.out_fp32) ? conv_gemm_tc_stat_tile(g) : 0;
+  const bool do_stats = stile > 0;
   if (do_stats) g.stat_part = ssum;
 
   int rc = 0;
@@ -156,11 +157,12 @@ static int run_case(const Case& c) {
            K, maxerr, maxref, ok ? "PASS" : "FAIL");
     if (!ok) rc = 1;
     if (pass == 0 && do_stats) {
-      std::vector<float> hp(tiles * c.N * 2), hs(c.B * c.N, 0.f), hq(c.B * c.N, 0.f);
-      cudaMemcpy(hp.data(), ssum, tiles * c.N * 8, cudaMemcpyDeviceToHost);
-      for (long long t = 0; t < tiles; ++t)
+      const long long stiles = M / stile;
+      std::vector<float> hp(stiles * c.N * 2), hs(c.B * c.N, 0.f), hq(c.B * c.N, 0.f);
+      cudaMemcpy(hp.data(), ssum, stiles * c.N * 8, cudaMemcpyDeviceToHost);
+      for (long long t = 0; t < stiles; ++t)
         for (int n = 0; n < c.N; ++n) {
-          const int b = int(t * 128 / rps);
+          const int b = int(t * stile / rps);
           hs[b * c.N + n] += hp[(t * c.N + n) * 2];
           hq[b * c.N + n] += hp[(t * c.N + n) * 2 + 1];
         }
@@ -187,18 +189,41 @@ static int run_case(const Case& c) {
   return rc;
 }
 
-static void bench_case(int B, int H, int W, int cin, int N, int ks) {
+__global__ void fill_bf16(__nv_bfloat16* p, long long n, float scale, unsigned seed) {
+  const long long i = blockIdx.x * 1ll * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned h = static_cast<unsigned>(i) * 2654435761u + seed;
+  h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+  p[i] = __float2bfloat16(((h & 0xffff) / 32768.f - 1.f) * scale);
+}
+
+// random (not zero) operands so that the power draw, and hence the clock, is representative;
+// epi = 0: plain store, 1: + bias + per-sample bias + GroupNorm statistics, 2: + residual
+static void bench_case(int B, int H, int W, int cin, int N, int ks, int epi) {
   const long long M = 1ll * B * H * W;
   const int K = ks * ks * cin;
-  __nv_bfloat16 *a, *w, *o;
+  __nv_bfloat16 *a, *w, *o, *res;
+  float *bias, *rb, *st;
   fail_if(cudaMalloc(&a, M * cin * 2), "malloc");
   fail_if(cudaMalloc(&w, 1ll * N * K * 2), "malloc");
   fail_if(cudaMalloc(&o, M * N * 2), "malloc");
-  cudaMemset(a, 0, M * cin * 2);
-  cudaMemset(w, 0, 1ll * N * K * 2);
+  fail_if(cudaMalloc(&res, M * N * 2), "malloc");
+  fail_if(cudaMalloc(&bias, N * 4), "malloc");
+  fail_if(cudaMalloc(&rb, 1ll * B * N * 4), "malloc");
+  fail_if(cudaMalloc(&st, (M / 128 + 1) * N * 8), "malloc");
+  fill_bf16<<<(unsigned)((M * cin + 255) / 256), 256>>>(a, M * cin, 1.f, 1u);
+  fill_bf16<<<(unsigned)((1ll * N * K + 255) / 256), 256>>>(w, 1ll * N * K, 0.05f, 2u);
+  fill_bf16<<<(unsigned)((M * N + 255) / 256), 256>>>(res, M * N, 1.f, 3u);
+  cudaMemset(bias, 0, N * 4);
+  cudaMemset(rb, 0, 1ll * B * N * 4);
   ConvGemmArgs g;
   g.a0 = a; g.c0 = cin; g.B = B; g.H = H; g.W = W; g.ksize = ks; g.w = w; g.N = N; g.out = o;
   g.rows_per_sample = H * W;
+  if (epi >= 1) {
+    g.bias = bias; g.rowbias = rb;
+    if (conv_gemm_tc_stat_tile(g) > 0) g.stat_part = st;
+  }
+  if (epi >= 2) { g.residual = res; g.alpha = 0.70710678f; }
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int i = 0; i < 3; ++i) conv_gemm_tc(g, 0);
@@ -210,9 +235,9 @@ static void bench_case(int B, int H, int W, int cin, int N, int ks) {
   float ms;
   cudaEventElapsedTime(&ms, e0, e1);
   ms /= iters;
-  printf("  bench B=%d %dx%d cin=%d N=%d k=%d: %.3f ms  %.1f TFLOP/s\n", B, H, W, cin, N, ks, ms,
+  printf("  bench B=%d %dx%d cin=%d N=%d k=%d epi=%d: %.3f ms  %.1f TFLOP/s\n", B, H, W, cin, N, ks, epi, ms,
          2.0 * M * N * K / (ms * 1e-3) / 1e12);
-  cudaFree(a); cudaFree(w); cudaFree(o);
+  cudaFree(a); cudaFree(w); cudaFree(o); cudaFree(res); cudaFree(bias); cudaFree(rb); cudaFree(st);
 }
 
 int main(int argc, char** argv) {
@@ -232,6 +257,11 @@ int main(int argc, char** argv) {
       {"conv3 32x32 res_up", 2, 32, 32, 256, 0, 3, 256, true, false, true, true, false, false},
       {"conv1 64x64 c384->128", 2, 64, 64, 256, 128, 1, 128, true, false, false, false, false, false},
       {"conv3 256x256 c256->256", 1, 256, 256, 256, 0, 3, 256, true, true, true, false, false, true},
+      {"conv3 4x4 c128->128 B=5 ragged", 5, 4, 4, 128, 0, 3, 128, true, true, true, false, false, false},
+      {"conv3 64x64 c64->192", 2, 64, 64, 64, 0, 3, 192, true, true, true, false, false, true},
+      {"conv3 16x16 res_up c128->128", 3, 16, 16, 128, 0, 3, 128, true, true, true, true, false, true},
+      {"gemm M=300 K=4096 N=512", 1, 1, 300, 4096, 0, 1, 512, false, false, false, false, false, false},
+      {"conv1 8x8 c256->256 B=70", 70, 8, 8, 256, 0, 1, 256, true, true, true, false, true, false},
   };
   int rc = 0;
   const char* only = getenv("T2P_SELFTEST_CASE");
@@ -241,14 +271,16 @@ int main(int argc, char** argv) {
     ++ci;
   }
   if (argc > 1) {
-    bench_case(64, 128, 128, 128, 128, 3);
-    bench_case(64, 128, 128, 256, 128, 3);
-    bench_case(64, 64, 64, 128, 128, 3);
-    bench_case(64, 32, 32, 256, 256, 3);
-    bench_case(64, 16, 16, 256, 256, 3);
-    bench_case(64, 8, 8, 256, 256, 3);
-    bench_case(64, 4, 4, 256, 256, 3);
-    bench_case(64, 128, 128, 256, 128, 1);
+    for (int epi = 0; epi < 3; ++epi) {
+      bench_case(64, 128, 128, 128, 128, 3, epi);
+      bench_case(64, 128, 128, 256, 128, 3, epi);
+      bench_case(64, 64, 64, 128, 128, 3, epi);
+      bench_case(64, 32, 32, 256, 256, 3, epi);
+      bench_case(64, 16, 16, 256, 256, 3, epi);
+      bench_case(64, 8, 8, 256, 256, 3, epi);
+      bench_case(64, 4, 4, 256, 256, 3, epi);
+      bench_case(64, 128, 128, 256, 128, 1, epi);
+    }
   }
   printf(rc ? "SELFTEST FAILED\n" : "SELFTEST OK\n");
   return rc;

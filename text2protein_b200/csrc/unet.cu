@@ -386,11 +386,9 @@ Act UNet::new_act(int B, int H, int W, int C, bool with_stats) {
   Act a;
   a.B = B; a.H = H; a.W = W; a.C = C;
   a.p = ws_.alloc(static_cast<size_t>(a.rows()) * C * dtype_size(cfg_.compute_dtype));
-  // the tensor-core epilogue can emit GroupNorm statistics when every 128-row tile lies inside one sample
-  if (with_stats && cfg_.compute_dtype == kBF16 && C >= 32 && (H * W) % 128 == 0) {
-    a.snblk = H * W / 128;
-    a.spart = static_cast<float*>(ws_.alloc(sizeof(float) * 2 * static_cast<size_t>(B) * a.snblk * C));
-  }
+  // the tensor-core epilogue can emit GroupNorm statistics when every pixel tile lies inside one sample; the
+  // partial-sum buffer is allocated by gemm() once the producing launch (and hence its tile size) is known
+  a.want_stats = with_stats && cfg_.compute_dtype == kBF16 && C >= 32;
   return a;
 }
 void UNet::free_act(Act& a) {
@@ -416,11 +414,13 @@ void UNet::gemm(const Linear& l, const Act& a0, const Act* a1, Act& out, const f
   g.out_dtype = out_dtype >= 0 ? out_dtype : cfg_.compute_dtype;
   g.out_nchw = out_nchw;
   const bool tc = cfg_.compute_dtype == kBF16 && !l.force_f32 && (g.c0 % 64 == 0) && (g.c1 % 64 == 0);
-  if (tc && out.spart) g.stat_part = out.spart;
-  if (!tc && out.spart) {  // only the tensor-core epilogue produces GroupNorm statistics
-    ws_.free(out.spart);
-    out.spart = nullptr;
-    out.snblk = 0;
+  if (tc && out.want_stats && g.out_dtype == kBF16) {  // only the tensor-core epilogue produces GroupNorm statistics
+    const int tile = conv_gemm_tc_stat_tile(g);
+    if (tile > 0) {
+      out.snblk = g.rows_per_sample / tile;
+      out.spart = static_cast<float*>(ws_.alloc(sizeof(float) * 2 * static_cast<size_t>(out.B) * out.snblk * l.N));
+      g.stat_part = out.spart;
+    }
   }
   ++launches_;
   if (dry_) return;
@@ -731,13 +731,20 @@ void UNet::forward_impl(const float* x, const long long* labels, float* h_out, i
     xa.B = 1; xa.H = 1; xa.W = B * N * N; xa.C = first_kpad_;
     xa.p = ws_.alloc(static_cast<size_t>(xa.W) * first_kpad_ * 2);
     launches_ += 2;
+    ConvGemmArgs g;
+    g.a0 = xa.p; g.c0 = first_kpad_; g.B = 1; g.H = 1; g.W = xa.W; g.ksize = 1;
+    g.w = first_wp_; g.N = nf; g.bias = pre_conv_.bp; g.out = h.p; g.out_dtype = kBF16;
+    g.rows_per_sample = N * N;
+    if (h.want_stats) {
+      const int tile = conv_gemm_tc_stat_tile(g);
+      if (tile > 0) {
+        h.snblk = N * N / tile;
+        h.spart = static_cast<float*>(ws_.alloc(sizeof(float) * 2 * static_cast<size_t>(B) * h.snblk * nf));
+        g.stat_part = h.spart;
+      }
+    }
     if (!dry_) {
       im2col3x3_nchw(x, B, C, N, N, first_kpad_, xa.p, st_);
-      ConvGemmArgs g;
-      g.a0 = xa.p; g.c0 = first_kpad_; g.B = 1; g.H = 1; g.W = xa.W; g.ksize = 1;
-      g.w = first_wp_; g.N = nf; g.bias = pre_conv_.bp; g.out = h.p; g.out_dtype = kBF16;
-      g.rows_per_sample = N * N;
-      g.stat_part = h.spart;
       conv_gemm_tc(g, st_);
     }
     ws_.free(xa.p);

@@ -64,6 +64,7 @@ struct Act {  // NHWC activation in the compute dtype (+ optional producer-side 
   int B = 0, H = 0, W = 0, C = 0;
   float* spart = nullptr;  // [B][snblk][C][2] per-tile {sum, sum of squares} left by the producer GEMM
   int snblk = 0;
+  bool want_stats = false;  // gemm() may attach spart when the producing launch can emit statistics
   long long rows() const { return static_cast<long long>(B) * H * W; }
 };
 
