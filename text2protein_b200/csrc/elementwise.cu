@@ -39,7 +39,10 @@ __global__ void temb_mlp_kernel(const long long* __restrict__ labels, int nf, fl
     if (lane == 0) h0[n] = acc + b0[n];
   }
   __syncthreads();
-  for (int n = warp; n < d; n += nw) {
+  // the second (d x d) layer is sliced over blockIdx.y; the cheap first layer is recomputed per slice
+  const int per = (d + gridDim.y - 1) / gridDim.y;
+  const int n_begin = blockIdx.y * per, n_end = min(d, n_begin + per);
+  for (int n = n_begin + warp; n < n_end; n += nw) {
     float acc = 0.f;
     for (int k = lane; k < d; k += 32) acc = fmaf(h0[k], w1[static_cast<long long>(n) * d + k], acc);
 #pragma unroll
@@ -56,8 +59,9 @@ template <>
 __device__ __forceinline__ void stv<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
 
 // conv weight [Cout][Cin][k][k] fp32 -> [Cout][k*k][cin_pad] (channels innermost, zero padded)
+// (row pitch `ld` elements: the packed row may be longer than k*k*cin_pad when extra K columns follow)
 template <typename TO>
-__global__ void pack_conv_kernel(const float* __restrict__ w, int cout, int cin, int kk, int cin_pad,
+__global__ void pack_conv_kernel(const float* __restrict__ w, int cout, int cin, int kk, int cin_pad, long long ld,
                                  TO* __restrict__ out) {
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long total = static_cast<long long>(cout) * kk * cin_pad;
@@ -66,19 +70,35 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, int cout, int cin,
   const int t = static_cast<int>((idx / cin_pad) % kk);
   const int o = static_cast<int>(idx / (static_cast<long long>(cin_pad) * kk));
   const float v = (c < cin) ? w[(static_cast<long long>(o) * cin + c) * kk + t] : 0.f;
-  stv(out + idx, v);
+  stv(out + static_cast<long long>(o) * ld + static_cast<long long>(t) * cin_pad + c, v);
+}
+
+// out[r][col0 + c] = (r == c) for an N x N identity block inside rows of pitch ld
+template <typename TO>
+__global__ void pack_identity_kernel(int n, long long ld, TO* __restrict__ out) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(n) * n) return;
+  const int c = static_cast<int>(idx % n);
+  const int r = static_cast<int>(idx / n);
+  stv(out + static_cast<long long>(r) * ld + c, r == c ? 1.f : 0.f);
 }
 
 // out[r][c] = in[c][r] (NIN.W is [in, out]; GEMM wants [out][in]); or plain copy when !transpose.
 template <typename TO>
-__global__ void pack_matrix_kernel(const float* __restrict__ w, int rows, int cols, int transpose,
+__global__ void pack_matrix_kernel(const float* __restrict__ w, int rows, int cols, int transpose, long long ld,
                                    TO* __restrict__ out) {
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= static_cast<long long>(rows) * cols) return;
   const int c = static_cast<int>(idx % cols);
   const int r = static_cast<int>(idx / cols);
   const float v = transpose ? w[static_cast<long long>(c) * rows + r] : w[idx];
-  stv(out + idx, v);
+  stv(out + static_cast<long long>(r) * ld + c, v);
+}
+
+__global__ void add_vectors_kernel(const float* __restrict__ a, const float* __restrict__ b, int n,
+                                   float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (a ? a[i] : 0.f) + (b ? b[i] : 0.f);
 }
 
 template <typename TO>
@@ -182,23 +202,38 @@ void temb_mlp(const long long* labels, int B, int nf, const float* w0, const flo
   const size_t smem = sizeof(float) * (nf + 4 * nf);
   // -(ln 10000 / (half - 1)) evaluated in double then rounded once, as Python does (layers.py:101-103)
   const float neg_coef = static_cast<float>(-(log(10000.0) / static_cast<double>(nf / 2 - 1)));
-  temb_mlp_kernel<<<B, 256, smem, st>>>(labels, nf, neg_coef, w0, b0, w1, b1, out);
+  temb_mlp_kernel<<<dim3(B, 8), 256, smem, st>>>(labels, nf, neg_coef, w0, b0, w1, b1, out);
   T2P_LAUNCH_CHECK();
 }
 
 void pack_conv_weight(const float* w, int cout, int cin, int k, int cin_pad, int out_dtype, void* out,
-                      cudaStream_t st) {
+                      cudaStream_t st, long long ld) {
   const long long total = static_cast<long long>(cout) * k * k * cin_pad;
+  if (ld <= 0) ld = static_cast<long long>(k) * k * cin_pad;
   const unsigned blocks = static_cast<unsigned>(cdiv64(total, 256));
-  if (out_dtype == kF32) pack_conv_kernel<float><<<blocks, 256, 0, st>>>(w, cout, cin, k * k, cin_pad, static_cast<float*>(out));
-  else pack_conv_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w, cout, cin, k * k, cin_pad, static_cast<__nv_bfloat16*>(out));
+  if (out_dtype == kF32) pack_conv_kernel<float><<<blocks, 256, 0, st>>>(w, cout, cin, k * k, cin_pad, ld, static_cast<float*>(out));
+  else pack_conv_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w, cout, cin, k * k, cin_pad, ld, static_cast<__nv_bfloat16*>(out));
   T2P_LAUNCH_CHECK();
 }
 
-void pack_matrix(const float* w, int rows, int cols, int transpose, int out_dtype, void* out, cudaStream_t st) {
+void pack_matrix(const float* w, int rows, int cols, int transpose, int out_dtype, void* out, cudaStream_t st,
+                 long long ld) {
+  if (ld <= 0) ld = cols;
   const unsigned blocks = static_cast<unsigned>(cdiv64(static_cast<long long>(rows) * cols, 256));
-  if (out_dtype == kF32) pack_matrix_kernel<float><<<blocks, 256, 0, st>>>(w, rows, cols, transpose, static_cast<float*>(out));
-  else pack_matrix_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w, rows, cols, transpose, static_cast<__nv_bfloat16*>(out));
+  if (out_dtype == kF32) pack_matrix_kernel<float><<<blocks, 256, 0, st>>>(w, rows, cols, transpose, ld, static_cast<float*>(out));
+  else pack_matrix_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w, rows, cols, transpose, ld, static_cast<__nv_bfloat16*>(out));
+  T2P_LAUNCH_CHECK();
+}
+
+void pack_identity(int n, long long ld, int out_dtype, void* out, cudaStream_t st) {
+  const unsigned blocks = static_cast<unsigned>(cdiv64(static_cast<long long>(n) * n, 256));
+  if (out_dtype == kF32) pack_identity_kernel<float><<<blocks, 256, 0, st>>>(n, ld, static_cast<float*>(out));
+  else pack_identity_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(n, ld, static_cast<__nv_bfloat16*>(out));
+  T2P_LAUNCH_CHECK();
+}
+
+void add_vectors_f32(const float* a, const float* b, int n, float* out, cudaStream_t st) {
+  add_vectors_kernel<<<cdiv(n, 256), 256, 0, st>>>(a, b, n, out);
   T2P_LAUNCH_CHECK();
 }
 

@@ -37,8 +37,11 @@ struct TcParams {
   CUtensorMap tm_out;    // channel-major kernel: [M][N] bf16 output, box 32 channels x 32 pixels (TMA store)
   CUtensorMap tm_res;    // channel-major kernel: residual tensor, same pixel box as A
   CUtensorMap tm_ident;  // channel-major kernel: 128 x 128 bf16 identity (residual added by the tensor core)
+  CUtensorMap tm_x0;     // channel-major kernel: centre-tap-only sources (folded skip path)
+  CUtensorMap tm_x1;
   int M, N;
   int c0, c1;
+  int xc0, xc1;
   int taps;          // 1 or 9
   int H, W;          // image geometry for tile -> (b, h, w)
   int mode2d;        // A is a plain [M, K] matrix
@@ -509,8 +512,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_tcT_kernel(const __g
 
   const int ctot = p.c0 + p.c1;
   const int chunks_per_tap = ctot / BK;
-  const int num_kb_main = p.taps * chunks_per_tap;
-  const int num_kb = num_kb_main + (p.residual ? 2 : 0);
+  const int x_chunks = (p.xc0 + p.xc1) / BK;
+  const int num_kb = p.taps * chunks_per_tap + x_chunks + (p.residual ? 2 : 0);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -542,6 +545,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_tcT_kernel(const __g
         ptx::prefetch_tmap(&p.tm_res);
         ptx::prefetch_tmap(&p.tm_ident);
       }
+      if (p.xc0 > 0) ptx::prefetch_tmap(&p.tm_x0);
+      if (p.xc1 > 0) ptx::prefetch_tmap(&p.tm_x1);
       const int pad = (p.taps == 9) ? 1 : 0;
       const int hw = p.H * p.W;
       int s = 0;
@@ -575,6 +580,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_tcT_kernel(const __g
               ptx::tma_load_4d(sp, &p.tm_a1, fb, ch - p.c0, w0 + kw - pad, h0 + kh - pad, b0);
             if (++s == C::STAGES) { s = 0; ph ^= 1; }
           }
+        }
+        // centre-tap-only sources (the skip path's 1x1 convolution folded into this GEMM)
+        for (int cc = 0; cc < x_chunks; ++cc, ++kb) {
+          ptx::mbar_wait(ptx::smem_u32(&empty_bar[s]), ph ^ 1);
+          const uint32_t fb = ptx::smem_u32(&full_bar[s]);
+          ptx::mbar_arrive_expect_tx(fb, C::STAGE_BYTES);
+          const uint32_t sw = tiles + s * C::STAGE_BYTES;
+          const uint32_t sp = sw + C::W_BYTES;
+          const int ch = cc * BK;
+          ptx::tma_load_4d(sw, &p.tm_w, fb, kb * BK, n0, 0, 0);
+          if (ch < p.xc0)
+            ptx::tma_load_4d(sp, &p.tm_x0, fb, ch, w0, h0, b0);
+          else
+            ptx::tma_load_4d(sp, &p.tm_x1, fb, ch - p.xc0, w0, h0, b0);
+          if (++s == C::STAGES) { s = 0; ph ^= 1; }
         }
         if (p.residual) {
           // residual[m][n0 .. n0 + 128) enters the accumulator through two identity k-blocks: exact in fp32,
@@ -875,6 +895,8 @@ Plan make_plan(const ConvGemmArgs& a) {
 
 }  // namespace
 
+bool conv_gemm_tc_channel_major(const ConvGemmArgs& a) { return make_plan(a).channel_major; }
+
 int conv_gemm_tc_stat_tile(const ConvGemmArgs& a) {
   ConvGemmArgs q = a;
   if (!q.stat_part) q.stat_part = reinterpret_cast<float*>(16);  // plan as if statistics were requested
@@ -884,7 +906,9 @@ int conv_gemm_tc_stat_tile(const ConvGemmArgs& a) {
 
 void conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
   T2P_CHECK(a.ksize == 1 || a.ksize == 3, "ksize must be 1 or 3");
-  T2P_CHECK(a.c0 > 0 && a.c0 % BK == 0 && a.c1 % BK == 0, "channel counts must be multiples of 64");
+  T2P_CHECK(a.c0 > 0 && a.c0 % BK == 0 && a.c1 % BK == 0 && a.xc0 % BK == 0 && a.xc1 % BK == 0,
+            "channel counts must be multiples of 64");
+  T2P_CHECK((a.xc0 == 0 || a.x0) && (a.xc1 == 0 || (a.x1 && a.xc0 > 0)), "bad extra sources");
   T2P_CHECK(a.out_dtype == kBF16 || a.out_dtype == kF32, "out dtype must be bf16 or fp32");
   const int ctot = a.c0 + a.c1;
   const int taps = a.ksize * a.ksize;
@@ -896,6 +920,8 @@ void conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
   p.N = a.N;
   p.c0 = a.c0;
   p.c1 = a.c1;
+  p.xc0 = a.xc0;
+  p.xc1 = a.xc1;
   p.taps = taps;
   p.H = a.H;
   p.W = a.W;
@@ -916,6 +942,7 @@ void conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
   if (a.res_up) T2P_CHECK(a.ksize == 3 && (a.H % 2 == 0) && (a.W % 2 == 0), "res_up needs an even image");
 
   const Plan pl = make_plan(a);
+  if (a.xc0 > 0) T2P_CHECK(pl.channel_major, "centre-tap sources need the channel-major kernel (N >= 128, bf16 out)");
   if (a.stat_part)
     T2P_CHECK(pl.stats_ok, "fused GroupNorm statistics need whole pixel tiles per sample and bf16 output "
                            "(ask conv_gemm_tc_stat_tile first)");
@@ -934,7 +961,7 @@ void conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
   p.tm_a0 = amap(a.a0, a.c0);
   p.tm_a1 = (a.c1 > 0) ? amap(a.a1, a.c1) : p.tm_a0;
   {
-    uint64_t d[4] = {static_cast<uint64_t>(taps) * ctot, static_cast<uint64_t>(a.N), 1, 1};
+    uint64_t d[4] = {static_cast<uint64_t>(taps) * ctot + a.xc0 + a.xc1, static_cast<uint64_t>(a.N), 1, 1};
     uint32_t b[4] = {BK, static_cast<uint32_t>(pl.channel_major ? 128 : pl.bn), 1, 1};
     p.tm_w = make_tmap_bf16(a.w, d, b);
   }
@@ -944,6 +971,8 @@ void conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
       uint32_t b[4] = {32, 32, 1, 1};
       p.tm_out = make_tmap_bf16(a.out, d, b, false);
     }
+    if (a.xc0 > 0) p.tm_x0 = amap(a.x0, a.xc0);
+    if (a.xc1 > 0) p.tm_x1 = amap(a.x1, a.xc1);
     if (a.residual) {
       p.tm_res = amap(a.residual, a.N);
       uint64_t d[4] = {128, 128, 1, 1};

@@ -31,6 +31,13 @@ struct ConvGemmArgs {
   // optional fused GroupNorm statistics of the stored output: per pixel tile and channel {sum, sum of squares},
   // [M / T][N][2] == part[B][rows_per_sample / T][N][2], T = conv_gemm_tc_stat_tile(args) (tcgen05 kernels only)
   float* stat_part = nullptr;
+  // extra sources entering through the centre tap only -- a 1x1 convolution over x0|x1 summed with the
+  // ksize x ksize one over a0|a1 (the ResBlock skip path folded into Conv_1): K grows by xc0 + xc1 and a weight
+  // row is [taps * (c0 + c1) | xc0 | xc1].  Channel-major tcgen05 kernel only (conv_gemm_tc_channel_major()).
+  const void* x0 = nullptr;
+  int xc0 = 0;
+  const void* x1 = nullptr;
+  int xc1 = 0;
   int rowbias_ld = 0;  // row pitch of rowbias (0 -> N)
   int out_nchw = 0;    // 1: store out as [B][N][H*W] (fp32 only; used by the final conv)
 };
@@ -40,6 +47,8 @@ void conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st);
 // pixel-tile size T the tcgen05 launch for these arguments uses for fused GroupNorm statistics
 // (rows_per_sample % T == 0), or 0 when it cannot produce them
 int conv_gemm_tc_stat_tile(const ConvGemmArgs& a);
+// true when these arguments run on the channel-major kernel (the one that accepts x0 / x1)
+bool conv_gemm_tc_channel_major(const ConvGemmArgs& a);
 // fp32 or bf16 SIMT path (verification mode and tiny-channel edge layers). dtype of A and W.
 void conv_gemm_simt(const ConvGemmArgs& a, int in_dtype, cudaStream_t st);
 
@@ -78,9 +87,13 @@ bool attention_mma_supported(const AttnArgs& a);
 // ----------------------------------------------------------------------------- helpers
 void temb_mlp(const long long* labels, int B, int nf, const float* w0, const float* b0, const float* w1,
               const float* b1, float* out, cudaStream_t st);
+// `ld` = row pitch of `out` in elements (0: dense); lets several K segments share one packed row
 void pack_conv_weight(const float* w, int cout, int cin, int k, int cin_pad, int out_dtype, void* out,
-                      cudaStream_t st);
-void pack_matrix(const float* w, int rows, int cols, int transpose, int out_dtype, void* out, cudaStream_t st);
+                      cudaStream_t st, long long ld = 0);
+void pack_matrix(const float* w, int rows, int cols, int transpose, int out_dtype, void* out, cudaStream_t st,
+                 long long ld = 0);
+void pack_identity(int n, long long ld, int out_dtype, void* out, cudaStream_t st);
+void add_vectors_f32(const float* a, const float* b, int n, float* out, cudaStream_t st);
 void convert_f32(const float* in, long long n, int out_dtype, void* out, cudaStream_t st);
 void nhwc_to_nchw_f32(const void* in, int dtype, int B, int HW, int C, float* out, cudaStream_t st);
 void nchw_f32_to_nhwc(const float* in, int B, int HW, int C, int cpad, int out_dtype, void* out, cudaStream_t st);

@@ -5,6 +5,8 @@
 // skip concat of the UNet up path (channels of two tensors, group boundaries straddling both) needs no copy.
 // Replaces nn.GroupNorm + nn.SiLU + naive_up/downsample_2d + torch.cat (score_sde_pytorch/models/layers.py:
 // 179-188,282-311; ncsnpp.py:250), nn.LayerNorm and GEGLU (model/attention.py:37-44,203-205).
+#include <algorithm>
+
 #include "kernels.h"
 
 namespace t2p {
@@ -53,6 +55,22 @@ struct Vec8<__nv_bfloat16> {
 };
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+
+// SiLU for the bf16 pipeline: x * sigmoid(x) = h + h * tanh(h), h = x / 2 -- one MUFU op per element; the
+// approximation error (~5e-4 relative) is below the bf16 rounding of the stored result.
+__device__ __forceinline__ float silu_tanh(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+template <typename T>
+__device__ __forceinline__ float silu_t(float x);
+template <>
+__device__ __forceinline__ float silu_t<float>(float x) { return silu_f(x); }
+template <>
+__device__ __forceinline__ float silu_t<__nv_bfloat16>(float x) { return silu_tanh(x); }
+
 
 // ------------------------------------------------------------------ statistics: per (sample, channel) sums
 // Deterministic two-level reduction (no atomics): each block reduces a contiguous run of pixels to
@@ -187,7 +205,7 @@ __global__ void gn_apply_kernel(const T* __restrict__ a0, int c0, const T* __res
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float y = fmaf(v.v[i], sc[i], sh[i]);
-          if (act) y = silu_f(y);
+          if (act) y = silu_t<T>(y);
           acc.v[i] += y;
           raw.v[i] += v.v[i];
         }
@@ -203,7 +221,7 @@ __global__ void gn_apply_kernel(const T* __restrict__ a0, int c0, const T* __res
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float y = fmaf(v.v[i], sc[i], sh[i]);
-      v.v[i] = act ? silu_f(y) : y;
+      v.v[i] = act ? silu_t<T>(y) : y;
     }
     if (MODE == 0) {
       v.store(out + ip * ctot + ch);
@@ -215,6 +233,59 @@ __global__ void gn_apply_kernel(const T* __restrict__ a0, int c0, const T* __res
           const long long op = (static_cast<long long>(b) * (2 * H) + (2 * oh + dy)) * (2 * W) + (2 * ow + dx);
           v.store(out + op * ctot + ch);
         }
+    }
+  }
+}
+
+// MODE 0 streaming path.  A block owns `ppb` consecutive pixels of one sample; thread = (pixel row, 8-channel
+// slot), so its 16 scale/shift values live in registers for the whole run and the block's accesses are one
+// contiguous stream per source.  UNROLL independent 16-byte loads are in flight per thread.
+template <typename T, int UNROLL>
+__global__ void __launch_bounds__(256) gn_apply_rows_kernel(const T* __restrict__ a0, int c0, const T* __restrict__ a1,
+                                                            int c1, int HW, int ppb, const float* __restrict__ scale,
+                                                            const float* __restrict__ shift, int act,
+                                                            T* __restrict__ out) {
+  const int ctot = c0 + c1;
+  const int slots = ctot >> 3;
+  const int rows = blockDim.x / slots;
+  const int slot = threadIdx.x % slots;
+  const int row = threadIdx.x / slots;
+  const int b = blockIdx.y;
+  const int ch = slot << 3;
+  const T* src;
+  int cs, co;
+  if (ch < c0) { src = a0; cs = c0; co = ch; }
+  else { src = a1; cs = c1; co = ch - c0; }
+  float sc[8], sh[8];
+  {
+    const float4* ps = reinterpret_cast<const float4*>(scale + static_cast<long long>(b) * ctot + ch);
+    const float4* ph = reinterpret_cast<const float4*>(shift + static_cast<long long>(b) * ctot + ch);
+    const float4 s0 = __ldg(ps), s1 = __ldg(ps + 1), h0 = __ldg(ph), h1 = __ldg(ph + 1);
+    sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+    sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
+  }
+  const int p0 = blockIdx.x * ppb;
+  const int p1 = min(HW, p0 + ppb);
+  const T* s = src + static_cast<long long>(b) * HW * cs + co;
+  T* o = out + static_cast<long long>(b) * HW * ctot + ch;
+  for (int p = p0 + row; p < p1; p += rows * UNROLL) {
+    Vec8<T> v[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int pp = p + u * rows;
+      if (pp < p1) v[u] = Vec8<T>::load(s + static_cast<long long>(pp) * cs);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int pp = p + u * rows;
+      if (pp < p1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float y = fmaf(v[u].v[i], sc[i], sh[i]);
+          v[u].v[i] = act ? silu_t<T>(y) : y;
+        }
+        v[u].store(o + static_cast<long long>(pp) * ctot);
+      }
     }
   }
 }
@@ -364,7 +435,19 @@ static void gn_apply_t(const void* a0, int c0, const void* a1, int c1, int B, in
   const T* p1 = static_cast<const T*>(a1);
   T* o = static_cast<T*>(out);
   T* r = static_cast<T*>(raw_out);
-  if (mode == 0) gn_apply_kernel<T, 0><<<blocks, 256, 0, st>>>(p0, c0, p1, c1, B, H, W, scale, shift, act, o, r);
+  if (mode == 0 && slots <= 256) {
+    constexpr int UNROLL = 4;
+    const int HW = H * W;
+    const int rows = 256 / slots;
+    const int threads = rows * slots;
+    // enough blocks to fill the machine several times over, up to 4 rounds of UNROLL vectors per thread
+    const int want_blocks = std::max(1, (148 * 8) / B);
+    int iters = HW / (rows * UNROLL * want_blocks);
+    iters = std::max(1, std::min(iters, 4));
+    const int ppb = rows * UNROLL * iters;
+    dim3 grid(cdiv(HW, ppb), B);
+    gn_apply_rows_kernel<T, UNROLL><<<grid, threads, 0, st>>>(p0, c0, p1, c1, HW, ppb, scale, shift, act, o);
+  } else if (mode == 0) gn_apply_kernel<T, 0><<<blocks, 256, 0, st>>>(p0, c0, p1, c1, B, H, W, scale, shift, act, o, r);
   else if (mode == 1) gn_apply_kernel<T, 1><<<blocks, 256, 0, st>>>(p0, c0, p1, c1, B, H, W, scale, shift, act, o, r);
   else gn_apply_kernel<T, 2><<<blocks, 256, 0, st>>>(p0, c0, p1, c1, B, H, W, scale, shift, act, o, r);
   T2P_LAUNCH_CHECK();
