@@ -160,6 +160,9 @@ typedef struct t2p_conv_args {
   int32_t in_dtype;                /* T2P_BF16 -> tcgen05 kernel (needs c % 64 == 0); T2P_F32 -> CUDA-core kernel */
   float* stat_part;                /* optional fused GroupNorm statistics, [B*H*W/T][N][2] {sum, sumsq} per
                                       T-pixel tile, T = t2p_conv2d_stat_tile(args) (tcgen05 kernel, bf16 out) */
+  const void* x0; int32_t xc0;     /* optional NHWC sources entering through the centre tap only: a 1x1 convolution */
+  const void* x1; int32_t xc1;     /* over x0|x1 summed with the one over a0|a1 (ResnetBlockBigGANpp Conv_2 folded into
+                                      Conv_1, layers.py:318-327); w rows are [k*k*(c0+c1) | xc0 | xc1].  bf16, N >= 128 */
 } t2p_conv_args;
 int t2p_conv2d(const t2p_conv_args* a, void* stream);        /* nn.Conv2d / NIN / nn.Linear: layers.py:82-95,128-137 */
 /* Pixel-tile size T of the fused GroupNorm statistics t2p_conv2d would write for these arguments (H*W % T == 0),

@@ -95,6 +95,40 @@ def test_conv2d_upsampled_residual_and_fused_stats(H, cin, cout):
     assert torch.allclose(tot[..., 1], (out * out).sum(dim=(2, 3)), rtol=1e-4, atol=1e-2)
 
 
+@pytest.mark.parametrize("H,cin,xc0,xc1,cout", [(16, 64, 128, 64, 128), (32, 128, 128, 0, 128), (8, 64, 64, 0, 256)])
+def test_conv2d_folded_skip_path(H, cin, xc0, xc1, cout):
+    """Conv_1(h) + Conv_2(cat(x0, x1)) [+ residual] as one launch (skip path as centre-tap K columns)."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B = 3
+    bf = lambda t: t.bfloat16().float()  # noqa: E731
+    h = bf(torch.randn(B, cin, H, H, device="cuda", generator=g))
+    x0 = bf(torch.randn(B, xc0, H, H, device="cuda", generator=g))
+    x1 = bf(torch.randn(B, xc1, H, H, device="cuda", generator=g)) if xc1 else None
+    w1 = bf(torch.randn(cout, cin, 3, 3, device="cuda", generator=g) / math.sqrt(9 * cin))
+    w2 = bf(torch.randn(cout, xc0 + xc1, 1, 1, device="cuda", generator=g) / math.sqrt(xc0 + xc1))
+    bias = torch.randn(cout, device="cuda", generator=g)
+    res = bf(torch.randn(B, cout, H, H, device="cuda", generator=g))
+    x = x0 if x1 is None else torch.cat([x0, x1], 1)
+    ref = (F.conv2d(h, w1, bias, padding=1) + F.conv2d(x, w2) + res) * 0.70710678
+    wp = torch.cat([w1.permute(0, 2, 3, 1).reshape(cout, -1), w2.reshape(cout, -1)], 1).bfloat16().contiguous()
+    A, X0 = nhwc(h, torch.bfloat16), nhwc(x0, torch.bfloat16)
+    X1 = nhwc(x1, torch.bfloat16) if x1 is not None else None
+    R = nhwc(res, torch.bfloat16)
+    out = torch.empty(B, H, H, cout, dtype=torch.bfloat16, device="cuda")
+    a = _lib.ConvArgs()
+    a.a0, a.c0, a.c1 = A.data_ptr(), cin, 0
+    a.B, a.H, a.W, a.ksize = B, H, H, 3
+    a.w, a.N, a.bias = wp.data_ptr(), cout, bias.data_ptr()
+    a.x0, a.xc0 = X0.data_ptr(), xc0
+    if X1 is not None:
+        a.x1, a.xc1 = X1.data_ptr(), xc1
+    a.residual, a.alpha = R.data_ptr(), 0.70710678
+    a.out, a.out_dtype, a.in_dtype = out.data_ptr(), _lib.torch_dtype_code(torch.bfloat16), _lib.torch_dtype_code(torch.bfloat16)
+    _lib.check(_lib.lib().t2p_conv2d(C.byref(a), _st()))
+    torch.cuda.synchronize()
+    assert rel_err(nchw(out.float()), ref) < 1.5e-2
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
 @pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("c0,c1,groups", [(64, 0, 16), (128, 64, 32), (256, 128, 32)])

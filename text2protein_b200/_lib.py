@@ -41,7 +41,8 @@ class ConvArgs(C.Structure):
                 ("H", C.c_int32), ("W", C.c_int32), ("ksize", C.c_int32), ("w", C.c_void_p), ("N", C.c_int32),
                 ("bias", C.c_void_p), ("rowbias", C.c_void_p), ("rowbias_ld", C.c_int32), ("residual", C.c_void_p),
                 ("res_up", C.c_int32), ("alpha", C.c_float), ("out", C.c_void_p), ("out_dtype", C.c_int32),
-                ("in_dtype", C.c_int32), ("stat_part", C.c_void_p)]
+                ("in_dtype", C.c_int32), ("stat_part", C.c_void_p), ("x0", C.c_void_p), ("xc0", C.c_int32),
+                ("x1", C.c_void_p), ("xc1", C.c_int32)]
 
 
 class GemmRecord(C.Structure):

@@ -356,6 +356,7 @@ static ConvGemmArgs conv_args_from_abi(const t2p_conv_args* a) {
   g.residual = a->residual; g.res_up = a->res_up; g.alpha = a->alpha;
   g.out = a->out; g.out_dtype = a->out_dtype;
   g.stat_part = a->stat_part;
+  g.x0 = a->x0; g.xc0 = a->xc0; g.x1 = a->x1; g.xc1 = a->xc1;
   return g;
 }
 
@@ -373,6 +374,8 @@ int t2p_conv2d(const t2p_conv_args* a, void* stream) {
   T2P_API_BEGIN
   T2P_CHECK(a && a->a0 && a->w && a->out, "null argument");
   ConvGemmArgs g = conv_args_from_abi(a);
+  if (a->xc0 > 0 || a->xc1 > 0)
+    T2P_CHECK(a->in_dtype == T2P_BF16 && a->c0 % 64 == 0 && a->c1 % 64 == 0, "centre-tap sources are tcgen05-only");
   if (a->in_dtype == T2P_BF16 && a->c0 % 64 == 0 && a->c1 % 64 == 0) conv_gemm_tc(g, S(stream));
   else conv_gemm_simt(g, a->in_dtype, S(stream));
   T2P_API_END

@@ -63,7 +63,8 @@ void gn_stats(const void* a0, int c0, const void* a1, int c1, int B, int HW, int
 void gn_finalize(const float* part0, int nblk0, int c0, const float* part1, int nblk1, int c1, const float* gamma,
                  const float* beta, int B, int G, int HW, float eps, float* scale, float* shift, cudaStream_t st);
 // y = act(x * scale + shift) over the (virtual) channel concat of a0|a1; mode 0 same size, 1 = 2x2 mean
-// after the activation (raw_out, optional, receives the 2x2 mean of the raw input), 2 = nearest x2 upsample.
+// after the activation (raw_out, optional, receives the 2x2 mean of the raw input), 2 = nearest x2 upsample
+// (raw_out, optional, receives the upsampled raw input).
 void gn_apply(const void* a0, int c0, const void* a1, int c1, int B, int H, int W, int dtype, const float* scale,
               const float* shift, int act, int mode, void* out, void* raw_out, cudaStream_t st);
 void layernorm(const void* x, const float* gamma, const float* beta, long long M, int C, float eps, int dtype,

@@ -218,6 +218,7 @@ __global__ void gn_apply_kernel(const T* __restrict__ a0, int c0, const T* __res
   } else {
     const long long ip = (static_cast<long long>(b) * H + oh) * W + ow;
     Vec8<T> v = Vec8<T>::load(src + ip * cs + co);
+    const Vec8<T> raw = v;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float y = fmaf(v.v[i], sc[i], sh[i]);
@@ -232,6 +233,7 @@ __global__ void gn_apply_kernel(const T* __restrict__ a0, int c0, const T* __res
         for (int dx = 0; dx < 2; ++dx) {
           const long long op = (static_cast<long long>(b) * (2 * H) + (2 * oh + dy)) * (2 * W) + (2 * ow + dx);
           v.store(out + op * ctot + ch);
+          if (raw_out) raw.store(raw_out + op * ctot + ch);  // nearest x2 of the raw input (folded skip path)
         }
     }
   }

@@ -143,6 +143,13 @@ ModuleM UNet::make_res(const std::string& key, int in_ch, int out_ch, bool up, b
   r.conv1 = make_conv(key + ".Conv_1", out_ch, out_ch, 3);
   r.has_skip_conv = (in_ch != out_ch) || up || down;
   if (r.has_skip_conv) r.conv2 = make_conv(key + ".Conv_2", in_ch, out_ch, 1);
+  // bf16 engine: the skip path (1x1 Conv_2, or the identity) becomes extra K columns of Conv_1 -- no separate
+  // launch, no skip tensor in HBM, no residual read in the epilogue
+  r.folded = cfg_.compute_dtype == kBF16 && out_ch >= 128 && out_ch % 64 == 0 && in_ch % 64 == 0;
+  if (r.folded) {
+    r.conv1.xk = in_ch;
+    if (r.has_skip_conv) { r.conv1.w_x = r.conv2.w; r.conv1.b_x = r.conv2.b; }
+  }
   r.temb_off = temb_total_;
   temb_total_ += out_ch;
   return m;
@@ -277,7 +284,7 @@ UNet::UNet(const UNetConfig& cfg) : cfg_(cfg) {
         all_res_.push_back(m.res.get());
         all_linear_.push_back(&m.res->conv0);
         all_linear_.push_back(&m.res->conv1);
-        if (m.res->has_skip_conv) all_linear_.push_back(&m.res->conv2);
+        if (m.res->has_skip_conv && !m.res->folded) all_linear_.push_back(&m.res->conv2);
       } else if (m.kind == 1) {
         all_linear_.push_back(&m.attn->qkv);
         all_linear_.push_back(&m.attn->proj);
@@ -334,15 +341,32 @@ void UNet::load(const std::string& name, const void* dev_ptr, const std::vector<
 
 void UNet::pack(Linear& l, cudaStream_t st) {
   const int wdt = l.force_f32 ? kF32 : cfg_.compute_dtype;
-  const size_t wbytes = static_cast<size_t>(l.N) * l.K() * dtype_size(wdt);
+  const size_t wbytes = static_cast<size_t>(l.N) * l.Ktot() * dtype_size(wdt);
   if (!l.wp) {
     T2P_CUDA(cudaMalloc(&l.wp, wbytes));
     owned_.push_back(l.wp);
   }
   if (l.w) {
-    if (l.ksize == 1) pack_matrix(static_cast<const float*>(l.w->data), l.N, l.cin, 0, wdt, l.wp, st);
-    else pack_conv_weight(static_cast<const float*>(l.w->data), l.N, l.cin, l.ksize, l.cin, wdt, l.wp, st);
+    if (l.ksize == 1) pack_matrix(static_cast<const float*>(l.w->data), l.N, l.cin, 0, wdt, l.wp, st, l.Ktot());
+    else pack_conv_weight(static_cast<const float*>(l.w->data), l.N, l.cin, l.ksize, l.cin, wdt, l.wp, st, l.Ktot());
     if (l.b) l.bp = static_cast<float*>(l.b->data);
+    if (l.xk > 0) {
+      char* xdst = static_cast<char*>(l.wp) + static_cast<size_t>(l.K()) * dtype_size(wdt);
+      if (l.w_x) {
+        pack_matrix(static_cast<const float*>(l.w_x->data), l.N, l.xk, 0, wdt, xdst, st, l.Ktot());
+        // bias of the folded GEMM = Conv_1.bias + Conv_2.bias
+        if (!l.bsum) {
+          T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&l.bsum), sizeof(float) * l.N));
+          owned_.push_back(l.bsum);
+        }
+        add_vectors_f32(l.b ? static_cast<const float*>(l.b->data) : nullptr,
+                        l.b_x ? static_cast<const float*>(l.b_x->data) : nullptr, l.N, l.bsum, st);
+        l.bp = l.bsum;
+      } else {
+        T2P_CHECK(l.xk == l.N, "identity skip needs in_ch == out_ch");
+        pack_identity(l.N, l.Ktot(), wdt, xdst, st);
+      }
+    }
   } else {
     int row = 0;
     for (Param* w : l.w_cat) {
@@ -398,11 +422,15 @@ void UNet::free_act(Act& a) {
 }
 
 void UNet::gemm(const Linear& l, const Act& a0, const Act* a1, Act& out, const float* rowbias, int rowbias_ld,
-                const void* residual, int res_up, float alpha, int out_dtype, int out_nchw) {
+                const void* residual, int res_up, float alpha, int out_dtype, int out_nchw, const Act* x0,
+                const Act* x1) {
   ConvGemmArgs g;
   g.a0 = a0.p; g.c0 = a0.C;
   if (a1) { g.a1 = a1->p; g.c1 = a1->C; }
+  if (x0) { g.x0 = x0->p; g.xc0 = x0->C; }
+  if (x1) { g.x1 = x1->p; g.xc1 = x1->C; }
   T2P_CHECK(g.c0 + g.c1 == l.cin, "GEMM input channels do not match the weight");
+  T2P_CHECK(g.xc0 + g.xc1 == l.xk, "folded skip sources do not match the weight");
   g.B = a0.B; g.H = a0.H; g.W = a0.W;
   g.ksize = l.ksize;
   g.w = l.wp; g.N = l.N;
@@ -435,7 +463,7 @@ void UNet::gemm(const Linear& l, const Act& a0, const Act* a1, Act& out, const f
   if (profile_) {
     T2P_CUDA(cudaEventRecord(e1, st_));
     GemmRecord r;
-    r.M = a0.rows(); r.N = l.N; r.K = l.K(); r.ksize = l.ksize; r.tc = tc ? 1 : 0;
+    r.M = a0.rows(); r.N = l.N; r.K = l.Kalg(); r.ksize = l.ksize; r.tc = tc ? 1 : 0;
     r.H = a0.H; r.W = a0.W;
     r.e0 = e0; r.e1 = e1;
     profile_log_.push_back(r);
@@ -518,15 +546,25 @@ Act UNet::run_res(ResBlockM& m, const Act& a0, const Act* a1) {
   const int OH = m.down ? H / 2 : (m.up ? H * 2 : H), OW = m.down ? W / 2 : (m.up ? W * 2 : W);
   const int mode = m.down ? 1 : (m.up ? 2 : 0);
   Act h = new_act(B, OH, OW, m.in_ch, false);
-  Act xr;  // 2x2 mean of the raw input (skip path of a down block)
-  if (m.down) xr = new_act(B, OH, OW, m.in_ch, false);
-  group_norm(m.gn0, a0, a1, 1, mode, h, m.down ? &xr : nullptr);
+  Act xr;  // resampled raw input: 2x2 mean (skip path of a down block) or, folded up block, nearest x2
+  if (m.down || (m.up && m.folded)) xr = new_act(B, OH, OW, m.in_ch, false);
+  group_norm(m.gn0, a0, a1, 1, mode, h, xr.p ? &xr : nullptr);
   Act h1 = new_act(B, OH, OW, m.out_ch, true);
   gemm(m.conv0, h, nullptr, h1, temb_all_ + m.temb_off, temb_total_, nullptr, 0, 1.f);
   free_act(h);
   Act h2 = new_act(B, OH, OW, m.out_ch, false);
   group_norm(m.gn1, h1, nullptr, 1, 0, h2, nullptr);
   free_act(h1);
+  if (m.folded) {
+    // out = (Conv_1(h2) + skip(x)) / sqrt(2) as ONE GEMM: the skip's channels are extra K columns (centre tap)
+    Act out = new_act(B, OH, OW, m.out_ch, true);
+    const Act* x0 = xr.p ? &xr : &a0;
+    const Act* x1 = xr.p ? nullptr : a1;
+    gemm(m.conv1, h2, nullptr, out, nullptr, 0, nullptr, 0, 0.70710678118654752f, -1, 0, x0, x1);
+    free_act(h2);
+    if (xr.p) free_act(xr);
+    return out;
+  }
   // skip path.  A 1x1 conv commutes with nearest upsampling, so for up blocks it runs at the low
   // resolution and the Conv_1 epilogue reads it through the 2x index map (res_up).
   Act skip;

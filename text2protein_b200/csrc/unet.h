@@ -76,9 +76,17 @@ struct Linear {  // packed [N][K] weight in compute dtype (or fp32 when force_f3
   bool nin = false;           // sources are NIN.W ([in, out]) and need a transpose
   int ksize = 1, cin = 0, N = 0;
   bool force_f32 = false;
+  // skip path folded into this GEMM (channel-major tcgen05 kernel): xk extra K columns holding the 1x1 skip
+  // convolution's weight (w_x, bias b_x added to the bias) or, for an identity skip, the identity matrix
+  int xk = 0;
+  Param* w_x = nullptr;
+  Param* b_x = nullptr;
+  float* bsum = nullptr;  // b + b_x
   void* wp = nullptr;
   float* bp = nullptr;
   int K() const { return ksize * ksize * cin; }
+  int Ktot() const { return K() + xk; }
+  int Kalg() const { return K() + (w_x ? xk : 0); }  // algorithmic K: identity columns are not counted as FLOPs
 };
 
 struct GroupNormP { Param* w = nullptr; Param* b = nullptr; int C = 0, G = 0; };
@@ -87,6 +95,7 @@ struct LayerNormP { Param* w = nullptr; Param* b = nullptr; int C = 0; };
 struct ResBlockM {
   int in_ch = 0, out_ch = 0;
   bool up = false, down = false, has_skip_conv = false;
+  bool folded = false;  // the skip path runs inside Conv_1's GEMM (bf16 engine, out_ch >= 128)
   GroupNormP gn0, gn1;
   Linear conv0, conv1, conv2;
   Param* dense_w = nullptr;
@@ -163,7 +172,8 @@ class UNet {
   Act new_act(int B, int H, int W, int C, bool with_stats);
   void free_act(Act& a);
   void gemm(const Linear& l, const Act& a0, const Act* a1, Act& out, const float* rowbias, int rowbias_ld,
-            const void* residual, int res_up, float alpha, int out_dtype = -1, int out_nchw = 0);
+            const void* residual, int res_up, float alpha, int out_dtype = -1, int out_nchw = 0,
+            const Act* x0 = nullptr, const Act* x1 = nullptr);
   void group_norm(const GroupNormP& g, const Act& a0, const Act* a1, int act, int mode, Act& out, Act* raw_out);
   void attention(const void* q, const void* k, const void* v, void* out, int B, int heads, int Tq, int Tk, int d,
                  long long ldq, long long ldk, long long ldv, long long ldo, float scale);
