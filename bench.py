@@ -303,6 +303,9 @@ def run_native(args, cfg):
         achieved = fl / (avg_ms * 1e-3) / 1e12
         tc_ms = sum(v[1] for k, v in groups.items() if k[0]) / reps
         all_ms = sum(v[1] for v in groups.values()) / reps
+        shapes = [{"k": k[1], "M": k[2], "N": k[3], "K": k[4], "n": v[0] // reps, "ms_each": v[1] / v[0],
+                   "tflops": v[2] / (v[1] / v[0] * 1e-3) / 1e12}
+                  for k, v in sorted(groups.items(), key=lambda kv: -kv[1][1])[:16]]
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak_sust, "unit": "TFLOP/s",
                 "frac": achieved / peak_sust, "traffic": None,
                 "kernel": f"conv_gemm_tc_kernel k={key[1]} M={key[2]} N={key[3]} K={key[4]}",
@@ -311,7 +314,8 @@ def run_native(args, cfg):
                 "share_of_gemm_time": ms / reps / all_ms,
                 "gemm_ms_per_forward": all_ms, "tc_gemm_ms_per_forward": tc_ms,
                 "gemm_flops_per_forward": fwd_flops,
-                "forward_tflops_incl_everything": (2 * fwd_flops) / (ms_step * 1e-3) / 1e12}
+                "forward_tflops_incl_everything": (2 * fwd_flops) / (ms_step * 1e-3) / 1e12,
+                "gemm_shapes_by_time": shapes}
 
     # ---------------- CPU baseline: the oracle port on this box's host cores, bounded sample
     cpu = None

@@ -173,6 +173,183 @@ __global__ void __launch_bounds__(NT) attention_mma_kernel(const Params p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Pipelined variant for head dims that fit shared memory whole (D <= 256): Q is staged once, K / V tiles are
+// double-buffered with cp.async so the loads of key tile i + 1 overlap the math of tile i.  Same math and
+// fragment layout as the kernel above.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;  // src-size 0 -> zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int W>
+__device__ __forceinline__ void load_tile_async(__nv_bfloat16* dst, const __nv_bfloat16* src, long long ld, int r0,
+                                                int rmax, int c0) {
+  constexpr int VPR = W / 8;
+  for (int i = threadIdx.x; i < 64 * VPR; i += NT) {
+    const int r = i / VPR, cv = i - r * VPR;
+    const bool ok = r0 + r < rmax;
+    const __nv_bfloat16* g = src + static_cast<long long>(ok ? r0 + r : 0) * ld + c0 + cv * 8;
+    cp_async16(smem_u32(dst + r * (W + 8) + cv * 8), g, ok);
+  }
+}
+
+template <int D, int DV>
+__global__ void __launch_bounds__(NT) attention_pipe_kernel(const Params p) {
+  extern __shared__ __align__(16) unsigned char smem_dyn[];
+  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem_dyn);
+  __nv_bfloat16* Ks = Qs + BM * (D + 8);            // [2][BN][D + 8]
+  __nv_bfloat16* Vs = Ks + 2 * BN * (D + 8);        // [2][BN][DV + 8]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  constexpr int slices = D / DV;
+  const int h = blockIdx.y / slices, sl = blockIdx.y - h * slices;
+  const int b = blockIdx.z;
+  const int m0 = blockIdx.x * BM;
+  const __nv_bfloat16* qb = p.q + static_cast<long long>(b) * p.Tq * p.ldq + h * D;
+  const __nv_bfloat16* kb = p.k + static_cast<long long>(b) * p.Tk * p.ldk + h * D;
+  const __nv_bfloat16* vb = p.v + static_cast<long long>(b) * p.Tk * p.ldv + h * D + sl * DV;
+
+  load_tile_async<D>(Qs, qb, p.ldq, m0, p.Tq, 0);
+  load_tile_async<D>(Ks, kb, p.ldk, 0, p.Tk, 0);
+  load_tile_async<DV>(Vs, vb, p.ldv, 0, p.Tk, 0);
+  cp_async_commit();
+
+  float o[DV / 8][4];
+#pragma unroll
+  for (int i = 0; i < DV / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+  float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
+
+  const int ntiles = (p.Tk + BN - 1) / BN;
+  for (int it = 0; it < ntiles; ++it) {
+    const int n0 = it * BN;
+    const int cur = it & 1;
+    if (it + 1 < ntiles) {  // prefetch the next key tile into the other buffer (its readers finished last iteration)
+      load_tile_async<D>(Ks + (cur ^ 1) * BN * (D + 8), kb, p.ldk, n0 + BN, p.Tk, 0);
+      load_tile_async<DV>(Vs + (cur ^ 1) * BN * (DV + 8), vb, p.ldv, n0 + BN, p.Tk, 0);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const __nv_bfloat16* Kc = Ks + cur * BN * (D + 8);
+    const __nv_bfloat16* Vc = Vs + cur * BN * (DV + 8);
+    float s[BN / 8][4];
+#pragma unroll
+    for (int i = 0; i < BN / 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < D / 16; ++kk) {
+      uint32_t a0, a1, a2, a3;
+      ldsm_x4(smem_u32(Qs + (warp * 16 + (lane & 15)) * (D + 8) + kk * 16 + (lane >> 4) * 8), a0, a1, a2, a3);
+#pragma unroll
+      for (int np = 0; np < BN / 16; ++np) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(smem_u32(Kc + (np * 16 + (lane & 7) + ((lane >> 4) << 3)) * (D + 8) + kk * 16 + ((lane >> 3) & 1) * 8),
+                b0, b1, b2, b3);
+        mma16816(s[2 * np], a0, a1, a2, a3, b0, b1);
+        mma16816(s[2 * np + 1], a0, a1, a2, a3, b2, b3);
+      }
+    }
+    float tmax[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int i = 0; i < BN / 8; ++i) {
+      const int key = n0 + i * 8 + tq * 2;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool valid = (key + (e & 1)) < p.Tk;
+        s[i][e] = valid ? s[i][e] * p.scale_log2 : -INFINITY;
+        tmax[e >> 1] = fmaxf(tmax[e >> 1], s[i][e]);
+      }
+    }
+    float corr[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      tmax[r] = fmaxf(tmax[r], __shfl_xor_sync(0xffffffffu, tmax[r], 1));
+      tmax[r] = fmaxf(tmax[r], __shfl_xor_sync(0xffffffffu, tmax[r], 2));
+      const float mn = fmaxf(mrow[r], tmax[r]);
+      corr[r] = exp2f(mrow[r] - mn);
+      mrow[r] = mn;
+    }
+    float psum[2] = {0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < BN / 8; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        s[i][e] = exp2f(s[i][e] - mrow[e >> 1]);
+        psum[e >> 1] += s[i][e];
+      }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) lrow[r] = lrow[r] * corr[r] + psum[r];
+#pragma unroll
+    for (int i = 0; i < DV / 8; ++i) {
+      o[i][0] *= corr[0]; o[i][1] *= corr[0];
+      o[i][2] *= corr[1]; o[i][3] *= corr[1];
+    }
+#pragma unroll
+    for (int j = 0; j < BN / 16; ++j) {
+      const uint32_t a0 = pack2(s[2 * j][0], s[2 * j][1]);
+      const uint32_t a1 = pack2(s[2 * j][2], s[2 * j][3]);
+      const uint32_t a2 = pack2(s[2 * j + 1][0], s[2 * j + 1][1]);
+      const uint32_t a3 = pack2(s[2 * j + 1][2], s[2 * j + 1][3]);
+#pragma unroll
+      for (int np = 0; np < DV / 16; ++np) {
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_t(smem_u32(Vc + (j * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * (DV + 8) + np * 16 + (lane >> 4) * 8),
+                  b0, b1, b2, b3);
+        mma16816(o[2 * np], a0, a1, a2, a3, b0, b1);
+        mma16816(o[2 * np + 1], a0, a1, a2, a3, b2, b3);
+      }
+    }
+    __syncthreads();  // everyone is done with buffer `cur` before the next iteration's prefetch overwrites it
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 1);
+    lrow[r] += __shfl_xor_sync(0xffffffffu, lrow[r], 2);
+  }
+  const float inv[2] = {1.f / lrow[0], 1.f / lrow[1]};
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = m0 + warp * 16 + g + r * 8;
+    if (row >= p.Tq) continue;
+    __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.Tq + row) * p.ldo + h * D + sl * DV;
+#pragma unroll
+    for (int i = 0; i < DV / 8; ++i)
+      *reinterpret_cast<uint32_t*>(orow + i * 8 + tq * 2) = pack2(o[i][2 * r] * inv[r], o[i][2 * r + 1] * inv[r]);
+  }
+}
+
+Params make_params(const AttnArgs& a) {
+  Params p;
+  p.q = static_cast<const __nv_bfloat16*>(a.q);
+  p.k = static_cast<const __nv_bfloat16*>(a.k);
+  p.v = static_cast<const __nv_bfloat16*>(a.v);
+  p.out = static_cast<__nv_bfloat16*>(a.out);
+  p.heads = a.heads; p.Tq = a.Tq; p.Tk = a.Tk; p.d = a.d;
+  p.ldq = a.ldq; p.ldk = a.ldk; p.ldv = a.ldv; p.ldo = a.ldo;
+  p.scale_log2 = a.scale * 1.4426950408889634f;
+  return p;
+}
+
+template <int D, int DV>
+void launch_pipe(const AttnArgs& a, cudaStream_t st) {
+  constexpr size_t smem = sizeof(__nv_bfloat16) * (BM * (D + 8) + 2 * BN * (D + 8) + 2 * BN * (DV + 8));
+  static bool configured = false;
+  if (!configured) {
+    T2P_CUDA(cudaFuncSetAttribute(attention_pipe_kernel<D, DV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    configured = true;
+  }
+  const Params p = make_params(a);
+  dim3 grid(cdiv(a.Tq, BM), a.heads * (D / DV), a.B);
+  attention_pipe_kernel<D, DV><<<grid, NT, smem, st>>>(p);
+  T2P_LAUNCH_CHECK();
+}
+
 template <int DK, int DV>
 void launch(const AttnArgs& a, cudaStream_t st) {
   Params p;
@@ -199,7 +376,12 @@ bool attention_mma_supported(const AttnArgs& a) {
 
 void attention_mma(const AttnArgs& a, cudaStream_t st) {
   T2P_CHECK(attention_mma_supported(a), "unsupported shape / alignment for the tensor-core attention kernel");
-  if (a.d == 16) launch<16, 16>(a, st);
+  if (a.d == 16) launch_pipe<16, 16>(a, st);
+  else if (a.d == 32) launch_pipe<32, 32>(a, st);
+  else if (a.d == 64) launch_pipe<64, 64>(a, st);
+  else if (a.d == 128) launch_pipe<128, 128>(a, st);
+  else if (a.d == 256) launch_pipe<256, 128>(a, st);
+  else if (a.d == 16) launch<16, 16>(a, st);
   else if (a.d == 32) launch<32, 32>(a, st);
   else if (a.d == 64) launch<64, 64>(a, st);
   else if (a.d % 128 == 0) launch<64, 128>(a, st);

@@ -442,10 +442,11 @@ static void gn_apply_t(const void* a0, int c0, const void* a1, int c1, int B, in
     const int HW = H * W;
     const int rows = 256 / slots;
     const int threads = rows * slots;
-    // enough blocks to fill the machine several times over, up to 4 rounds of UNROLL vectors per thread
-    const int want_blocks = std::max(1, (148 * 8) / B);
-    int iters = HW / (rows * UNROLL * want_blocks);
-    iters = std::max(1, std::min(iters, 4));
+    // many more blocks than the machine holds at once (148 SMs x 8), so the last partial wave is a small
+    // fraction of the run; at most 2 rounds of UNROLL vectors per thread
+    const long long want_blocks = 148ll * 8 * 6;
+    int iters = static_cast<int>(static_cast<long long>(HW) * B / (static_cast<long long>(rows) * UNROLL * want_blocks));
+    iters = std::max(1, std::min(iters, 2));
     const int ppb = rows * UNROLL * iters;
     dim3 grid(cdiv(HW, ppb), B);
     gn_apply_rows_kernel<T, UNROLL><<<grid, threads, 0, st>>>(p0, c0, p1, c1, HW, ppb, scale, shift, act, o);

@@ -3,6 +3,7 @@
 // Build: see __graft_entry__.build();  run on a B200:  build/selftest_gemm
 #include <cmath>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "kernels.h"
@@ -263,6 +264,12 @@ int main(int argc, char** argv) {
       {"gemm M=300 K=4096 N=512", 1, 1, 300, 4096, 0, 1, 512, false, false, false, false, false, false},
       {"conv1 8x8 c256->256 B=70", 70, 8, 8, 256, 0, 1, 256, true, true, true, false, true, false},
   };
+  if (argc > 1 && std::string(argv[1]) == "one") {
+    // single shape for ncu captures: one <B> <H> <W> <cin> <N> <ks> <epi>
+    if (argc < 9) { fprintf(stderr, "usage: selftest_gemm one B H W cin N ks epi\n"); return 2; }
+    bench_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]), atoi(argv[8]));
+    return 0;
+  }
   int rc = 0;
   const char* only = getenv("T2P_SELFTEST_CASE");
   int ci = 0;
