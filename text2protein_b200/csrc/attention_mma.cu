@@ -213,6 +213,8 @@ __global__ void __launch_bounds__(NT) attention_pipe_kernel(const Params p) {
   const __nv_bfloat16* kb = p.k + static_cast<long long>(b) * p.Tk * p.ldk + h * D;
   const __nv_bfloat16* vb = p.v + static_cast<long long>(b) * p.Tk * p.ldv + h * D + sl * DV;
 
+  pdl_trigger();
+  pdl_wait();
   load_tile_async<D>(Qs, qb, p.ldq, m0, p.Tq, 0);
   load_tile_async<D>(Ks, kb, p.ldk, 0, p.Tk, 0);
   load_tile_async<DV>(Vs, vb, p.ldv, 0, p.Tk, 0);
@@ -346,8 +348,7 @@ void launch_pipe(const AttnArgs& a, cudaStream_t st) {
   }
   const Params p = make_params(a);
   dim3 grid(cdiv(a.Tq, BM), a.heads * (D / DV), a.B);
-  attention_pipe_kernel<D, DV><<<grid, NT, smem, st>>>(p);
-  T2P_LAUNCH_CHECK();
+  launch_pdl(attention_pipe_kernel<D, DV>, grid, dim3(NT), smem, st, p);
 }
 
 template <int DK, int DV>

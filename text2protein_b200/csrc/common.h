@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 
@@ -45,6 +46,37 @@ void set_last_error(const std::string& m);
   } while (0)
 
 #define T2P_LAUNCH_CHECK() T2P_CUDA(cudaGetLastError())
+
+// ---- programmatic dependent launch (PDL).  A kernel launched through launch_pdl() may become resident while
+// its predecessor in the stream is still draining: it calls pdl_trigger() first (its own successor may be
+// scheduled once every CTA of this grid has started), runs its prologue (barrier init, TMEM allocation,
+// tensor-map prefetch) and calls pdl_wait() BEFORE its first global-memory access that depends on a predecessor;
+// pdl_wait() returns when the preceding grids have completed and flushed.  Captured into CUDA graphs as
+// programmatic edges.  Measured on B200 (profiles/r01_pdl_ab.txt): 3 % SLOWER for this network (27.58 vs 26.74 ms per
+// PC iteration), so it is opt-in (T2P_PDL=1); by default the same kernels launch with ordinary stream ordering.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... P, typename... A>
+inline void launch_pdl(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  static const bool on = [] {
+    const char* e = getenv("T2P_PDL");
+    return e && atoi(e) != 0;
+  }();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = on ? 1 : 0;
+  T2P_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...));
+}
+#endif
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -141,6 +141,8 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, int B, int HW,
 // 3x3, stride 1, zero padding 1.  One thread writes 8 consecutive k (16 bytes).
 __global__ void im2col3x3_nchw_kernel(const float* __restrict__ x, int B, int C, int H, int W, int kpad,
                                       __nv_bfloat16* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int kv = kpad >> 3;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long total = static_cast<long long>(B) * H * W * kv;
@@ -261,9 +263,8 @@ void nchw_f32_to_nhwc(const float* in, int B, int HW, int C, int cpad, int out_d
 void im2col3x3_nchw(const float* x, int B, int C, int H, int W, int kpad, void* out, cudaStream_t st) {
   T2P_CHECK(kpad % 8 == 0 && kpad >= 9 * C, "bad im2col padding");
   const long long total = static_cast<long long>(B) * H * W * (kpad / 8);
-  im2col3x3_nchw_kernel<<<static_cast<unsigned>(cdiv64(total, 256)), 256, 0, st>>>(x, B, C, H, W, kpad,
-                                                                                   static_cast<__nv_bfloat16*>(out));
-  T2P_LAUNCH_CHECK();
+  launch_pdl(im2col3x3_nchw_kernel, dim3(static_cast<unsigned>(cdiv64(total, 256))), dim3(256), 0, st, x, B, C, H, W, kpad,
+             static_cast<__nv_bfloat16*>(out));
 }
 
 void pack_first_conv(const float* w, int cout, int C, int kpad, void* out, cudaStream_t st) {

@@ -58,6 +58,7 @@ struct TcParams {
   int out_nchw;
   int n_tiles;       // tiles along N
   int num_tiles;     // m_tiles * n_tiles
+  int reverse;       // walk the tiles from the last to the first (see ConvGemmArgs::reverse)
 };
 
 template <int BN>
@@ -213,6 +214,7 @@ template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_tc_kernel(const __grid_constant__ TcParams p) {
   using C = Cfg<BN>;
   constexpr int CH = C::CH;
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[C::STAGES];
   __shared__ __align__(8) uint64_t empty_bar[C::STAGES];
@@ -249,6 +251,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_tc_kernel(const __gr
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -261,9 +264,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_tc_kernel(const __gr
       int s = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-        const int mt = t / p.n_tiles;
+        const int tt = p.reverse ? p.num_tiles - 1 - t : t;
+        const int mt = tt / p.n_tiles;
         const int m0 = mt * BM;
-        const int n0 = (t - mt * p.n_tiles) * BN;
+        const int n0 = (tt - mt * p.n_tiles) * BN;
         int b0 = 0, h0 = 0, w0 = m0;
         if (!p.mode2d) {
           b0 = m0 / hw;
@@ -330,10 +334,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_tc_kernel(const __gr
     uint32_t tl = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tl) {
       const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
-      const int mt = t / p.n_tiles;
+      const int tt = p.reverse ? p.num_tiles - 1 - t : t;
+        const int mt = tt / p.n_tiles;
       const int m0 = mt * BM;
       EpiRow er;
-      er.n0 = (t - mt * p.n_tiles) * BN;
+      er.n0 = (tt - mt * p.n_tiles) * BN;
       er.m = m0 + q * 32 + lane;
       er.row_ok = er.m < p.M;
       er.sample = (p.rows_per_sample > 0) ? (er.m / p.rows_per_sample) : 0;
@@ -498,6 +503,7 @@ __device__ __forceinline__ void epilogue_chunk_t(const TcParams& p, const EpiT& 
 template <int PX>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_tcT_kernel(const __grid_constant__ TcParams p) {
   using C = CfgT<PX>;
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[C::STAGES];
   __shared__ __align__(8) uint64_t empty_bar[C::STAGES];
@@ -534,6 +540,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_tcT_kernel(const __g
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -552,9 +559,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_tcT_kernel(const __g
       int s = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-        const int pt = t / p.n_tiles;
+        const int tt = p.reverse ? p.num_tiles - 1 - t : t;
+        const int pt = tt / p.n_tiles;
         const int m0 = pt * PX;
-        const int n0 = (t - pt * p.n_tiles) * 128;
+        const int n0 = (tt - pt * p.n_tiles) * 128;
         int b0 = 0, h0 = 0, w0 = m0;
         if (!p.mode2d) {
           b0 = m0 / hw;
@@ -648,8 +656,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_tcT_kernel(const __g
     uint32_t nstore = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tl) {
       const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
-      const int pt = t / p.n_tiles;
-      const int nw0 = (t - pt * p.n_tiles) * 128 + q * 32;  // first channel of this warp
+      const int tt = p.reverse ? p.num_tiles - 1 - t : t;
+        const int pt = tt / p.n_tiles;
+      const int nw0 = (tt - pt * p.n_tiles) * 128 + q * 32;  // first channel of this warp
       et.m0 = pt * PX;
       et.n = nw0 + lane;
       et.ch_ok = et.n < p.N;
@@ -671,7 +680,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_tcT_kernel(const __g
       // TMA clips rows >= M and channels >= N, so ragged edges need no masks here.
       auto store_chunk = [&](const unsigned short (&h)[32], int c) {
         const uint32_t buf = obuf + (nstore & 1) * (32 * 32 * 2);
-        __syncwarp();  // lane 0 has waited for the store that last read this buffer
+        // the store issued two chunks ago read this buffer: at most one (the previous chunk's) may be pending
+        if (lane == 0) ptx::tma_store_wait_read<1>();
+        __syncwarp();
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           asm volatile("st.shared.u16 [%0], %1;" ::"r"(buf + j * 64 + lane * 2), "h"(h[j]) : "memory");
@@ -680,7 +691,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_tcT_kernel(const __g
         if (lane == 0 && nw0 < p.N && et.m0 + c * 32 < p.M) {
           ptx::tma_store_4d(&p.tm_out, buf, nw0, et.m0 + c * 32, 0, 0);
           ptx::tma_store_commit();
-          ptx::tma_store_wait_read<1>();  // the previous store (other buffer) has finished reading smem
         }
         ++nstore;
       };
@@ -813,8 +823,7 @@ void launch(TcParams& p, cudaStream_t st) {
   p.n_tiles = cdiv(p.N, BN);
   p.num_tiles = cdiv(p.M, BM) * p.n_tiles;
   const int grid = std::min(p.num_tiles, sm_count());
-  conv_gemm_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p);
-  T2P_LAUNCH_CHECK();
+  launch_pdl(conv_gemm_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, st, p);
 }
 
 template <int PX>
@@ -829,8 +838,7 @@ void launch_t(TcParams& p, cudaStream_t st) {
   p.n_tiles = cdiv(p.N, 128);
   p.num_tiles = cdiv(p.M, PX) * p.n_tiles;
   const int grid = std::min(p.num_tiles, sm_count());
-  conv_gemm_tcT_kernel<PX><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(p);
-  T2P_LAUNCH_CHECK();
+  launch_pdl(conv_gemm_tcT_kernel<PX>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, st, p);
 }
 
 // `rows` consecutive pixels (b, h, w raster order) as one TMA box (tw, th, tb) of the NHWC tensor
@@ -936,6 +944,7 @@ void conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
   p.stat_part = a.stat_part;
   p.rowbias_ld = a.rowbias_ld > 0 ? a.rowbias_ld : a.N;
   p.out_nchw = a.out_nchw;
+  p.reverse = a.reverse;
   p.mode2d = (a.ksize == 1) ? 1 : 0;
   if (a.out_nchw) T2P_CHECK(a.out_dtype == kF32 && a.residual == nullptr, "out_nchw is fp32-only, without residual");
   if (a.rowbias) T2P_CHECK(a.rows_per_sample > 0, "rows_per_sample required");

@@ -39,6 +39,9 @@ struct ConvGemmArgs {
   const void* x1 = nullptr;
   int xc1 = 0;
   int rowbias_ld = 0;  // row pitch of rowbias (0 -> N)
+  // 1: process the pixel tiles from the last to the first.  Consecutive streaming kernels alternate direction so
+  // that each starts on the part of its input the previous kernel wrote last (still resident in the 126 MB L2).
+  int reverse = 0;
   int out_nchw = 0;    // 1: store out as [B][N][H*W] (fp32 only; used by the final conv)
 };
 
@@ -66,7 +69,7 @@ void gn_finalize(const float* part0, int nblk0, int c0, const float* part1, int 
 // after the activation (raw_out, optional, receives the 2x2 mean of the raw input), 2 = nearest x2 upsample
 // (raw_out, optional, receives the upsampled raw input).
 void gn_apply(const void* a0, int c0, const void* a1, int c1, int B, int H, int W, int dtype, const float* scale,
-              const float* shift, int act, int mode, void* out, void* raw_out, cudaStream_t st);
+              const float* shift, int act, int mode, void* out, void* raw_out, cudaStream_t st, int reverse = 0);
 void layernorm(const void* x, const float* gamma, const float* beta, long long M, int C, float eps, int dtype,
                void* y, cudaStream_t st);
 void geglu(const void* z, long long M, int D, int dtype, void* out, cudaStream_t st);

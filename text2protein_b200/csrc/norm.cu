@@ -78,6 +78,8 @@ __device__ __forceinline__ float silu_t<__nv_bfloat16>(float x) { return silu_ta
 template <typename T>
 __global__ void gn_stats_kernel(const T* __restrict__ a0, int c0, const T* __restrict__ a1, int c1, int HW,
                                 int pix_per_block, float* __restrict__ part) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];  // [rows][2 * ctot]
   const int ctot = c0 + c1;
   const int slots = ctot >> 3;
@@ -122,6 +124,8 @@ __global__ void gn_finalize_kernel(const float* __restrict__ part0, int nblk0, i
                                    const float* __restrict__ part1, int nblk1, int c1,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, int G, int HW,
                                    float eps, float* __restrict__ scale, float* __restrict__ shift, int total) {
+  pdl_trigger();
+  pdl_wait();
   const int C = c0 + c1;
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -167,6 +171,8 @@ template <typename T, int MODE>
 __global__ void gn_apply_kernel(const T* __restrict__ a0, int c0, const T* __restrict__ a1, int c1, int B, int H,
                                 int W, const float* __restrict__ scale, const float* __restrict__ shift, int act,
                                 T* __restrict__ out, T* __restrict__ raw_out) {
+  pdl_trigger();
+  pdl_wait();
   const int ctot = c0 + c1;
   const int slots = ctot >> 3;
   const int OH = (MODE == 1) ? H >> 1 : H, OW = (MODE == 1) ? W >> 1 : W;  // iteration space
@@ -246,13 +252,17 @@ template <typename T, int UNROLL>
 __global__ void __launch_bounds__(256) gn_apply_rows_kernel(const T* __restrict__ a0, int c0, const T* __restrict__ a1,
                                                             int c1, int HW, int ppb, const float* __restrict__ scale,
                                                             const float* __restrict__ shift, int act,
-                                                            T* __restrict__ out) {
+                                                            T* __restrict__ out, int reverse) {
+  pdl_trigger();
+  pdl_wait();
   const int ctot = c0 + c1;
   const int slots = ctot >> 3;
   const int rows = blockDim.x / slots;
   const int slot = threadIdx.x % slots;
   const int row = threadIdx.x / slots;
-  const int b = blockIdx.y;
+  // blocks are dispatched in (x fastest, then y) order: reversed, the kernel sweeps memory from the end
+  const int b = reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
+  const int bx = reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
   const int ch = slot << 3;
   const T* src;
   int cs, co;
@@ -266,7 +276,7 @@ __global__ void __launch_bounds__(256) gn_apply_rows_kernel(const T* __restrict_
     sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
     sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
   }
-  const int p0 = blockIdx.x * ppb;
+  const int p0 = bx * ppb;
   const int p1 = min(HW, p0 + ppb);
   const T* s = src + static_cast<long long>(b) * HW * cs + co;
   T* o = out + static_cast<long long>(b) * HW * ctot + ch;
@@ -296,6 +306,8 @@ __global__ void __launch_bounds__(256) gn_apply_rows_kernel(const T* __restrict_
 template <typename T, int MAXV>
 __global__ void layernorm_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, int M, int C, float eps, T* __restrict__ y) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= M) return;
@@ -347,6 +359,8 @@ template <typename T>
 __global__ void layernorm_generic_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
                                          const float* __restrict__ beta, int M, int C, float eps,
                                          T* __restrict__ y) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= M) return;
@@ -368,6 +382,8 @@ __global__ void layernorm_generic_kernel(const T* __restrict__ x, const float* _
 // ------------------------------------------------------------------ GEGLU: out = a * gelu_erf(gate)
 template <typename T>
 __global__ void geglu_kernel(const T* __restrict__ z, long long M, int D, T* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const int slots = D >> 3;
   if (idx >= M * slots) return;
@@ -405,14 +421,13 @@ void gn_stats(const void* a0, int c0, const void* a1, int c1, int B, int HW, int
   if (dtype == kF32) {
     static bool cfgd = false;
     if (!cfgd) { T2P_CUDA(cudaFuncSetAttribute(gn_stats_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); cfgd = true; }
-    gn_stats_kernel<float><<<grid, threads, smem, st>>>(static_cast<const float*>(a0), c0,
-                                                        static_cast<const float*>(a1), c1, HW, ppb, part);
+    launch_pdl(gn_stats_kernel<float>, grid, dim3(threads), smem, st, static_cast<const float*>(a0), c0,
+               static_cast<const float*>(a1), c1, HW, ppb, part);
   } else {
     static bool cfgd = false;
     if (!cfgd) { T2P_CUDA(cudaFuncSetAttribute(gn_stats_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); cfgd = true; }
-    gn_stats_kernel<__nv_bfloat16><<<grid, threads, smem, st>>>(static_cast<const __nv_bfloat16*>(a0), c0,
-                                                                static_cast<const __nv_bfloat16*>(a1), c1, HW, ppb,
-                                                                part);
+    launch_pdl(gn_stats_kernel<__nv_bfloat16>, grid, dim3(threads), smem, st, static_cast<const __nv_bfloat16*>(a0), c0,
+               static_cast<const __nv_bfloat16*>(a1), c1, HW, ppb, part);
   }
   T2P_LAUNCH_CHECK();
 }
@@ -421,14 +436,13 @@ void gn_finalize(const float* part0, int nblk0, int c0, const float* part1, int 
                  const float* beta, int B, int G, int HW, float eps, float* scale, float* shift, cudaStream_t st) {
   T2P_CHECK((c0 + c1) % G == 0, "channels not divisible by groups");
   const int total = B * G;
-  gn_finalize_kernel<<<cdiv(total, 4), 128, 0, st>>>(part0, nblk0, c0, part1, nblk1, c1, gamma, beta, G, HW, eps,
-                                                       scale, shift, total);
-  T2P_LAUNCH_CHECK();
+  launch_pdl(gn_finalize_kernel, dim3(cdiv(total, 4)), dim3(128), 0, st, part0, nblk0, c0, part1, nblk1, c1, gamma, beta,
+             G, HW, eps, scale, shift, total);
 }
 
 template <typename T>
 static void gn_apply_t(const void* a0, int c0, const void* a1, int c1, int B, int H, int W, const float* scale,
-                       const float* shift, int act, int mode, void* out, void* raw_out, cudaStream_t st) {
+                       const float* shift, int act, int mode, void* out, void* raw_out, cudaStream_t st, int reverse) {
   const int slots = (c0 + c1) / 8;
   const int OH = mode == 1 ? H / 2 : H, OW = mode == 1 ? W / 2 : W;
   const long long total = static_cast<long long>(B) * OH * OW * slots;
@@ -442,26 +456,24 @@ static void gn_apply_t(const void* a0, int c0, const void* a1, int c1, int B, in
     const int HW = H * W;
     const int rows = 256 / slots;
     const int threads = rows * slots;
-    // many more blocks than the machine holds at once (148 SMs x 8), so the last partial wave is a small
-    // fraction of the run; at most 2 rounds of UNROLL vectors per thread
-    const long long want_blocks = 148ll * 8 * 6;
-    int iters = static_cast<int>(static_cast<long long>(HW) * B / (static_cast<long long>(rows) * UNROLL * want_blocks));
-    iters = std::max(1, std::min(iters, 2));
+    // enough blocks to fill the machine several times over, up to 4 rounds of UNROLL vectors per thread
+    const int want_blocks = std::max(1, (148 * 8) / B);
+    int iters = HW / (rows * UNROLL * want_blocks);
+    iters = std::max(1, std::min(iters, 4));
     const int ppb = rows * UNROLL * iters;
     dim3 grid(cdiv(HW, ppb), B);
-    gn_apply_rows_kernel<T, UNROLL><<<grid, threads, 0, st>>>(p0, c0, p1, c1, HW, ppb, scale, shift, act, o);
-  } else if (mode == 0) gn_apply_kernel<T, 0><<<blocks, 256, 0, st>>>(p0, c0, p1, c1, B, H, W, scale, shift, act, o, r);
-  else if (mode == 1) gn_apply_kernel<T, 1><<<blocks, 256, 0, st>>>(p0, c0, p1, c1, B, H, W, scale, shift, act, o, r);
-  else gn_apply_kernel<T, 2><<<blocks, 256, 0, st>>>(p0, c0, p1, c1, B, H, W, scale, shift, act, o, r);
-  T2P_LAUNCH_CHECK();
+    launch_pdl(gn_apply_rows_kernel<T, UNROLL>, grid, dim3(threads), 0, st, p0, c0, p1, c1, HW, ppb, scale, shift, act, o, reverse);
+  } else if (mode == 0) launch_pdl(gn_apply_kernel<T, 0>, dim3(blocks), dim3(256), 0, st, p0, c0, p1, c1, B, H, W, scale, shift, act, o, r);
+  else if (mode == 1) launch_pdl(gn_apply_kernel<T, 1>, dim3(blocks), dim3(256), 0, st, p0, c0, p1, c1, B, H, W, scale, shift, act, o, r);
+  else launch_pdl(gn_apply_kernel<T, 2>, dim3(blocks), dim3(256), 0, st, p0, c0, p1, c1, B, H, W, scale, shift, act, o, r);
 }
 
 void gn_apply(const void* a0, int c0, const void* a1, int c1, int B, int H, int W, int dtype, const float* scale,
-              const float* shift, int act, int mode, void* out, void* raw_out, cudaStream_t st) {
+              const float* shift, int act, int mode, void* out, void* raw_out, cudaStream_t st, int reverse) {
   T2P_CHECK(mode >= 0 && mode <= 2, "bad resample mode");
   if (mode == 1) T2P_CHECK(H % 2 == 0 && W % 2 == 0, "downsample needs even H, W");
-  if (dtype == kF32) gn_apply_t<float>(a0, c0, a1, c1, B, H, W, scale, shift, act, mode, out, raw_out, st);
-  else gn_apply_t<__nv_bfloat16>(a0, c0, a1, c1, B, H, W, scale, shift, act, mode, out, raw_out, st);
+  if (dtype == kF32) gn_apply_t<float>(a0, c0, a1, c1, B, H, W, scale, shift, act, mode, out, raw_out, st, reverse);
+  else gn_apply_t<__nv_bfloat16>(a0, c0, a1, c1, B, H, W, scale, shift, act, mode, out, raw_out, st, reverse);
 }
 
 void layernorm(const void* x, const float* gamma, const float* beta, long long M, int C, float eps, int dtype,
@@ -469,11 +481,11 @@ void layernorm(const void* x, const float* gamma, const float* beta, long long M
   const unsigned blocks = static_cast<unsigned>(cdiv64(M, 8));
   const bool fast = (C % 256 == 0) && C <= 1024;
   if (dtype == kF32) {
-    if (fast) layernorm_kernel<float, 4><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), gamma, beta, (int)M, C, eps, static_cast<float*>(y));
-    else layernorm_generic_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), gamma, beta, (int)M, C, eps, static_cast<float*>(y));
+    if (fast) launch_pdl(layernorm_kernel<float, 4>, dim3(blocks), dim3(256), 0, st, static_cast<const float*>(x), gamma, beta, (int)M, C, eps, static_cast<float*>(y));
+    else launch_pdl(layernorm_generic_kernel<float>, dim3(blocks), dim3(256), 0, st, static_cast<const float*>(x), gamma, beta, (int)M, C, eps, static_cast<float*>(y));
   } else {
-    if (fast) layernorm_kernel<__nv_bfloat16, 4><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), gamma, beta, (int)M, C, eps, static_cast<__nv_bfloat16*>(y));
-    else layernorm_generic_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), gamma, beta, (int)M, C, eps, static_cast<__nv_bfloat16*>(y));
+    if (fast) launch_pdl(layernorm_kernel<__nv_bfloat16, 4>, dim3(blocks), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(x), gamma, beta, (int)M, C, eps, static_cast<__nv_bfloat16*>(y));
+    else launch_pdl(layernorm_generic_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(x), gamma, beta, (int)M, C, eps, static_cast<__nv_bfloat16*>(y));
   }
   T2P_LAUNCH_CHECK();
 }
@@ -481,8 +493,8 @@ void layernorm(const void* x, const float* gamma, const float* beta, long long M
 void geglu(const void* z, long long M, int D, int dtype, void* out, cudaStream_t st) {
   T2P_CHECK(D % 8 == 0, "GEGLU width must be a multiple of 8");
   const unsigned blocks = static_cast<unsigned>(cdiv64(M * (D / 8), 256));
-  if (dtype == kF32) geglu_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(z), M, D, static_cast<float*>(out));
-  else geglu_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(z), M, D, static_cast<__nv_bfloat16*>(out));
+  if (dtype == kF32) launch_pdl(geglu_kernel<float>, dim3(blocks), dim3(256), 0, st, static_cast<const float*>(z), M, D, static_cast<float*>(out));
+  else launch_pdl(geglu_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(z), M, D, static_cast<__nv_bfloat16*>(out));
   T2P_LAUNCH_CHECK();
 }
 

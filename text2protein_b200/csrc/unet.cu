@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace t2p {
 
@@ -441,6 +442,7 @@ void UNet::gemm(const Linear& l, const Act& a0, const Act* a1, Act& out, const f
   g.out = out.p;
   g.out_dtype = out_dtype >= 0 ? out_dtype : cfg_.compute_dtype;
   g.out_nchw = out_nchw;
+  g.reverse = serpentine_ ? static_cast<int>(stream_seq_++ & 1) : 0;
   const bool tc = cfg_.compute_dtype == kBF16 && !l.force_f32 && (g.c0 % 64 == 0) && (g.c1 % 64 == 0);
   if (tc && out.want_stats && g.out_dtype == kBF16) {  // only the tensor-core epilogue produces GroupNorm statistics
     const int tile = conv_gemm_tc_stat_tile(g);
@@ -517,11 +519,12 @@ void UNet::group_norm(const GroupNormP& gn, const Act& a0, const Act* a1, int ac
   float* scale = static_cast<float*>(ws_.alloc(sizeof(float) * 2 * B * C));
   float* shift = scale + static_cast<size_t>(B) * C;
   launches_ += 2;  // finalize + apply
+  ++stream_seq_;
   if (!dry_) {
     gn_finalize(part[0], nblk[0], a0.C, part[1], nblk[1], a1 ? a1->C : 0, static_cast<const float*>(gn.w->data),
                 static_cast<const float*>(gn.b->data), B, gn.G, HW, 1e-6f, scale, shift, st_);
     gn_apply(a0.p, a0.C, a1 ? a1->p : nullptr, a1 ? a1->C : 0, B, a0.H, a0.W, cfg_.compute_dtype, scale, shift, act,
-             mode, out.p, raw_out ? raw_out->p : nullptr, st_);
+             mode, out.p, raw_out ? raw_out->p : nullptr, st_, serpentine_ ? static_cast<int>(stream_seq_ & 1) : 0);
   }
   for (int i = 0; i < 2; ++i)
     if (owned[i]) ws_.free(owned[i]);
@@ -748,6 +751,11 @@ void UNet::set_context(const float* ctx, int B, int L, cudaStream_t st) {
 void UNet::forward_impl(const float* x, const long long* labels, float* h_out, int B) {
   const int N = cfg_.max_res_num, C = cfg_.num_channels, nf = cfg_.nf;
   launches_ = 0;
+  stream_seq_ = 0;
+  {
+    static const bool on = [] { const char* e = getenv("T2P_SERPENTINE"); return !e || atoi(e) != 0; }();
+    serpentine_ = on;
+  }
   temb_all_ = static_cast<float*>(ws_.alloc(sizeof(float) * static_cast<size_t>(B) * temb_total_));
   {
     float* temb = static_cast<float*>(ws_.alloc(sizeof(float) * static_cast<size_t>(B) * 4 * nf));

@@ -213,6 +213,10 @@ class UNet {
   std::vector<GemmRecord> profile_log_;
   int planned_B_ = -1;
   long long launches_ = 0;
+  // Serpentine sweep: consecutive streaming kernels (GEMM, GroupNorm apply) walk their tiles in alternating
+  // direction, so each begins on the data its predecessor wrote last -- still resident in the 126 MB L2.
+  bool serpentine_ = true;
+  unsigned stream_seq_ = 0;
   float* temb_all_ = nullptr;
   int ctx_B_ = 0, ctx_L_ = 0;
   std::map<std::string, std::pair<float*, std::vector<int64_t>>> taps_;
