@@ -95,3 +95,15 @@ def test_state_dict_roundtrip_through_dataparallel_checkpoint(tmp_path):
     a = model(x.cuda(), labels.cuda(), ctx.cuda())
     b = model2(x.cuda(), labels.cuda(), ctx.cuda())
     assert state2["step"] == 5 and torch.equal(a, b)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_two_lane_half_batches_are_bit_identical_to_separate_runs(dtype):
+    """B >= 8 runs as two half-batches on two streams; every sample's arithmetic is unchanged."""
+    cfg, model, sd = make_native(tiny_cfg(5), dtype)
+    x, labels, ctx = synthetic_inputs(cfg, 8, 9, seed=11)
+    x, labels, ctx = x.cuda(), labels.cuda(), ctx.cuda()
+    whole = model(x, labels, ctx)
+    lo = model(x[:4].contiguous(), labels[:4].contiguous(), ctx[:4].contiguous())
+    hi = model(x[4:].contiguous(), labels[4:].contiguous(), ctx[4:].contiguous())
+    assert torch.equal(whole, torch.cat([lo, hi]))

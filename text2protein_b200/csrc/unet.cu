@@ -320,6 +320,9 @@ UNet::~UNet() {
   for (void* p : owned_) cudaFree(p);
   for (auto& kv : taps_) cudaFree(kv.second.first);
   if (h_scratch_) cudaFree(h_scratch_);
+  if (side_) cudaStreamDestroy(side_);
+  if (ev_fork_) cudaEventDestroy(ev_fork_);
+  if (ev_join_) cudaEventDestroy(ev_join_);
 }
 
 void UNet::load(const std::string& name, const void* dev_ptr, const std::vector<int64_t>& shape, int dtype,
@@ -410,15 +413,15 @@ void UNet::finalize(cudaStream_t st) {
 Act UNet::new_act(int B, int H, int W, int C, bool with_stats) {
   Act a;
   a.B = B; a.H = H; a.W = W; a.C = C;
-  a.p = ws_.alloc(static_cast<size_t>(a.rows()) * C * dtype_size(cfg_.compute_dtype));
+  a.p = ln_->ws.alloc(static_cast<size_t>(a.rows()) * C * dtype_size(cfg_.compute_dtype));
   // the tensor-core epilogue can emit GroupNorm statistics when every pixel tile lies inside one sample; the
   // partial-sum buffer is allocated by gemm() once the producing launch (and hence its tile size) is known
   a.want_stats = with_stats && cfg_.compute_dtype == kBF16 && C >= 32;
   return a;
 }
 void UNet::free_act(Act& a) {
-  ws_.free(a.p);
-  if (a.spart) ws_.free(a.spart);
+  ln_->ws.free(a.p);
+  if (a.spart) ln_->ws.free(a.spart);
   a = Act{};
 }
 
@@ -442,13 +445,13 @@ void UNet::gemm(const Linear& l, const Act& a0, const Act* a1, Act& out, const f
   g.out = out.p;
   g.out_dtype = out_dtype >= 0 ? out_dtype : cfg_.compute_dtype;
   g.out_nchw = out_nchw;
-  g.reverse = serpentine_ ? static_cast<int>(stream_seq_++ & 1) : 0;
+  g.reverse = serpentine_ ? static_cast<int>(ln_->seq++ & 1) : 0;
   const bool tc = cfg_.compute_dtype == kBF16 && !l.force_f32 && (g.c0 % 64 == 0) && (g.c1 % 64 == 0);
   if (tc && out.want_stats && g.out_dtype == kBF16) {  // only the tensor-core epilogue produces GroupNorm statistics
     const int tile = conv_gemm_tc_stat_tile(g);
     if (tile > 0) {
       out.snblk = g.rows_per_sample / tile;
-      out.spart = static_cast<float*>(ws_.alloc(sizeof(float) * 2 * static_cast<size_t>(out.B) * out.snblk * l.N));
+      out.spart = static_cast<float*>(ln_->ws.alloc(sizeof(float) * 2 * static_cast<size_t>(out.B) * out.snblk * l.N));
       g.stat_part = out.spart;
     }
   }
@@ -458,12 +461,12 @@ void UNet::gemm(const Linear& l, const Act& a0, const Act* a1, Act& out, const f
   if (profile_) {
     T2P_CUDA(cudaEventCreate(&e0));
     T2P_CUDA(cudaEventCreate(&e1));
-    T2P_CUDA(cudaEventRecord(e0, st_));
+    T2P_CUDA(cudaEventRecord(e0, ln_->st));
   }
-  if (tc) conv_gemm_tc(g, st_);
-  else conv_gemm_simt(g, l.force_f32 ? kF32 : cfg_.compute_dtype, st_);
+  if (tc) conv_gemm_tc(g, ln_->st);
+  else conv_gemm_simt(g, l.force_f32 ? kF32 : cfg_.compute_dtype, ln_->st);
   if (profile_) {
-    T2P_CUDA(cudaEventRecord(e1, st_));
+    T2P_CUDA(cudaEventRecord(e1, ln_->st));
     GemmRecord r;
     r.M = a0.rows(); r.N = l.N; r.K = l.Kalg(); r.ksize = l.ksize; r.tc = tc ? 1 : 0;
     r.H = a0.H; r.W = a0.W;
@@ -511,24 +514,24 @@ void UNet::group_norm(const GroupNormP& gn, const Act& a0, const Act* a1, int ac
       continue;
     }
     nblk[i] = gn_stats_blocks(B, HW);
-    owned[i] = static_cast<float*>(ws_.alloc(sizeof(float) * 2 * static_cast<size_t>(B) * nblk[i] * src[i]->C));
+    owned[i] = static_cast<float*>(ln_->ws.alloc(sizeof(float) * 2 * static_cast<size_t>(B) * nblk[i] * src[i]->C));
     part[i] = owned[i];
     ++launches_;
-    if (!dry_) gn_stats(src[i]->p, src[i]->C, nullptr, 0, B, HW, cfg_.compute_dtype, owned[i], st_);
+    if (!dry_) gn_stats(src[i]->p, src[i]->C, nullptr, 0, B, HW, cfg_.compute_dtype, owned[i], ln_->st);
   }
-  float* scale = static_cast<float*>(ws_.alloc(sizeof(float) * 2 * B * C));
+  float* scale = static_cast<float*>(ln_->ws.alloc(sizeof(float) * 2 * B * C));
   float* shift = scale + static_cast<size_t>(B) * C;
   launches_ += 2;  // finalize + apply
-  ++stream_seq_;
+  ++ln_->seq;
   if (!dry_) {
     gn_finalize(part[0], nblk[0], a0.C, part[1], nblk[1], a1 ? a1->C : 0, static_cast<const float*>(gn.w->data),
-                static_cast<const float*>(gn.b->data), B, gn.G, HW, 1e-6f, scale, shift, st_);
+                static_cast<const float*>(gn.b->data), B, gn.G, HW, 1e-6f, scale, shift, ln_->st);
     gn_apply(a0.p, a0.C, a1 ? a1->p : nullptr, a1 ? a1->C : 0, B, a0.H, a0.W, cfg_.compute_dtype, scale, shift, act,
-             mode, out.p, raw_out ? raw_out->p : nullptr, st_, serpentine_ ? static_cast<int>(stream_seq_ & 1) : 0);
+             mode, out.p, raw_out ? raw_out->p : nullptr, ln_->st, serpentine_ ? static_cast<int>(ln_->seq & 1) : 0);
   }
   for (int i = 0; i < 2; ++i)
-    if (owned[i]) ws_.free(owned[i]);
-  ws_.free(scale);
+    if (owned[i]) ln_->ws.free(owned[i]);
+  ln_->ws.free(scale);
 }
 
 void UNet::attention(const void* q, const void* k, const void* v, void* out, int B, int heads, int Tq, int Tk, int d,
@@ -539,8 +542,8 @@ void UNet::attention(const void* q, const void* k, const void* v, void* out, int
   a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo; a.scale = scale;
   ++launches_;
   if (dry_) return;
-  if (cfg_.compute_dtype == kBF16 && attention_mma_supported(a)) attention_mma(a, st_);
-  else attention_simt(a, cfg_.compute_dtype, st_);
+  if (cfg_.compute_dtype == kBF16 && attention_mma_supported(a)) attention_mma(a, ln_->st);
+  else attention_simt(a, cfg_.compute_dtype, ln_->st);
 }
 
 // ResnetBlockBigGANpp.forward, layers.py:303-327
@@ -553,7 +556,7 @@ Act UNet::run_res(ResBlockM& m, const Act& a0, const Act* a1) {
   if (m.down || (m.up && m.folded)) xr = new_act(B, OH, OW, m.in_ch, false);
   group_norm(m.gn0, a0, a1, 1, mode, h, xr.p ? &xr : nullptr);
   Act h1 = new_act(B, OH, OW, m.out_ch, true);
-  gemm(m.conv0, h, nullptr, h1, temb_all_ + m.temb_off, temb_total_, nullptr, 0, 1.f);
+  gemm(m.conv0, h, nullptr, h1, ln_->temb_all + m.temb_off, temb_total_, nullptr, 0, 1.f);
   free_act(h);
   Act h2 = new_act(B, OH, OW, m.out_ch, false);
   group_norm(m.gn1, h1, nullptr, 1, 0, h2, nullptr);
@@ -619,12 +622,13 @@ Act UNet::run_st(TransformerM& m, const Act& x) {
   const int B = x.B, H = x.H, W = x.W, T = H * W, C = m.C, d = C / m.heads;
   const size_t es = dtype_size(cfg_.compute_dtype);
   const float scale = 1.f / std::sqrt(static_cast<float>(d));
-  T2P_CHECK(m.kv != nullptr && ctx_B_ == B, "set_context() must be called with the same batch before forward");
+  T2P_CHECK(m.kv != nullptr && ln_->batch_off + B <= ctx_B_ && (ln_->batch_off > 0 || nlanes_ > 1 || ctx_B_ == B),
+            "set_context() must be called with the same batch before forward");
   auto ln = [&](const LayerNormP& l, const Act& in, Act& out) {
     ++launches_;
     if (!dry_)
       layernorm(in.p, static_cast<const float*>(l.w->data), static_cast<const float*>(l.b->data), in.rows(), C,
-                1e-5f, cfg_.compute_dtype, out.p, st_);
+                1e-5f, cfg_.compute_dtype, out.p, ln_->st);
   };
   Act hn = new_act(B, H, W, C, false);
   group_norm(m.norm, x, nullptr, 0, 0, hn, nullptr);
@@ -648,7 +652,7 @@ Act UNet::run_st(TransformerM& m, const Act& x) {
   Act q = new_act(B, H, W, C, false);
   gemm(m.q2, hn, nullptr, q, nullptr, 0, nullptr, 0, 1.f);
   {
-    const char* kv = static_cast<const char*>(m.kv);
+    const char* kv = static_cast<const char*>(m.kv) + static_cast<size_t>(ln_->batch_off) * ctx_L_ * 2 * C * es;
     attention(q.p, kv, kv + C * es, ao.p, B, m.heads, T, ctx_L_, d, C, 2 * C, 2 * C, C, scale);
   }
   free_act(q);
@@ -663,7 +667,7 @@ Act UNet::run_st(TransformerM& m, const Act& x) {
   free_act(hn);
   Act gz = new_act(B, H, W, 4 * C, false);
   ++launches_;
-  if (!dry_) geglu(z.p, z.rows(), 4 * C, cfg_.compute_dtype, gz.p, st_);
+  if (!dry_) geglu(z.p, z.rows(), 4 * C, cfg_.compute_dtype, gz.p, ln_->st);
   free_act(z);
   Act t4 = new_act(B, H, W, C, false);
   gemm(m.ff_out, gz, nullptr, t4, nullptr, 0, t3.p, 0, 1.f);
@@ -710,7 +714,7 @@ void UNet::record_tap(const std::string& name, const Act& a, int dtype) {
     taps_[name] = {buf, {a.B, a.C, a.H, a.W}};
     it = taps_.find(name);
   }
-  nhwc_to_nchw_f32(a.p, dtype, a.B, a.H * a.W, a.C, it->second.first, st_);
+  nhwc_to_nchw_f32(a.p, dtype, a.B, a.H * a.W, a.C, it->second.first, ln_->st);
 }
 
 bool UNet::tap(const std::string& name, float* dst, int64_t capacity, int64_t shape[4], cudaStream_t st) {
@@ -750,32 +754,31 @@ void UNet::set_context(const float* ctx, int B, int L, cudaStream_t st) {
 // UNetModel.forward, ncsnpp.py:220-263
 void UNet::forward_impl(const float* x, const long long* labels, float* h_out, int B) {
   const int N = cfg_.max_res_num, C = cfg_.num_channels, nf = cfg_.nf;
-  launches_ = 0;
-  stream_seq_ = 0;
+  ln_->seq = 0;
   {
     static const bool on = [] { const char* e = getenv("T2P_SERPENTINE"); return !e || atoi(e) != 0; }();
     serpentine_ = on;
   }
-  temb_all_ = static_cast<float*>(ws_.alloc(sizeof(float) * static_cast<size_t>(B) * temb_total_));
+  ln_->temb_all = static_cast<float*>(ln_->ws.alloc(sizeof(float) * static_cast<size_t>(B) * temb_total_));
   {
-    float* temb = static_cast<float*>(ws_.alloc(sizeof(float) * static_cast<size_t>(B) * 4 * nf));
+    float* temb = static_cast<float*>(ln_->ws.alloc(sizeof(float) * static_cast<size_t>(B) * 4 * nf));
     launches_ += 2;
     if (!dry_) {
       temb_mlp(labels, B, nf, static_cast<const float*>(pre0_w_->data), static_cast<const float*>(pre0_b_->data),
-               static_cast<const float*>(pre1_w_->data), static_cast<const float*>(pre1_b_->data), temb, st_);
+               static_cast<const float*>(pre1_w_->data), static_cast<const float*>(pre1_b_->data), temb, ln_->st);
       ConvGemmArgs g;
       g.a0 = temb; g.c0 = 4 * nf; g.B = 1; g.H = 1; g.W = B; g.ksize = 1;
-      g.w = dense_all_.wp; g.N = temb_total_; g.bias = dense_all_.bp; g.out = temb_all_; g.out_dtype = kF32;
-      conv_gemm_simt(g, kF32, st_);
+      g.w = dense_all_.wp; g.N = temb_total_; g.bias = dense_all_.bp; g.out = ln_->temb_all; g.out_dtype = kF32;
+      conv_gemm_simt(g, kF32, ln_->st);
     }
-    ws_.free(temb);
+    ln_->ws.free(temb);
   }
   Act h = new_act(B, N, N, nf, true);
   if (cfg_.compute_dtype == kBF16) {
     // pre_conv (Cin = 5 / 8) as a tensor-core GEMM over the im2col of the fp32 state, K padded to 64
     Act xa;
     xa.B = 1; xa.H = 1; xa.W = B * N * N; xa.C = first_kpad_;
-    xa.p = ws_.alloc(static_cast<size_t>(xa.W) * first_kpad_ * 2);
+    xa.p = ln_->ws.alloc(static_cast<size_t>(xa.W) * first_kpad_ * 2);
     launches_ += 2;
     ConvGemmArgs g;
     g.a0 = xa.p; g.c0 = first_kpad_; g.B = 1; g.H = 1; g.W = xa.W; g.ksize = 1;
@@ -785,24 +788,24 @@ void UNet::forward_impl(const float* x, const long long* labels, float* h_out, i
       const int tile = conv_gemm_tc_stat_tile(g);
       if (tile > 0) {
         h.snblk = N * N / tile;
-        h.spart = static_cast<float*>(ws_.alloc(sizeof(float) * 2 * static_cast<size_t>(B) * h.snblk * nf));
+        h.spart = static_cast<float*>(ln_->ws.alloc(sizeof(float) * 2 * static_cast<size_t>(B) * h.snblk * nf));
         g.stat_part = h.spart;
       }
     }
     if (!dry_) {
-      im2col3x3_nchw(x, B, C, N, N, first_kpad_, xa.p, st_);
-      conv_gemm_tc(g, st_);
+      im2col3x3_nchw(x, B, C, N, N, first_kpad_, xa.p, ln_->st);
+      conv_gemm_tc(g, ln_->st);
     }
-    ws_.free(xa.p);
+    ln_->ws.free(xa.p);
   } else {
     // verification path: NCHW -> NHWC fp32, then the CUDA-core GEMM (K = 9*C)
-    float* xn = static_cast<float*>(ws_.alloc(sizeof(float) * static_cast<size_t>(B) * N * N * C));
+    float* xn = static_cast<float*>(ln_->ws.alloc(sizeof(float) * static_cast<size_t>(B) * N * N * C));
     launches_ += 1;
-    if (!dry_) nchw_f32_to_nhwc(x, B, N * N, C, C, kF32, xn, st_);
+    if (!dry_) nchw_f32_to_nhwc(x, B, N * N, C, C, kF32, xn, ln_->st);
     Act xa;
     xa.p = xn; xa.B = B; xa.H = N; xa.W = N; xa.C = C;
     gemm(pre_conv_, xa, nullptr, h, nullptr, 0, nullptr, 0, 1.f);
-    ws_.free(xn);
+    ln_->ws.free(xn);
   }
   record_tap("pre_conv", h);
   std::vector<Act> hs{h};
@@ -829,24 +832,51 @@ void UNet::forward_impl(const float* x, const long long* labels, float* h_out, i
   o.p = h_out; o.B = B; o.H = N; o.W = N; o.C = C;
   gemm(out_conv_, hn, nullptr, o, nullptr, 0, nullptr, 0, 1.f, kF32);
   free_act(hn);
-  ws_.free(temb_all_);
-  temb_all_ = nullptr;
+  ln_->ws.free(ln_->temb_all);
+  ln_->temb_all = nullptr;
 }
 
 void UNet::forward_raw(const float* x, const long long* labels, float* h_out, int B, cudaStream_t st) {
   T2P_CHECK(finalized_, "finalize() before forward()");
-  st_ = st;
-  if (planned_B_ != B) {
-    // dry pass: same code path, no launches; sizes the arena for this batch
+  // Two half-batches on two streams: the tensor-bound GEMMs of one lane overlap the HBM-bound normalisation /
+  // attention kernels of the other (every sample's arithmetic is unchanged, so results are bit-identical).
+  static const bool split_on = [] { const char* e = getenv("T2P_SPLIT"); return !e || atoi(e) != 0; }();
+  const int nl = (split_on && !profile_ && !debug_ && B >= 8 && B % 2 == 0) ? 2 : 1;
+  const int Bl = B / nl;
+  nlanes_ = nl;
+  if (planned_B_ != Bl) {
+    // dry pass: same code path, no launches; sizes the arena for this (per-lane) batch
+    ln_ = &lanes_[0];
     dry_ = true;
-    ws_.begin(true);
-    forward_impl(x, labels, h_out, B);
+    ln_->ws.begin(true);
+    forward_impl(x, labels, h_out, Bl);
     dry_ = false;
-    ws_.reserve(ws_.peak());
-    planned_B_ = B;
+    planned_B_ = Bl;
   }
-  ws_.begin(false);
-  forward_impl(x, labels, h_out, B);
+  for (int l = 0; l < nl; ++l) lanes_[l].ws.reserve(lanes_[0].ws.peak());
+  launches_ = 0;
+  if (nl == 2 && !side_) {
+    T2P_CUDA(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking));
+    T2P_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+    T2P_CUDA(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
+  }
+  if (nl == 2) {
+    T2P_CUDA(cudaEventRecord(ev_fork_, st));
+    T2P_CUDA(cudaStreamWaitEvent(side_, ev_fork_, 0));
+  }
+  const long long per_sample = static_cast<long long>(cfg_.num_channels) * cfg_.max_res_num * cfg_.max_res_num;
+  for (int l = 0; l < nl; ++l) {
+    ln_ = &lanes_[l];
+    ln_->st = (l == 0) ? st : side_;
+    ln_->batch_off = l * Bl;
+    ln_->ws.begin(false);
+    forward_impl(x + l * Bl * per_sample, labels + l * Bl, h_out + l * Bl * per_sample, Bl);
+  }
+  ln_ = &lanes_[0];
+  if (nl == 2) {
+    T2P_CUDA(cudaEventRecord(ev_join_, side_));
+    T2P_CUDA(cudaStreamWaitEvent(st, ev_join_, 0));
+  }
 }
 
 void UNet::forward(const float* x, const long long* labels, void* out, int out_dtype, int B, cudaStream_t st) {

@@ -154,7 +154,7 @@ class UNet {
   void set_profile(bool on);
   int profile_records(GemmRecord* out, int cap);
   long long generation() const { return generation_; }  // bumped by finalize() / set_context()
-  size_t workspace_bytes() const { return ws_.capacity(); }
+  size_t workspace_bytes() const { return lanes_[0].ws.capacity() + lanes_[1].ws.capacity(); }
   long long launches_per_forward() const { return launches_; }
 
  private:
@@ -203,9 +203,20 @@ class UNet {
   bool finalized_ = false;
   std::vector<void*> owned_;  // device allocations freed in the destructor
 
-  // per-forward state
-  Workspace ws_;
-  cudaStream_t st_ = nullptr;
+  // per-forward state.  A lane is one execution context (stream + arena); forward_raw() runs the two halves of
+  // the batch on two lanes so that tensor-bound and HBM-bound kernels of different halves overlap.
+  struct Lane {
+    Workspace ws;
+    cudaStream_t st = nullptr;
+    float* temb_all = nullptr;
+    unsigned seq = 0;     // serpentine direction counter
+    int batch_off = 0;    // first sample of this lane (indexes the hoisted text K|V)
+  };
+  Lane lanes_[2];
+  Lane* ln_ = &lanes_[0];
+  int nlanes_ = 1;
+  cudaStream_t side_ = nullptr;
+  cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;
   bool dry_ = false;
   bool debug_ = false;
   bool profile_ = false;
@@ -216,8 +227,6 @@ class UNet {
   // Serpentine sweep: consecutive streaming kernels (GEMM, GroupNorm apply) walk their tiles in alternating
   // direction, so each begins on the data its predecessor wrote last -- still resident in the 126 MB L2.
   bool serpentine_ = true;
-  unsigned stream_seq_ = 0;
-  float* temb_all_ = nullptr;
   int ctx_B_ = 0, ctx_L_ = 0;
   std::map<std::string, std::pair<float*, std::vector<int64_t>>> taps_;
   float* h_scratch_ = nullptr;
