@@ -60,7 +60,8 @@ def _conv(a0, w, ksize, bias=None, a1=None, rowbias=None, residual=None, res_up=
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 1.5e-2)])
 @pytest.mark.parametrize("H,cin,cin1,cout,k", [(32, 64, 0, 128, 3), (16, 128, 64, 64, 3), (8, 128, 0, 128, 3),
-                                               (4, 64, 0, 192, 3), (16, 64, 128, 64, 1), (64, 64, 0, 5, 3)])
+                                               (4, 64, 0, 192, 3), (16, 64, 128, 64, 1), (64, 64, 0, 5, 3),
+                                               (128, 64, 64, 128, 3), (128, 128, 0, 256, 3)])
 def test_conv2d_matches_torch(dtype, tol, H, cin, cin1, cout, k):
     g = torch.Generator(device="cuda").manual_seed(1)
     B = 3
@@ -95,7 +96,8 @@ def test_conv2d_upsampled_residual_and_fused_stats(H, cin, cout):
     assert torch.allclose(tot[..., 1], (out * out).sum(dim=(2, 3)), rtol=1e-4, atol=1e-2)
 
 
-@pytest.mark.parametrize("H,cin,xc0,xc1,cout", [(16, 64, 128, 64, 128), (32, 128, 128, 0, 128), (8, 64, 64, 0, 256)])
+@pytest.mark.parametrize("H,cin,xc0,xc1,cout", [(16, 64, 128, 64, 128), (32, 128, 128, 0, 128), (8, 64, 64, 0, 256),
+                                                (128, 64, 64, 64, 128)])
 def test_conv2d_folded_skip_path(H, cin, xc0, xc1, cout):
     """Conv_1(h) + Conv_2(cat(x0, x1)) [+ residual] as one launch (skip path as centre-tap K columns)."""
     g = torch.Generator(device="cuda").manual_seed(5)

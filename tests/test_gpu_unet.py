@@ -98,8 +98,10 @@ def test_state_dict_roundtrip_through_dataparallel_checkpoint(tmp_path):
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
-def test_two_lane_half_batches_are_bit_identical_to_separate_runs(dtype):
-    """B >= 8 runs as two half-batches on two streams; every sample's arithmetic is unchanged."""
+def test_two_lane_half_batches_are_bit_identical_to_separate_runs(dtype, monkeypatch):
+    """With T2P_SPLIT=1, B >= 8 runs as two half-batches on two streams; every sample's arithmetic is unchanged.
+    (The switch is read once per process: run this test alone with T2P_SPLIT=1 to exercise the two-lane path;
+    without it the test checks batch-composition independence of the single-lane path.)"""
     cfg, model, sd = make_native(tiny_cfg(5), dtype)
     x, labels, ctx = synthetic_inputs(cfg, 8, 9, seed=11)
     x, labels, ctx = x.cuda(), labels.cuda(), ctx.cuda()

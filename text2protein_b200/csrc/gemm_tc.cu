@@ -722,6 +722,250 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_tcT_kernel(const __g
   if (warp == 1) ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
+// =====================================================================================================
+// Halo variant of the channel-major kernel for 3x3 convolutions on 128-pixel-wide images (the layers that hold
+// most of the FLOPs).  A pixel tile is two whole image rows; for each (kh, channel chunk) ONE box of
+// 2 rows x 130 pixels (one-pixel halo left and right, zero-filled by TMA at the image border) is staged and the
+// three horizontal taps read it through descriptors shifted by kw rows of 128 bytes -- the 128-byte swizzle is a
+// function of the absolute shared-memory address, so a row-shifted window of a swizzled tile is itself a valid
+// operand (probe: csrc/probe_shift.cu).  The L2 -> SMEM stream per (kh, chunk) drops from 3 x (16 + 32) KB to
+// 3 x 16 + 32.5 KB.  Pixels and weights run through separate TMA rings.
+struct CfgH {
+  static constexpr int W_BYTES = 128 * BK * 2;           // 16 KB weight tile (128 channels x 64 k)
+  static constexpr int P_ROWPITCH = 130;                 // pixels per staged image row (128 + halo)
+  static constexpr int P_LOAD_BYTES = 2 * P_ROWPITCH * BK * 2;  // 33 280
+  static constexpr int P_BYTES = 33 * 1024;              // buffer pitch (1 KB multiple)
+  static constexpr int NP = 3;                           // pixel buffers
+  static constexpr int NW = 6;                           // weight buffers
+  static constexpr int OUT_BYTES = 4 * 2 * 32 * 32 * 2;
+  static constexpr int SMEM_BYTES = NP * P_BYTES + NW * W_BYTES + OUT_BYTES + 1024;
+  static constexpr int PX = 256;
+  static constexpr int TMEM_COLS = 2 * PX;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_tcH_kernel(const __grid_constant__ TcParams p) {
+  using C = CfgH;
+  constexpr int PX = C::PX;
+  pdl_trigger();
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t pfull_bar[C::NP], pempty_bar[C::NP];
+  __shared__ __align__(8) uint64_t wfull_bar[C::NW], wempty_bar[C::NW];
+  __shared__ __align__(8) uint64_t tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t pbase = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t wbase = pbase + C::NP * C::P_BYTES;
+  const uint32_t out_stage = wbase + C::NW * C::W_BYTES;
+
+  const int chunks = (p.c0 + p.c1) / BK;      // channel chunks of the 3x3 sources
+  const int x_chunks = (p.xc0 + p.xc1) / BK;  // centre-tap-only sources
+  const int r_chunks = p.residual ? 2 : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::NP; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&pfull_bar[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&pempty_bar[s]), 1);
+    }
+    for (int s = 0; s < C::NW; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&wfull_bar[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&wempty_bar[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&tfull_bar[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&tempty_bar[s]), 4);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(ptx::smem_u32(&tmem_base_slot), C::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      ptx::prefetch_tmap(&p.tm_a0);
+      ptx::prefetch_tmap(&p.tm_w);
+      if (p.c1 > 0) ptx::prefetch_tmap(&p.tm_a1);
+      if (p.xc0 > 0) ptx::prefetch_tmap(&p.tm_x0);
+      if (p.xc1 > 0) ptx::prefetch_tmap(&p.tm_x1);
+      if (p.residual) {
+        ptx::prefetch_tmap(&p.tm_res);
+        ptx::prefetch_tmap(&p.tm_ident);
+      }
+      const int hw = p.H * p.W;
+      int ps = 0, ws = 0;
+      uint32_t pph = 0, wph = 0;
+      auto load_w = [&](const CUtensorMap* tm, int c0, int c1) {
+        ptx::mbar_wait(ptx::smem_u32(&wempty_bar[ws]), wph ^ 1);
+        const uint32_t fb = ptx::smem_u32(&wfull_bar[ws]);
+        ptx::mbar_arrive_expect_tx(fb, C::W_BYTES);
+        ptx::tma_load_4d(wbase + ws * C::W_BYTES, tm, fb, c0, c1, 0, 0);
+        if (++ws == C::NW) { ws = 0; wph ^= 1; }
+      };
+      auto load_p = [&](const CUtensorMap* tm, int bytes, int ch, int w, int h, int b) {
+        ptx::mbar_wait(ptx::smem_u32(&pempty_bar[ps]), pph ^ 1);
+        const uint32_t fb = ptx::smem_u32(&pfull_bar[ps]);
+        ptx::mbar_arrive_expect_tx(fb, bytes);
+        ptx::tma_load_4d(pbase + ps * C::P_BYTES, tm, fb, ch, w, h, b);
+        if (++ps == C::NP) { ps = 0; pph ^= 1; }
+      };
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int tt = p.reverse ? p.num_tiles - 1 - t : t;
+        const int pt = tt / p.n_tiles;
+        const int m0 = pt * PX;
+        const int n0 = (tt - pt * p.n_tiles) * 128;
+        const int b0 = m0 / hw;
+        const int h0 = (m0 - b0 * hw) / p.W;  // even; the tile is image rows h0, h0 + 1
+        for (int kh = 0; kh < 3; ++kh) {
+          for (int cc = 0; cc < chunks; ++cc) {
+            const int ch = cc * BK;
+            if (ch < p.c0) load_p(&p.tm_a0, C::P_LOAD_BYTES, ch, -1, h0 + kh - 1, b0);
+            else load_p(&p.tm_a1, C::P_LOAD_BYTES, ch - p.c0, -1, h0 + kh - 1, b0);
+            for (int kw = 0; kw < 3; ++kw) load_w(&p.tm_w, ((kh * 3 + kw) * chunks + cc) * BK, n0);
+          }
+        }
+        int kb = 9 * chunks;
+        for (int cc = 0; cc < x_chunks; ++cc, ++kb) {  // folded skip path: centre tap, plain 2 x 128 pixel box
+          const int ch = cc * BK;
+          if (ch < p.xc0) load_p(&p.tm_x0, PX * BK * 2, ch, 0, h0, b0);
+          else load_p(&p.tm_x1, PX * BK * 2, ch - p.xc0, 0, h0, b0);
+          load_w(&p.tm_w, kb * BK, n0);
+        }
+        for (int j = 0; j < r_chunks; ++j) {  // residual through identity k-blocks
+          load_p(&p.tm_res, PX * BK * 2, n0 + j * BK, 0, h0, b0);
+          load_w(&p.tm_ident, j * BK, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(128);  // M = 128 channels, N = 128 pixels (one image row)
+      int ps = 0, ws = 0;
+      uint32_t pph = 0, wph = 0;
+      uint32_t tl = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tl) {
+        const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
+        ptx::mbar_wait(ptx::smem_u32(&tempty_bar[as]), aph ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + as * PX;
+        bool first = true;
+        // one weight tile against the two image rows of a staged pixel buffer (row pitch / tap shift in pixels)
+        auto mma_block = [&](uint32_t pbuf, int rowpitch, int shift) {
+          ptx::mbar_wait(ptx::smem_u32(&wfull_bar[ws]), wph);
+          ptx::tc_fence_after();
+          const uint64_t dw = ptx::umma_desc_k_sw128(wbase + ws * C::W_BYTES);
+          const uint64_t d0 = ptx::umma_desc_k_sw128(pbuf + shift * 128);
+          const uint64_t d1 = ptx::umma_desc_k_sw128(pbuf + (rowpitch + shift) * 128);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint32_t acc = (first && k == 0) ? 0u : 1u;
+            ptx::umma_bf16(tmem_acc, dw + 2 * k, d0 + 2 * k, idesc, acc);
+            ptx::umma_bf16(tmem_acc + 128, dw + 2 * k, d1 + 2 * k, idesc, acc);
+          }
+          first = false;
+          ptx::umma_commit(ptx::smem_u32(&wempty_bar[ws]));
+          if (++ws == C::NW) { ws = 0; wph ^= 1; }
+        };
+        for (int kc = 0; kc < 3 * chunks; ++kc) {
+          ptx::mbar_wait(ptx::smem_u32(&pfull_bar[ps]), pph);
+          ptx::tc_fence_after();
+          const uint32_t pbuf = pbase + ps * C::P_BYTES;
+          for (int kw = 0; kw < 3; ++kw) mma_block(pbuf, C::P_ROWPITCH, kw);
+          ptx::umma_commit(ptx::smem_u32(&pempty_bar[ps]));
+          if (++ps == C::NP) { ps = 0; pph ^= 1; }
+        }
+        for (int kc = 0; kc < x_chunks + r_chunks; ++kc) {
+          ptx::mbar_wait(ptx::smem_u32(&pfull_bar[ps]), pph);
+          ptx::tc_fence_after();
+          mma_block(pbase + ps * C::P_BYTES, 128, 0);
+          ptx::umma_commit(ptx::smem_u32(&pempty_bar[ps]));
+          if (++ps == C::NP) { ps = 0; pph ^= 1; }
+        }
+        ptx::umma_commit(ptx::smem_u32(&tfull_bar[as]));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5): thread = channel
+    const int q = warp & 3;
+    EpiT et;
+    et.rb_uniform = p.rowbias != nullptr && (p.rows_per_sample % PX) == 0;
+    const uint32_t obuf = out_stage + q * (2 * 32 * 32 * 2);
+    uint32_t tl = 0;
+    uint32_t nstore = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tl) {
+      const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
+      const int tt = p.reverse ? p.num_tiles - 1 - t : t;
+      const int pt = tt / p.n_tiles;
+      const int nw0 = (tt - pt * p.n_tiles) * 128 + q * 32;
+      et.m0 = pt * PX;
+      et.n = nw0 + lane;
+      et.ch_ok = et.n < p.N;
+      et.bch = 0.f;
+      if (et.ch_ok) {
+        if (p.bias) et.bch = __ldg(p.bias + et.n);
+        if (et.rb_uniform)
+          et.bch += __ldg(p.rowbias + static_cast<long long>(et.m0 / p.rows_per_sample) * p.rowbias_ld + et.n);
+      }
+      ptx::mbar_wait(ptx::smem_u32(&tfull_bar[as]), aph);
+      ptx::tc_fence_after();
+      const uint32_t tbase = tmem_base + as * PX + (static_cast<uint32_t>(q * 32) << 16);
+      auto release_acc = [&]() {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[as]));
+      };
+      auto store_chunk = [&](const unsigned short (&h)[32], int c) {
+        const uint32_t buf = obuf + (nstore & 1) * (32 * 32 * 2);
+        if (lane == 0) ptx::tma_store_wait_read<1>();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(buf + j * 64 + lane * 2), "h"(h[j]) : "memory");
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && nw0 < p.N && et.m0 + c * 32 < p.M) {
+          ptx::tma_store_4d(&p.tm_out, buf, nw0, et.m0 + c * 32, 0, 0);
+          ptx::tma_store_commit();
+        }
+        ++nstore;
+      };
+      constexpr int NCH = PX / 32;
+      float ssum = 0.f, ssq = 0.f;
+      uint32_t r0[32], r1[32];
+      unsigned short h[32];
+      ptx::tmem_ld_32x32(tbase, r0);
+#pragma unroll 1
+      for (int c = 0; c < NCH; c += 2) {
+        ptx::tmem_ld_wait();
+        ptx::tmem_ld_32x32(tbase + (c + 1) * 32, r1);
+        epilogue_chunk_t(p, et, r0, c, ssum, ssq, h);
+        store_chunk(h, c);
+        ptx::tmem_ld_wait();
+        if (c + 2 < NCH) ptx::tmem_ld_32x32(tbase + (c + 2) * 32, r0);
+        else release_acc();
+        epilogue_chunk_t(p, et, r1, c + 1, ssum, ssq, h);
+        store_chunk(h, c + 1);
+      }
+      if (p.stat_part && et.ch_ok)
+        *reinterpret_cast<float2*>(p.stat_part + (static_cast<long long>(pt) * p.N + et.n) * 2) = make_float2(ssum, ssq);
+    }
+    if (lane == 0) ptx::tma_store_wait_read<0>();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
 // ------------------------------------------------------------------------------------ host side
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -841,6 +1085,19 @@ void launch_t(TcParams& p, cudaStream_t st) {
   launch_pdl(conv_gemm_tcT_kernel<PX>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, st, p);
 }
 
+void launch_h(TcParams& p, cudaStream_t st) {
+  using C = CfgH;
+  static bool configured = false;
+  if (!configured) {
+    T2P_CUDA(cudaFuncSetAttribute(conv_gemm_tcH_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    configured = true;
+  }
+  p.n_tiles = cdiv(p.N, 128);
+  p.num_tiles = cdiv(p.M, C::PX) * p.n_tiles;
+  const int grid = std::min(p.num_tiles, sm_count());
+  launch_pdl(conv_gemm_tcH_kernel, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, st, p);
+}
+
 // `rows` consecutive pixels (b, h, w raster order) as one TMA box (tw, th, tb) of the NHWC tensor
 bool pixel_box(const ConvGemmArgs& a, int rows, uint32_t& tw, uint32_t& th, uint32_t& tb) {
   if (a.ksize == 1) { tw = rows; th = 1; tb = 1; return true; }
@@ -858,6 +1115,7 @@ bool pixel_box(const ConvGemmArgs& a, int rows, uint32_t& tw, uint32_t& th, uint
 }
 
 struct Plan {
+  bool halo = false;  // channel-major halo kernel (3x3, W == 128, two image rows per tile)
   bool channel_major = false;
   int rows = BM;  // pixels per tile
   int bn = 128;   // pixel-major kernel: channels per tile
@@ -883,6 +1141,8 @@ Plan make_plan(const ConvGemmArgs& a) {
       pl.channel_major = true;
       pl.rows = pick;
       pixel_box(a, pick, pl.tw, pl.th, pl.tb);
+      static const bool halo_on = [] { const char* e = getenv("T2P_HALO"); return !e || atoi(e) != 0; }();
+      pl.halo = halo_on && pick == 256 && a.ksize == 3 && a.W == 128 && a.H % 2 == 0;
       pl.stats_ok = want_stats && a.out_dtype == kBF16;
       return pl;
     }
@@ -967,8 +1227,14 @@ void conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
     uint32_t b[4] = {BK, pl.tw, pl.th, pl.tb};
     return make_tmap_bf16(ptr, d, b);
   };
-  p.tm_a0 = amap(a.a0, a.c0);
-  p.tm_a1 = (a.c1 > 0) ? amap(a.a1, a.c1) : p.tm_a0;
+  auto amap_halo = [&](const void* ptr, int c) {  // 2 image rows x (W + 2) pixels
+    uint64_t d[4] = {static_cast<uint64_t>(c), static_cast<uint64_t>(a.W), static_cast<uint64_t>(a.H),
+                     static_cast<uint64_t>(a.B)};
+    uint32_t b[4] = {BK, static_cast<uint32_t>(CfgH::P_ROWPITCH), 2, 1};
+    return make_tmap_bf16(ptr, d, b);
+  };
+  p.tm_a0 = pl.halo ? amap_halo(a.a0, a.c0) : amap(a.a0, a.c0);
+  p.tm_a1 = (a.c1 > 0) ? (pl.halo ? amap_halo(a.a1, a.c1) : amap(a.a1, a.c1)) : p.tm_a0;
   {
     uint64_t d[4] = {static_cast<uint64_t>(taps) * ctot + a.xc0 + a.xc1, static_cast<uint64_t>(a.N), 1, 1};
     uint32_t b[4] = {BK, static_cast<uint32_t>(pl.channel_major ? 128 : pl.bn), 1, 1};
@@ -987,6 +1253,10 @@ void conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
       uint64_t d[4] = {128, 128, 1, 1};
       uint32_t b[4] = {BK, 128, 1, 1};
       p.tm_ident = make_tmap_bf16(identity128(), d, b);
+    }
+    if (pl.halo) {
+      launch_h(p, st);
+      return;
     }
     switch (pl.rows) {
       case 256: launch_t<256>(p, st); break;

@@ -17,6 +17,19 @@ struct Vec8;
 template <>
 struct Vec8<float> {
   float v[8];
+  struct Raw { float4 a, b; };
+  __device__ static Raw load_raw(const float* p) {
+    Raw r;
+    r.a = reinterpret_cast<const float4*>(p)[0];
+    r.b = reinterpret_cast<const float4*>(p)[1];
+    return r;
+  }
+  __device__ static Vec8 unpack(const Raw& t) {
+    Vec8 r;
+    r.v[0] = t.a.x; r.v[1] = t.a.y; r.v[2] = t.a.z; r.v[3] = t.a.w;
+    r.v[4] = t.b.x; r.v[5] = t.b.y; r.v[6] = t.b.z; r.v[7] = t.b.w;
+    return r;
+  }
   __device__ static Vec8 load(const float* p) {
     Vec8 r;
     const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
@@ -32,6 +45,18 @@ struct Vec8<float> {
 template <>
 struct Vec8<__nv_bfloat16> {
   float v[8];
+  using Raw = uint4;
+  __device__ static Raw load_raw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+  __device__ static Vec8 unpack(const Raw& t) {
+    Vec8 r;
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      r.v[2 * i] = __uint_as_float(w[i] << 16);
+      r.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+    return r;
+  }
   __device__ static Vec8 load(const __nv_bfloat16* p) {
     Vec8 r;
     const uint4 t = *reinterpret_cast<const uint4*>(p);
@@ -249,7 +274,7 @@ __global__ void gn_apply_kernel(const T* __restrict__ a0, int c0, const T* __res
 // slot), so its 16 scale/shift values live in registers for the whole run and the block's accesses are one
 // contiguous stream per source.  UNROLL independent 16-byte loads are in flight per thread.
 template <typename T, int UNROLL>
-__global__ void __launch_bounds__(256) gn_apply_rows_kernel(const T* __restrict__ a0, int c0, const T* __restrict__ a1,
+__global__ void __launch_bounds__(256, sizeof(T) == 2 ? 4 : 2) gn_apply_rows_kernel(const T* __restrict__ a0, int c0, const T* __restrict__ a1,
                                                             int c1, int HW, int ppb, const float* __restrict__ scale,
                                                             const float* __restrict__ shift, int act,
                                                             T* __restrict__ out, int reverse) {
@@ -278,25 +303,27 @@ __global__ void __launch_bounds__(256) gn_apply_rows_kernel(const T* __restrict_
   }
   const int p0 = bx * ppb;
   const int p1 = min(HW, p0 + ppb);
-  const T* s = src + static_cast<long long>(b) * HW * cs + co;
-  T* o = out + static_cast<long long>(b) * HW * ctot + ch;
-  for (int p = p0 + row; p < p1; p += rows * UNROLL) {
-    Vec8<T> v[UNROLL];
+  // pointer-bumped streams: sp / op advance by one round (rows * UNROLL pixels) per iteration
+  const T* sp = src + (static_cast<long long>(b) * HW + p0 + row) * cs + co;
+  T* op = out + (static_cast<long long>(b) * HW + p0 + row) * ctot + ch;
+  const long long sstep = static_cast<long long>(rows) * cs, ostep = static_cast<long long>(rows) * ctot;
+  for (int p = p0 + row; p < p1; p += rows * UNROLL, sp += UNROLL * sstep, op += UNROLL * ostep) {
+    // raw (still packed) vectors first: UNROLL independent loads in flight at 4 registers each for bf16
+    typename Vec8<T>::Raw raw[UNROLL];
+    const bool full = p + (UNROLL - 1) * rows < p1;
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+      if (full || p + u * rows < p1) raw[u] = Vec8<T>::load_raw(sp + u * sstep);
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-      const int pp = p + u * rows;
-      if (pp < p1) v[u] = Vec8<T>::load(s + static_cast<long long>(pp) * cs);
-    }
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const int pp = p + u * rows;
-      if (pp < p1) {
+      if (full || p + u * rows < p1) {
+        Vec8<T> v = Vec8<T>::unpack(raw[u]);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float y = fmaf(v[u].v[i], sc[i], sh[i]);
-          v[u].v[i] = act ? silu_t<T>(y) : y;
+          const float y = fmaf(v.v[i], sc[i], sh[i]);
+          v.v[i] = act ? silu_t<T>(y) : y;
         }
-        v[u].store(o + static_cast<long long>(pp) * ctot);
+        v.store(op + u * ostep);
       }
     }
   }

@@ -211,7 +211,7 @@ static void bench_case(int B, int H, int W, int cin, int N, int ks, int epi) {
   fail_if(cudaMalloc(&res, M * N * 2), "malloc");
   fail_if(cudaMalloc(&bias, N * 4), "malloc");
   fail_if(cudaMalloc(&rb, 1ll * B * N * 4), "malloc");
-  fail_if(cudaMalloc(&st, (M / 128 + 1) * N * 8), "malloc");
+  fail_if(cudaMalloc(&st, (M / 64 + 1) * N * 8), "malloc");  // statistics tiles are >= 64 pixels
   fill_bf16<<<(unsigned)((M * cin + 255) / 256), 256>>>(a, M * cin, 1.f, 1u);
   fill_bf16<<<(unsigned)((1ll * N * K + 255) / 256), 256>>>(w, 1ll * N * K, 0.05f, 2u);
   fill_bf16<<<(unsigned)((M * N + 255) / 256), 256>>>(res, M * N, 1.f, 3u);
@@ -258,6 +258,7 @@ int main(int argc, char** argv) {
       {"conv3 32x32 res_up", 2, 32, 32, 256, 0, 3, 256, true, false, true, true, false, false},
       {"conv1 64x64 c384->128", 2, 64, 64, 256, 128, 1, 128, true, false, false, false, false, false},
       {"conv3 256x256 c256->256", 1, 256, 256, 256, 0, 3, 256, true, true, true, false, false, true},
+      {"conv3 128x128 c64+64->128 res", 3, 128, 128, 64, 64, 3, 128, true, true, true, false, false, true},
       {"conv3 4x4 c128->128 B=5 ragged", 5, 4, 4, 128, 0, 3, 128, true, true, true, false, false, false},
       {"conv3 64x64 c64->192", 2, 64, 64, 64, 0, 3, 192, true, true, true, false, false, true},
       {"conv3 16x16 res_up c128->128", 3, 16, 16, 128, 0, 3, 128, true, true, true, true, false, true},

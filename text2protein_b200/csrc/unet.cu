@@ -838,9 +838,11 @@ void UNet::forward_impl(const float* x, const long long* labels, float* h_out, i
 
 void UNet::forward_raw(const float* x, const long long* labels, float* h_out, int B, cudaStream_t st) {
   T2P_CHECK(finalized_, "finalize() before forward()");
-  // Two half-batches on two streams: the tensor-bound GEMMs of one lane overlap the HBM-bound normalisation /
-  // attention kernels of the other (every sample's arithmetic is unchanged, so results are bit-identical).
-  static const bool split_on = [] { const char* e = getenv("T2P_SPLIT"); return !e || atoi(e) != 0; }();
+  // Optional (T2P_SPLIT=1): two half-batches on two streams, so that the GEMMs of one lane overlap the HBM-bound
+  // normalisation / attention kernels of the other (every sample's arithmetic is unchanged: bit-identical results).
+  // Measured on B200 at cfg2: 26.99 vs 26.91 ms per PC iteration -- no gain, both kernel kinds are bound by the same
+  // L2 / HBM path -- so it is off by default (it also doubles the activation arena).
+  static const bool split_on = [] { const char* e = getenv("T2P_SPLIT"); return e && atoi(e) != 0; }();
   const int nl = (split_on && !profile_ && !debug_ && B >= 8 && B % 2 == 0) ? 2 : 1;
   const int Bl = B / nl;
   nlanes_ = nl;
