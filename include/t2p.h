@@ -181,6 +181,31 @@ int t2p_attention(const void* q, const void* k, const void* v, void* out, int B,
                   int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, float scale, int dtype, int use_tensor_cores,
                   void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Callers either side of the sampling loop, generated on the device from small integer inputs. */
+
+/* Text context from token ids: rows of llm.model.embed_tokens (sampling_6d.py:134-137) gathered straight into the
+ * engine's context buffer, then the hoisted K|V projections (attention.py:174-175).  table: [vocab][context_dim],
+ * T2P_F32 or T2P_BF16; tokens: int64 [B][L]. */
+int t2p_unet_set_context_tokens(t2p_unet* u, const void* table, int table_dtype, int64_t vocab, const int64_t* tokens,
+                                int B, int L, void* stream);
+/* Stand-alone gather: out fp32 [n][D] = table[tokens[i]] (what `llm.model.embed_tokens(tokens)` returns). */
+int t2p_embed_tokens(const void* table, int table_dtype, int64_t vocab, int D, const int64_t* tokens, int64_t n,
+                     float* out, void* stream);
+/* out[b][i][j] = (i < lengths[b] && j < lengths[b]) as bytes: the "length" condition, utils.py:89-93,139-148. */
+int t2p_length_mask(const int32_t* lengths, int B, int N, uint8_t* out, void* stream);
+/* out[b][i][j] = sel(i) | sel(j), sel = union of the inclusive residue ranges [R][2] (shared) or [B][R][2]
+ * (per_sample): selected_mask_batch / the outer-OR of random_mask_batch, utils.py:56-58,62-81. */
+int t2p_inpaint_mask(const int32_t* ranges, int R, int per_sample, int B, int N, uint8_t* out, void* stream);
+/* The sampler's conditional mask [B][C][N][N] (1 = free to evolve), sampling.py:258-281, for the condition keys
+ * length (lengths != NULL), ss (has_ss) and inpainting (ranges != NULL). */
+int t2p_condition_mask(const int32_t* lengths, const int32_t* ranges, int R, int per_sample, int has_ss, int B, int C,
+                       int N, uint8_t* out, void* stream);
+/* sampling_rosetta.py:69-96: mask = round(sample[:, -1]) == 1; L_out[b] = sqrt(count) (or -1 when not an integer);
+ * out fp32 [B][8][N*N]: per channel the masked entries in raster order (first L*L values, rest 0) of
+ * dist, omega, theta, phi clipped to [-1, 1], then dist_abs, omega_abs, theta_abs, phi_abs. */
+int t2p_postprocess_6d(const float* sample, int B, int C, int N, float* out, int32_t* L_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

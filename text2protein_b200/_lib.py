@@ -77,6 +77,15 @@ SIGNATURES = {
                                     C.c_void_p]),
     "t2p_philox_bits": (C.c_int, [C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "t2p_pc_run": (C.c_int, [C.c_void_p, C.POINTER(RunArgs), C.c_void_p]),
+    "t2p_unet_set_context_tokens": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int,
+                                              C.c_void_p]),
+    "t2p_embed_tokens": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
+                                   C.c_void_p]),
+    "t2p_length_mask": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "t2p_inpaint_mask": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "t2p_condition_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_void_p]),
+    "t2p_postprocess_6d": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "t2p_conv2d": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "t2p_conv2d_stat_tile": (C.c_int, [C.POINTER(ConvArgs)]),
     "t2p_groupnorm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

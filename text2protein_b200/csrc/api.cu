@@ -138,6 +138,51 @@ int t2p_unet_set_context(t2p_unet* u, const float* ctx, int B, int L, void* stre
   T2P_API_END
 }
 
+int t2p_unet_set_context_tokens(t2p_unet* u, const void* table, int table_dtype, int64_t vocab, const int64_t* tokens,
+                                int B, int L, void* stream) {
+  T2P_API_BEGIN
+  T2P_CHECK(u && table && tokens && B > 0 && L > 0 && vocab > 0, "bad token context");
+  u->net->set_context_tokens(table, table_dtype, vocab, reinterpret_cast<const long long*>(tokens), B, L, S(stream));
+  T2P_API_END
+}
+
+int t2p_embed_tokens(const void* table, int table_dtype, int64_t vocab, int D, const int64_t* tokens, int64_t n,
+                     float* out, void* stream) {
+  T2P_API_BEGIN
+  T2P_CHECK(table && tokens && out && n > 0, "null argument");
+  embed_gather(table, table_dtype, vocab, D, reinterpret_cast<const long long*>(tokens), n, out, nullptr, S(stream));
+  T2P_API_END
+}
+
+int t2p_length_mask(const int32_t* lengths, int B, int N, uint8_t* out, void* stream) {
+  T2P_API_BEGIN
+  T2P_CHECK(lengths && out && B > 0 && N > 0, "null argument");
+  length_mask(lengths, B, N, out, S(stream));
+  T2P_API_END
+}
+
+int t2p_inpaint_mask(const int32_t* ranges, int R, int per_sample, int B, int N, uint8_t* out, void* stream) {
+  T2P_API_BEGIN
+  T2P_CHECK(out && B > 0 && N > 0 && R >= 0 && (R == 0 || ranges), "null argument");
+  inpaint_mask(ranges, R, per_sample, B, N, out, S(stream));
+  T2P_API_END
+}
+
+int t2p_condition_mask(const int32_t* lengths, const int32_t* ranges, int R, int per_sample, int has_ss, int B, int C,
+                       int N, uint8_t* out, void* stream) {
+  T2P_API_BEGIN
+  T2P_CHECK(out && B > 0 && C > 0 && N > 0, "null argument");
+  condition_mask(lengths, ranges, R, per_sample, has_ss, B, C, N, out, S(stream));
+  T2P_API_END
+}
+
+int t2p_postprocess_6d(const float* sample, int B, int C, int N, float* out, int32_t* L_out, void* stream) {
+  T2P_API_BEGIN
+  T2P_CHECK(sample && out && L_out && B > 0 && N > 0, "null argument");
+  postprocess_6d(sample, B, C, N, out, L_out, S(stream));
+  T2P_API_END
+}
+
 int t2p_unet_forward(t2p_unet* u, const float* x, const int64_t* labels, void* out, int out_dtype, int B,
                      void* stream) {
   T2P_API_BEGIN

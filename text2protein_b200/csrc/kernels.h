@@ -142,4 +142,13 @@ void run_prep(long long* state, const long long* label_table, const float* g_tab
               cudaStream_t st);
 void apply_mask(float* x, const unsigned char* mask, const float* fixed, long long n, cudaStream_t st);
 
+// ----------------------------------------------------------------------------- callers of the loop (conditions.cu)
+void length_mask(const int* lengths, int B, int N, unsigned char* out, cudaStream_t st);
+void inpaint_mask(const int* ranges, int R, int per_sample, int B, int N, unsigned char* out, cudaStream_t st);
+void condition_mask(const int* lengths, const int* ranges, int R, int per_sample, int has_ss, int B, int C, int N,
+                    unsigned char* out, cudaStream_t st);
+void embed_gather(const void* table, int table_dtype, long long V, int D, const long long* tokens, long long n,
+                  float* out_f32, void* out_bf16, cudaStream_t st);
+void postprocess_6d(const float* x, int B, int C, int N, float* out, int* L_out, cudaStream_t st);
+
 }  // namespace t2p

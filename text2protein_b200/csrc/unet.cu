@@ -728,13 +728,28 @@ bool UNet::tap(const std::string& name, float* dst, int64_t capacity, int64_t sh
 }
 
 void UNet::set_context(const float* ctx, int B, int L, cudaStream_t st) {
+  set_context_impl(ctx, nullptr, 0, 0, nullptr, B, L, st);
+}
+
+// Text context straight from token ids: gathers rows of the text encoder's embedding table
+// (llm.model.embed_tokens, reference sampling_6d.py:134-137) into the compute-dtype context buffer on the
+// device -- the [B, L, context_dim] fp32 tensor never exists on the host or in HBM -- then projects K|V.
+void UNet::set_context_tokens(const void* table, int table_dtype, long long V, const long long* tokens, int B, int L,
+                              cudaStream_t st) {
+  set_context_impl(nullptr, table, table_dtype, V, tokens, B, L, st);
+}
+
+void UNet::set_context_impl(const float* ctx, const void* table, int table_dtype, long long V, const long long* tokens,
+                            int B, int L, cudaStream_t st) {
   T2P_CHECK(finalized_, "finalize() before set_context()");
   const int D = cfg_.context_dim;
   const size_t es = dtype_size(cfg_.compute_dtype);
   const long long rows = static_cast<long long>(B) * L;
   void* cbuf = nullptr;
   T2P_CUDA(cudaMalloc(&cbuf, std::max<size_t>(256, rows * D * es)));
-  convert_f32(ctx, rows * D, cfg_.compute_dtype, cbuf, st);
+  if (ctx) convert_f32(ctx, rows * D, cfg_.compute_dtype, cbuf, st);
+  else if (cfg_.compute_dtype == kBF16) embed_gather(table, table_dtype, V, D, tokens, rows, nullptr, cbuf, st);
+  else embed_gather(table, table_dtype, V, D, tokens, rows, static_cast<float*>(cbuf), nullptr, st);
   for (TransformerM* t : all_st_) {
     if (t->kv) { T2P_CUDA(cudaFree(t->kv)); t->kv = nullptr; }
     T2P_CUDA(cudaMalloc(&t->kv, std::max<size_t>(256, rows * 2 * t->C * es)));

@@ -141,6 +141,9 @@ class UNet {
   // ctx: fp32 [B][L][context_dim] on the device.  Projects K|V of every cross-attention once (the
   // reference recomputes them in all 2*num_scales forwards, attention.py:174-175).
   void set_context(const float* ctx, int B, int L, cudaStream_t st);
+  // same, from token ids [B][L] and the embedding table [V][context_dim] (fp32 or bf16) -- SURVEY 8f rank 3
+  void set_context_tokens(const void* table, int table_dtype, long long V, const long long* tokens, int B, int L,
+                          cudaStream_t st);
   // x: fp32 NCHW [B][C][N][N]; labels: int64 [B]; h_out: fp32 NHWC [B][N][N][C] un-scaled final conv
   // (what the fused PC-step kernels consume).  Returns through `h_out` only.
   void forward_raw(const float* x, const long long* labels, float* h_out, int B, cudaStream_t st);
@@ -167,6 +170,8 @@ class UNet {
   ModuleM make_attn(const std::string& key, int C);
   ModuleM make_st(const std::string& key, int C);
   void pack(Linear& l, cudaStream_t st);
+  void set_context_impl(const float* ctx, const void* table, int table_dtype, long long V, const long long* tokens, int B,
+                        int L, cudaStream_t st);
 
   // forward helpers (all honour dry_)
   Act new_act(int B, int H, int W, int C, bool with_stats);

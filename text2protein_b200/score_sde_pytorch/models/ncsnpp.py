@@ -62,6 +62,24 @@ def _fan_avg_uniform_(t, scale, in_axis, out_axis):
         t.uniform_(-bound, bound)
 
 
+class TokenContext:
+    """Text context given as token ids [B, L] (int64) plus the text encoder's embedding table [vocab, context_dim]
+    (fp32 or bf16), both on the device: pass it wherever the reference API takes ``context``."""
+
+    def __init__(self, table, tokens):
+        assert table.is_cuda and table.dim() == 2 and table.dtype in (torch.float32, torch.bfloat16)
+        self.table = table.contiguous()
+        self.tokens = tokens.to(device=table.device, dtype=torch.int64).contiguous()
+        assert self.tokens.dim() == 2
+
+    def version(self):
+        return (self.table._version, self.tokens._version)
+
+    @property
+    def shape(self):
+        return (self.tokens.shape[0], self.tokens.shape[1], self.table.shape[1])
+
+
 class UNetModel(nn.Module):
     """``UNetModel(config)``; ``config.model.compute_dtype`` (optional, default 'bf16') selects the tcgen05
     path ('bf16') or the CUDA-core verification path ('fp32')."""
@@ -175,10 +193,23 @@ class UNetModel(nn.Module):
         self._ctx_key = None
 
     def set_context(self, text_emb):
-        """Projects K|V of every cross-attention for this text context once (hoisted out of the loop)."""
+        """Projects K|V of every cross-attention for this text context once (hoisted out of the loop).  ``text_emb``
+        is the reference's [B, L, context_dim] embedding tensor or a ``TokenContext`` (token ids + embedding table:
+        the gather of ``llm.model.embed_tokens``, sampling_6d.py:134-137, then runs on the device too)."""
         if text_emb is None:
             raise TypeError("context=None is not supported: the reference model crashes on it as well "
                             "(to_k expects context_dim inputs, model/attention.py:161-175)")
+        if isinstance(text_emb, TokenContext):
+            tc = text_emb
+            if self._ctx_key is not None and self._ctx_key[0] is tc and self._ctx_key[1] == tc.version():
+                return
+            if tc.table.shape[1] != self.context_dim:
+                raise ValueError(f"embedding table width {tc.table.shape[1]} != context_dim {self.context_dim}")
+            _lib.check(_lib.lib().t2p_unet_set_context_tokens(
+                self._handle, _lib.ptr(tc.table), _lib.torch_dtype_code(tc.table.dtype), tc.table.shape[0],
+                _lib.ptr(tc.tokens), tc.tokens.shape[0], tc.tokens.shape[1], _lib.current_stream()))
+            self._ctx_key = (tc, tc.version())
+            return
         # identity + version of the tensor OBJECT (kept alive here): a pointer-based key would be fooled by the
         # caching allocator handing the same address to a new context tensor
         if self._ctx_key is not None and self._ctx_key[0] is text_emb and self._ctx_key[1] == text_emb._version:
