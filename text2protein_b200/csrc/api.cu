@@ -331,7 +331,7 @@ int t2p_pc_run(t2p_unet* u, const t2p_run_args* a, void* stream) {
   T2P_CUDA(cudaMemsetAsync(u->state, 0, sizeof(long long) * 2, st));
 
   PcStepArgs base;
-  base.x = a->x; base.score = u->h; base.score_dtype = kF32; base.score_nhwc = 1;
+  base.x = a->x; base.score = u->h; base.score_dtype = kF32; base.score_nhwc = 0;
   base.sigmas = c.scale_by_sigma ? net.sigmas() : nullptr;
   base.labels = u->labels; base.G = u->G;
   base.probability_flow = a->probability_flow; base.snr = a->snr;

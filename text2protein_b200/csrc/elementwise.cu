@@ -189,10 +189,8 @@ __global__ void scale_by_sigma_kernel(const float* __restrict__ h, const long lo
                                       TO* __restrict__ out) {
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= static_cast<long long>(B) * HW * C) return;
-  const int p = static_cast<int>(idx % HW);
-  const int c = static_cast<int>((idx / HW) % C);
   const int b = static_cast<int>(idx / (static_cast<long long>(HW) * C));
-  double v = static_cast<double>(h[(static_cast<long long>(b) * HW + p) * C + c]);
+  double v = static_cast<double>(h[idx]);  // h is NCHW, like out
   if (do_scale) v = v / sigmas[labels[b]];
   out[idx] = static_cast<TO>(v);
 }
@@ -272,13 +270,13 @@ void pack_first_conv(const float* w, int cout, int C, int kpad, void* out, cudaS
   T2P_LAUNCH_CHECK();
 }
 
-void scale_by_sigma(const float* h_nhwc, const long long* labels, const double* sigmas, int B, int HW, int C,
+void scale_by_sigma(const float* h_nchw, const long long* labels, const double* sigmas, int B, int HW, int C,
                     int do_scale, int out_dtype, void* out, cudaStream_t st) {
   const unsigned blocks = static_cast<unsigned>(cdiv64(static_cast<long long>(B) * HW * C, 256));
   if (out_dtype == kF64)
-    scale_by_sigma_kernel<double><<<blocks, 256, 0, st>>>(h_nhwc, labels, sigmas, B, HW, C, do_scale, static_cast<double*>(out));
+    scale_by_sigma_kernel<double><<<blocks, 256, 0, st>>>(h_nchw, labels, sigmas, B, HW, C, do_scale, static_cast<double*>(out));
   else if (out_dtype == kF32)
-    scale_by_sigma_kernel<float><<<blocks, 256, 0, st>>>(h_nhwc, labels, sigmas, B, HW, C, do_scale, static_cast<float*>(out));
+    scale_by_sigma_kernel<float><<<blocks, 256, 0, st>>>(h_nchw, labels, sigmas, B, HW, C, do_scale, static_cast<float*>(out));
   else T2P_CHECK(false, "score output must be fp64 or fp32");
   T2P_LAUNCH_CHECK();
 }

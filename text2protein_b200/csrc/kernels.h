@@ -104,7 +104,7 @@ void nchw_f32_to_nhwc(const float* in, int B, int HW, int C, int cpad, int out_d
 // first conv (Cin = 5 / 8) as a K = kpad GEMM on the tensor cores: im2col of the fp32 NCHW state + matching weights
 void im2col3x3_nchw(const float* x, int B, int C, int H, int W, int kpad, void* out, cudaStream_t st);
 void pack_first_conv(const float* w, int cout, int C, int kpad, void* out, cudaStream_t st);
-void scale_by_sigma(const float* h_nhwc, const long long* labels, const double* sigmas, int B, int HW, int C,
+void scale_by_sigma(const float* h_nchw, const long long* labels, const double* sigmas, int B, int HW, int C,
                     int do_scale, int out_dtype, void* out, cudaStream_t st);
 
 // ----------------------------------------------------------------------------- PC sampler steps

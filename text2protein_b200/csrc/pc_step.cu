@@ -48,64 +48,98 @@ struct StepParams {
   double* partial;          // [B*chunks][2]
 };
 
-__device__ __forceinline__ double load_score(const StepParams& p, int b, long long e) {
-  long long idx;
-  if (p.score_nhwc) {
-    const int c = static_cast<int>(e / p.HW);
-    const int pix = static_cast<int>(e - static_cast<long long>(c) * p.HW);
-    idx = (static_cast<long long>(b) * p.HW + pix) * p.C + c;
-  } else {
-    idx = static_cast<long long>(b) * p.E + e;
-  }
-  double s = p.score_f64 ? static_cast<const double*>(p.score)[idx]
-                         : static_cast<double>(static_cast<const float*>(p.score)[idx]);
-  if (p.sigmas) s = s / p.sigmas[p.labels[b]];
-  return s;
-}
-
 __device__ __forceinline__ unsigned long long stream_of(const StepParams& p) {
   const long long it = p.iter_ptr ? *p.iter_ptr : 0;
   return static_cast<unsigned long long>(p.stream_base + it * p.stream_mul);
 }
 
-__device__ __forceinline__ void finish(const StepParams& p, long long gi, double xn, double xm) {
-  float xf = static_cast<float>(xn);
-  float mf = static_cast<float>(xm);
-  if (p.mask && !p.mask[gi]) {
-    xf = p.x_init[gi];
-    mf = xf;
-  }
-  p.x[gi] = xf;
-  if (p.x_mean_out) p.x_mean_out[gi] = mf;
-}
-
-__global__ void __launch_bounds__(256) predictor_kernel(const StepParams p) {
-  const long long quads = static_cast<long long>(p.B) * p.E / 4;
-  const unsigned long long stream = stream_of(p);
-  for (long long qi = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; qi < quads;
-       qi += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long gi0 = qi * 4;
-    const int b = static_cast<int>(gi0 / p.E);
-    const long long e0 = gi0 - static_cast<long long>(b) * p.E;
-    float z[4] = {0.f, 0.f, 0.f, 0.f};
-    if (p.add_noise) philox_normal4(p.seed, stream, static_cast<unsigned long long>(p.sample_offset * p.E / 4 + qi), z);
-    const float G = p.G[b];
-    const float g2 = G * G;  // fp32, as G[:, None, None, None] ** 2
-    const float4 xv = *reinterpret_cast<const float4*>(p.x + gi0);
-    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+// score of 4 consecutive elements [e0, e0 + 4) of sample b, as the reference's float64 `h / used_sigmas`
+// (1 / sigma is formed once per sample: 1 ulp of float64, far below the single float rounding of the state)
+template <bool FAST>
+__device__ __forceinline__ void load_score4(const StepParams& p, int b, long long e0, double inv_sigma, double (&s)[4]) {
+  if (FAST || (!p.score_nhwc && !p.score_f64)) {
+    const float4 v = *reinterpret_cast<const float4*>(static_cast<const float*>(p.score) + static_cast<long long>(b) * p.E + e0);
+    s[0] = v.x; s[1] = v.y; s[2] = v.z; s[3] = v.w;
+  } else if constexpr (!FAST) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const double s = load_score(p, b, e0 + i);
-      float f = 0.f;
-      if (p.sqrt_alpha) f = __fsub_rn(__fmul_rn(p.sqrt_alpha[b], xs[i]), xs[i]);
-      const double rev_f = static_cast<double>(f) - static_cast<double>(g2) * s * static_cast<double>(p.drift_scale);
-      const double xm = static_cast<double>(xs[i]) - rev_f;
-      const double xn = xm + static_cast<double>(__fmul_rn(G, z[i]));
-      finish(p, gi0 + i, p.add_noise ? xn : xm, xm);
+      long long idx;
+      if (p.score_nhwc) {
+        const int c = static_cast<int>((e0 + i) / p.HW);
+        const int pix = static_cast<int>((e0 + i) - static_cast<long long>(c) * p.HW);
+        idx = (static_cast<long long>(b) * p.HW + pix) * p.C + c;
+      } else {
+        idx = static_cast<long long>(b) * p.E + e0 + i;
+      }
+      s[i] = p.score_f64 ? static_cast<const double*>(p.score)[idx]
+                         : static_cast<double>(static_cast<const float*>(p.score)[idx]);
     }
+  }
+  if (p.sigmas) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[i] *= inv_sigma;
   }
 }
 
+// rounds the 4 updated values once to float, applies the condition mask (bit-exact: masked-out positions take
+// x_initial) and stores x (and x_mean) as one 16-byte vector each
+__device__ __forceinline__ void finish4(const StepParams& p, long long gi0, const double (&xn)[4], const double (&xm)[4]) {
+  float xf[4], mf[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    xf[i] = static_cast<float>(xn[i]);
+    mf[i] = static_cast<float>(xm[i]);
+  }
+  if (p.mask) {
+    const uchar4 m = *reinterpret_cast<const uchar4*>(p.mask + gi0);
+    if (!(m.x && m.y && m.z && m.w)) {
+      const float4 xi = *reinterpret_cast<const float4*>(p.x_init + gi0);
+      if (!m.x) { xf[0] = xi.x; mf[0] = xi.x; }
+      if (!m.y) { xf[1] = xi.y; mf[1] = xi.y; }
+      if (!m.z) { xf[2] = xi.z; mf[2] = xi.z; }
+      if (!m.w) { xf[3] = xi.w; mf[3] = xi.w; }
+    }
+  }
+  *reinterpret_cast<float4*>(p.x + gi0) = make_float4(xf[0], xf[1], xf[2], xf[3]);
+  if (p.x_mean_out) *reinterpret_cast<float4*>(p.x_mean_out + gi0) = make_float4(mf[0], mf[1], mf[2], mf[3]);
+}
+
+// grid = (slices of a sample, B): no per-element index arithmetic, 16-byte accesses throughout
+// FAST: fp32 NCHW score, VE SDE (no drift), noise on -- the configuration of every shipped sampling config; the
+// generic instantiation keeps the fp64 / NHWC score, VP drift and probability-flow variants of the API.
+template <bool FAST>
+__global__ void __launch_bounds__(256) predictor_kernel(const StepParams p) {
+  const int b = blockIdx.y;
+  const long long qps = p.E / 4;  // quads per sample
+  const unsigned long long stream = stream_of(p);
+  const float G = p.G[b];
+  const float g2 = G * G;  // fp32, as G[:, None, None, None] ** 2
+  const double gs = static_cast<double>(g2) * static_cast<double>(p.drift_scale);
+  const double inv_sigma = p.sigmas ? 1.0 / p.sigmas[p.labels[b]] : 1.0;
+  const float sa = p.sqrt_alpha ? p.sqrt_alpha[b] : 0.f;
+  for (long long ql = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; ql < qps;
+       ql += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long gi0 = static_cast<long long>(b) * p.E + ql * 4;
+    const float4 xv = *reinterpret_cast<const float4*>(p.x + gi0);
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+    double s[4], xn[4], xm[4];
+    load_score4<FAST>(p, b, ql * 4, inv_sigma, s);
+    float z[4] = {0.f, 0.f, 0.f, 0.f};
+    if (FAST || p.add_noise)
+      philox_normal4(p.seed, stream, static_cast<unsigned long long>((p.sample_offset + b) * qps + ql), z);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float f = 0.f;
+      if (!FAST && p.sqrt_alpha) f = __fsub_rn(__fmul_rn(sa, xs[i]), xs[i]);
+      const double rev_f = static_cast<double>(f) - gs * s[i];  // f == 0 for VE: exactly x + G^2 * score
+      xm[i] = static_cast<double>(xs[i]) - rev_f;
+      xn[i] = (FAST || p.add_noise) ? xm[i] + static_cast<double>(__fmul_rn(G, z[i])) : xm[i];
+    }
+    finish4(p, gi0, xn, xm);
+  }
+}
+
+template <bool FAST>
 __global__ void __launch_bounds__(256) corrector_kernel(const StepParams p) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double red[2][8];
@@ -120,14 +154,16 @@ __global__ void __launch_bounds__(256) corrector_kernel(const StepParams p) {
     const int b = static_cast<int>(item / p.chunks);
     const int ck = static_cast<int>(item - static_cast<long long>(b) * p.chunks);
     double sg = 0.0, sn = 0.0;
+    const double inv_sigma = p.sigmas ? 1.0 / p.sigmas[p.labels[b]] : 1.0;
     for (long long ql = threadIdx.x; ql < quads_per_chunk; ql += blockDim.x) {
       const long long qs = ck * quads_per_chunk + ql;  // quad within the sample
       float z[4];
       philox_normal4(p.seed, stream, static_cast<unsigned long long>((p.sample_offset + b) * (p.E / 4) + qs), z);
+      double s[4];
+      load_score4<FAST>(p, b, qs * 4, inv_sigma, s);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const double s = load_score(p, b, qs * 4 + i);
-        sg += s * s;
+        sg += s[i] * s[i];
         sn += static_cast<double>(z[i]) * static_cast<double>(z[i]);
       }
     }
@@ -182,25 +218,29 @@ __global__ void __launch_bounds__(256) corrector_kernel(const StepParams p) {
   }
   const float step0 = step_sh;
 
-  // ---- phase 2: apply
-  const long long quads = static_cast<long long>(p.B) * p.E / 4;
-  for (long long qi = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; qi < quads;
-       qi += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long gi0 = qi * 4;
-    const int b = static_cast<int>(gi0 / p.E);
-    const long long e0 = gi0 - static_cast<long long>(b) * p.E;
-    float z[4];
-    philox_normal4(p.seed, stream, static_cast<unsigned long long>(p.sample_offset * (p.E / 4) + qi), z);
+  // ---- phase 2: apply (one (sample, chunk) item per block iteration, as in phase 1)
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const int b = static_cast<int>(item / p.chunks);
+    const int ck = static_cast<int>(item - static_cast<long long>(b) * p.chunks);
+    const double inv_sigma = p.sigmas ? 1.0 / p.sigmas[p.labels[b]] : 1.0;
     const float step = p.alpha ? __fmul_rn(step0, p.alpha[b]) : step0;
     const float nscale = sqrtf(__fmul_rn(step, 2.f));
-    const float4 xv = *reinterpret_cast<const float4*>(p.x + gi0);
-    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+    const double dstep = static_cast<double>(step);
+    for (long long ql = threadIdx.x; ql < quads_per_chunk; ql += blockDim.x) {
+      const long long qs = ck * quads_per_chunk + ql;
+      const long long gi0 = static_cast<long long>(b) * p.E + qs * 4;
+      float z[4];
+      philox_normal4(p.seed, stream, static_cast<unsigned long long>((p.sample_offset + b) * (p.E / 4) + qs), z);
+      const float4 xv = *reinterpret_cast<const float4*>(p.x + gi0);
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+      double s[4], xn[4], xm[4];
+      load_score4<FAST>(p, b, qs * 4, inv_sigma, s);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const double s = load_score(p, b, e0 + i);
-      const double xm = static_cast<double>(xs[i]) + static_cast<double>(step) * s;
-      const double xn = xm + static_cast<double>(__fmul_rn(nscale, z[i]));
-      finish(p, gi0 + i, xn, xm);
+      for (int i = 0; i < 4; ++i) {
+        xm[i] = static_cast<double>(xs[i]) + dstep * s[i];
+        xn[i] = xm[i] + static_cast<double>(__fmul_rn(nscale, z[i]));
+      }
+      finish4(p, gi0, xn, xm);
     }
   }
 }
@@ -257,6 +297,10 @@ StepParams to_params(const PcStepArgs& a) {
   p.B = a.B; p.C = a.C; p.HW = a.HW; p.E = static_cast<long long>(a.C) * a.HW;
   T2P_CHECK(p.E % 4 == 0, "C*N*N must be a multiple of 4");
   T2P_CHECK((reinterpret_cast<uintptr_t>(a.x) & 15) == 0, "x must be 16-byte aligned");
+  T2P_CHECK((reinterpret_cast<uintptr_t>(a.score) & 15) == 0, "score must be 16-byte aligned");
+  T2P_CHECK((reinterpret_cast<uintptr_t>(a.mask) & 3) == 0, "mask must be 4-byte aligned");
+  T2P_CHECK((reinterpret_cast<uintptr_t>(a.x_init) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.x_mean_out) & 15) == 0,
+            "x_init / x_mean_out must be 16-byte aligned");
   if (a.sigmas) T2P_CHECK(a.labels != nullptr, "labels required with sigmas");
   if (a.mask) T2P_CHECK(a.x_init != nullptr, "x_init required with mask");
   p.partial = a.partial;
@@ -278,16 +322,19 @@ int num_sms() {
 void pc_predictor_step(const PcStepArgs& a, cudaStream_t st) {
   StepParams p = to_params(a);
   T2P_CHECK(a.G != nullptr, "predictor needs G");
-  const long long quads = static_cast<long long>(p.B) * p.E / 4;
-  const int blocks = static_cast<int>(std::min<long long>(cdiv64(quads, 256), static_cast<long long>(num_sms()) * 8));
-  predictor_kernel<<<blocks, 256, 0, st>>>(p);
+  const long long qps = p.E / 4;
+  const int bx = static_cast<int>(std::max<long long>(1, std::min<long long>(cdiv64(qps, 256), cdiv64(num_sms() * 8LL, p.B))));
+  const bool fast = !p.score_nhwc && !p.score_f64 && p.sqrt_alpha == nullptr && p.add_noise;
+  if (fast) predictor_kernel<true><<<dim3(bx, p.B), 256, 0, st>>>(p);
+  else predictor_kernel<false><<<dim3(bx, p.B), 256, 0, st>>>(p);
   T2P_LAUNCH_CHECK();
 }
 
 int pc_corrector_chunks(int B, long long E) {
   const long long q = E / 4;
   int chunks = 1;
-  while (static_cast<long long>(B) * chunks * 2 <= 2LL * num_sms() && (q % (chunks * 2) == 0) && q / (chunks * 2) >= 256)
+  // several (sample, chunk) items per resident block, each chunk still at least one quad per thread
+  while (static_cast<long long>(B) * chunks < 8LL * num_sms() && (q % (chunks * 2) == 0) && q / (chunks * 2) >= 256)
     chunks *= 2;
   return chunks;
 }
@@ -297,16 +344,19 @@ void pc_corrector_step(const PcStepArgs& a, cudaStream_t st) {
   T2P_CHECK(a.partial != nullptr && a.chunks > 0, "corrector needs the partial-sum workspace");
   T2P_CHECK((p.E / 4) % a.chunks == 0, "chunks must divide the quads of a sample");
   p.chunks = a.chunks;
-  static int max_blocks = [] {
+  const bool fast = !p.score_nhwc && !p.score_f64;
+  static int max_blocks[2] = {0, 0};
+  if (!max_blocks[fast]) {
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, corrector_kernel, 256, 0);
-    return std::max(1, per_sm) * num_sms();
-  }();
-  const long long quads = static_cast<long long>(p.B) * p.E / 4;
-  const long long want = std::max<long long>(static_cast<long long>(p.B) * p.chunks, std::min<long long>(cdiv64(quads, 256), 4LL * num_sms()));
-  const int blocks = static_cast<int>(std::min<long long>(want, max_blocks));
+    if (fast) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, corrector_kernel<true>, 256, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, corrector_kernel<false>, 256, 0);
+    max_blocks[fast] = std::max(1, per_sm) * num_sms();
+  }
+  // cooperative launch: every block must be resident; blocks loop over the (sample, chunk) items
+  const int blocks = static_cast<int>(std::min<long long>(static_cast<long long>(p.B) * p.chunks, max_blocks[fast]));
   void* args[] = {&p};
-  T2P_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(corrector_kernel), dim3(blocks), dim3(256), args, 0, st));
+  void* fn = fast ? reinterpret_cast<void*>(corrector_kernel<true>) : reinterpret_cast<void*>(corrector_kernel<false>);
+  T2P_CUDA(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(256), args, 0, st));
 }
 
 void philox_normal_fill(unsigned long long seed, unsigned long long stream, long long first_element, long long count,

@@ -33,13 +33,15 @@ __device__ __forceinline__ void philox_normal4(unsigned long long seed, unsigned
   const float u0 = philox_uniform(r.x), u1 = philox_uniform(r.y);
   const float u2 = philox_uniform(r.z), u3 = philox_uniform(r.w);
   const float r0 = sqrtf(-2.f * logf(u0)), r1 = sqrtf(-2.f * logf(u2));
+  // angle 2 pi u in (0, 2 pi]: evaluated as -(cos, sin)(2 pi u - pi) so that the MUFU sine / cosine run inside
+  // [-pi, pi], where their absolute error is 2^-21.4 (the normals stay within 3e-6 of the numpy restatement)
   float s0, c0, s1, c1;
-  sincosf(6.283185307179586f * u1, &s0, &c0);
-  sincosf(6.283185307179586f * u3, &s1, &c1);
-  z[0] = r0 * c0;
-  z[1] = r0 * s0;
-  z[2] = r1 * c1;
-  z[3] = r1 * s1;
+  __sincosf(fmaf(6.283185307179586f, u1, -3.14159265358979f), &s0, &c0);
+  __sincosf(fmaf(6.283185307179586f, u3, -3.14159265358979f), &s1, &c1);
+  z[0] = -r0 * c0;
+  z[1] = -r0 * s0;
+  z[2] = -r1 * c1;
+  z[3] = -r1 * s1;
 }
 
 }  // namespace t2p

@@ -845,7 +845,7 @@ void UNet::forward_impl(const float* x, const long long* labels, float* h_out, i
   free_act(h);
   Act o;
   o.p = h_out; o.B = B; o.H = N; o.W = N; o.C = C;
-  gemm(out_conv_, hn, nullptr, o, nullptr, 0, nullptr, 0, 1.f, kF32);
+  gemm(out_conv_, hn, nullptr, o, nullptr, 0, nullptr, 0, 1.f, kF32, /*out_nchw=*/1);
   free_act(hn);
   ln_->ws.free(ln_->temb_all);
   ln_->temb_all = nullptr;
@@ -906,10 +906,17 @@ void UNet::forward(const float* x, const long long* labels, void* out, int out_d
   }
   forward_raw(x, labels, h_scratch_, B, st);
   scale_by_sigma(h_scratch_, labels, sigmas(), B, N * N, C, cfg_.scale_by_sigma, out_dtype, out, st);
-  if (debug_) {
-    Act o;
-    o.p = h_scratch_; o.B = B; o.H = N; o.W = N; o.C = C;
-    record_tap("out", o, kF32);  // the final conv output is fp32 regardless of the compute dtype
+  if (debug_) {  // the final conv output is fp32 NCHW regardless of the compute dtype: the tap is a plain copy
+    const int64_t n = static_cast<int64_t>(B) * C * N * N;
+    auto it = taps_.find("out");
+    if (it == taps_.end() || it->second.second != std::vector<int64_t>{B, C, N, N}) {
+      if (it != taps_.end()) cudaFree(it->second.first);
+      float* buf = nullptr;
+      T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&buf), sizeof(float) * n));
+      taps_["out"] = {buf, {B, C, N, N}};
+      it = taps_.find("out");
+    }
+    T2P_CUDA(cudaMemcpyAsync(it->second.first, h_scratch_, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
   }
 }
 

@@ -144,7 +144,7 @@ class UNet {
   // same, from token ids [B][L] and the embedding table [V][context_dim] (fp32 or bf16) -- SURVEY 8f rank 3
   void set_context_tokens(const void* table, int table_dtype, long long V, const long long* tokens, int B, int L,
                           cudaStream_t st);
-  // x: fp32 NCHW [B][C][N][N]; labels: int64 [B]; h_out: fp32 NHWC [B][N][N][C] un-scaled final conv
+  // x: fp32 NCHW [B][C][N][N]; labels: int64 [B]; h_out: fp32 NCHW [B][C][N][N] un-scaled final conv
   // (what the fused PC-step kernels consume).  Returns through `h_out` only.
   void forward_raw(const float* x, const long long* labels, float* h_out, int B, cudaStream_t st);
   // Reference-shaped output: NCHW, divided by sigmas[labels] in double (ncsnpp.py:259-261), fp64 or fp32.
