@@ -310,10 +310,13 @@ def run_native(args, cfg):
                                       snr=cfg.sampling.snr, n_steps=1, eps=1e-5, device=cfg.device, seed=2024,
                                       num_iters=K, sample_offset=rank * B)
     out_pin = torch.empty(shape, dtype=torch.float32).pin_memory()
+    ctx_in = torch.empty_like(ctx_pin, device=dev)                   # a serving loop's persistent input buffers
+    len_in = torch.empty_like(len_pin, device=dev)
 
     def e2e_once():
-        c = ctx_pin.to(dev, non_blocking=True)                       # H2D: text context
-        cd = {"length": len_pin.to(dev, non_blocking=True)}          # H2D: length mask
+        ctx_in.copy_(ctx_pin, non_blocking=True)                     # H2D: text context (268 MB fp32)
+        len_in.copy_(len_pin, non_blocking=True)                     # H2D: length mask
+        c, cd = ctx_in, {"length": len_in}
         s, _ = sampler(model, cd, c)
         if world > 1:                                                # final NCCL all-gather of the samples
             gather_samples(s, world * B)

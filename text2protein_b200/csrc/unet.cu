@@ -319,6 +319,9 @@ UNet::UNet(const UNetConfig& cfg) : cfg_(cfg) {
 UNet::~UNet() {
   for (void* p : owned_) cudaFree(p);
   for (auto& kv : taps_) cudaFree(kv.second.first);
+  for (TransformerM* t : all_st_)
+    if (t->kv) cudaFree(t->kv);
+  if (ctx_buf_) cudaFree(ctx_buf_);
   if (h_scratch_) cudaFree(h_scratch_);
   if (side_) cudaStreamDestroy(side_);
   if (ev_fork_) cudaEventDestroy(ev_fork_);
@@ -745,22 +748,30 @@ void UNet::set_context_impl(const float* ctx, const void* table, int table_dtype
   const int D = cfg_.context_dim;
   const size_t es = dtype_size(cfg_.compute_dtype);
   const long long rows = static_cast<long long>(B) * L;
-  void* cbuf = nullptr;
-  T2P_CUDA(cudaMalloc(&cbuf, std::max<size_t>(256, rows * D * es)));
+  // grow-only staging / K|V buffers: cudaMalloc / cudaFree of these 100 MB-class blocks cost up to a second per
+  // call on a busy allocator, and nothing here needs a host synchronisation once they persist
+  auto ensure = [&](void*& ptr, size_t& cap, size_t bytes) {
+    bytes = std::max<size_t>(256, bytes);
+    if (bytes <= cap) return;
+    if (ptr) T2P_CUDA(cudaFree(ptr));
+    ptr = nullptr;
+    cap = 0;
+    T2P_CUDA(cudaMalloc(&ptr, bytes));
+    cap = bytes;
+  };
+  ensure(ctx_buf_, ctx_buf_bytes_, rows * D * es);
+  void* cbuf = ctx_buf_;
   if (ctx) convert_f32(ctx, rows * D, cfg_.compute_dtype, cbuf, st);
   else if (cfg_.compute_dtype == kBF16) embed_gather(table, table_dtype, V, D, tokens, rows, nullptr, cbuf, st);
   else embed_gather(table, table_dtype, V, D, tokens, rows, static_cast<float*>(cbuf), nullptr, st);
   for (TransformerM* t : all_st_) {
-    if (t->kv) { T2P_CUDA(cudaFree(t->kv)); t->kv = nullptr; }
-    T2P_CUDA(cudaMalloc(&t->kv, std::max<size_t>(256, rows * 2 * t->C * es)));
+    ensure(t->kv, t->kv_bytes, rows * 2 * t->C * es);
     ConvGemmArgs g;
     g.a0 = cbuf; g.c0 = D; g.B = 1; g.H = 1; g.W = static_cast<int>(rows); g.ksize = 1;
     g.w = t->kv2.wp; g.N = 2 * t->C; g.out = t->kv; g.out_dtype = cfg_.compute_dtype;
     if (cfg_.compute_dtype == kBF16 && D % 64 == 0) conv_gemm_tc(g, st);
     else conv_gemm_simt(g, cfg_.compute_dtype, st);
   }
-  T2P_CUDA(cudaStreamSynchronize(st));
-  T2P_CUDA(cudaFree(cbuf));
   ctx_B_ = B;
   ctx_L_ = L;
   ++generation_;

@@ -112,7 +112,8 @@ struct TransformerM {
   GroupNormP norm;
   Linear proj_in, proj_out, qkv1, out1, q2, kv2, out2, ff_in, ff_out;
   LayerNormP ln1, ln2, ln3;
-  void* kv = nullptr;  // hoisted K|V projection of the text context, [B*L][2C]
+  void* kv = nullptr;  // hoisted K|V projection of the text context, [B*L][2C] (grow-only buffer)
+  size_t kv_bytes = 0;
 };
 struct ModuleM {
   int kind = 0;  // 0 ResBlock, 1 AttnBlock, 2 SpatialTransformer
@@ -234,6 +235,8 @@ class UNet {
   bool serpentine_ = true;
   int ctx_B_ = 0, ctx_L_ = 0;
   std::map<std::string, std::pair<float*, std::vector<int64_t>>> taps_;
+  void* ctx_buf_ = nullptr;  // text context in the compute dtype (grow-only staging buffer of set_context)
+  size_t ctx_buf_bytes_ = 0;
   float* h_scratch_ = nullptr;
   size_t h_scratch_bytes_ = 0;
 };
