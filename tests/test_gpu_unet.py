@@ -97,15 +97,19 @@ def test_state_dict_roundtrip_through_dataparallel_checkpoint(tmp_path):
     assert state2["step"] == 5 and torch.equal(a, b)
 
 
-@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
-def test_two_lane_half_batches_are_bit_identical_to_separate_runs(dtype, monkeypatch):
-    """With T2P_SPLIT=1, B >= 8 runs as two half-batches on two streams; every sample's arithmetic is unchanged.
-    (The switch is read once per process: run this test alone with T2P_SPLIT=1 to exercise the two-lane path;
-    without it the test checks batch-composition independence of the single-lane path.)"""
+@pytest.mark.parametrize("dtype,tol", [("fp32", 1e-5), ("bf16", 2e-2)])
+def test_concurrent_lowres_lanes_match_separate_runs(dtype, tol):
+    """With B >= 4 the low-resolution section of the network runs as batch slices on concurrent lanes; every
+    sample's arithmetic is unchanged, so the result agrees with running the halves separately (to rounding: the
+    tile plan of the full-resolution layers depends on the launch size)."""
     cfg, model, sd = make_native(tiny_cfg(5), dtype)
     x, labels, ctx = synthetic_inputs(cfg, 8, 9, seed=11)
     x, labels, ctx = x.cuda(), labels.cuda(), ctx.cuda()
     whole = model(x, labels, ctx)
-    lo = model(x[:4].contiguous(), labels[:4].contiguous(), ctx[:4].contiguous())
-    hi = model(x[4:].contiguous(), labels[4:].contiguous(), ctx[4:].contiguous())
-    assert torch.equal(whole, torch.cat([lo, hi]))
+    again = model(x, labels, ctx)
+    assert torch.equal(whole, again)  # deterministic with the lanes
+    lo = model(x[:2].contiguous(), labels[:2].contiguous(), ctx[:2].contiguous())   # B = 2: single lane
+    hi = model(x[2:].contiguous(), labels[2:].contiguous(), ctx[2:].contiguous())
+    assert rel_err(whole, torch.cat([lo, hi])) < tol
+    ref = unet_ref.unet_forward(sd, cfg, x.cpu(), labels.cpu(), ctx.cpu())
+    assert rel_err(whole, ref) < (FP32_TOL if dtype == "fp32" else BF16_TOL)
