@@ -169,6 +169,12 @@ int t2p_conv2d(const t2p_conv_args* a, void* stream);        /* nn.Conv2d / NIN 
  * or 0 when this launch cannot produce them (then stat_part must be NULL).  Host-only, no GPU work. */
 int t2p_conv2d_stat_tile(const t2p_conv_args* a);
 
+/* Last layer, ncsnpp.py:212-216,257: out fp32 NCHW [B][nout][H][W] = Conv3x3(SiLU(x * scale + shift)) + bias, with x the
+ * raw bf16 NHWC activation [B][H][W][cin], scale / shift the per-(sample, channel) GroupNorm affine [B][cin] and w the
+ * packed bf16 weight [nout][9][cin] (cin in {64, 128, 256}, nout <= 8, W % 16 == 0). */
+int t2p_final_conv(const void* x, const float* scale, const float* shift, const void* w, const float* bias, float* out,
+                   int B, int H, int W, int cin, int nout, void* stream);
+
 /* nn.GroupNorm(G, C, eps) [+ SiLU] [+ 2x2 mean | nearest x2] over the concat of a0|a1: layers.py:282-311 */
 int t2p_groupnorm(const void* a0, int c0, const void* a1, int c1, int B, int H, int W, int dtype, int groups,
                   float eps, const float* gamma, const float* beta, int silu, int resample_mode, void* out,

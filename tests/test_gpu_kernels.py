@@ -287,3 +287,25 @@ def test_pc_steps_match_oracle_math(B, Cc, N):
         got = got.cpu()
         assert torch.equal(got[~mask], x_init[~mask])            # mask handling is bit-exact
         assert rel_err(got, ref) < 2e-6
+
+
+@pytest.mark.parametrize("B,H,W,cin,nout", [(2, 128, 128, 128, 5), (3, 32, 32, 64, 8), (1, 30, 48, 128, 5),
+                                            (2, 64, 64, 256, 5), (1, 256, 256, 128, 5)])
+def test_final_conv_fused_matches_torch(B, H, W, cin, nout):
+    """GroupNorm-affine + SiLU + 3x3 conv to the map channels in one kernel (padding applied after the activation)."""
+    g = torch.Generator(device="cuda").manual_seed(8)
+    x = (torch.randn(B, cin, H, W, device="cuda", generator=g) * 2).bfloat16().float()
+    scale = 1 + 0.3 * torch.randn(B, cin, device="cuda", generator=g)
+    shift = 0.5 * torch.randn(B, cin, device="cuda", generator=g)
+    w = (torch.randn(nout, cin, 3, 3, device="cuda", generator=g) / math.sqrt(9 * cin)).bfloat16().float()
+    bias = torch.randn(nout, device="cuda", generator=g)
+    y = F.silu(x * scale[:, :, None, None] + shift[:, :, None, None]).bfloat16().float()
+    ref = F.conv2d(y, w, bias, padding=1)
+    X = nhwc(x, torch.bfloat16)
+    wp = w.permute(0, 2, 3, 1).contiguous().reshape(nout, -1).bfloat16().contiguous()
+    out = torch.full((B, nout, H, W), float("nan"), device="cuda")
+    _lib.check(_lib.lib().t2p_final_conv(_lib.ptr(X), _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(wp), _lib.ptr(bias),
+                                         _lib.ptr(out), B, H, W, cin, nout, _st()))
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    assert rel_err(out, ref) < 1.5e-2

@@ -88,6 +88,8 @@ SIGNATURES = {
     "t2p_postprocess_6d": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "t2p_conv2d": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "t2p_conv2d_stat_tile": (C.c_int, [C.POINTER(ConvArgs)]),
+    "t2p_final_conv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                 C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "t2p_groupnorm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                 C.c_void_p]),

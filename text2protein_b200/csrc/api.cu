@@ -319,7 +319,10 @@ int t2p_pc_run(t2p_unet* u, const t2p_run_args* a, void* stream) {
   T2P_CUDA(cudaStreamWaitEvent(st, u->ev_in, 0));
   struct Rejoin {
     t2p_unet* u; cudaStream_t user;
-    ~Rejoin() { if (cudaEventRecord(u->ev_out, u->run_stream) == cudaSuccess) cudaStreamWaitEvent(user, u->ev_out, 0); }
+    ~Rejoin() {
+      u->net->set_reuse_temb(false);  // also on the error path
+      if (cudaEventRecord(u->ev_out, u->run_stream) == cudaSuccess) cudaStreamWaitEvent(user, u->ev_out, 0);
+    }
   } rejoin{u, user};
   UNet& net = *u->net;
   const UNetConfig& c = net.cfg();
@@ -344,13 +347,18 @@ int t2p_pc_run(t2p_unet* u, const t2p_run_args* a, void* stream) {
 
   auto iteration = [&]() {
     run_prep(u->state, u->label_table, u->g_table, B, u->labels, u->G, st);
+    // every score evaluation of one iteration is at the same noise level: the time-embedding path (pre_blocks
+    // MLP + 42 Dense_0 projections) is computed by the first one and reused by the rest
+    net.set_reuse_temb(false);
     for (int j = 0; j < a->n_steps; ++j) {  // Langevin corrector, sampling.py:188-197
       net.forward_raw(a->x, u->labels, u->h, B, st);
+      net.set_reuse_temb(true);
       PcStepArgs s = base;
       s.stream_base = 1 + j;
       pc_corrector_step(s, st);
     }
     net.forward_raw(a->x, u->labels, u->h, B, st);  // reverse-diffusion predictor, sampling.py:162-167
+    net.set_reuse_temb(false);
     PcStepArgs s = base;
     s.stream_base = 1 + a->n_steps;
     s.x_mean_out = a->x_mean;
@@ -423,6 +431,14 @@ int t2p_conv2d(const t2p_conv_args* a, void* stream) {
     T2P_CHECK(a->in_dtype == T2P_BF16 && a->c0 % 64 == 0 && a->c1 % 64 == 0, "centre-tap sources are tcgen05-only");
   if (a->in_dtype == T2P_BF16 && a->c0 % 64 == 0 && a->c1 % 64 == 0) conv_gemm_tc(g, S(stream));
   else conv_gemm_simt(g, a->in_dtype, S(stream));
+  T2P_API_END
+}
+
+int t2p_final_conv(const void* x, const float* scale, const float* shift, const void* w, const float* bias, float* out,
+                   int B, int H, int W, int cin, int nout, void* stream) {
+  T2P_API_BEGIN
+  T2P_CHECK(x && scale && shift && w && bias && out, "null argument");
+  final_conv_fused(x, scale, shift, w, bias, out, B, H, W, cin, nout, S(stream));
   T2P_API_END
 }
 

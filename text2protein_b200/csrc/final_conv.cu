@@ -1,0 +1,199 @@
+// Last layer of the score network: GroupNorm-apply + SiLU + 3x3 convolution to the C (5 or 8) map channels
+// (reference ncsnpp.py:212-216 `out`, applied at ncsnpp.py:257), fp32 NCHW output for the PC step kernels.
+//
+// As an implicit GEMM this layer is all activation traffic (N = 5 output channels): the tcgen05 path spends a full
+// 128-row MMA tile on it and re-reads the activation nine times from L2, and the normalised tensor has to make a
+// round trip through HBM first.  Here a CTA stages a (2 + 2 halo) x (TW + 2 halo) pixel tile of the RAW activation
+// in shared memory, normalising it on the way in (zero padding is applied after the activation, as the reference
+// pads the conv input), and runs the nine taps from shared memory with mma.sync m16n8k16 (8 = C padded).
+#include "kernels.h"
+
+namespace t2p {
+namespace {
+
+constexpr int FC_THREADS = 256;
+constexpr int FC_ROWS = 2;  // output rows per CTA
+
+__device__ __forceinline__ uint32_t fc_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ float fc_silu(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
+struct FinalConvParams {
+  const __nv_bfloat16* x;  // [B][H][W][CIN] raw (pre-norm) activation
+  const float* scale;      // [B][CIN]
+  const float* shift;
+  const __nv_bfloat16* w;  // [nout][9][CIN]
+  const float* bias;       // [nout]
+  float* out;              // [B][nout][H][W]
+  int B, H, W, nout;
+};
+
+constexpr int FC_CH = 64;  // channels staged per pass: keeps the tile under half an SM's shared memory (2 CTAs / SM)
+
+template <int CIN, int TW>
+__global__ void __launch_bounds__(FC_THREADS, 2) final_conv_kernel(const FinalConvParams p) {
+  constexpr int PITCH = FC_CH + 8;        // bf16 elements per staged pixel (16-byte pad: conflict-free ldmatrix)
+  constexpr int WPITCH = CIN + 8;
+  constexpr int VPP = FC_CH / 8;          // 16-byte vectors per pixel and pass
+  constexpr int PXW = TW + 2;
+  extern __shared__ __align__(16) unsigned char fc_smem[];
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(fc_smem);            // [4][PXW][PITCH]
+  __nv_bfloat16* ws = xs + (FC_ROWS + 2) * PXW * PITCH;                      // [9][8][WPITCH]
+  float* sc = reinterpret_cast<float*>(ws + 9 * 8 * WPITCH);                 // [CIN]
+  float* sh = sc + CIN;
+  const int b = blockIdx.z;
+  const int h0 = blockIdx.x * FC_ROWS;
+  const int w0 = blockIdx.y * TW;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (int c = tid; c < CIN; c += FC_THREADS) {
+    sc[c] = p.scale[static_cast<long long>(b) * CIN + c];
+    sh[c] = p.shift[static_cast<long long>(b) * CIN + c];
+  }
+  for (int i = tid; i < 9 * 8 * (CIN / 8); i += FC_THREADS) {
+    const int cv = i % (CIN / 8), n = (i / (CIN / 8)) % 8, tap = i / ((CIN / 8) * 8);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (n < p.nout) v = *reinterpret_cast<const uint4*>(p.w + (static_cast<long long>(n) * 9 + tap) * CIN + cv * 8);
+    *reinterpret_cast<uint4*>(ws + (tap * 8 + n) * WPITCH + cv * 8) = v;
+  }
+
+  constexpr int MT_PER_ROW = TW / 16;
+  constexpr int MT = FC_ROWS * MT_PER_ROW;
+  constexpr int MT_PER_WARP = (MT + FC_THREADS / 32 - 1) / (FC_THREADS / 32);
+  float acc[MT_PER_WARP][4];
+#pragma unroll
+  for (int m = 0; m < MT_PER_WARP; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f;
+
+  constexpr int TOTAL = (FC_ROWS + 2) * PXW * VPP;
+  constexpr int U = 8;
+  for (int c0 = 0; c0 < CIN; c0 += FC_CH) {
+    __syncthreads();  // scale / weights staged (first pass); previous pass's MMAs done with xs (later passes)
+    // stage + normalise channels [c0, c0 + 64) of rows h0-1 .. h0+2, pixels w0-1 .. w0+TW; U independent 16-byte
+    // loads in flight per thread before the first is consumed
+    for (int i0 = tid; i0 < TOTAL; i0 += FC_THREADS * U) {
+      uint4 t[U];
+      bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * FC_THREADS;
+        const int cv = i % VPP, px = (i / VPP) % PXW, r = i / (VPP * PXW);
+        const int ih = h0 - 1 + r, iw = w0 - 1 + px;
+        ok[u] = i < TOTAL && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
+        t[u] = make_uint4(0, 0, 0, 0);
+        if (ok[u])
+          t[u] = *reinterpret_cast<const uint4*>(p.x + ((static_cast<long long>(b) * p.H + ih) * p.W + iw) * CIN + c0 + cv * 8);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * FC_THREADS;
+        if (i >= TOTAL) break;
+        const int cv = i % VPP, px = (i / VPP) % PXW, r = i / (VPP * PXW);
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (ok[u]) {
+          const uint32_t wv[4] = {t[u].x, t[u].y, t[u].z, t[u].w};
+          uint32_t ov[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = c0 + cv * 8 + 2 * j;
+            const float a = fc_silu(fmaf(__uint_as_float(wv[j] << 16), sc[c], sh[c]));
+            const float d = fc_silu(fmaf(__uint_as_float(wv[j] & 0xffff0000u), sc[c + 1], sh[c + 1]));
+            __nv_bfloat162 hh = __floats2bfloat162_rn(a, d);
+            ov[j] = *reinterpret_cast<uint32_t*>(&hh);
+          }
+          o = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+        }
+        *reinterpret_cast<uint4*>(xs + (r * PXW + px) * PITCH + cv * 8) = o;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < MT_PER_WARP; ++m) {
+      const int mt = warp + m * (FC_THREADS / 32);
+      if (mt >= MT) break;
+      const int orow = mt / MT_PER_ROW, ow0 = (mt % MT_PER_ROW) * 16;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int kh = tap / 3, kw = tap % 3;
+        const uint32_t abase = fc_smem_u32(xs + ((orow + kh) * PXW + ow0 + kw + (lane & 15)) * PITCH + (lane >> 4) * 8);
+        const uint32_t bbase = fc_smem_u32(ws + (tap * 8 + (lane & 7)) * WPITCH + c0 + ((lane >> 3) & 1) * 8);
+#pragma unroll
+        for (int kc = 0; kc < FC_CH / 16; ++kc) {
+          uint32_t a0, a1, a2, a3, b0, b1;
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(abase + kc * 32));
+          asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(bbase + kc * 32));
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                       : "+f"(acc[m][0]), "+f"(acc[m][1]), "+f"(acc[m][2]), "+f"(acc[m][3])
+                       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+        }
+      }
+    }
+  }
+  const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+  for (int m = 0; m < MT_PER_WARP; ++m) {
+    const int mt = warp + m * (FC_THREADS / 32);
+    if (mt >= MT) break;
+    const int orow = mt / MT_PER_ROW, ow0 = (mt % MT_PER_ROW) * 16;
+    const int oh = h0 + orow;
+    if (oh < p.H) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int n = tq * 2 + (e & 1);
+        const int ow = w0 + ow0 + g + (e >> 1) * 8;
+        if (n < p.nout && ow < p.W)
+          p.out[((static_cast<long long>(b) * p.nout + n) * p.H + oh) * p.W + ow] = acc[m][e] + p.bias[n];
+      }
+    }
+  }
+}
+
+template <int CIN, int TW>
+void fc_launch(const FinalConvParams& p, cudaStream_t st) {
+  constexpr size_t smem = sizeof(__nv_bfloat16) * ((FC_ROWS + 2) * (TW + 2) * (FC_CH + 8) + 9 * 8 * (CIN + 8)) +
+                          sizeof(float) * 2 * CIN;
+  static bool configured = false;
+  if (!configured) {
+    T2P_CUDA(cudaFuncSetAttribute(final_conv_kernel<CIN, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    configured = true;
+  }
+  dim3 grid(cdiv(p.H, FC_ROWS), cdiv(p.W, TW), p.B);
+  final_conv_kernel<CIN, TW><<<grid, FC_THREADS, smem, st>>>(p);
+  T2P_LAUNCH_CHECK();
+}
+
+}  // namespace
+
+bool final_conv_fused_supported(int cin, int nout, int H, int W) {
+  return (cin == 64 || cin == 128 || cin == 256) && nout >= 1 && nout <= 8 && W % 16 == 0 && W >= 16 && H >= 1;
+}
+
+void final_conv_fused(const void* x, const float* scale, const float* shift, const void* w, const float* bias, float* out,
+                      int B, int H, int W, int cin, int nout, cudaStream_t st) {
+  T2P_CHECK(final_conv_fused_supported(cin, nout, H, W), "unsupported shape for the fused final convolution");
+  FinalConvParams p{static_cast<const __nv_bfloat16*>(x), scale, shift, static_cast<const __nv_bfloat16*>(w), bias, out,
+                    B, H, W, nout};
+  if (cin == 64) {
+    if (W >= 128) fc_launch<64, 128>(p, st);
+    else if (W >= 64) fc_launch<64, 64>(p, st);
+    else if (W >= 32) fc_launch<64, 32>(p, st);
+    else fc_launch<64, 16>(p, st);
+  } else if (cin == 128) {
+    if (W >= 128) fc_launch<128, 128>(p, st);
+    else if (W >= 64) fc_launch<128, 64>(p, st);
+    else if (W >= 32) fc_launch<128, 32>(p, st);
+    else fc_launch<128, 16>(p, st);
+  } else {
+    if (W >= 128) fc_launch<256, 128>(p, st);
+    else if (W >= 64) fc_launch<256, 64>(p, st);
+    else if (W >= 32) fc_launch<256, 32>(p, st);
+    else fc_launch<256, 16>(p, st);
+  }
+}
+
+}  // namespace t2p

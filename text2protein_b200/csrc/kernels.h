@@ -142,6 +142,13 @@ void run_prep(long long* state, const long long* label_table, const float* g_tab
               cudaStream_t st);
 void apply_mask(float* x, const unsigned char* mask, const float* fixed, long long n, cudaStream_t st);
 
+// ----------------------------------------------------------------------------- last layer (final_conv.cu)
+// out[B][nout][H][W] fp32 = conv3x3(silu(x * scale + shift)) + bias on the RAW bf16 NHWC activation x; w is the
+// packed [nout][9][cin] bf16 weight.  GroupNorm-apply, SiLU and the convolution in one pass over the tensor.
+bool final_conv_fused_supported(int cin, int nout, int H, int W);
+void final_conv_fused(const void* x, const float* scale, const float* shift, const void* w, const float* bias, float* out,
+                      int B, int H, int W, int cin, int nout, cudaStream_t st);
+
 // ----------------------------------------------------------------------------- callers of the loop (conditions.cu)
 void length_mask(const int* lengths, int B, int N, unsigned char* out, cudaStream_t st);
 void inpaint_mask(const int* ranges, int R, int per_sample, int B, int N, unsigned char* out, cudaStream_t st);

@@ -323,6 +323,7 @@ UNet::~UNet() {
     if (t->kv) cudaFree(t->kv);
   if (ctx_buf_) cudaFree(ctx_buf_);
   if (h_scratch_) cudaFree(h_scratch_);
+  if (temb_persist_) cudaFree(temb_persist_);
   if (side_) cudaStreamDestroy(side_);
   if (ev_fork_) cudaEventDestroy(ev_fork_);
   if (ev_join_) cudaEventDestroy(ev_join_);
@@ -500,7 +501,8 @@ int UNet::profile_records(GemmRecord* out, int cap) {
   return n;
 }
 
-void UNet::group_norm(const GroupNormP& gn, const Act& a0, const Act* a1, int act, int mode, Act& out, Act* raw_out) {
+void UNet::group_norm(const GroupNormP& gn, const Act& a0, const Act* a1, int act, int mode, Act& out, Act* raw_out,
+                      float** affine_out) {
   const int C = a0.C + (a1 ? a1->C : 0);
   T2P_CHECK(C == gn.C, "GroupNorm channel mismatch");
   const int B = a0.B, HW = a0.H * a0.W;
@@ -524,6 +526,17 @@ void UNet::group_norm(const GroupNormP& gn, const Act& a0, const Act* a1, int ac
   }
   float* scale = static_cast<float*>(ln_->ws.alloc(sizeof(float) * 2 * B * C));
   float* shift = scale + static_cast<size_t>(B) * C;
+  if (affine_out) {
+    // statistics -> per-(sample, channel) affine only; the consumer applies it itself (fused final convolution)
+    launches_ += 1;
+    if (!dry_)
+      gn_finalize(part[0], nblk[0], a0.C, part[1], nblk[1], a1 ? a1->C : 0, static_cast<const float*>(gn.w->data),
+                  static_cast<const float*>(gn.b->data), B, gn.G, HW, 1e-6f, scale, shift, ln_->st);
+    for (int i = 0; i < 2; ++i)
+      if (owned[i]) ln_->ws.free(owned[i]);
+    *affine_out = scale;  // [2][B][C]: scale then shift; the caller returns it to the arena
+    return;
+  }
   launches_ += 2;  // finalize + apply
   ++ln_->seq;
   if (!dry_) {
@@ -785,11 +798,27 @@ void UNet::forward_impl(const float* x, const long long* labels, float* h_out, i
     static const bool on = [] { const char* e = getenv("T2P_SERPENTINE"); return !e || atoi(e) != 0; }();
     serpentine_ = on;
   }
-  ln_->temb_all = static_cast<float*>(ln_->ws.alloc(sizeof(float) * static_cast<size_t>(B) * temb_total_));
+  // Time-embedding path (pre_blocks MLP + every ResBlock's Dense_0): a function of the labels only.  It lives in a
+  // persistent buffer so that a caller evaluating the network twice at the same noise level (corrector, then
+  // predictor of one PC iteration) can ask for it to be reused.
+  const size_t temb_bytes = sizeof(float) * static_cast<size_t>(B) * temb_total_;
+  if (!dry_ && temb_bytes > temb_persist_bytes_) {
+    if (temb_persist_) T2P_CUDA(cudaFree(temb_persist_));
+    temb_persist_ = nullptr;
+    temb_persist_bytes_ = 0;
+    T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&temb_persist_), temb_bytes));
+    temb_persist_bytes_ = temb_bytes;
+    temb_valid_B_ = 0;
+  }
+  ln_->temb_all = temb_persist_;
   {
+    // (the scratch is taken from the arena even when the result is reused, so that the arena's allocation
+    // sequence -- planned once per batch size -- does not depend on the flag)
     float* temb = static_cast<float*>(ln_->ws.alloc(sizeof(float) * static_cast<size_t>(B) * 4 * nf));
-    launches_ += 2;
-    if (!dry_) {
+    const bool reuse = reuse_temb_ && temb_valid_B_ == B;
+    if (!reuse) launches_ += 2;
+    if (!dry_ && !reuse) {
+      temb_valid_B_ = B;
       temb_mlp(labels, B, nf, static_cast<const float*>(pre0_w_->data), static_cast<const float*>(pre0_b_->data),
                static_cast<const float*>(pre1_w_->data), static_cast<const float*>(pre1_b_->data), temb, ln_->st);
       ConvGemmArgs g;
@@ -851,25 +880,36 @@ void UNet::forward_impl(const float* x, const long long* labels, float* h_out, i
     h_owned = true;
   }
   T2P_CHECK(hs.empty(), "skip stack not drained");
-  Act hn = new_act(B, N, N, h.C, false);
-  group_norm(out_gn_, h, nullptr, 1, 0, hn, nullptr);
-  free_act(h);
-  Act o;
-  o.p = h_out; o.B = B; o.H = N; o.W = N; o.C = C;
-  gemm(out_conv_, hn, nullptr, o, nullptr, 0, nullptr, 0, 1.f, kF32, /*out_nchw=*/1);
-  free_act(hn);
-  ln_->ws.free(ln_->temb_all);
+  static const bool fuse_out = [] { const char* e = getenv("T2P_FUSED_OUT"); return !e || atoi(e) != 0; }();
+  if (fuse_out && cfg_.compute_dtype == kBF16 && final_conv_fused_supported(h.C, C, N, N)) {
+    // out = Conv3x3(SiLU(GroupNorm(h))) in one pass over h (final_conv.cu): no normalised copy of the largest tensor
+    float* affine = nullptr;
+    Act none;
+    group_norm(out_gn_, h, nullptr, 1, 0, none, nullptr, &affine);
+    ++launches_;
+    if (!dry_)
+      final_conv_fused(h.p, affine, affine + static_cast<size_t>(B) * h.C, out_conv_.wp, out_conv_.bp, h_out, B, N, N, h.C,
+                       C, ln_->st);
+    ln_->ws.free(affine);
+    free_act(h);
+  } else {
+    Act hn = new_act(B, N, N, h.C, false);
+    group_norm(out_gn_, h, nullptr, 1, 0, hn, nullptr);
+    free_act(h);
+    Act o;
+    o.p = h_out; o.B = B; o.H = N; o.W = N; o.C = C;
+    gemm(out_conv_, hn, nullptr, o, nullptr, 0, nullptr, 0, 1.f, kF32, /*out_nchw=*/1);
+    free_act(hn);
+  }
   ln_->temb_all = nullptr;
 }
 
 void UNet::forward_raw(const float* x, const long long* labels, float* h_out, int B, cudaStream_t st) {
   T2P_CHECK(finalized_, "finalize() before forward()");
-  // Optional (T2P_SPLIT=1): two half-batches on two streams, so that the GEMMs of one lane overlap the HBM-bound
-  // normalisation / attention kernels of the other (every sample's arithmetic is unchanged: bit-identical results).
-  // Measured on B200 at cfg2: 26.99 vs 26.91 ms per PC iteration -- no gain, both kernel kinds are bound by the same
-  // L2 / HBM path -- so it is off by default (it also doubles the activation arena).
-  static const bool split_on = [] { const char* e = getenv("T2P_SPLIT"); return e && atoi(e) != 0; }();
-  const int nl = (split_on && !profile_ && !debug_ && B >= 8 && B % 2 == 0) ? 2 : 1;
+  // Measured and retired: two half-batches on two streams, so that the GEMMs of one lane overlap the HBM-bound
+  // normalisation / attention kernels of the other -- 26.99 vs 26.91 ms per PC iteration at cfg2 (no gain: both
+  // kernel kinds are bound by the same L2 / HBM path), at twice the activation arena.
+  const int nl = 1;  // (the two-lane variant is retired; the lane plumbing is kept for the single lane)
   const int Bl = B / nl;
   nlanes_ = nl;
   if (planned_B_ != Bl) {

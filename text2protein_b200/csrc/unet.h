@@ -148,6 +148,9 @@ class UNet {
   // x: fp32 NCHW [B][C][N][N]; labels: int64 [B]; h_out: fp32 NCHW [B][C][N][N] un-scaled final conv
   // (what the fused PC-step kernels consume).  Returns through `h_out` only.
   void forward_raw(const float* x, const long long* labels, float* h_out, int B, cudaStream_t st);
+  // true: the next forward passes may reuse the time-embedding biases of the previous one (same labels, same B);
+  // the PC loop sets it for the predictor evaluation that follows a corrector evaluation at the same noise level
+  void set_reuse_temb(bool on) { reuse_temb_ = on; }
   // Reference-shaped output: NCHW, divided by sigmas[labels] in double (ncsnpp.py:259-261), fp64 or fp32.
   void forward(const float* x, const long long* labels, void* out, int out_dtype, int B, cudaStream_t st);
   const double* sigmas() const { return static_cast<const double*>(sigmas_->data); }
@@ -180,7 +183,8 @@ class UNet {
   void gemm(const Linear& l, const Act& a0, const Act* a1, Act& out, const float* rowbias, int rowbias_ld,
             const void* residual, int res_up, float alpha, int out_dtype = -1, int out_nchw = 0,
             const Act* x0 = nullptr, const Act* x1 = nullptr);
-  void group_norm(const GroupNormP& g, const Act& a0, const Act* a1, int act, int mode, Act& out, Act* raw_out);
+  void group_norm(const GroupNormP& g, const Act& a0, const Act* a1, int act, int mode, Act& out, Act* raw_out,
+                  float** affine_out = nullptr);
   void attention(const void* q, const void* k, const void* v, void* out, int B, int heads, int Tq, int Tk, int d,
                  long long ldq, long long ldk, long long ldv, long long ldo, float scale);
   Act run_res(ResBlockM& m, const Act& a0, const Act* a1);
@@ -237,6 +241,10 @@ class UNet {
   std::map<std::string, std::pair<float*, std::vector<int64_t>>> taps_;
   void* ctx_buf_ = nullptr;  // text context in the compute dtype (grow-only staging buffer of set_context)
   size_t ctx_buf_bytes_ = 0;
+  float* temb_persist_ = nullptr;  // [B][temb_total_] Dense_0(act(temb)) of the last evaluated labels
+  size_t temb_persist_bytes_ = 0;
+  int temb_valid_B_ = 0;
+  bool reuse_temb_ = false;
   float* h_scratch_ = nullptr;
   size_t h_scratch_bytes_ = 0;
 };
