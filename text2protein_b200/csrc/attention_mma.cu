@@ -185,11 +185,11 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int W>
+template <int W, int ROWS, int NTHREADS>
 __device__ __forceinline__ void load_tile_async(__nv_bfloat16* dst, const __nv_bfloat16* src, long long ld, int r0,
                                                 int rmax, int c0) {
   constexpr int VPR = W / 8;
-  for (int i = threadIdx.x; i < 64 * VPR; i += NT) {
+  for (int i = threadIdx.x; i < ROWS * VPR; i += NTHREADS) {
     const int r = i / VPR, cv = i - r * VPR;
     const bool ok = r0 + r < rmax;
     const __nv_bfloat16* g = src + static_cast<long long>(ok ? r0 + r : 0) * ld + c0 + cv * 8;
@@ -197,27 +197,30 @@ __device__ __forceinline__ void load_tile_async(__nv_bfloat16* dst, const __nv_b
   }
 }
 
-template <int D, int DV>
-__global__ void __launch_bounds__(NT) attention_pipe_kernel(const Params p) {
+// WARPS x 16 query rows per CTA (each warp owns 16 rows; K / V tiles are shared by all warps)
+template <int D, int DV, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) attention_pipe_kernel(const Params p) {
+  constexpr int QROWS = WARPS * 16;
+  constexpr int NTH = WARPS * 32;
   extern __shared__ __align__(16) unsigned char smem_dyn[];
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem_dyn);
-  __nv_bfloat16* Ks = Qs + BM * (D + 8);            // [2][BN][D + 8]
+  __nv_bfloat16* Ks = Qs + QROWS * (D + 8);            // [2][BN][D + 8]
   __nv_bfloat16* Vs = Ks + 2 * BN * (D + 8);        // [2][BN][DV + 8]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tq = lane & 3;
   constexpr int slices = D / DV;
   const int h = blockIdx.y / slices, sl = blockIdx.y - h * slices;
   const int b = blockIdx.z;
-  const int m0 = blockIdx.x * BM;
+  const int m0 = blockIdx.x * QROWS;
   const __nv_bfloat16* qb = p.q + static_cast<long long>(b) * p.Tq * p.ldq + h * D;
   const __nv_bfloat16* kb = p.k + static_cast<long long>(b) * p.Tk * p.ldk + h * D;
   const __nv_bfloat16* vb = p.v + static_cast<long long>(b) * p.Tk * p.ldv + h * D + sl * DV;
 
   pdl_trigger();
   pdl_wait();
-  load_tile_async<D>(Qs, qb, p.ldq, m0, p.Tq, 0);
-  load_tile_async<D>(Ks, kb, p.ldk, 0, p.Tk, 0);
-  load_tile_async<DV>(Vs, vb, p.ldv, 0, p.Tk, 0);
+  load_tile_async<D, QROWS, NTH>(Qs, qb, p.ldq, m0, p.Tq, 0);
+  load_tile_async<D, BN, NTH>(Ks, kb, p.ldk, 0, p.Tk, 0);
+  load_tile_async<DV, BN, NTH>(Vs, vb, p.ldv, 0, p.Tk, 0);
   cp_async_commit();
 
   float o[DV / 8][4];
@@ -230,8 +233,8 @@ __global__ void __launch_bounds__(NT) attention_pipe_kernel(const Params p) {
     const int n0 = it * BN;
     const int cur = it & 1;
     if (it + 1 < ntiles) {  // prefetch the next key tile into the other buffer (its readers finished last iteration)
-      load_tile_async<D>(Ks + (cur ^ 1) * BN * (D + 8), kb, p.ldk, n0 + BN, p.Tk, 0);
-      load_tile_async<DV>(Vs + (cur ^ 1) * BN * (DV + 8), vb, p.ldv, n0 + BN, p.Tk, 0);
+      load_tile_async<D, BN, NTH>(Ks + (cur ^ 1) * BN * (D + 8), kb, p.ldk, n0 + BN, p.Tk, 0);
+      load_tile_async<DV, BN, NTH>(Vs + (cur ^ 1) * BN * (DV + 8), vb, p.ldv, n0 + BN, p.Tk, 0);
       cp_async_commit();
       cp_async_wait<1>();
     } else {
@@ -337,18 +340,19 @@ Params make_params(const AttnArgs& a) {
   return p;
 }
 
-template <int D, int DV>
+template <int D, int DV, int WARPS>
 void launch_pipe(const AttnArgs& a, cudaStream_t st) {
-  constexpr size_t smem = sizeof(__nv_bfloat16) * (BM * (D + 8) + 2 * BN * (D + 8) + 2 * BN * (DV + 8));
+  constexpr int QROWS = WARPS * 16;
+  constexpr size_t smem = sizeof(__nv_bfloat16) * (QROWS * (D + 8) + 2 * BN * (D + 8) + 2 * BN * (DV + 8));
   static bool configured = false;
   if (!configured) {
-    T2P_CUDA(cudaFuncSetAttribute(attention_pipe_kernel<D, DV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    T2P_CUDA(cudaFuncSetAttribute(attention_pipe_kernel<D, DV, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
     configured = true;
   }
   const Params p = make_params(a);
-  dim3 grid(cdiv(a.Tq, BM), a.heads * (D / DV), a.B);
-  launch_pdl(attention_pipe_kernel<D, DV>, grid, dim3(NT), smem, st, p);
+  dim3 grid(cdiv(a.Tq, QROWS), a.heads * (D / DV), a.B);
+  launch_pdl(attention_pipe_kernel<D, DV, WARPS>, grid, dim3(WARPS * 32), smem, st, p);
 }
 
 template <int DK, int DV>
@@ -377,11 +381,14 @@ bool attention_mma_supported(const AttnArgs& a) {
 
 void attention_mma(const AttnArgs& a, cudaStream_t st) {
   T2P_CHECK(attention_mma_supported(a), "unsupported shape / alignment for the tensor-core attention kernel");
-  if (a.d == 16) launch_pipe<16, 16>(a, st);
-  else if (a.d == 32) launch_pipe<32, 32>(a, st);
-  else if (a.d == 64) launch_pipe<64, 64>(a, st);
-  else if (a.d == 128) launch_pipe<128, 128>(a, st);
-  else if (a.d == 256) launch_pipe<256, 128>(a, st);
+  // 128 query rows per CTA when the sequence has them (K / V tiles are then read half as often), else 64; the
+  // 256-wide single head of AttnBlockpp keeps its whole value dimension in one CTA (scores computed once)
+  const bool wide = a.Tq >= 128;
+  if (a.d == 16) { if (wide) launch_pipe<16, 16, 8>(a, st); else launch_pipe<16, 16, 4>(a, st); }
+  else if (a.d == 32) { if (wide) launch_pipe<32, 32, 8>(a, st); else launch_pipe<32, 32, 4>(a, st); }
+  else if (a.d == 64) { if (wide) launch_pipe<64, 64, 8>(a, st); else launch_pipe<64, 64, 4>(a, st); }
+  else if (a.d == 128) { if (wide) launch_pipe<128, 128, 8>(a, st); else launch_pipe<128, 128, 4>(a, st); }
+  else if (a.d == 256) { if (wide) launch_pipe<256, 256, 8>(a, st); else launch_pipe<256, 128, 4>(a, st); }
   else if (a.d == 16) launch<16, 16>(a, st);
   else if (a.d == 32) launch<32, 32>(a, st);
   else if (a.d == 64) launch<64, 64>(a, st);

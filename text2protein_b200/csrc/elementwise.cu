@@ -139,6 +139,36 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, int B, int HW,
 
 // First conv as a plain GEMM: A[m][k] with k = tap * C + c (zero padded to kpad), from the fp32 NCHW state.
 // 3x3, stride 1, zero padding 1.  One thread writes 8 consecutive k (16 bytes).
+// One thread per pixel, all 9 * C taps of its row of the im2col matrix (C is a compile-time 5 or 8: the tap loops
+// unroll, there is no per-element index arithmetic); consecutive lanes are consecutive pixels, so the fp32 NCHW reads
+// are coalesced per (channel, tap) and each thread writes its KPAD-wide bf16 row as 16-byte vectors.
+template <int C, int KPAD>
+__global__ void __launch_bounds__(256) im2col3x3_pixel_kernel(const float* __restrict__ x, int B, int H, int W,
+                                                              __nv_bfloat16* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  const long long m = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (m >= static_cast<long long>(B) * H * W) return;
+  const int w = static_cast<int>(m % W);
+  const int h = static_cast<int>((m / W) % H);
+  const int b = static_cast<int>(m / (static_cast<long long>(W) * H));
+  const float* xb = x + static_cast<long long>(b) * C * H * W;
+  __align__(16) __nv_bfloat16 vals[KPAD];
+#pragma unroll
+  for (int k = 9 * C; k < KPAD; ++k) vals[k] = __float2bfloat16(0.f);
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int ih = h + tap / 3 - 1, iw = w + tap % 3 - 1;
+    const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      vals[tap * C + c] = __float2bfloat16(ok ? xb[(static_cast<long long>(c) * H + ih) * W + iw] : 0.f);
+  }
+  uint4* dst = reinterpret_cast<uint4*>(out + m * KPAD);
+#pragma unroll
+  for (int i = 0; i < KPAD / 8; ++i) dst[i] = reinterpret_cast<const uint4*>(vals)[i];
+}
+
 __global__ void im2col3x3_nchw_kernel(const float* __restrict__ x, int B, int C, int H, int W, int kpad,
                                       __nv_bfloat16* __restrict__ out) {
   pdl_trigger();
@@ -260,6 +290,17 @@ void nchw_f32_to_nhwc(const float* in, int B, int HW, int C, int cpad, int out_d
 
 void im2col3x3_nchw(const float* x, int B, int C, int H, int W, int kpad, void* out, cudaStream_t st) {
   T2P_CHECK(kpad % 8 == 0 && kpad >= 9 * C, "bad im2col padding");
+  const long long pixels = static_cast<long long>(B) * H * W;
+  if (C == 5 && kpad == 64) {
+    launch_pdl(im2col3x3_pixel_kernel<5, 64>, dim3(static_cast<unsigned>(cdiv64(pixels, 256))), dim3(256), 0, st, x, B, H, W,
+               static_cast<__nv_bfloat16*>(out));
+    return;
+  }
+  if (C == 8 && kpad == 128) {
+    launch_pdl(im2col3x3_pixel_kernel<8, 128>, dim3(static_cast<unsigned>(cdiv64(pixels, 256))), dim3(256), 0, st, x, B, H, W,
+               static_cast<__nv_bfloat16*>(out));
+    return;
+  }
   const long long total = static_cast<long long>(B) * H * W * (kpad / 8);
   launch_pdl(im2col3x3_nchw_kernel, dim3(static_cast<unsigned>(cdiv64(total, 256))), dim3(256), 0, st, x, B, C, H, W, kpad,
              static_cast<__nv_bfloat16*>(out));

@@ -329,46 +329,71 @@ __global__ void __launch_bounds__(256, sizeof(T) == 2 ? 4 : 2) gn_apply_rows_ker
   }
 }
 
-// ------------------------------------------------------------------ LayerNorm over the last dim (one warp/row)
-template <typename T, int MAXV>
+// ------------------------------------------------------------------ LayerNorm over the last dim
+// One warp normalises ROWS rows at a time (their loads are issued together, the shuffle reductions interleave), the
+// affine parameters are read once per warp as 16-byte vectors.  C = 256 * nv, nv <= MAXV.
+template <typename T, int MAXV, int ROWS>
 __global__ void layernorm_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, int M, int C, float eps, T* __restrict__ y) {
   pdl_trigger();
   pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= M) return;
-  const int nv = C >> 8;  // 8-element vectors per lane (C % 256 == 0) -- else handled by the scalar kernel
-  float v[MAXV][8];
-  float s = 0.f;
+  const int row0 = warp * ROWS;
+  if (row0 >= M) return;
+  const int nv = C >> 8;  // 8-element vectors per lane
+  float v[ROWS][MAXV][8];
+  float s[ROWS];
 #pragma unroll
-  for (int j = 0; j < MAXV; ++j)
-    if (j < nv) {
-      const Vec8<T> t = Vec8<T>::load(x + static_cast<long long>(warp) * C + (j * 32 + lane) * 8);
+  for (int r = 0; r < ROWS; ++r) {
+    s[r] = 0.f;
+    const bool ok = row0 + r < M;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { v[j][i] = t.v[i]; s += t.v[i]; }
-    }
+    for (int j = 0; j < MAXV; ++j)
+      if (j < nv) {
+        Vec8<T> t;
+        if (ok) t = Vec8<T>::load(x + static_cast<long long>(row0 + r) * C + (j * 32 + lane) * 8);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / C;
-  float q = 0.f;
+        for (int i = 0; i < 8; ++i) { v[r][j][i] = ok ? t.v[i] : 0.f; s[r] += v[r][j][i]; }
+      }
+  }
 #pragma unroll
-  for (int j = 0; j < MAXV; ++j)
-    if (j < nv) {
+  for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { const float d = v[j][i] - mean; q += d * d; }
-    }
+    for (int r = 0; r < ROWS; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+  float q[ROWS], mean[ROWS];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = rsqrtf(q / C + eps);
+  for (int r = 0; r < ROWS; ++r) {
+    mean[r] = s[r] / C;
+    q[r] = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j)
+      if (j < nv) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float d = v[r][j][i] - mean[r]; q[r] += d * d; }
+      }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) q[r] += __shfl_xor_sync(0xffffffffu, q[r], o);
 #pragma unroll
   for (int j = 0; j < MAXV; ++j)
     if (j < nv) {
       const int c = (j * 32 + lane) * 8;
-      Vec8<T> t;
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) t.v[i] = (v[j][i] - mean) * rstd * gamma[c + i] + beta[c + i];
-      t.store(y + static_cast<long long>(warp) * C + c);
+      for (int r = 0; r < ROWS; ++r) {
+        if (row0 + r >= M) break;
+        const float rstd = rsqrtf(q[r] / C + eps);
+        Vec8<T> t;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t.v[i] = (v[r][j][i] - mean[r]) * rstd * gm[i] + bt[i];
+        t.store(y + static_cast<long long>(row0 + r) * C + c);
+      }
     }
 }
 
@@ -505,13 +530,17 @@ void gn_apply(const void* a0, int c0, const void* a1, int c1, int B, int H, int 
 
 void layernorm(const void* x, const float* gamma, const float* beta, long long M, int C, float eps, int dtype,
                void* y, cudaStream_t st) {
-  const unsigned blocks = static_cast<unsigned>(cdiv64(M, 8));
   const bool fast = (C % 256 == 0) && C <= 1024;
+  const bool narrow = fast && C <= 512;  // 4 rows per warp while the row cache stays in registers
+  const int rows_per_block = narrow ? 8 * 4 : 8;
+  const unsigned blocks = static_cast<unsigned>(cdiv64(M, rows_per_block));
   if (dtype == kF32) {
-    if (fast) launch_pdl(layernorm_kernel<float, 4>, dim3(blocks), dim3(256), 0, st, static_cast<const float*>(x), gamma, beta, (int)M, C, eps, static_cast<float*>(y));
+    if (narrow) launch_pdl(layernorm_kernel<float, 2, 4>, dim3(blocks), dim3(256), 0, st, static_cast<const float*>(x), gamma, beta, (int)M, C, eps, static_cast<float*>(y));
+    else if (fast) launch_pdl(layernorm_kernel<float, 4, 1>, dim3(blocks), dim3(256), 0, st, static_cast<const float*>(x), gamma, beta, (int)M, C, eps, static_cast<float*>(y));
     else launch_pdl(layernorm_generic_kernel<float>, dim3(blocks), dim3(256), 0, st, static_cast<const float*>(x), gamma, beta, (int)M, C, eps, static_cast<float*>(y));
   } else {
-    if (fast) launch_pdl(layernorm_kernel<__nv_bfloat16, 4>, dim3(blocks), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(x), gamma, beta, (int)M, C, eps, static_cast<__nv_bfloat16*>(y));
+    if (narrow) launch_pdl(layernorm_kernel<__nv_bfloat16, 2, 4>, dim3(blocks), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(x), gamma, beta, (int)M, C, eps, static_cast<__nv_bfloat16*>(y));
+    else if (fast) launch_pdl(layernorm_kernel<__nv_bfloat16, 4, 1>, dim3(blocks), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(x), gamma, beta, (int)M, C, eps, static_cast<__nv_bfloat16*>(y));
     else launch_pdl(layernorm_generic_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(x), gamma, beta, (int)M, C, eps, static_cast<__nv_bfloat16*>(y));
   }
   T2P_LAUNCH_CHECK();
