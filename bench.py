@@ -223,6 +223,43 @@ def _step_kernel_roofline(dev, B, shape, L, mask_u8, hbm_gbs):
     return out
 
 
+def _gn_apply_roofline(dev, B, cfg, L, hbm_gbs):
+    """GroupNorm-apply + SiLU (the largest HBM-bound kernel of the forward, 18 % of its time) on the biggest tensor of
+    the network, [B, N, N, nf] bf16: 2 B read + 2 B written per element."""
+    from text2protein_b200 import _lib
+    N, nf = cfg.data.max_res_num, cfg.model.nf
+    sets = 3  # 3 x (268 + 268 MB) > L2
+    xs = [torch.randn(B, N, N, nf, device=dev).bfloat16() for _ in range(sets)]
+    ys = [torch.empty_like(x) for x in xs]
+    scale = 1 + 0.1 * torch.randn(B, nf, device=dev)
+    shift = 0.1 * torch.randn(B, nf, device=dev)
+    def launch(i):
+        _lib.check(L.t2p_groupnorm_apply(_lib.ptr(xs[i]), nf, None, 0, B, N, N, 1, _lib.ptr(scale), _lib.ptr(shift), 1, 0,
+                                         _lib.ptr(ys[i]), None, _lib.current_stream()))
+    for i in range(sets):
+        launch(i)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=torch.cuda.Stream(device=dev)):
+        for i in range(sets):
+            launch(i)
+    graph.replay()
+    torch.cuda.synchronize()
+    reps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / (reps * sets)
+    nbytes = xs[0].numel() * 4
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    return {"gn_apply_rows_kernel": {"ms": ms, "algorithmic_bytes": nbytes, "achieved_gbs": gbs, "peak_gbs": hbm_gbs,
+                                     "frac": gbs / hbm_gbs, "bound": "hbm",
+                                     "note": f"[{B},{N},{N},{nf}] bf16, graph-replayed back to back over 3 buffer sets (> L2)"}}
+
+
 # ------------------------------------------------------------------------------------------------ native arm
 def run_native(args, cfg):
     import torch.distributed as dist
@@ -389,6 +426,7 @@ def run_native(args, cfg):
     steps = None
     if rank == 0:
         steps = _step_kernel_roofline(dev, B, shape, L, mask_u8, hbm)
+        steps.update(_gn_apply_roofline(dev, B, cfg, L, hbm))
         if roof is not None:
             roof["traffic"] = _traffic_lookup(roof)
 

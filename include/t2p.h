@@ -179,6 +179,10 @@ int t2p_final_conv(const void* x, const float* scale, const float* shift, const 
 int t2p_groupnorm(const void* a0, int c0, const void* a1, int c1, int B, int H, int W, int dtype, int groups,
                   float eps, const float* gamma, const float* beta, int silu, int resample_mode, void* out,
                   void* raw_out, void* stream);
+/* The apply pass alone, given the per-(sample, channel) affine [B][c0+c1]: y = act(x * scale + shift) [+ resampling].
+ * This is the HBM-bound kernel the engine launches after the GEMM epilogue has produced the statistics. */
+int t2p_groupnorm_apply(const void* a0, int c0, const void* a1, int c1, int B, int H, int W, int dtype, const float* scale,
+                        const float* shift, int silu, int resample_mode, void* out, void* raw_out, void* stream);
 int t2p_layernorm(const void* x, const float* gamma, const float* beta, int64_t M, int C, float eps, int dtype,
                   void* y, void* stream);                     /* attention.py:203-205 */
 int t2p_geglu(const void* z, int64_t M, int D, int dtype, void* out, void* stream); /* attention.py:42-44 */

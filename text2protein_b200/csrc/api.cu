@@ -442,6 +442,14 @@ int t2p_final_conv(const void* x, const float* scale, const float* shift, const 
   T2P_API_END
 }
 
+int t2p_groupnorm_apply(const void* a0, int c0, const void* a1, int c1, int B, int H, int W, int dtype, const float* scale,
+                        const float* shift, int silu, int resample_mode, void* out, void* raw_out, void* stream) {
+  T2P_API_BEGIN
+  T2P_CHECK(a0 && scale && shift && out, "null argument");
+  gn_apply(a0, c0, a1, c1, B, H, W, dtype, scale, shift, silu, resample_mode, out, raw_out, S(stream));
+  T2P_API_END
+}
+
 int t2p_groupnorm(const void* a0, int c0, const void* a1, int c1, int B, int H, int W, int dtype, int groups,
                   float eps, const float* gamma, const float* beta, int silu, int resample_mode, void* out,
                   void* raw_out, void* stream) {
