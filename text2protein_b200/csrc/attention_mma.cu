@@ -177,6 +177,11 @@ __global__ void __launch_bounds__(NT) attention_mma_kernel(const Params p) {
 // Pipelined variant for head dims that fit shared memory whole (D <= 256): Q is staged once, K / V tiles are
 // double-buffered with cp.async so the loads of key tile i + 1 overlap the math of tile i.  Same math and
 // fragment layout as the kernel above.
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
   const int sz = valid ? 16 : 0;  // src-size 0 -> zero fill
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
@@ -259,32 +264,38 @@ __global__ void __launch_bounds__(WARPS * 32) attention_pipe_kernel(const Params
         mma16816(s[2 * np + 1], a0, a1, a2, a3, b2, b3);
       }
     }
+    // (this kernel is issue-bound on the softmax arithmetic: the key-range mask is applied on the ragged last
+    // tile only, the scaling is folded into the exponent's FMA and exp2 is the single-instruction MUFU form)
     float tmax[2] = {-INFINITY, -INFINITY};
+    if (n0 + BN > p.Tk) {
 #pragma unroll
-    for (int i = 0; i < BN / 8; ++i) {
-      const int key = n0 + i * 8 + tq * 2;
+      for (int i = 0; i < BN / 8; ++i) {
+        const int key = n0 + i * 8 + tq * 2;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const bool valid = (key + (e & 1)) < p.Tk;
-        s[i][e] = valid ? s[i][e] * p.scale_log2 : -INFINITY;
-        tmax[e >> 1] = fmaxf(tmax[e >> 1], s[i][e]);
+        for (int e = 0; e < 4; ++e)
+          if (key + (e & 1) >= p.Tk) s[i][e] = -INFINITY;
       }
     }
-    float corr[2];
+#pragma unroll
+    for (int i = 0; i < BN / 8; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) tmax[e >> 1] = fmaxf(tmax[e >> 1], s[i][e]);
+    float corr[2], moff[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       tmax[r] = fmaxf(tmax[r], __shfl_xor_sync(0xffffffffu, tmax[r], 1));
       tmax[r] = fmaxf(tmax[r], __shfl_xor_sync(0xffffffffu, tmax[r], 2));
-      const float mn = fmaxf(mrow[r], tmax[r]);
-      corr[r] = exp2f(mrow[r] - mn);
+      const float mn = fmaxf(mrow[r], tmax[r] * p.scale_log2);  // running max of the SCALED scores (scale > 0)
+      corr[r] = fast_exp2(mrow[r] - mn);
       mrow[r] = mn;
+      moff[r] = -mn;
     }
     float psum[2] = {0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < BN / 8; ++i)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        s[i][e] = exp2f(s[i][e] - mrow[e >> 1]);
+        s[i][e] = fast_exp2(fmaf(s[i][e], p.scale_log2, moff[e >> 1]));
         psum[e >> 1] += s[i][e];
       }
 #pragma unroll
