@@ -442,7 +442,9 @@ struct CfgT {
   static constexpr int P_BYTES = PX * BK * 2;
   static constexpr int STAGE_BYTES = W_BYTES + P_BYTES;
   static constexpr int STAGES = (SMEM_TILE_BUDGET / STAGE_BYTES) < 8 ? (SMEM_TILE_BUDGET / STAGE_BYTES) : 8;
-  static constexpr int OUT_BYTES = 4 * 2 * 32 * 32 * 2;  // per epilogue warp: 2 buffers of 32 px x 32 ch bf16
+  static constexpr int EPI_WARPS = 8;  // two per TMEM lane quadrant: each takes half of the tile's pixel columns
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int OUT_BYTES = EPI_WARPS * 2 * 32 * 32 * 2;  // per epilogue warp: 2 buffers of 32 px x 32 ch bf16
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_BYTES + 1024;
   static constexpr int TMEM_COLS = 2 * PX;
 };
@@ -501,7 +503,7 @@ __device__ __forceinline__ void epilogue_chunk_t(const TcParams& p, const EpiT& 
 }
 
 template <int PX>
-__global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_tcT_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(CfgT<PX>::THREADS, 1) conv_gemm_tcT_kernel(const __grid_constant__ TcParams p) {
   using C = CfgT<PX>;
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
@@ -528,7 +530,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_tcT_kernel(const __g
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(ptx::smem_u32(&tfull_bar[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&tempty_bar[s]), 4);
+      ptx::mbar_init(ptx::smem_u32(&tempty_bar[s]), C::EPI_WARPS);
     }
     ptx::fence_mbar_init();
   }
@@ -647,11 +649,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_tcT_kernel(const __g
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5): thread = channel
+    // ------------------------------------------------------------ epilogue (warps 2..9): thread = channel.
+    // Two warps share each TMEM lane quadrant (warp % 4) and split the tile's pixel columns in halves: a CTA with a
+    // single tile (the many latency-bound launches at 16 x 16 and below) drains its accumulator twice as fast.
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     EpiT et;
     et.rb_uniform = p.rowbias != nullptr && (p.rows_per_sample % PX) == 0;
-    const uint32_t obuf = out_stage + q * (2 * 32 * 32 * 2);  // this warp's two [32 px][32 ch] bf16 buffers
+    const uint32_t obuf = out_stage + (warp - 2) * (2 * 32 * 32 * 2);  // this warp's two [32 px][32 ch] bf16 buffers
     uint32_t tl = 0;
     uint32_t nstore = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tl) {
@@ -694,25 +699,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_tcT_kernel(const __g
         }
         ++nstore;
       };
-      constexpr int NCH = PX / 32;
+      constexpr int HC = PX / 64;  // 32-pixel chunks per warp (half of the tile)
+      const int cf = half * HC;
       float ssum = 0.f, ssq = 0.f;
       uint32_t r0[32], r1[32];
       unsigned short h[32];
-      ptx::tmem_ld_32x32(tbase, r0);
+      ptx::tmem_ld_32x32(tbase + cf * 32, r0);
 #pragma unroll 1
-      for (int c = 0; c < NCH; c += 2) {
+      for (int i = 0; i < HC; i += 2) {
         ptx::tmem_ld_wait();
-        ptx::tmem_ld_32x32(tbase + (c + 1) * 32, r1);
-        epilogue_chunk_t(p, et, r0, c, ssum, ssq, h);
-        store_chunk(h, c);
-        ptx::tmem_ld_wait();
-        if (c + 2 < NCH) ptx::tmem_ld_32x32(tbase + (c + 2) * 32, r0);
+        if (i + 1 < HC) ptx::tmem_ld_32x32(tbase + (cf + i + 1) * 32, r1);
         else release_acc();
-        epilogue_chunk_t(p, et, r1, c + 1, ssum, ssq, h);
-        store_chunk(h, c + 1);
+        epilogue_chunk_t(p, et, r0, cf + i, ssum, ssq, h);
+        store_chunk(h, cf + i);
+        if (i + 1 < HC) {
+          ptx::tmem_ld_wait();
+          if (i + 2 < HC) ptx::tmem_ld_32x32(tbase + (cf + i + 2) * 32, r0);
+          else release_acc();
+          epilogue_chunk_t(p, et, r1, cf + i + 1, ssum, ssq, h);
+          store_chunk(h, cf + i + 1);
+        }
       }
+      // statistics tile = this warp's half of the pixel tile (PX / 2 pixels): index 2 * pt + half
       if (p.stat_part && et.ch_ok)
-        *reinterpret_cast<float2*>(p.stat_part + (static_cast<long long>(pt) * p.N + et.n) * 2) = make_float2(ssum, ssq);
+        *reinterpret_cast<float2*>(p.stat_part + (static_cast<long long>(2 * pt + half) * p.N + et.n) * 2) =
+            make_float2(ssum, ssq);
     }
     if (lane == 0) ptx::tma_store_wait_read<0>();  // smem must stay valid until the last store has read it
   }
@@ -1082,7 +1093,7 @@ void launch_t(TcParams& p, cudaStream_t st) {
   p.n_tiles = cdiv(p.N, 128);
   p.num_tiles = cdiv(p.M, PX) * p.n_tiles;
   const int grid = std::min(p.num_tiles, sm_count());
-  launch_pdl(conv_gemm_tcT_kernel<PX>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, st, p);
+  launch_pdl(conv_gemm_tcT_kernel<PX>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, p);
 }
 
 void launch_h(TcParams& p, cudaStream_t st) {
@@ -1169,7 +1180,9 @@ int conv_gemm_tc_stat_tile(const ConvGemmArgs& a) {
   ConvGemmArgs q = a;
   if (!q.stat_part) q.stat_part = reinterpret_cast<float*>(16);  // plan as if statistics were requested
   const Plan pl = make_plan(q);
-  return pl.stats_ok ? pl.rows : 0;
+  if (!pl.stats_ok) return 0;
+  // the channel-major kernel's epilogue warps each own half a pixel tile; the halo kernel's own a whole one
+  return (pl.channel_major && !pl.halo) ? pl.rows / 2 : pl.rows;
 }
 
 void conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
