@@ -158,15 +158,44 @@ __global__ void gn_finalize_kernel(const float* __restrict__ part0, int nblk0, i
   const int g = wid % G, b = wid / G;
   const int cpg = C / G;
   double s = 0, q = 0;
-  for (int ci = 0; ci < cpg; ++ci) {
-    const int c = g * cpg + ci;
+  // Channels are taken four at a time so that every lane has four independent L2 loads in flight (a plain
+  // channel-by-channel loop serialises one round trip per partial).  The order of the additions is fixed.
+  auto locate = [&](int c, const float*& base, long long& pitch, int& nblk) {
     const bool first = c < c0;
-    const float* part = first ? part0 : part1;
-    const int nblk = first ? nblk0 : nblk1;
     const int cs = first ? c0 : c1;
-    const int cc = first ? c : c - c0;
+    nblk = first ? nblk0 : nblk1;
+    base = (first ? part0 : part1) + (static_cast<long long>(b) * nblk * cs + (first ? c : c - c0)) * 2;
+    pitch = static_cast<long long>(cs) * 2;
+  };
+  int ci = 0;
+  {
+    for (; ci + 4 <= cpg; ci += 4) {
+      const int c = g * cpg + ci;
+      if (c < c0 && c + 3 >= c0) break;  // the four channels straddle the two sources: finish one by one
+      const float* base;
+      long long pitch;
+      int nblk;
+      locate(c, base, pitch, nblk);
+      for (int k = lane; k < nblk; k += 32) {
+        const float* pk = base + k * pitch;
+        const float2 v0 = __ldg(reinterpret_cast<const float2*>(pk));
+        const float2 v1 = __ldg(reinterpret_cast<const float2*>(pk + 2));
+        const float2 v2 = __ldg(reinterpret_cast<const float2*>(pk + 4));
+        const float2 v3 = __ldg(reinterpret_cast<const float2*>(pk + 6));
+        s += static_cast<double>(v0.x); q += static_cast<double>(v0.y);
+        s += static_cast<double>(v1.x); q += static_cast<double>(v1.y);
+        s += static_cast<double>(v2.x); q += static_cast<double>(v2.y);
+        s += static_cast<double>(v3.x); q += static_cast<double>(v3.y);
+      }
+    }
+  }
+  for (; ci < cpg; ++ci) {
+    const float* base;
+    long long pitch;
+    int nblk;
+    locate(g * cpg + ci, base, pitch, nblk);
     for (int k = lane; k < nblk; k += 32) {
-      const float2 v = *reinterpret_cast<const float2*>(part + ((static_cast<long long>(b) * nblk + k) * cs + cc) * 2);
+      const float2 v = __ldg(reinterpret_cast<const float2*>(base + k * pitch));
       s += static_cast<double>(v.x);
       q += static_cast<double>(v.y);
     }
