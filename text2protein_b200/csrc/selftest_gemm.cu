@@ -99,7 +99,7 @@ static int run_case(const Case& c) {
   fail_if(cudaMalloc(&ref, M * c.N * 4), "malloc");
   fail_if(cudaMalloc(&out32, M * c.N * 4), "malloc");
   fail_if(cudaMalloc(&out16, M * c.N * 2), "malloc");
-  const long long tiles = (M + 63) / 64;  // upper bound on the number of statistics tiles
+  const long long tiles = (M + 31) / 32;  // upper bound on the number of statistics tiles (>= 32 pixels each)
   fail_if(cudaMalloc(&ssum, tiles * c.N * 8), "malloc");
   ssq = nullptr;
   cudaMemset(out32, 0xff, M * c.N * 4);
@@ -211,7 +211,7 @@ static void bench_case(int B, int H, int W, int cin, int N, int ks, int epi) {
   fail_if(cudaMalloc(&res, M * N * 2), "malloc");
   fail_if(cudaMalloc(&bias, N * 4), "malloc");
   fail_if(cudaMalloc(&rb, 1ll * B * N * 4), "malloc");
-  fail_if(cudaMalloc(&st, (M / 64 + 1) * N * 8), "malloc");  // statistics tiles are >= 64 pixels
+  fail_if(cudaMalloc(&st, (M / 32 + 1) * N * 8), "malloc");  // statistics tiles are >= 32 pixels
   fill_bf16<<<(unsigned)((M * cin + 255) / 256), 256>>>(a, M * cin, 1.f, 1u);
   fill_bf16<<<(unsigned)((1ll * N * K + 255) / 256), 256>>>(w, 1ll * N * K, 0.05f, 2u);
   fill_bf16<<<(unsigned)((M * N + 255) / 256), 256>>>(res, M * N, 1.f, 3u);
