@@ -84,5 +84,16 @@ def build_selftest():
     return out
 
 
+def build_probe():
+    """Hardware probe of row-shifted swizzled UMMA operands (build/probe_shift), see csrc/probe_shift.cu."""
+    out = os.path.join(os.path.dirname(HERE), "build", "probe_shift")
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    cmd = [_nvcc()] + flags + ["-o", out, os.path.join(CSRC, "probe_shift.cu"), "-lcuda"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"probe build failed:\n{r.stdout}\n{r.stderr}")
+    return out
+
+
 if __name__ == "__main__":
     print(build(force=False, verbose=True))
