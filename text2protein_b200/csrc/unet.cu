@@ -709,6 +709,10 @@ Act UNet::run_block(BlockM& blk, const Act& a0, const Act* a1, const std::string
     } else if (m.kind == 1) {
       next = run_attn(*m.attn, cur);
     } else {
+      // timing experiment only (breaks the numerics): T2P_DEBUG_SKIP_ST=1 drops the SpatialTransformer blocks so
+      // that their share of the captured forward can be read off a bench run
+      static const bool skip_st = std::getenv("T2P_DEBUG_SKIP_ST") != nullptr;
+      if (skip_st) continue;
       next = run_st(*m.st, cur);
     }
     if (j > 0) free_act(cur);
