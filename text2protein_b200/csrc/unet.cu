@@ -324,9 +324,6 @@ UNet::~UNet() {
   if (ctx_buf_) cudaFree(ctx_buf_);
   if (h_scratch_) cudaFree(h_scratch_);
   if (temb_persist_) cudaFree(temb_persist_);
-  if (side_) cudaStreamDestroy(side_);
-  if (ev_fork_) cudaEventDestroy(ev_fork_);
-  if (ev_join_) cudaEventDestroy(ev_join_);
 }
 
 void UNet::load(const std::string& name, const void* dev_ptr, const std::vector<int64_t>& shape, int dtype,
@@ -638,7 +635,7 @@ Act UNet::run_st(TransformerM& m, const Act& x) {
   const int B = x.B, H = x.H, W = x.W, T = H * W, C = m.C, d = C / m.heads;
   const size_t es = dtype_size(cfg_.compute_dtype);
   const float scale = 1.f / std::sqrt(static_cast<float>(d));
-  T2P_CHECK(m.kv != nullptr && ln_->batch_off + B <= ctx_B_ && (ln_->batch_off > 0 || nlanes_ > 1 || ctx_B_ == B),
+  T2P_CHECK(m.kv != nullptr && ctx_B_ == B,
             "set_context() must be called with the same batch before forward");
   auto ln = [&](const LayerNormP& l, const Act& in, Act& out) {
     ++launches_;
@@ -668,7 +665,7 @@ Act UNet::run_st(TransformerM& m, const Act& x) {
   Act q = new_act(B, H, W, C, false);
   gemm(m.q2, hn, nullptr, q, nullptr, 0, nullptr, 0, 1.f);
   {
-    const char* kv = static_cast<const char*>(m.kv) + static_cast<size_t>(ln_->batch_off) * ctx_L_ * 2 * C * es;
+    const char* kv = static_cast<const char*>(m.kv);
     attention(q.p, kv, kv + C * es, ao.p, B, m.heads, T, ctx_L_, d, C, 2 * C, 2 * C, C, scale);
   }
   free_act(q);
@@ -910,45 +907,22 @@ void UNet::forward_impl(const float* x, const long long* labels, float* h_out, i
 
 void UNet::forward_raw(const float* x, const long long* labels, float* h_out, int B, cudaStream_t st) {
   T2P_CHECK(finalized_, "finalize() before forward()");
-  // Measured and retired: two half-batches on two streams, so that the GEMMs of one lane overlap the HBM-bound
-  // normalisation / attention kernels of the other -- 26.99 vs 26.91 ms per PC iteration at cfg2 (no gain: both
-  // kernel kinds are bound by the same L2 / HBM path), at twice the activation arena.
-  const int nl = 1;  // (the two-lane variant is retired; the lane plumbing is kept for the single lane)
-  const int Bl = B / nl;
-  nlanes_ = nl;
-  if (planned_B_ != Bl) {
-    // dry pass: same code path, no launches; sizes the arena for this (per-lane) batch
-    ln_ = &lanes_[0];
+  // (Measured and retired: two half-batches on two streams, so that the GEMMs of one half overlap the HBM-bound
+  // normalisation / attention kernels of the other -- 26.99 vs 26.91 ms per PC iteration at cfg2, no gain at twice
+  // the activation arena: both kernel kinds are bound by the same L2 / HBM path.)
+  if (planned_B_ != B) {
+    // dry pass: same code path, no launches; sizes the arena for this batch
     dry_ = true;
     ln_->ws.begin(true);
-    forward_impl(x, labels, h_out, Bl);
+    forward_impl(x, labels, h_out, B);
     dry_ = false;
-    planned_B_ = Bl;
+    planned_B_ = B;
   }
-  for (int l = 0; l < nl; ++l) lanes_[l].ws.reserve(lanes_[0].ws.peak());
+  ln_->ws.reserve(ln_->ws.peak());
   launches_ = 0;
-  if (nl == 2 && !side_) {
-    T2P_CUDA(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking));
-    T2P_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
-    T2P_CUDA(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
-  }
-  if (nl == 2) {
-    T2P_CUDA(cudaEventRecord(ev_fork_, st));
-    T2P_CUDA(cudaStreamWaitEvent(side_, ev_fork_, 0));
-  }
-  const long long per_sample = static_cast<long long>(cfg_.num_channels) * cfg_.max_res_num * cfg_.max_res_num;
-  for (int l = 0; l < nl; ++l) {
-    ln_ = &lanes_[l];
-    ln_->st = (l == 0) ? st : side_;
-    ln_->batch_off = l * Bl;
-    ln_->ws.begin(false);
-    forward_impl(x + l * Bl * per_sample, labels + l * Bl, h_out + l * Bl * per_sample, Bl);
-  }
-  ln_ = &lanes_[0];
-  if (nl == 2) {
-    T2P_CUDA(cudaEventRecord(ev_join_, side_));
-    T2P_CUDA(cudaStreamWaitEvent(st, ev_join_, 0));
-  }
+  ln_->st = st;
+  ln_->ws.begin(false);
+  forward_impl(x, labels, h_out, B);
 }
 
 void UNet::forward(const float* x, const long long* labels, void* out, int out_dtype, int B, cudaStream_t st) {

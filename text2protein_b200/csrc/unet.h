@@ -161,7 +161,7 @@ class UNet {
   void set_profile(bool on);
   int profile_records(GemmRecord* out, int cap);
   long long generation() const { return generation_; }  // bumped by finalize() / set_context()
-  size_t workspace_bytes() const { return lanes_[0].ws.capacity() + lanes_[1].ws.capacity(); }
+  size_t workspace_bytes() const { return lane_.ws.capacity(); }
   long long launches_per_forward() const { return launches_; }
 
  private:
@@ -213,20 +213,15 @@ class UNet {
   bool finalized_ = false;
   std::vector<void*> owned_;  // device allocations freed in the destructor
 
-  // per-forward state.  A lane is one execution context (stream + arena); forward_raw() runs the two halves of
-  // the batch on two lanes so that tensor-bound and HBM-bound kernels of different halves overlap.
+  // per-forward state: the execution context (stream + activation arena) of the forward being recorded
   struct Lane {
     Workspace ws;
     cudaStream_t st = nullptr;
     float* temb_all = nullptr;
-    unsigned seq = 0;     // serpentine direction counter
-    int batch_off = 0;    // first sample of this lane (indexes the hoisted text K|V)
+    unsigned seq = 0;  // serpentine direction counter
   };
-  Lane lanes_[2];
-  Lane* ln_ = &lanes_[0];
-  int nlanes_ = 1;
-  cudaStream_t side_ = nullptr;
-  cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;
+  Lane lane_;
+  Lane* ln_ = &lane_;
   bool dry_ = false;
   bool debug_ = false;
   bool profile_ = false;
