@@ -53,16 +53,17 @@ void set_last_error(const std::string& m);
 // tensor-map prefetch) and calls pdl_wait() BEFORE its first global-memory access that depends on a predecessor;
 // pdl_wait() returns when the preceding grids have completed and flushed.  Captured into CUDA graphs as
 // programmatic edges.  Measured on B200 (profiles/r01_pdl_ab.txt): 3 % SLOWER for this network (27.58 vs 26.74 ms per
-// PC iteration), so it is opt-in (T2P_PDL=1); by default the same kernels launch with ordinary stream ordering.
+// PC iteration), so it is opt-in (T2P_PDL=<class mask>, 15 = all); by default the same kernels launch with ordinary stream ordering.
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-template <typename... P, typename... A>
+// CLS: kernel class bit tested against the T2P_PDL mask (1 tcgen05 GEMMs, 2 gn_finalize, 4 gn_apply, 8 everything else)
+template <int CLS = 8, typename... P, typename... A>
 inline void launch_pdl(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
   static const bool on = [] {
     const char* e = getenv("T2P_PDL");
-    return e && atoi(e) != 0;
+    return e && (atoi(e) & CLS) != 0;
   }();
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;

@@ -1078,7 +1078,7 @@ void launch(TcParams& p, cudaStream_t st) {
   p.n_tiles = cdiv(p.N, BN);
   p.num_tiles = cdiv(p.M, BM) * p.n_tiles;
   const int grid = std::min(p.num_tiles, sm_count());
-  launch_pdl(conv_gemm_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, st, p);
+  launch_pdl<1>(conv_gemm_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, st, p);
 }
 
 template <int PX>
@@ -1093,7 +1093,7 @@ void launch_t(TcParams& p, cudaStream_t st) {
   p.n_tiles = cdiv(p.N, 128);
   p.num_tiles = cdiv(p.M, PX) * p.n_tiles;
   const int grid = std::min(p.num_tiles, sm_count());
-  launch_pdl(conv_gemm_tcT_kernel<PX>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, p);
+  launch_pdl<1>(conv_gemm_tcT_kernel<PX>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, p);
 }
 
 void launch_h(TcParams& p, cudaStream_t st) {
@@ -1106,7 +1106,7 @@ void launch_h(TcParams& p, cudaStream_t st) {
   p.n_tiles = cdiv(p.N, 128);
   p.num_tiles = cdiv(p.M, C::PX) * p.n_tiles;
   const int grid = std::min(p.num_tiles, sm_count());
-  launch_pdl(conv_gemm_tcH_kernel, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, st, p);
+  launch_pdl<1>(conv_gemm_tcH_kernel, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, st, p);
 }
 
 // `rows` consecutive pixels (b, h, w raster order) as one TMA box (tw, th, tb) of the NHWC tensor

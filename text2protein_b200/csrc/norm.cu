@@ -517,7 +517,7 @@ void gn_finalize(const float* part0, int nblk0, int c0, const float* part1, int 
                  const float* beta, int B, int G, int HW, float eps, float* scale, float* shift, cudaStream_t st) {
   T2P_CHECK((c0 + c1) % G == 0, "channels not divisible by groups");
   const int total = B * G;
-  launch_pdl(gn_finalize_kernel, dim3(cdiv(total, 4)), dim3(128), 0, st, part0, nblk0, c0, part1, nblk1, c1, gamma, beta,
+  launch_pdl<2>(gn_finalize_kernel, dim3(cdiv(total, 4)), dim3(128), 0, st, part0, nblk0, c0, part1, nblk1, c1, gamma, beta,
              G, HW, eps, scale, shift, total);
 }
 
@@ -543,10 +543,10 @@ static void gn_apply_t(const void* a0, int c0, const void* a1, int c1, int B, in
     iters = std::max(1, std::min(iters, 4));
     const int ppb = rows * UNROLL * iters;
     dim3 grid(cdiv(HW, ppb), B);
-    launch_pdl(gn_apply_rows_kernel<T, UNROLL>, grid, dim3(threads), 0, st, p0, c0, p1, c1, HW, ppb, scale, shift, act, o, reverse);
-  } else if (mode == 0) launch_pdl(gn_apply_kernel<T, 0>, dim3(blocks), dim3(256), 0, st, p0, c0, p1, c1, B, H, W, scale, shift, act, o, r);
-  else if (mode == 1) launch_pdl(gn_apply_kernel<T, 1>, dim3(blocks), dim3(256), 0, st, p0, c0, p1, c1, B, H, W, scale, shift, act, o, r);
-  else launch_pdl(gn_apply_kernel<T, 2>, dim3(blocks), dim3(256), 0, st, p0, c0, p1, c1, B, H, W, scale, shift, act, o, r);
+    launch_pdl<4>(gn_apply_rows_kernel<T, UNROLL>, grid, dim3(threads), 0, st, p0, c0, p1, c1, HW, ppb, scale, shift, act, o, reverse);
+  } else if (mode == 0) launch_pdl<4>(gn_apply_kernel<T, 0>, dim3(blocks), dim3(256), 0, st, p0, c0, p1, c1, B, H, W, scale, shift, act, o, r);
+  else if (mode == 1) launch_pdl<4>(gn_apply_kernel<T, 1>, dim3(blocks), dim3(256), 0, st, p0, c0, p1, c1, B, H, W, scale, shift, act, o, r);
+  else launch_pdl<4>(gn_apply_kernel<T, 2>, dim3(blocks), dim3(256), 0, st, p0, c0, p1, c1, B, H, W, scale, shift, act, o, r);
 }
 
 void gn_apply(const void* a0, int c0, const void* a1, int c1, int B, int H, int W, int dtype, const float* scale,
