@@ -449,56 +449,172 @@ struct CfgT {
   static constexpr int TMEM_COLS = 2 * PX;
 };
 
-struct EpiT {
-  int n;            // output channel of this thread
-  bool ch_ok;
-  float bch;        // bias[n] (+ rowbias[sample][n] when the tile lies inside one sample)
-  bool rb_uniform;
-  int m0;
+// Epilogue of the channel-major kernels.  The accumulator is read in the fragment layout of tcgen05.ld.16x256b:
+// thread t of a warp owns channels nw0 + t / 4 + 8 k (k = 0..3) and, in every group of 8 pixel columns, the two
+// adjacent pixels 2 (t % 4) + {0, 1} -- one packed bf16x2 conversion per pair, and a transposing stmatrix lays
+// the pairs down as [pixel][channel] rows for the TMA store (4 stmatrix per 32 x 32 chunk).  The code is
+// specialised on the two launch-uniform options that would otherwise cost issue slots in every chunk:
+//   RBVAR  the per-sample bias changes inside a tile (tiles wider than a sample: the 8 x 8 and 4 x 4 levels)
+//   STATS  GroupNorm statistics wanted
+struct EpiQ {
+  int nw0;        // first channel of this warp
+  int m0;         // first pixel of the tile
+  bool ok[4];     // channel < N
+  float bch[4];   // (bias[n] + rowbias[sample][n] when the tile lies inside one sample) * alpha
+  float ssum[4], ssq[4];
 };
 
-// 32 consecutive pixels [m0 + c * 32, +32) of this thread's channel -> bf16 in h[] (two pixels per word)
-__device__ __forceinline__ void epilogue_chunk_t(const TcParams& p, const EpiT& et, const uint32_t (&r)[32], int c,
-                                                 float& ssum, float& ssq, unsigned short (&h)[32]) {
-  const int mb = et.m0 + c * 32;
-  float v[32];
+template <bool RBVAR>
+__device__ __forceinline__ void epi_begin_tile(const TcParams& p, EpiQ& eq, int lane) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + et.bch;
-  if (p.rowbias && !et.rb_uniform && et.ch_ok) {
-    int cur = -1;
-    float rbv = 0.f;
+  for (int k = 0; k < 4; ++k) {
+    const int n = eq.nw0 + (lane >> 2) + 8 * k;
+    eq.ok[k] = n < p.N;
+    float b = 0.f;
+    eq.ssum[k] = 0.f;
+    eq.ssq[k] = 0.f;
+    if (eq.ok[k]) {
+      if (p.bias) b = __ldg(p.bias + n);
+      if (!RBVAR && p.rowbias)
+        b += __ldg(p.rowbias + static_cast<long long>(eq.m0 / p.rows_per_sample) * p.rowbias_ld + n);
+    }
+    eq.bch[k] = b * p.alpha;
+  }
+}
+
+// 32 channels x 32 pixels [mb, mb + 32): out = acc * alpha + bias * alpha -> bf16, statistics over the values as
+// stored, then the chunk goes to `buf` ([32 px][32 ch] bf16, 64-byte rows, 64-byte swizzle = the output tensor
+// map's) -- conflict-free: the 8 rows of each 8 x 8 matrix land in 8 different 16-byte slots of a 128-byte line.
+template <bool RBVAR, bool STATS>
+__device__ __forceinline__ void epilogue_chunk_q(const TcParams& p, EpiQ& eq, const uint32_t (&lo)[16],
+                                                 const uint32_t (&hi)[16], int mb, uint32_t buf, int lane) {
+  uint32_t pk[4][4];  // [channel slot k][column group n]
+  const int px_t = 2 * (lane & 3);
+  const bool full = mb + 32 <= p.M;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int sm = min(mb + j, p.M - 1) / p.rows_per_sample;
-      if (sm != cur) {
-        cur = sm;
-        rbv = __ldg(p.rowbias + static_cast<long long>(sm) * p.rowbias_ld + et.n);
+  for (int n = 0; n < 4; ++n) {
+    const float v[4][2] = {{__uint_as_float(lo[4 * n]), __uint_as_float(lo[4 * n + 1])},
+                           {__uint_as_float(lo[4 * n + 2]), __uint_as_float(lo[4 * n + 3])},
+                           {__uint_as_float(hi[4 * n]), __uint_as_float(hi[4 * n + 1])},
+                           {__uint_as_float(hi[4 * n + 2]), __uint_as_float(hi[4 * n + 3])}};
+    const int px = mb + 8 * n + px_t;  // the pair (px, px + 1) never straddles a sample: rows_per_sample is even
+    const bool in_m = full || px < p.M;
+    const float* rb_row = nullptr;
+    if (RBVAR) rb_row = p.rowbias + static_cast<long long>(min(px, p.M - 1) / p.rows_per_sample) * p.rowbias_ld +
+                        eq.nw0 + (lane >> 2);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float b = eq.bch[k];
+      if (RBVAR && eq.ok[k]) b = fmaf(__ldg(rb_row + 8 * k), p.alpha, b);
+      pk[k][n] = ptx::pack_bf16x2(fmaf(v[k][0], p.alpha, b), fmaf(v[k][1], p.alpha, b));
+      if (STATS && in_m) {  // over the values as stored
+        const float f0 = __uint_as_float(pk[k][n] << 16), f1 = __uint_as_float(pk[k][n] & 0xffff0000u);
+        eq.ssum[k] += f0 + f1;
+        eq.ssq[k] = fmaf(f0, f0, fmaf(f1, f1, eq.ssq[k]));
       }
-      v[j] += rbv;
     }
   }
+  const int mt = lane >> 3, row = lane & 7;
+  const uint32_t rowaddr = buf + (8 * (mt >> 1) + row) * 64;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const __nv_bfloat16 b = __float2bfloat16(v[j] * p.alpha);
-    h[j] = __bfloat16_as_ushort(b);
-    v[j] = __bfloat162float(b);  // statistics over the values as stored
+  for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+    for (int ph = 0; ph < 2; ++ph)
+      ptx::stmatrix_x4_trans(rowaddr + ph * (16 * 64) + ((((2 * hf + (mt & 1)) ^ (row >> 1)) & 3) << 4), pk[2 * hf][2 * ph],
+                             pk[2 * hf + 1][2 * ph], pk[2 * hf][2 * ph + 1], pk[2 * hf + 1][2 * ph + 1]);
+}
+
+// per-channel statistics of the tile: the four threads sharing a channel hold disjoint pixel subsets
+__device__ __forceinline__ void epi_write_stats(const TcParams& p, EpiQ& eq, long long stat_tile, int lane) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float s = eq.ssum[k], q = eq.ssq[k];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    q += __shfl_xor_sync(0xffffffffu, q, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    q += __shfl_xor_sync(0xffffffffu, q, 2);
+    if ((lane & 3) == 0 && eq.ok[k])
+      *reinterpret_cast<float2*>(p.stat_part + (stat_tile * p.N + eq.nw0 + (lane >> 2) + 8 * k) * 2) = make_float2(s, q);
   }
-  if (p.stat_part && et.ch_ok) {
-    if (mb + 32 <= p.M) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        ssum += v[j];
-        ssq = fmaf(v[j], v[j], ssq);
+}
+
+// One epilogue warp's loop over the CTA's tiles.  The warp drains TMEM lane quadrant q, pixel chunks
+// [cf, cf + NCH) of each PX-pixel accumulator (two accumulators, ping-pong), through its two staging buffers at
+// `obuf`; statistics tile index = stat_mul * pixel_tile + stat_add.
+template <int PX, int NCH, bool RBVAR, bool STATS>
+__device__ __forceinline__ void epilogue_role(const TcParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
+                                              uint64_t* tempty_bar, uint32_t obuf, int q, int cf, int stat_mul,
+                                              int stat_add, int lane) {
+  EpiQ eq;
+  uint32_t tl = 0;
+  uint32_t nstore = 0;
+  for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tl) {
+    const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
+    const int tt = p.reverse ? p.num_tiles - 1 - t : t;
+    const int pt = tt / p.n_tiles;
+    eq.nw0 = (tt - pt * p.n_tiles) * 128 + q * 32;  // first channel of this warp
+    eq.m0 = pt * PX;
+    epi_begin_tile<RBVAR>(p, eq, lane);
+    ptx::mbar_wait(ptx::smem_u32(&tfull_bar[as]), aph);
+    ptx::tc_fence_after();
+    const uint32_t tbase = tmem_base + as * PX + (static_cast<uint32_t>(q * 32) << 16);
+    auto release_acc = [&]() {
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[as]));
+    };
+    auto load_chunk = [&](int c, uint32_t (&lo)[16], uint32_t (&hi)[16]) {
+      ptx::tmem_ld_16x256_x4(tbase + c * 32, lo);
+      ptx::tmem_ld_16x256_x4(tbase + (16u << 16) + c * 32, hi);
+    };
+    // one chunk -> this warp's staging buffer -> one TMA store.  TMA clips rows >= M and channels >= N, so
+    // ragged edges need no masks here.
+    auto emit_chunk = [&](const uint32_t (&lo)[16], const uint32_t (&hi)[16], int c) {
+      const uint32_t buf = obuf + (nstore & 1) * (32 * 32 * 2);
+      // the store issued two chunks ago read this buffer: at most one (the previous chunk's) may be pending
+      if (lane == 0) ptx::tma_store_wait_read<1>();
+      __syncwarp();
+      epilogue_chunk_q<RBVAR, STATS>(p, eq, lo, hi, eq.m0 + c * 32, buf, lane);
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && eq.nw0 < p.N && eq.m0 + c * 32 < p.M) {
+        ptx::tma_store_4d(&p.tm_out, buf, eq.nw0, eq.m0 + c * 32, 0, 0);
+        ptx::tma_store_commit();
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (mb + j < p.M) {
-          ssum += v[j];
-          ssq = fmaf(v[j], v[j], ssq);
-        }
+      ++nstore;
+    };
+    uint32_t lo0[16], hi0[16], lo1[16], hi1[16];
+    load_chunk(cf, lo0, hi0);
+#pragma unroll 1
+    for (int i = 0; i < NCH; i += 2) {
+      ptx::tmem_ld_wait();
+      if (i + 1 < NCH) load_chunk(cf + i + 1, lo1, hi1);
+      else release_acc();
+      emit_chunk(lo0, hi0, cf + i);
+      if (i + 1 < NCH) {
+        ptx::tmem_ld_wait();
+        if (i + 2 < NCH) load_chunk(cf + i + 2, lo0, hi0);
+        else release_acc();
+        emit_chunk(lo1, hi1, cf + i + 1);
       }
     }
+    if (STATS) epi_write_stats(p, eq, static_cast<long long>(stat_mul) * pt + stat_add, lane);
+  }
+  if (lane == 0) ptx::tma_store_wait_read<0>();  // smem must stay valid until the last store has read it
+}
+
+template <int PX, int NCH>
+__device__ __forceinline__ void epilogue_dispatch(const TcParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
+                                                  uint64_t* tempty_bar, uint32_t obuf, int q, int cf, int stat_mul,
+                                                  int stat_add, int lane) {
+  const bool rbvar = p.rowbias != nullptr && (p.rows_per_sample % PX) != 0;
+  const bool stats = p.stat_part != nullptr;
+  if (rbvar) {
+    if (stats) epilogue_role<PX, NCH, true, true>(p, tmem_base, tfull_bar, tempty_bar, obuf, q, cf, stat_mul, stat_add, lane);
+    else epilogue_role<PX, NCH, true, false>(p, tmem_base, tfull_bar, tempty_bar, obuf, q, cf, stat_mul, stat_add, lane);
+  } else {
+    if (stats) epilogue_role<PX, NCH, false, true>(p, tmem_base, tfull_bar, tempty_bar, obuf, q, cf, stat_mul, stat_add, lane);
+    else epilogue_role<PX, NCH, false, false>(p, tmem_base, tfull_bar, tempty_bar, obuf, q, cf, stat_mul, stat_add, lane);
   }
 }
 
@@ -654,78 +770,10 @@ __global__ void __launch_bounds__(CfgT<PX>::THREADS, 1) conv_gemm_tcT_kernel(con
     // single tile (the many latency-bound launches at 16 x 16 and below) drains its accumulator twice as fast.
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    EpiT et;
-    et.rb_uniform = p.rowbias != nullptr && (p.rows_per_sample % PX) == 0;
-    const uint32_t obuf = out_stage + (warp - 2) * (2 * 32 * 32 * 2);  // this warp's two [32 px][32 ch] bf16 buffers
-    uint32_t tl = 0;
-    uint32_t nstore = 0;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tl) {
-      const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
-      const int tt = p.reverse ? p.num_tiles - 1 - t : t;
-        const int pt = tt / p.n_tiles;
-      const int nw0 = (tt - pt * p.n_tiles) * 128 + q * 32;  // first channel of this warp
-      et.m0 = pt * PX;
-      et.n = nw0 + lane;
-      et.ch_ok = et.n < p.N;
-      et.bch = 0.f;
-      if (et.ch_ok) {
-        if (p.bias) et.bch = __ldg(p.bias + et.n);
-        if (et.rb_uniform)
-          et.bch += __ldg(p.rowbias + static_cast<long long>(et.m0 / p.rows_per_sample) * p.rowbias_ld + et.n);
-      }
-      ptx::mbar_wait(ptx::smem_u32(&tfull_bar[as]), aph);
-      ptx::tc_fence_after();
-      const uint32_t tbase = tmem_base + as * PX + (static_cast<uint32_t>(q * 32) << 16);
-      auto release_acc = [&]() {
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[as]));
-      };
-      // bf16 values -> this warp's staging buffer ([pixel][channel], 64-byte rows) -> one TMA store per chunk.
-      // TMA clips rows >= M and channels >= N, so ragged edges need no masks here.
-      auto store_chunk = [&](const unsigned short (&h)[32], int c) {
-        const uint32_t buf = obuf + (nstore & 1) * (32 * 32 * 2);
-        // the store issued two chunks ago read this buffer: at most one (the previous chunk's) may be pending
-        if (lane == 0) ptx::tma_store_wait_read<1>();
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          asm volatile("st.shared.u16 [%0], %1;" ::"r"(buf + j * 64 + lane * 2), "h"(h[j]) : "memory");
-        ptx::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0 && nw0 < p.N && et.m0 + c * 32 < p.M) {
-          ptx::tma_store_4d(&p.tm_out, buf, nw0, et.m0 + c * 32, 0, 0);
-          ptx::tma_store_commit();
-        }
-        ++nstore;
-      };
-      constexpr int HC = PX / 64;  // 32-pixel chunks per warp (half of the tile)
-      const int cf = half * HC;
-      float ssum = 0.f, ssq = 0.f;
-      uint32_t r0[32], r1[32];
-      unsigned short h[32];
-      ptx::tmem_ld_32x32(tbase + cf * 32, r0);
-#pragma unroll 1
-      for (int i = 0; i < HC; i += 2) {
-        ptx::tmem_ld_wait();
-        if (i + 1 < HC) ptx::tmem_ld_32x32(tbase + (cf + i + 1) * 32, r1);
-        else release_acc();
-        epilogue_chunk_t(p, et, r0, cf + i, ssum, ssq, h);
-        store_chunk(h, cf + i);
-        if (i + 1 < HC) {
-          ptx::tmem_ld_wait();
-          if (i + 2 < HC) ptx::tmem_ld_32x32(tbase + (cf + i + 2) * 32, r0);
-          else release_acc();
-          epilogue_chunk_t(p, et, r1, cf + i + 1, ssum, ssq, h);
-          store_chunk(h, cf + i + 1);
-        }
-      }
-      // statistics tile = this warp's half of the pixel tile (PX / 2 pixels): index 2 * pt + half
-      if (p.stat_part && et.ch_ok)
-        *reinterpret_cast<float2*>(p.stat_part + (static_cast<long long>(2 * pt + half) * p.N + et.n) * 2) =
-            make_float2(ssum, ssq);
-    }
-    if (lane == 0) ptx::tma_store_wait_read<0>();  // smem must stay valid until the last store has read it
+    constexpr int HC = PX / 64;  // 32-pixel chunks per warp (half of the tile)
+    // this warp's two [32 px][32 ch] bf16 staging buffers; statistics tile = its half of the pixel tile: 2 * pt + half
+    epilogue_dispatch<PX, HC>(p, tmem_base, tfull_bar, tempty_bar, out_stage + (warp - 2) * (2 * 32 * 32 * 2), q,
+                              half * HC, 2, half, lane);
   }
 
   ptx::tc_fence_before();
@@ -907,69 +955,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_tcH_kernel(const __g
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..5): thread = channel
     const int q = warp & 3;
-    EpiT et;
-    et.rb_uniform = p.rowbias != nullptr && (p.rows_per_sample % PX) == 0;
-    const uint32_t obuf = out_stage + q * (2 * 32 * 32 * 2);
-    uint32_t tl = 0;
-    uint32_t nstore = 0;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tl) {
-      const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
-      const int tt = p.reverse ? p.num_tiles - 1 - t : t;
-      const int pt = tt / p.n_tiles;
-      const int nw0 = (tt - pt * p.n_tiles) * 128 + q * 32;
-      et.m0 = pt * PX;
-      et.n = nw0 + lane;
-      et.ch_ok = et.n < p.N;
-      et.bch = 0.f;
-      if (et.ch_ok) {
-        if (p.bias) et.bch = __ldg(p.bias + et.n);
-        if (et.rb_uniform)
-          et.bch += __ldg(p.rowbias + static_cast<long long>(et.m0 / p.rows_per_sample) * p.rowbias_ld + et.n);
-      }
-      ptx::mbar_wait(ptx::smem_u32(&tfull_bar[as]), aph);
-      ptx::tc_fence_after();
-      const uint32_t tbase = tmem_base + as * PX + (static_cast<uint32_t>(q * 32) << 16);
-      auto release_acc = [&]() {
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[as]));
-      };
-      auto store_chunk = [&](const unsigned short (&h)[32], int c) {
-        const uint32_t buf = obuf + (nstore & 1) * (32 * 32 * 2);
-        if (lane == 0) ptx::tma_store_wait_read<1>();
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          asm volatile("st.shared.u16 [%0], %1;" ::"r"(buf + j * 64 + lane * 2), "h"(h[j]) : "memory");
-        ptx::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0 && nw0 < p.N && et.m0 + c * 32 < p.M) {
-          ptx::tma_store_4d(&p.tm_out, buf, nw0, et.m0 + c * 32, 0, 0);
-          ptx::tma_store_commit();
-        }
-        ++nstore;
-      };
-      constexpr int NCH = PX / 32;
-      float ssum = 0.f, ssq = 0.f;
-      uint32_t r0[32], r1[32];
-      unsigned short h[32];
-      ptx::tmem_ld_32x32(tbase, r0);
-#pragma unroll 1
-      for (int c = 0; c < NCH; c += 2) {
-        ptx::tmem_ld_wait();
-        ptx::tmem_ld_32x32(tbase + (c + 1) * 32, r1);
-        epilogue_chunk_t(p, et, r0, c, ssum, ssq, h);
-        store_chunk(h, c);
-        ptx::tmem_ld_wait();
-        if (c + 2 < NCH) ptx::tmem_ld_32x32(tbase + (c + 2) * 32, r0);
-        else release_acc();
-        epilogue_chunk_t(p, et, r1, c + 1, ssum, ssq, h);
-        store_chunk(h, c + 1);
-      }
-      if (p.stat_part && et.ch_ok)
-        *reinterpret_cast<float2*>(p.stat_part + (static_cast<long long>(pt) * p.N + et.n) * 2) = make_float2(ssum, ssq);
-    }
-    if (lane == 0) ptx::tma_store_wait_read<0>();
+    epilogue_dispatch<PX, PX / 32>(p, tmem_base, tfull_bar, tempty_bar, out_stage + q * (2 * 32 * 32 * 2), q, 0, 1, 0, lane);
   }
 
   ptx::tc_fence_before();
@@ -1019,10 +1005,11 @@ struct TmapKeyHash {
 
 // bf16 tensor with dims d[0] (innermost, contiguous) .. d[3]; dense strides; box b[0..3]; 128-byte swizzle
 // (operand tiles) or none (the epilogue's store tiles).
-CUtensorMap make_tmap_bf16(const void* ptr, const uint64_t d[4], const uint32_t b[4], bool swizzle128 = true) {
+// swizzle: 0 none, 2 = 64-byte, 3 = 128-byte (operand tiles)
+CUtensorMap make_tmap_bf16(const void* ptr, const uint64_t d[4], const uint32_t b[4], int swizzle = 3) {
   static std::mutex mu;
   static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
-  TmapKey key{ptr, {d[0], d[1], d[2], d[3]}, {b[0], b[1], b[2], b[3]}, swizzle128 ? 1 : 0};
+  TmapKey key{ptr, {d[0], d[1], d[2], d[3]}, {b[0], b[1], b[2], b[3]}, swizzle};
   std::lock_guard<std::mutex> lk(mu);
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
@@ -1035,7 +1022,8 @@ CUtensorMap make_tmap_bf16(const void* ptr, const uint64_t d[4], const uint32_t 
   T2P_CHECK((strides[0] & 15) == 0, "TMA row pitch must be a multiple of 16 bytes");
   CUresult r = encode_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims,
                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                           swizzle == 3 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                        : (swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   T2P_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code " + std::to_string(int(r)));
   if (cache.size() > 65536) cache.clear();
@@ -1257,7 +1245,7 @@ void conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
     {
       uint64_t d[4] = {static_cast<uint64_t>(a.N), static_cast<uint64_t>(M), 1, 1};
       uint32_t b[4] = {32, 32, 1, 1};
-      p.tm_out = make_tmap_bf16(a.out, d, b, false);
+      p.tm_out = make_tmap_bf16(a.out, d, b, 2);  // 64-byte swizzle: the epilogue's staging layout
     }
     if (a.xc0 > 0) p.tm_x0 = amap(a.x0, a.xc0);
     if (a.xc1 > 0) p.tm_x1 = amap(a.x1, a.xc1);

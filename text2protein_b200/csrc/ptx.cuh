@@ -144,6 +144,33 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "r"(taddr)
       : "memory");
 }
+// 16 lanes x 32 consecutive fp32 columns in the accumulator-fragment layout (.16x256b, 4 repeats of 8 columns):
+// thread t receives, for repeat n, r[4n + 0..1] = (lane base + t / 4,     columns 8n + 2 (t % 4) + {0, 1}) and
+//                                  r[4n + 2..3] = (lane base + t / 4 + 8, same columns)
+// -- two adjacent columns of one lane per register pair, which is what a transposing stmatrix wants.
+__device__ __forceinline__ void tmem_ld_16x256_x4(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// four 8 x 8 b16 matrices, transposed on the way out: register m of thread t holds rows 2 (t % 4) + {0, 1} (low,
+// high half) of column t / 4 of matrix m; thread i supplies the address of row i % 8 of matrix i / 8
+__device__ __forceinline__ void stmatrix_x4_trans(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a),
+               "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+// two fp32 -> packed bf16x2 (lo in the low half), round to nearest even: one F2FP on the ALU pipe
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "

@@ -200,7 +200,7 @@ __global__ void fill_bf16(__nv_bfloat16* p, long long n, float scale, unsigned s
 
 // random (not zero) operands so that the power draw, and hence the clock, is representative;
 // epi = 0: plain store, 1: + bias + per-sample bias + GroupNorm statistics, 2: + residual
-static void bench_case(int B, int H, int W, int cin, int N, int ks, int epi) {
+static void bench_case(int B, int H, int W, int cin, int N, int ks, int epi, int iters = 10) {
   const long long M = 1ll * B * H * W;
   const int K = ks * ks * cin;
   __nv_bfloat16 *a, *w, *o, *res;
@@ -229,7 +229,6 @@ static void bench_case(int B, int H, int W, int cin, int N, int ks, int epi) {
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int i = 0; i < 3; ++i) conv_gemm_tc(g, 0);
   cudaEventRecord(e0);
-  const int iters = 10;
   for (int i = 0; i < iters; ++i) conv_gemm_tc(g, 0);
   cudaEventRecord(e1);
   fail_if(cudaDeviceSynchronize(), "bench");
@@ -267,8 +266,9 @@ int main(int argc, char** argv) {
   };
   if (argc > 1 && std::string(argv[1]) == "one") {
     // single shape for ncu captures: one <B> <H> <W> <cin> <N> <ks> <epi>
-    if (argc < 9) { fprintf(stderr, "usage: selftest_gemm one B H W cin N ks epi\n"); return 2; }
-    bench_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]), atoi(argv[8]));
+    if (argc < 9) { fprintf(stderr, "usage: selftest_gemm one B H W cin N ks epi [iters]\n"); return 2; }
+    bench_case(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7]), atoi(argv[8]),
+               argc > 9 ? atoi(argv[9]) : 10);
     return 0;
   }
   int rc = 0;
