@@ -290,7 +290,8 @@ def test_pc_steps_match_oracle_math(B, Cc, N):
 
 
 @pytest.mark.parametrize("B,H,W,cin,nout", [(2, 128, 128, 128, 5), (3, 32, 32, 64, 8), (1, 30, 48, 128, 5),
-                                            (2, 64, 64, 256, 5), (1, 256, 256, 128, 5)])
+                                            (2, 64, 64, 256, 5), (1, 256, 256, 128, 5), (2, 4, 16, 64, 5),
+                                            (1, 16, 32, 128, 8)])
 def test_final_conv_fused_matches_torch(B, H, W, cin, nout):
     """GroupNorm-affine + SiLU + 3x3 conv to the map channels in one kernel (padding applied after the activation)."""
     g = torch.Generator(device="cuda").manual_seed(8)

@@ -20,4 +20,11 @@ for _ in range(4):
     _lib.check(_lib.lib().t2p_final_conv(_lib.ptr(X), _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(wp), _lib.ptr(bias),
                                          _lib.ptr(out), B, H, W, cin, nout, _lib.current_stream()))
 torch.cuda.synchronize()
-print("ok")
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(20):
+    _lib.check(_lib.lib().t2p_final_conv(_lib.ptr(X), _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(wp), _lib.ptr(bias),
+                                         _lib.ptr(out), B, H, W, cin, nout, _lib.current_stream()))
+e1.record()
+torch.cuda.synchronize()
+print(f"ok {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per launch")
