@@ -1126,7 +1126,9 @@ Plan make_plan(const ConvGemmArgs& a) {
   Plan pl;
   const long long M = static_cast<long long>(a.B) * a.H * a.W;
   const bool want_stats = a.stat_part != nullptr;
-  if (a.N >= 128 && a.N % 8 == 0 && a.out_dtype == kBF16 && !a.out_nchw && !a.res_up) {
+  // (the channel-major epilogue handles pixels in pairs that must not straddle two samples' per-sample bias)
+  const bool pairs_ok = a.rowbias == nullptr || (a.rows_per_sample % 2) == 0;
+  if (a.N >= 128 && a.N % 8 == 0 && a.out_dtype == kBF16 && !a.out_nchw && !a.res_up && pairs_ok) {
     // channel-major kernel: widest pixel tile that still spreads the problem over (most of) the SMs
     int pick = 0;
     for (int px : {256, 128, 64}) {
