@@ -61,7 +61,9 @@ def _conv(a0, w, ksize, bias=None, a1=None, rowbias=None, residual=None, res_up=
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 1.5e-2)])
 @pytest.mark.parametrize("H,cin,cin1,cout,k", [(32, 64, 0, 128, 3), (16, 128, 64, 64, 3), (8, 128, 0, 128, 3),
                                                (4, 64, 0, 192, 3), (16, 64, 128, 64, 1), (64, 64, 0, 5, 3),
-                                               (128, 64, 64, 128, 3), (128, 128, 0, 256, 3)])
+                                               (128, 64, 64, 128, 3), (128, 128, 0, 256, 3),
+                                               # one pixel per sample: the per-sample bias changes inside a pixel pair
+                                               (1, 128, 0, 256, 1)])
 def test_conv2d_matches_torch(dtype, tol, H, cin, cin1, cout, k):
     g = torch.Generator(device="cuda").manual_seed(1)
     B = 3

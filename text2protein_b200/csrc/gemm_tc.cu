@@ -497,16 +497,21 @@ __device__ __forceinline__ void epilogue_chunk_q(const TcParams& p, EpiQ& eq, co
                            {__uint_as_float(lo[4 * n + 2]), __uint_as_float(lo[4 * n + 3])},
                            {__uint_as_float(hi[4 * n]), __uint_as_float(hi[4 * n + 1])},
                            {__uint_as_float(hi[4 * n + 2]), __uint_as_float(hi[4 * n + 3])}};
-    const int px = mb + 8 * n + px_t;  // the pair (px, px + 1) never straddles a sample: rows_per_sample is even
-    const bool in_m = full || px < p.M;
-    const float* rb_row = nullptr;
-    if (RBVAR) rb_row = p.rowbias + static_cast<long long>(min(px, p.M - 1) / p.rows_per_sample) * p.rowbias_ld +
-                        eq.nw0 + (lane >> 2);
+    const int px = mb + 8 * n + px_t;  // this thread's pixel pair (px, px + 1)
+    const bool in_m = full || px < p.M;  // M is even whenever it matters: a pair is inside or outside as a whole
+    const float *rb_row0 = nullptr, *rb_row1 = nullptr;
+    if (RBVAR) {  // the two pixels may belong to different samples (odd pixel counts per sample)
+      rb_row0 = p.rowbias + static_cast<long long>(min(px, p.M - 1) / p.rows_per_sample) * p.rowbias_ld + eq.nw0 + (lane >> 2);
+      rb_row1 = p.rowbias + static_cast<long long>(min(px + 1, p.M - 1) / p.rows_per_sample) * p.rowbias_ld + eq.nw0 + (lane >> 2);
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      float b = eq.bch[k];
-      if (RBVAR && eq.ok[k]) b = fmaf(__ldg(rb_row + 8 * k), p.alpha, b);
-      pk[k][n] = ptx::pack_bf16x2(fmaf(v[k][0], p.alpha, b), fmaf(v[k][1], p.alpha, b));
+      float b = eq.bch[k], b1 = eq.bch[k];
+      if (RBVAR && eq.ok[k]) {
+        b = fmaf(__ldg(rb_row0 + 8 * k), p.alpha, b);
+        b1 = fmaf(__ldg(rb_row1 + 8 * k), p.alpha, b1);
+      }
+      pk[k][n] = ptx::pack_bf16x2(fmaf(v[k][0], p.alpha, b), fmaf(v[k][1], p.alpha, RBVAR ? b1 : b));
       if (STATS && in_m) {  // over the values as stored
         const float f0 = __uint_as_float(pk[k][n] << 16), f1 = __uint_as_float(pk[k][n] & 0xffff0000u);
         eq.ssum[k] += f0 + f1;
@@ -1126,9 +1131,7 @@ Plan make_plan(const ConvGemmArgs& a) {
   Plan pl;
   const long long M = static_cast<long long>(a.B) * a.H * a.W;
   const bool want_stats = a.stat_part != nullptr;
-  // (the channel-major epilogue handles pixels in pairs that must not straddle two samples' per-sample bias)
-  const bool pairs_ok = a.rowbias == nullptr || (a.rows_per_sample % 2) == 0;
-  if (a.N >= 128 && a.N % 8 == 0 && a.out_dtype == kBF16 && !a.out_nchw && !a.res_up && pairs_ok) {
+  if (a.N >= 128 && a.N % 8 == 0 && a.out_dtype == kBF16 && !a.out_nchw && !a.res_up) {
     // channel-major kernel: widest pixel tile that still spreads the problem over (most of) the SMs
     int pick = 0;
     for (int px : {256, 128, 64}) {
