@@ -275,6 +275,8 @@ def run_native(args, cfg):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own log (its version banner when NCCL_DEBUG is set) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     cfg.device = f"cuda:{local}"
