@@ -156,7 +156,7 @@ def run_reference(args, cfg):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                              "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def _traffic_lookup(roof):
@@ -275,8 +275,6 @@ def run_native(args, cfg):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own log (its version banner when NCCL_DEBUG is set) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     cfg.device = f"cuda:{local}"
@@ -455,12 +453,31 @@ def run_native(args, cfg):
                 "gpu_launches": gpu_launches, "launches_per_forward": launches_fwd,
                 "roofline": roof, "step_kernels": steps, "cpu_baseline": cpu, "clocks": clk,
                 "workspace_gb": L.t2p_unet_workspace_bytes(model.native_handle) / 1e9}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line: keep a private handle on the real stdout for it and point fd 1 at
+    stderr, so that anything a library prints there (NCCL's version banner under NCCL_DEBUG, for one) cannot get
+    in front of the line."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def _emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
