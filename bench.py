@@ -159,13 +159,22 @@ def run_reference(args, cfg):
     _emit(line)
 
 
+def _gemm_kernel_name(ksize, pixels_per_sample, n):
+    """Which tcgen05 kernel the plan in csrc/gemm_tc.cu picks for a bf16 GEMM of this shape (make_plan)."""
+    if n < 128:
+        return "conv_gemm_tc_kernel"      # pixel-major
+    if ksize == 3 and pixels_per_sample == 128 * 128:
+        return "conv_gemm_tcH_kernel"     # halo variant: 3x3 on 128-pixel-wide images
+    return "conv_gemm_tcT_kernel"         # channel-major
+
+
 def _traffic_lookup(roof):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
     `ncu --set full` captures (profiles/r01_traffic.json, keyed by the kernel string bench reports)."""
     p = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if not os.path.exists(p):
         return None
-    return json.load(open(p)).get(roof["kernel"])
+    return json.load(open(p)).get(roof["kernel"].split(" ", 1)[1])  # keyed by the shape part
 
 
 def _step_kernel_roofline(dev, B, shape, L, mask_u8, hbm_gbs):
@@ -412,7 +421,7 @@ def run_native(args, cfg):
                   for k, v in sorted(groups.items(), key=lambda kv: -kv[1][1])[:16]]
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak_sust, "unit": "TFLOP/s",
                 "frac": achieved / peak_sust, "traffic": None,
-                "kernel": f"conv_gemm_tc_kernel k={key[1]} M={key[2]} N={key[3]} K={key[4]}",
+                "kernel": f"{_gemm_kernel_name(key[1], key[2] // B, key[3])} k={key[1]} M={key[2]} N={key[3]} K={key[4]}",
                 "launches_per_forward": cnt // reps, "avg_launch_ms": avg_ms,
                 "flops_per_launch": fl, "peak_source": f"{src} sustained (burst {peak_burst})",
                 "share_of_gemm_time": ms / reps / all_ms,
