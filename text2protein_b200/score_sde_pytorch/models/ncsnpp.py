@@ -8,6 +8,7 @@ the way ``UNetModel.__init__`` does (reference :74-217); there is no PyTorch imp
 pass and no CPU fallback.
 """
 import ctypes as C
+import itertools
 import math
 
 import numpy as np
@@ -165,8 +166,10 @@ class UNetModel(nn.Module):
 
     # ------------------------------------------------------------------ weights -> engine
     def _weights_version(self):
-        return tuple(t._version for t in self.state_dict(keep_vars=True).values()) + \
-            tuple(t.data_ptr() for t in self.state_dict(keep_vars=True).values())
+        # one walk over the parameter / buffer objects (no state_dict: building its prefixed key strings twice made
+        # this check 2 ms of every sampler call)
+        ts = list(itertools.chain(self.parameters(), self.buffers()))
+        return tuple(t._version for t in ts) + tuple(t.data_ptr() for t in ts)
 
     def sync_weights(self, force=False):
         """Pushes the current parameters (e.g. after load_state_dict / ema.copy_to) to the engine and repacks
