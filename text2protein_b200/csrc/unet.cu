@@ -498,6 +498,20 @@ int UNet::profile_records(GemmRecord* out, int cap) {
   return n;
 }
 
+// Timing experiments only (they break the numerics): T2P_DEBUG_SKIP is a mask of kernel classes that are NOT
+// launched -- 1 gn_finalize, 2 gn_apply, 4 attention, 8 LayerNorm + GEGLU, 16 final layer, 64 gn_stats -- so that the
+// share of each class in the captured forward can be read off two bench runs (see also T2P_DEBUG_SKIP_ST).
+static int debug_skip() {
+  static const int m = [] { const char* e = std::getenv("T2P_DEBUG_SKIP"); return e ? std::atoi(e) : 0; }();
+  return m;
+}
+// T2P_DEBUG_DUP: same classes, launched TWICE (results unchanged) -- the honest way to time the classes whose
+// removal would turn the activations into NaNs (and NaN operands make every GEMM draw less power and run faster).
+static int debug_dup() {
+  static const int m = [] { const char* e = std::getenv("T2P_DEBUG_DUP"); return e ? std::atoi(e) : 0; }();
+  return m;
+}
+
 void UNet::group_norm(const GroupNormP& gn, const Act& a0, const Act* a1, int act, int mode, Act& out, Act* raw_out,
                       float** affine_out) {
   const int C = a0.C + (a1 ? a1->C : 0);
@@ -519,14 +533,16 @@ void UNet::group_norm(const GroupNormP& gn, const Act& a0, const Act* a1, int ac
     owned[i] = static_cast<float*>(ln_->ws.alloc(sizeof(float) * 2 * static_cast<size_t>(B) * nblk[i] * src[i]->C));
     part[i] = owned[i];
     ++launches_;
-    if (!dry_) gn_stats(src[i]->p, src[i]->C, nullptr, 0, B, HW, cfg_.compute_dtype, owned[i], ln_->st);
+    for (int rep = 0; rep < 1 + ((debug_dup() & 64) ? 1 : 0); ++rep)
+      if (!dry_ && !(debug_skip() & 64)) gn_stats(src[i]->p, src[i]->C, nullptr, 0, B, HW, cfg_.compute_dtype, owned[i], ln_->st);
   }
   float* scale = static_cast<float*>(ln_->ws.alloc(sizeof(float) * 2 * B * C));
   float* shift = scale + static_cast<size_t>(B) * C;
   if (affine_out) {
     // statistics -> per-(sample, channel) affine only; the consumer applies it itself (fused final convolution)
     launches_ += 1;
-    if (!dry_)
+    for (int rep = 0; rep < 1 + ((debug_dup() & 1) ? 1 : 0); ++rep)
+    if (!dry_ && !(debug_skip() & 1))
       gn_finalize(part[0], nblk[0], a0.C, part[1], nblk[1], a1 ? a1->C : 0, static_cast<const float*>(gn.w->data),
                   static_cast<const float*>(gn.b->data), B, gn.G, HW, 1e-6f, scale, shift, ln_->st);
     for (int i = 0; i < 2; ++i)
@@ -537,8 +553,12 @@ void UNet::group_norm(const GroupNormP& gn, const Act& a0, const Act* a1, int ac
   launches_ += 2;  // finalize + apply
   ++ln_->seq;
   if (!dry_) {
-    gn_finalize(part[0], nblk[0], a0.C, part[1], nblk[1], a1 ? a1->C : 0, static_cast<const float*>(gn.w->data),
-                static_cast<const float*>(gn.b->data), B, gn.G, HW, 1e-6f, scale, shift, ln_->st);
+    for (int rep = 0; rep < 1 + ((debug_dup() & 1) ? 1 : 0); ++rep)
+    if (!(debug_skip() & 1))
+      gn_finalize(part[0], nblk[0], a0.C, part[1], nblk[1], a1 ? a1->C : 0, static_cast<const float*>(gn.w->data),
+                  static_cast<const float*>(gn.b->data), B, gn.G, HW, 1e-6f, scale, shift, ln_->st);
+    for (int rep = 0; rep < 1 + ((debug_dup() & 2) ? 1 : 0); ++rep)
+    if (!(debug_skip() & 2))
     gn_apply(a0.p, a0.C, a1 ? a1->p : nullptr, a1 ? a1->C : 0, B, a0.H, a0.W, cfg_.compute_dtype, scale, shift, act,
              mode, out.p, raw_out ? raw_out->p : nullptr, ln_->st, serpentine_ ? static_cast<int>(ln_->seq & 1) : 0);
   }
@@ -554,7 +574,7 @@ void UNet::attention(const void* q, const void* k, const void* v, void* out, int
   a.B = B; a.heads = heads; a.Tq = Tq; a.Tk = Tk; a.d = d;
   a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo; a.scale = scale;
   ++launches_;
-  if (dry_) return;
+  if (dry_ || (debug_skip() & 4)) return;
   if (cfg_.compute_dtype == kBF16 && attention_mma_supported(a)) attention_mma(a, ln_->st);
   else attention_simt(a, cfg_.compute_dtype, ln_->st);
 }
@@ -639,7 +659,7 @@ Act UNet::run_st(TransformerM& m, const Act& x) {
             "set_context() must be called with the same batch before forward");
   auto ln = [&](const LayerNormP& l, const Act& in, Act& out) {
     ++launches_;
-    if (!dry_)
+    if (!dry_ && !(debug_skip() & 8))
       layernorm(in.p, static_cast<const float*>(l.w->data), static_cast<const float*>(l.b->data), in.rows(), C,
                 1e-5f, cfg_.compute_dtype, out.p, ln_->st);
   };
@@ -680,7 +700,7 @@ Act UNet::run_st(TransformerM& m, const Act& x) {
   free_act(hn);
   Act gz = new_act(B, H, W, 4 * C, false);
   ++launches_;
-  if (!dry_) geglu(z.p, z.rows(), 4 * C, cfg_.compute_dtype, gz.p, ln_->st);
+  if (!dry_ && !(debug_skip() & 8)) geglu(z.p, z.rows(), 4 * C, cfg_.compute_dtype, gz.p, ln_->st);
   free_act(z);
   Act t4 = new_act(B, H, W, C, false);
   gemm(m.ff_out, gz, nullptr, t4, nullptr, 0, t3.p, 0, 1.f);
@@ -888,7 +908,8 @@ void UNet::forward_impl(const float* x, const long long* labels, float* h_out, i
     Act none;
     group_norm(out_gn_, h, nullptr, 1, 0, none, nullptr, &affine);
     ++launches_;
-    if (!dry_)
+    for (int rep = 0; rep < 1 + ((debug_dup() & 16) ? 1 : 0); ++rep)
+    if (!dry_ && !(debug_skip() & 16))
       final_conv_fused(h.p, affine, affine + static_cast<size_t>(B) * h.C, out_conv_.wp, out_conv_.bp, h_out, B, N, N, h.C,
                        C, ln_->st);
     ln_->ws.free(affine);
