@@ -426,6 +426,20 @@ void UNet::free_act(Act& a) {
   a = Act{};
 }
 
+// Timing experiments only (they break the numerics): T2P_DEBUG_SKIP is a mask of kernel classes that are NOT
+// launched -- 1 gn_finalize, 2 gn_apply, 4 attention, 8 LayerNorm + GEGLU, 16 final layer, 64 gn_stats (T2P_DEBUG_DUP also: 128 halo-shaped 3x3 GEMMs, 256 other 3x3 GEMMs, 512 1x1 / linear GEMMs) -- so that the
+// share of each class in the captured forward can be read off two bench runs (see also T2P_DEBUG_SKIP_ST).
+static int debug_skip() {
+  static const int m = [] { const char* e = std::getenv("T2P_DEBUG_SKIP"); return e ? std::atoi(e) : 0; }();
+  return m;
+}
+// T2P_DEBUG_DUP: same classes, launched TWICE (results unchanged) -- the honest way to time the classes whose
+// removal would turn the activations into NaNs (and NaN operands make every GEMM draw less power and run faster).
+static int debug_dup() {
+  static const int m = [] { const char* e = std::getenv("T2P_DEBUG_DUP"); return e ? std::atoi(e) : 0; }();
+  return m;
+}
+
 void UNet::gemm(const Linear& l, const Act& a0, const Act* a1, Act& out, const float* rowbias, int rowbias_ld,
                 const void* residual, int res_up, float alpha, int out_dtype, int out_nchw, const Act* x0,
                 const Act* x1) {
@@ -464,8 +478,11 @@ void UNet::gemm(const Linear& l, const Act& a0, const Act* a1, Act& out, const f
     T2P_CUDA(cudaEventCreate(&e1));
     T2P_CUDA(cudaEventRecord(e0, ln_->st));
   }
-  if (tc) conv_gemm_tc(g, ln_->st);
-  else conv_gemm_simt(g, l.force_f32 ? kF32 : cfg_.compute_dtype, ln_->st);
+  const int cls = (l.ksize == 3 && l.N >= 128 && a0.W == 128) ? 128 : (l.ksize == 3 ? 256 : 512);
+  for (int rep = 0; rep < 1 + ((debug_dup() & cls) ? 1 : 0); ++rep) {
+    if (tc) conv_gemm_tc(g, ln_->st);
+    else conv_gemm_simt(g, l.force_f32 ? kF32 : cfg_.compute_dtype, ln_->st);
+  }
   if (profile_) {
     T2P_CUDA(cudaEventRecord(e1, ln_->st));
     GemmRecord r;
@@ -496,20 +513,6 @@ int UNet::profile_records(GemmRecord* out, int cap) {
     ++n;
   }
   return n;
-}
-
-// Timing experiments only (they break the numerics): T2P_DEBUG_SKIP is a mask of kernel classes that are NOT
-// launched -- 1 gn_finalize, 2 gn_apply, 4 attention, 8 LayerNorm + GEGLU, 16 final layer, 64 gn_stats -- so that the
-// share of each class in the captured forward can be read off two bench runs (see also T2P_DEBUG_SKIP_ST).
-static int debug_skip() {
-  static const int m = [] { const char* e = std::getenv("T2P_DEBUG_SKIP"); return e ? std::atoi(e) : 0; }();
-  return m;
-}
-// T2P_DEBUG_DUP: same classes, launched TWICE (results unchanged) -- the honest way to time the classes whose
-// removal would turn the activations into NaNs (and NaN operands make every GEMM draw less power and run faster).
-static int debug_dup() {
-  static const int m = [] { const char* e = std::getenv("T2P_DEBUG_DUP"); return e ? std::atoi(e) : 0; }();
-  return m;
 }
 
 void UNet::group_norm(const GroupNormP& gn, const Act& a0, const Act* a1, int act, int mode, Act& out, Act* raw_out,
