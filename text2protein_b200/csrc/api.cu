@@ -242,7 +242,8 @@ static PcStepArgs step_args(const t2p_step_args* a) {
 }
 
 int64_t t2p_corrector_workspace_bytes(int B, int64_t elems_per_sample) {
-  return static_cast<int64_t>(sizeof(double)) * 2 * B * pc_corrector_chunks(B, elems_per_sample);
+  (void)elems_per_sample;
+  return static_cast<int64_t>(sizeof(double)) * pc_corrector_workspace_doubles(B);
 }
 
 int t2p_predictor_step(const t2p_step_args* a, void* stream) {
@@ -256,7 +257,6 @@ int t2p_corrector_step(const t2p_step_args* a, void* stream) {
   T2P_API_BEGIN
   T2P_CHECK(a && a->x && a->score && a->workspace, "null argument");
   PcStepArgs p = step_args(a);
-  p.chunks = pc_corrector_chunks(a->B, static_cast<long long>(a->C) * a->HW);
   p.partial = a->workspace;
   pc_corrector_step(p, S(stream));
   T2P_API_END
@@ -291,7 +291,7 @@ static void ensure_run_buffers(t2p_unet* u, int B, int K) {
     T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->G), sizeof(float) * B));
     T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->state), sizeof(long long) * 2));
     T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->h), sizeof(float) * B * E));
-    T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->partial), sizeof(double) * 2 * B * pc_corrector_chunks(B, E)));
+    T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->partial), sizeof(double) * pc_corrector_workspace_doubles(B)));
     u->run_B = B;
   }
   if (u->run_K < K) {
@@ -342,7 +342,6 @@ int t2p_pc_run(t2p_unet* u, const t2p_run_args* a, void* stream) {
   base.seed = a->seed; base.stream_mul = a->n_steps + 1; base.iter_ptr = u->state;
   base.sample_offset = a->sample_offset;
   base.B = B; base.C = c.num_channels; base.HW = HW;
-  base.chunks = pc_corrector_chunks(B, static_cast<long long>(c.num_channels) * HW);
   base.partial = u->partial;
 
   auto iteration = [&]() {

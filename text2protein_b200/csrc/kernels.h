@@ -128,12 +128,11 @@ struct PcStepArgs {
   const long long* iter_ptr = nullptr;
   long long sample_offset = 0;
   int B = 0, C = 0, HW = 0;
-  int chunks = 0;            // corrector only: pc_corrector_chunks(B, C*HW)
-  double* partial = nullptr; // corrector only: [B*chunks*2]
+  double* partial = nullptr; // corrector only: pc_corrector_workspace_doubles(B) doubles
 };
 void pc_predictor_step(const PcStepArgs& a, cudaStream_t st);
 void pc_corrector_step(const PcStepArgs& a, cudaStream_t st);
-int pc_corrector_chunks(int B, long long E);
+long long pc_corrector_workspace_doubles(int B);
 void philox_normal_fill(unsigned long long seed, unsigned long long stream, long long first_element, long long count,
                         float scale, float* out, cudaStream_t st);
 void philox_bits_fill(unsigned long long seed, unsigned long long stream, long long first_quad, long long quads,

@@ -9,9 +9,17 @@
 //   both      : x = where(mask, x, x_initial).float()
 // The arithmetic follows the reference's dtype promotions (score is float64): products with the
 // score run in double, noise terms in float, the state is rounded to float once per half-step.
-// The corrector is a cooperative kernel: phase 1 reduces the per-sample squared norms of score and noise
-// into per-chunk partials (no atomics, no zeroing), grid.sync(), phase 2 regenerates the same Philox
-// normals and applies the update.  Memory traffic is the algorithmic 12 B/element (+1 B mask).
+//
+// Work decomposition (both kernels): a sample is cut into rows of kThreads quads (4 consecutive elements, one
+// 16-byte access per tensor); the B * rows_per_sample rows are dealt out in contiguous, equal (+-1) ranges to a
+// single wave of resident blocks (2 x 512 threads per SM), so there is no partial second wave and no
+// per-element index arithmetic (the sample index is uniform per row).
+//
+// The corrector is a cooperative kernel.  Phase 1 generates the normals of the block's rows ONCE, keeps them in
+// shared memory (8 KB per row, up to 13 rows per block; rows beyond the cache are regenerated in phase 2),
+// accumulates sum(score^2) and sum(z^2) per (block, sample) into a partial slot (no atomics, no zeroing, fixed
+// order) and prefetches the block's x rows into L2; grid.sync(); every block folds the partials into the
+// batch-mean step size; phase 2 applies the update.  DRAM traffic is the algorithmic 12 B/element (+1 B mask).
 #include <cooperative_groups.h>
 
 #include "kernels.h"
@@ -21,6 +29,10 @@ namespace cg = cooperative_groups;
 
 namespace t2p {
 namespace {
+
+constexpr int kThreads = 512;       // threads per block = quads per row
+constexpr int kMaxCacheRows = 13;   // 13 x 8 KB of cached normals per block, two blocks per SM
+constexpr int kMaxBlocks = 4096;    // bound used to size the corrector's partial workspace
 
 struct StepParams {
   float* x;
@@ -37,15 +49,20 @@ struct StepParams {
   float snr;
   const unsigned char* mask;  // [B*E] 1 = free to evolve, or null
   const float* x_init;
-  float* x_mean_out;          // optional: masked x_mean (float), written by the predictor
+  float* x_mean_out;          // optional: masked x_mean (float)
   unsigned long long seed;
   long long stream_base, stream_mul;  // stream = stream_base + iter * stream_mul
   const long long* iter_ptr;          // device iteration counter or null (iter = 0)
   long long sample_offset;            // global index of local sample 0 (multi-GPU sharding)
   int B, C, HW;
   long long E;              // C*HW
-  int chunks;               // chunks per sample (corrector)
-  double* partial;          // [B*chunks][2]
+  int qps;                  // quads per sample, E / 4
+  int rps;                  // rows per sample, ceil(qps / kThreads)
+  int rows;                 // B * rps
+  int cache_rows;           // corrector: rows of normals a block keeps in shared memory
+  int prefetch;             // corrector: phase 1 prefetches the x rows of phase 2 into L2
+  int skip_conditioned;     // fully conditioned quads copy x_initial without loading x / score or drawing noise
+  double* partial;          // corrector: [gridDim.x + B][2], slot = block + sample
 };
 
 __device__ __forceinline__ unsigned long long stream_of(const StepParams& p) {
@@ -53,10 +70,22 @@ __device__ __forceinline__ unsigned long long stream_of(const StepParams& p) {
   return static_cast<unsigned long long>(p.stream_base + it * p.stream_mul);
 }
 
-// score of 4 consecutive elements [e0, e0 + 4) of sample b, as the reference's float64 `h / used_sigmas`
+// contiguous row range of this block: [rows * j / G, rows * (j + 1) / G)
+__device__ __forceinline__ void block_rows(const StepParams& p, int& r0, int& r1) {
+  r0 = static_cast<int>(static_cast<long long>(p.rows) * blockIdx.x / gridDim.x);
+  r1 = static_cast<int>(static_cast<long long>(p.rows) * (blockIdx.x + 1) / gridDim.x);
+}
+
+// the block whose range holds row r (inverse of block_rows)
+__device__ __forceinline__ int block_of_row(const StepParams& p, int r) {
+  return static_cast<int>((static_cast<long long>(r + 1) * gridDim.x + p.rows - 1) / p.rows) - 1;
+}
+
+// RAW network output of 4 consecutive elements [e0, e0 + 4) of sample b as doubles; the 1 / sigma of the
+// reference's float64 `h / used_sigmas` is folded into the per-sample coefficient that multiplies it
 // (1 / sigma is formed once per sample: 1 ulp of float64, far below the single float rounding of the state)
 template <bool FAST>
-__device__ __forceinline__ void load_score4(const StepParams& p, int b, long long e0, double inv_sigma, double (&s)[4]) {
+__device__ __forceinline__ void load_score4(const StepParams& p, int b, long long e0, double (&s)[4]) {
   if (FAST || (!p.score_nhwc && !p.score_f64)) {
     const float4 v = *reinterpret_cast<const float4*>(static_cast<const float*>(p.score) + static_cast<long long>(b) * p.E + e0);
     s[0] = v.x; s[1] = v.y; s[2] = v.z; s[3] = v.w;
@@ -75,141 +104,207 @@ __device__ __forceinline__ void load_score4(const StepParams& p, int b, long lon
                          : static_cast<double>(static_cast<const float*>(p.score)[idx]);
     }
   }
-  if (p.sigmas) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) s[i] *= inv_sigma;
-  }
+}
+
+__device__ __forceinline__ double inv_sigma_of(const StepParams& p, int b) {
+  return p.sigmas ? 1.0 / p.sigmas[p.labels[b]] : 1.0;
 }
 
 // rounds the 4 updated values once to float, applies the condition mask (bit-exact: masked-out positions take
 // x_initial) and stores x (and x_mean) as one 16-byte vector each
-__device__ __forceinline__ void finish4(const StepParams& p, long long gi0, const double (&xn)[4], const double (&xm)[4]) {
+__device__ __forceinline__ void finish4(const StepParams& p, long long gi0, uchar4 m, const double (&xn)[4], const double (&xm)[4]) {
   float xf[4], mf[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     xf[i] = static_cast<float>(xn[i]);
     mf[i] = static_cast<float>(xm[i]);
   }
-  if (p.mask) {
-    const uchar4 m = *reinterpret_cast<const uchar4*>(p.mask + gi0);
-    if (!(m.x && m.y && m.z && m.w)) {
-      const float4 xi = *reinterpret_cast<const float4*>(p.x_init + gi0);
-      if (!m.x) { xf[0] = xi.x; mf[0] = xi.x; }
-      if (!m.y) { xf[1] = xi.y; mf[1] = xi.y; }
-      if (!m.z) { xf[2] = xi.z; mf[2] = xi.z; }
-      if (!m.w) { xf[3] = xi.w; mf[3] = xi.w; }
-    }
+  if (!(m.x && m.y && m.z && m.w)) {
+    const float4 xi = *reinterpret_cast<const float4*>(p.x_init + gi0);
+    if (!m.x) { xf[0] = xi.x; mf[0] = xi.x; }
+    if (!m.y) { xf[1] = xi.y; mf[1] = xi.y; }
+    if (!m.z) { xf[2] = xi.z; mf[2] = xi.z; }
+    if (!m.w) { xf[3] = xi.w; mf[3] = xi.w; }
   }
   *reinterpret_cast<float4*>(p.x + gi0) = make_float4(xf[0], xf[1], xf[2], xf[3]);
   if (p.x_mean_out) *reinterpret_cast<float4*>(p.x_mean_out + gi0) = make_float4(mf[0], mf[1], mf[2], mf[3]);
 }
 
-// grid = (slices of a sample, B): no per-element index arithmetic, 16-byte accesses throughout
+__device__ __forceinline__ uchar4 load_mask4(const StepParams& p, long long gi0) {
+  return p.mask ? *reinterpret_cast<const uchar4*>(p.mask + gi0) : make_uchar4(1, 1, 1, 1);
+}
+
+// walks the rows [r0, r1) of a block keeping (sample, row within the sample) without a division per row
+struct RowIter {
+  int r, r1, b, rq;
+  __device__ __forceinline__ RowIter(const StepParams& p, int r0_, int r1_) : r(r0_), r1(r1_) {
+    b = r0_ / p.rps;
+    rq = r0_ - b * p.rps;
+  }
+  __device__ __forceinline__ bool done() const { return r >= r1; }
+  __device__ __forceinline__ void next(const StepParams& p) {
+    ++r;
+    if (++rq == p.rps) { rq = 0; ++b; }
+  }
+  __device__ __forceinline__ int quad() const { return rq * kThreads + static_cast<int>(threadIdx.x); }  // within the sample
+  __device__ __forceinline__ bool valid(const StepParams& p) const { return r < r1 && quad() < p.qps; }
+  __device__ __forceinline__ long long element(const StepParams& p) const {
+    return static_cast<long long>(b) * p.E + static_cast<long long>(quad()) * 4;
+  }
+};
+
+// The mask of a row is loaded one row ahead: a quad whose 4 positions are all conditioned (mask == 0) takes
+// x_initial whatever the update would be, so its x / score loads and its Philox + Box-Muller work are skipped
+// (with a length condition more than half of the quads, whole warps at a time: one image row of 128 residues is
+// one warp).  The result is bit-identical to computing the update and discarding it.
+__device__ __forceinline__ bool all_conditioned(uchar4 m) { return !(m.x | m.y | m.z | m.w); }
+
+__device__ __forceinline__ void copy_initial4(const StepParams& p, long long gi0) {
+  const float4 xi = *reinterpret_cast<const float4*>(p.x_init + gi0);
+  *reinterpret_cast<float4*>(p.x + gi0) = xi;
+  if (p.x_mean_out) *reinterpret_cast<float4*>(p.x_mean_out + gi0) = xi;
+}
+
 // FAST: fp32 NCHW score, VE SDE (no drift), noise on -- the configuration of every shipped sampling config; the
 // generic instantiation keeps the fp64 / NHWC score, VP drift and probability-flow variants of the API.
 template <bool FAST>
-__global__ void __launch_bounds__(256) predictor_kernel(const StepParams p) {
-  const int b = blockIdx.y;
-  const long long qps = p.E / 4;  // quads per sample
+__global__ void __launch_bounds__(kThreads, 2) predictor_kernel(const StepParams p) {
+  int r0, r1;
+  block_rows(p, r0, r1);
   const unsigned long long stream = stream_of(p);
-  const float G = p.G[b];
-  const float g2 = G * G;  // fp32, as G[:, None, None, None] ** 2
-  const double gs = static_cast<double>(g2) * static_cast<double>(p.drift_scale);
-  const double inv_sigma = p.sigmas ? 1.0 / p.sigmas[p.labels[b]] : 1.0;
-  const float sa = p.sqrt_alpha ? p.sqrt_alpha[b] : 0.f;
-  for (long long ql = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; ql < qps;
-       ql += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long gi0 = static_cast<long long>(b) * p.E + ql * 4;
-    const float4 xv = *reinterpret_cast<const float4*>(p.x + gi0);
-    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-    double s[4], xn[4], xm[4];
-    load_score4<FAST>(p, b, ql * 4, inv_sigma, s);
-    float z[4] = {0.f, 0.f, 0.f, 0.f};
-    if (FAST || p.add_noise)
-      philox_normal4(p.seed, stream, static_cast<unsigned long long>((p.sample_offset + b) * qps + ql), z);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float f = 0.f;
-      if (!FAST && p.sqrt_alpha) f = __fsub_rn(__fmul_rn(sa, xs[i]), xs[i]);
-      const double rev_f = static_cast<double>(f) - gs * s[i];  // f == 0 for VE: exactly x + G^2 * score
-      xm[i] = static_cast<double>(xs[i]) - rev_f;
-      xn[i] = (FAST || p.add_noise) ? xm[i] + static_cast<double>(__fmul_rn(G, z[i])) : xm[i];
+  int cur_b = -1;
+  float G = 0.f, sa = 0.f;
+  double coef = 0.0;  // G^2 (fp32, as G[:, None, None, None] ** 2) * drift_scale / sigma
+  RowIter it(p, r0, r1);
+  uchar4 m = it.valid(p) ? load_mask4(p, it.element(p)) : make_uchar4(1, 1, 1, 1);
+  while (!it.done()) {
+    RowIter nx = it;
+    nx.next(p);
+    const uchar4 m_next = nx.valid(p) ? load_mask4(p, nx.element(p)) : make_uchar4(1, 1, 1, 1);
+    const int b = it.b, ql = it.quad();
+    if (b != cur_b) {  // uniform: a block crosses a sample boundary at most every rps rows
+      cur_b = b;
+      G = p.G[b];
+      coef = static_cast<double>(__fmul_rn(G, G)) * static_cast<double>(p.drift_scale) * inv_sigma_of(p, b);
+      sa = p.sqrt_alpha ? p.sqrt_alpha[b] : 0.f;
     }
-    finish4(p, gi0, xn, xm);
+    if (ql < p.qps) {
+      const long long gi0 = it.element(p);
+      if (p.skip_conditioned && all_conditioned(m)) {
+        copy_initial4(p, gi0);
+      } else {
+        const float4 xv = *reinterpret_cast<const float4*>(p.x + gi0);
+        double s[4], xn[4], xm[4];
+        load_score4<FAST>(p, b, static_cast<long long>(ql) * 4, s);
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+        float z[4] = {0.f, 0.f, 0.f, 0.f};
+        if (FAST || p.add_noise)
+          philox_normal4(p.seed, stream, static_cast<unsigned long long>((p.sample_offset + b) * p.qps + ql), z);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          double base = static_cast<double>(xs[i]);  // x - f; f == 0 for VE: exactly x + G^2 * score
+          if (!FAST && p.sqrt_alpha) base -= static_cast<double>(__fsub_rn(__fmul_rn(sa, xs[i]), xs[i]));
+          xm[i] = fma(coef, s[i], base);
+          xn[i] = (FAST || p.add_noise) ? xm[i] + static_cast<double>(__fmul_rn(G, z[i])) : xm[i];
+        }
+        finish4(p, gi0, m, xn, xm);
+      }
+    }
+    m = m_next;
+    it = nx;
   }
 }
 
+// block-wide sum of two doubles (result valid in thread 0); `red` is reused, hence the trailing barrier
+__device__ __forceinline__ void block_sum2(double& a, double& c, double (*red)[kThreads / 32]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  if (lane == 0) { red[0][warp] = a; red[1][warp] = c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a = 0.0; c = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) { a += red[0][w]; c += red[1][w]; }
+  }
+  __syncthreads();
+}
+
 template <bool FAST>
-__global__ void __launch_bounds__(256) corrector_kernel(const StepParams p) {
+__global__ void __launch_bounds__(kThreads, 2) corrector_kernel(const StepParams p) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ double red[2][8];
+  extern __shared__ float4 zcache[];  // [cache_rows][kThreads] normals of this block's first rows
+  __shared__ double red[2][kThreads / 32];
   __shared__ float step_sh;
   const unsigned long long stream = stream_of(p);
-  const long long items = static_cast<long long>(p.B) * p.chunks;
-  const long long quads_per_chunk = p.E / 4 / p.chunks;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int r0, r1;
+  block_rows(p, r0, r1);
 
-  // ---- phase 1: partial squared norms of score and noise per (sample, chunk)
-  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
-    const int b = static_cast<int>(item / p.chunks);
-    const int ck = static_cast<int>(item - static_cast<long long>(b) * p.chunks);
+  // ---- phase 1: normals (kept), partial squared norms of the RAW score and of the noise per (block, sample)
+  {
     double sg = 0.0, sn = 0.0;
-    const double inv_sigma = p.sigmas ? 1.0 / p.sigmas[p.labels[b]] : 1.0;
-    for (long long ql = threadIdx.x; ql < quads_per_chunk; ql += blockDim.x) {
-      const long long qs = ck * quads_per_chunk + ql;  // quad within the sample
-      float z[4];
-      philox_normal4(p.seed, stream, static_cast<unsigned long long>((p.sample_offset + b) * (p.E / 4) + qs), z);
-      double s[4];
-      load_score4<FAST>(p, b, qs * 4, inv_sigma, s);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        sg += s[i] * s[i];
-        sn += static_cast<double>(z[i]) * static_cast<double>(z[i]);
+    int cur_b = r0 < r1 ? r0 / p.rps : 0;
+    auto flush = [&](int b) {
+      block_sum2(sg, sn, red);
+      if (threadIdx.x == 0) {
+        const double inv = inv_sigma_of(p, b);
+        p.partial[2 * (blockIdx.x + b)] = sg * inv * inv;  // sum (h / sigma)^2
+        p.partial[2 * (blockIdx.x + b) + 1] = sn;
       }
-    }
+      sg = 0.0; sn = 0.0;
+    };
+    int b = cur_b, rq = r0 - b * p.rps;
+    for (int r = r0; r < r1; ++r, ++rq) {
+      if (rq == p.rps) { rq = 0; ++b; }
+      if (b != cur_b) { flush(cur_b); cur_b = b; }
+      const int ql = rq * kThreads + static_cast<int>(threadIdx.x);
+      if (ql >= p.qps) continue;
+      const long long gi0 = static_cast<long long>(b) * p.E + static_cast<long long>(ql) * 4;
+      double s[4];
+      load_score4<FAST>(p, b, static_cast<long long>(ql) * 4, s);
+      if (p.prefetch) {  // phase 2's first-touch operands: x (one 128-byte line per 8 threads) and the mask (per warp)
+        if ((threadIdx.x & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + gi0));
+        if ((threadIdx.x & 31) == 0 && p.mask) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.mask + gi0));
+      }
+      float z[4];
+      philox_normal4(p.seed, stream, static_cast<unsigned long long>((p.sample_offset + b) * p.qps + ql), z);
+      if (r - r0 < p.cache_rows) zcache[(r - r0) * kThreads + threadIdx.x] = make_float4(z[0], z[1], z[2], z[3]);
+      if constexpr (FAST) {
+        // squares of 4 elements summed in float (the inputs are floats), the running sums in double
+        const float h0 = static_cast<float>(s[0]), h1 = static_cast<float>(s[1]), h2 = static_cast<float>(s[2]),
+                    h3 = static_cast<float>(s[3]);
+        sg += static_cast<double>(__fmaf_rn(h3, h3, __fmaf_rn(h2, h2, __fmaf_rn(h1, h1, __fmul_rn(h0, h0)))));
+      } else {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      sg += __shfl_xor_sync(0xffffffffu, sg, o);
-      sn += __shfl_xor_sync(0xffffffffu, sn, o);
+        for (int i = 0; i < 4; ++i) sg += s[i] * s[i];
+      }
+      sn += static_cast<double>(__fmaf_rn(z[3], z[3], __fmaf_rn(z[2], z[2], __fmaf_rn(z[1], z[1], __fmul_rn(z[0], z[0])))));
     }
-    if (lane == 0) { red[0][warp] = sg; red[1][warp] = sn; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double a = 0.0, c = 0.0;
-      for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) { a += red[0][w]; c += red[1][w]; }
-      p.partial[2 * item] = a;
-      p.partial[2 * item + 1] = c;
-    }
-    __syncthreads();
+    if (r0 < r1) flush(cur_b);
   }
   grid.sync();
 
-  // ---- step size from the batch-mean norms (every block recomputes it; B*chunks doubles)
+  // ---- step size from the batch-mean norms (every block recomputes it from the (block, sample) partials)
   {
-    double gsum = 0.0;
+    double gsum = 0.0, nsum_d = 0.0;
     float nsum = 0.f;
-    for (int b = threadIdx.x; b < p.B; b += blockDim.x) {
+    for (int b = threadIdx.x; b < p.B; b += kThreads) {
+      const int j0 = block_of_row(p, b * p.rps), j1 = block_of_row(p, (b + 1) * p.rps - 1);
       double a = 0.0, c = 0.0;
-      for (int ck = 0; ck < p.chunks; ++ck) {
-        a += p.partial[2 * (static_cast<long long>(b) * p.chunks + ck)];
-        c += p.partial[2 * (static_cast<long long>(b) * p.chunks + ck) + 1];
+      for (int j = j0; j <= j1; ++j) {
+        a += p.partial[2 * (j + b)];
+        c += p.partial[2 * (j + b) + 1];
       }
       gsum += sqrt(a);                        // ||grad_b||  (float64)
       nsum += static_cast<float>(sqrt(c));    // ||noise_b|| (float32 tensor in the reference)
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
-      nsum += __shfl_xor_sync(0xffffffffu, nsum, o);
-    }
-    if (lane == 0) { red[0][warp] = gsum; red[1][warp] = static_cast<double>(nsum); }
-    __syncthreads();
+    nsum_d = static_cast<double>(nsum);
+    block_sum2(gsum, nsum_d, red);
     if (threadIdx.x == 0) {
-      double a = 0.0;
-      float c = 0.f;
-      for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) { a += red[0][w]; c += static_cast<float>(red[1][w]); }
-      const double grad_norm = a / p.B;
-      const float noise_norm = c / static_cast<float>(p.B);
+      const double grad_norm = gsum / p.B;
+      const float noise_norm = static_cast<float>(nsum_d) / static_cast<float>(p.B);
       const float sn = __fmul_rn(p.snr, noise_norm);  // python float * fp32 0-dim tensor -> fp32
       const double r = static_cast<double>(sn) / grad_norm;
       step_sh = static_cast<float>(r * r * 2.0);      // * alpha (fp32 [B]) demotes the 0-dim double
@@ -218,30 +313,49 @@ __global__ void __launch_bounds__(256) corrector_kernel(const StepParams p) {
   }
   const float step0 = step_sh;
 
-  // ---- phase 2: apply (one (sample, chunk) item per block iteration, as in phase 1)
-  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
-    const int b = static_cast<int>(item / p.chunks);
-    const int ck = static_cast<int>(item - static_cast<long long>(b) * p.chunks);
-    const double inv_sigma = p.sigmas ? 1.0 / p.sigmas[p.labels[b]] : 1.0;
-    const float step = p.alpha ? __fmul_rn(step0, p.alpha[b]) : step0;
-    const float nscale = sqrtf(__fmul_rn(step, 2.f));
-    const double dstep = static_cast<double>(step);
-    for (long long ql = threadIdx.x; ql < quads_per_chunk; ql += blockDim.x) {
-      const long long qs = ck * quads_per_chunk + ql;
-      const long long gi0 = static_cast<long long>(b) * p.E + qs * 4;
-      float z[4];
-      philox_normal4(p.seed, stream, static_cast<unsigned long long>((p.sample_offset + b) * (p.E / 4) + qs), z);
-      const float4 xv = *reinterpret_cast<const float4*>(p.x + gi0);
-      const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-      double s[4], xn[4], xm[4];
-      load_score4<FAST>(p, b, qs * 4, inv_sigma, s);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        xm[i] = static_cast<double>(xs[i]) + dstep * s[i];
-        xn[i] = xm[i] + static_cast<double>(__fmul_rn(nscale, z[i]));
-      }
-      finish4(p, gi0, xn, xm);
+  // ---- phase 2: apply
+  int cur_b = -1;
+  float nscale = 0.f;
+  double coef = 0.0;  // step / sigma
+  RowIter it(p, r0, r1);
+  uchar4 m = it.valid(p) ? load_mask4(p, it.element(p)) : make_uchar4(1, 1, 1, 1);
+  while (!it.done()) {
+    RowIter nx = it;
+    nx.next(p);
+    const uchar4 m_next = nx.valid(p) ? load_mask4(p, nx.element(p)) : make_uchar4(1, 1, 1, 1);
+    const int b = it.b, ql = it.quad(), slot = it.r - r0;
+    if (b != cur_b) {
+      cur_b = b;
+      const float step = p.alpha ? __fmul_rn(step0, p.alpha[b]) : step0;
+      nscale = sqrtf(__fmul_rn(step, 2.f));
+      coef = static_cast<double>(step) * inv_sigma_of(p, b);
     }
+    if (ql < p.qps) {
+      const long long gi0 = it.element(p);
+      if (p.skip_conditioned && all_conditioned(m)) {
+        copy_initial4(p, gi0);
+      } else {
+        const float4 xv = *reinterpret_cast<const float4*>(p.x + gi0);
+        double s[4], xn[4], xm[4];
+        load_score4<FAST>(p, b, static_cast<long long>(ql) * 4, s);
+        float z[4];
+        if (slot < p.cache_rows) {
+          const float4 zv = zcache[slot * kThreads + threadIdx.x];
+          z[0] = zv.x; z[1] = zv.y; z[2] = zv.z; z[3] = zv.w;
+        } else {
+          philox_normal4(p.seed, stream, static_cast<unsigned long long>((p.sample_offset + b) * p.qps + ql), z);
+        }
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          xm[i] = fma(coef, s[i], static_cast<double>(xs[i]));
+          xn[i] = xm[i] + static_cast<double>(__fmul_rn(nscale, z[i]));
+        }
+        finish4(p, gi0, m, xn, xm);
+      }
+    }
+    m = m_next;
+    it = nx;
   }
 }
 
@@ -295,7 +409,12 @@ StepParams to_params(const PcStepArgs& a) {
   p.seed = a.seed; p.stream_base = a.stream_base; p.stream_mul = a.stream_mul; p.iter_ptr = a.iter_ptr;
   p.sample_offset = a.sample_offset;
   p.B = a.B; p.C = a.C; p.HW = a.HW; p.E = static_cast<long long>(a.C) * a.HW;
-  T2P_CHECK(p.E % 4 == 0, "C*N*N must be a multiple of 4");
+  T2P_CHECK(a.B > 0 && p.E > 0 && p.E % 4 == 0, "C*N*N must be a positive multiple of 4");
+  T2P_CHECK(p.E / 4 < (1LL << 30), "sample too large");
+  p.qps = static_cast<int>(p.E / 4);
+  p.rps = (p.qps + kThreads - 1) / kThreads;
+  T2P_CHECK(static_cast<long long>(a.B) * p.rps < (1LL << 31), "batch too large");
+  p.rows = a.B * p.rps;
   T2P_CHECK((reinterpret_cast<uintptr_t>(a.x) & 15) == 0, "x must be 16-byte aligned");
   T2P_CHECK((reinterpret_cast<uintptr_t>(a.score) & 15) == 0, "score must be 16-byte aligned");
   T2P_CHECK((reinterpret_cast<uintptr_t>(a.mask) & 3) == 0, "mask must be 4-byte aligned");
@@ -304,6 +423,8 @@ StepParams to_params(const PcStepArgs& a) {
   if (a.sigmas) T2P_CHECK(a.labels != nullptr, "labels required with sigmas");
   if (a.mask) T2P_CHECK(a.x_init != nullptr, "x_init required with mask");
   p.partial = a.partial;
+  static const bool no_skip = getenv("T2P_STEP_NOSKIP") != nullptr;  // A/B knob
+  p.skip_conditioned = (a.mask != nullptr && !no_skip) ? 1 : 0;
   return p;
 }
 
@@ -317,46 +438,60 @@ int num_sms() {
   return n;
 }
 
+// resident blocks of `fn` over the whole device (one wave), at `smem` bytes of dynamic shared memory
+int resident_blocks(const void* fn, size_t smem) {
+  int per_sm = 0;
+  T2P_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, smem));
+  T2P_CHECK(per_sm > 0, "step kernel does not fit on an SM");
+  return std::min(per_sm * num_sms(), kMaxBlocks);
+}
+
 }  // namespace
 
 void pc_predictor_step(const PcStepArgs& a, cudaStream_t st) {
   StepParams p = to_params(a);
   T2P_CHECK(a.G != nullptr, "predictor needs G");
-  const long long qps = p.E / 4;
-  const int bx = static_cast<int>(std::max<long long>(1, std::min<long long>(cdiv64(qps, 256), cdiv64(num_sms() * 8LL, p.B))));
   const bool fast = !p.score_nhwc && !p.score_f64 && p.sqrt_alpha == nullptr && p.add_noise;
-  if (fast) predictor_kernel<true><<<dim3(bx, p.B), 256, 0, st>>>(p);
-  else predictor_kernel<false><<<dim3(bx, p.B), 256, 0, st>>>(p);
+  static int wave[2] = {0, 0};
+  if (!wave[fast])
+    wave[fast] = resident_blocks(fast ? reinterpret_cast<const void*>(predictor_kernel<true>)
+                                      : reinterpret_cast<const void*>(predictor_kernel<false>), 0);
+  const int blocks = std::min(wave[fast], p.rows);
+  if (fast) predictor_kernel<true><<<blocks, kThreads, 0, st>>>(p);
+  else predictor_kernel<false><<<blocks, kThreads, 0, st>>>(p);
   T2P_LAUNCH_CHECK();
 }
 
-int pc_corrector_chunks(int B, long long E) {
-  const long long q = E / 4;
-  int chunks = 1;
-  // several (sample, chunk) items per resident block, each chunk still at least one quad per thread
-  while (static_cast<long long>(B) * chunks < 8LL * num_sms() && (q % (chunks * 2) == 0) && q / (chunks * 2) >= 256)
-    chunks *= 2;
-  return chunks;
-}
+// doubles of partial-sum workspace the corrector needs for a batch of B samples: one (score, noise) slot per
+// (block, sample) pair that occurs, indexed block + sample
+long long pc_corrector_workspace_doubles(int B) { return 2LL * (kMaxBlocks + static_cast<long long>(B)); }
 
 void pc_corrector_step(const PcStepArgs& a, cudaStream_t st) {
   StepParams p = to_params(a);
-  T2P_CHECK(a.partial != nullptr && a.chunks > 0, "corrector needs the partial-sum workspace");
-  T2P_CHECK((p.E / 4) % a.chunks == 0, "chunks must divide the quads of a sample");
-  p.chunks = a.chunks;
+  T2P_CHECK(a.partial != nullptr, "corrector needs the partial-sum workspace");
   const bool fast = !p.score_nhwc && !p.score_f64;
-  static int max_blocks[2] = {0, 0};
-  if (!max_blocks[fast]) {
-    int per_sm = 0;
-    if (fast) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, corrector_kernel<true>, 256, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, corrector_kernel<false>, 256, 0);
-    max_blocks[fast] = std::max(1, per_sm) * num_sms();
+  const void* fn = fast ? reinterpret_cast<const void*>(corrector_kernel<true>)
+                        : reinterpret_cast<const void*>(corrector_kernel<false>);
+  constexpr size_t kRowBytes = sizeof(float4) * kThreads;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[fast]) {
+    T2P_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxCacheRows * kRowBytes)));
+    T2P_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    attr_set[fast] = true;
   }
-  // cooperative launch: every block must be resident; blocks loop over the (sample, chunk) items
-  const int blocks = static_cast<int>(std::min<long long>(static_cast<long long>(p.B) * p.chunks, max_blocks[fast]));
+  // shared-memory cache sized for the rows a block gets when two blocks per SM are resident
+  static const bool no_cache = getenv("T2P_STEP_NOCACHE") != nullptr;
+  static const bool no_prefetch = getenv("T2P_STEP_NOPREFETCH") != nullptr;
+  const int want = static_cast<int>(cdiv64(p.rows, 2LL * num_sms()));
+  p.cache_rows = no_cache ? 0 : std::min(want, kMaxCacheRows);
+  p.prefetch = no_prefetch ? 0 : 1;
+  const size_t smem = p.cache_rows * kRowBytes;
+  static int wave[2][kMaxCacheRows + 1] = {};
+  if (!wave[fast][p.cache_rows]) wave[fast][p.cache_rows] = resident_blocks(fn, smem);
+  // cooperative launch: every block must be resident
+  const int blocks = std::min(wave[fast][p.cache_rows], p.rows);
   void* args[] = {&p};
-  void* fn = fast ? reinterpret_cast<void*>(corrector_kernel<true>) : reinterpret_cast<void*>(corrector_kernel<false>);
-  T2P_CUDA(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(256), args, 0, st));
+  T2P_CUDA(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(kThreads), args, smem, st));
 }
 
 void philox_normal_fill(unsigned long long seed, unsigned long long stream, long long first_element, long long count,
