@@ -178,8 +178,11 @@ def _traffic_lookup(roof):
 
 
 def _step_kernel_roofline(dev, B, shape, L, mask_u8, hbm_gbs):
-    """Predictor / corrector half-step kernels timed alone.  Algorithmic bytes per element:
-    read x (4) + read score (4) + write x (4) + mask (1) [+ write x_mean (4) for the predictor]."""
+    """Predictor / corrector half-step kernels timed alone, configured as t2p_pc_run launches them (conditioned
+    positions hold x_init from the start of the run and are not touched).  Algorithmic bytes per element
+    (DESIGN.md 4.3), given the mask: a quad with a free position reads x (4), score (4), mask (1) and writes x (4)
+    [+ x_mean (4) for the predictor]; a fully conditioned quad costs its mask byte; the corrector also reads the
+    whole score once for the norms (4; the update's second read of it hits L2)."""
     from text2protein_b200 import _lib
     E = shape[1] * shape[2] * shape[3]
     n = B * E
@@ -190,8 +193,10 @@ def _step_kernel_roofline(dev, B, shape, L, mask_u8, hbm_gbs):
     xm = [torch.empty(shape, device=dev) for _ in range(sets)]
     G = torch.full((B,), 0.3, device=dev)
     ws = torch.empty(max(1, L.t2p_corrector_workspace_bytes(B, E) // 8), dtype=torch.float64, device=dev)
+    free_quads = mask_u8.reshape(-1, 4).any(-1).float().mean().item()  # fraction of quads with a free position
     out = {}
-    for name, fn, bytes_per in (("predictor_kernel", L.t2p_predictor_step, 17), ("corrector_kernel", L.t2p_corrector_step, 13)):
+    for name, fn, free_b, cond_b in (("predictor_kernel", L.t2p_predictor_step, 17, 1),
+                                     ("corrector_kernel", L.t2p_corrector_step, 13, 5)):
         args = []
         for i in range(sets):
             a = _lib.StepArgs()
@@ -200,6 +205,7 @@ def _step_kernel_roofline(dev, B, shape, L, mask_u8, hbm_gbs):
             a.G = G.data_ptr()
             a.snr = 0.17
             a.mask, a.x_init = mask_u8.data_ptr(), xi[i].data_ptr()
+            a.conditioned_in_place = 1
             a.x_mean_out = xm[i].data_ptr() if name == "predictor_kernel" else None
             a.seed, a.stream_id, a.sample_offset = 2024, 5, 0
             a.B, a.C, a.HW = B, shape[1], shape[2] * shape[3]
@@ -225,10 +231,13 @@ def _step_kernel_roofline(dev, B, shape, L, mask_u8, hbm_gbs):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / (reps * sets)
-        gbs = n * bytes_per / (ms * 1e-3) / 1e9
-        out[name] = {"ms": ms, "algorithmic_bytes": n * bytes_per, "achieved_gbs": gbs, "peak_gbs": hbm_gbs,
-                     "frac": gbs / hbm_gbs, "bound": "hbm",
-                     "note": "graph-replayed launches back to back; inputs rotate over 8 sets (> L2)"}
+        nbytes = n * (free_quads * free_b + (1.0 - free_quads) * cond_b)
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out[name] = {"ms": ms, "algorithmic_bytes": nbytes, "achieved_gbs": gbs, "peak_gbs": hbm_gbs,
+                     "frac": gbs / hbm_gbs, "bound": "hbm", "free_quad_fraction": free_quads,
+                     "unmasked_bytes": n * free_b,
+                     "note": "graph-replayed launches back to back; inputs rotate over 8 sets (> L2); bytes count "
+                             "what the bench's length mask leaves to update (unmasked_bytes = every position free)"}
     return out
 
 

@@ -108,6 +108,10 @@ typedef struct t2p_step_args {
   int64_t sample_offset;    /* global index of local sample 0 (batch sharding) */
   int32_t B, C, HW;
   double* workspace;        /* corrector: >= t2p_corrector_workspace_bytes(B, C*HW) bytes */
+  int32_t conditioned_in_place; /* caller guarantees that x (and x_mean_out) already hold x_init wherever mask == 0
+                                 * (true inside a sampling run after the first mask application, sampling.py:283-287
+                                 * being idempotent there): fully conditioned quads are then not read or written */
+  int32_t reserved;
 } t2p_step_args;
 
 int64_t t2p_corrector_workspace_bytes(int B, int64_t elems_per_sample);

@@ -291,6 +291,99 @@ def test_pc_steps_match_oracle_math(B, Cc, N):
         assert rel_err(got, ref) < 2e-6
 
 
+def _length_mask(B, Cc, N, g, lo):
+    """conditional_mask of a length condition (utils.py:62-81 shape): free inside the L x L corner, padding channel fixed."""
+    lengths = torch.randint(lo, N + 1, (B,), generator=g)
+    ar = torch.arange(N)
+    lm = (ar[None, :, None] < lengths[:, None, None]) & (ar[None, None, :] < lengths[:, None, None])
+    mask = torch.ones(B, Cc, N, N, dtype=torch.bool) * lm[:, None]
+    mask[:, -1] = False
+    return mask
+
+
+# NCHW fp32 score = the layout of the sampling loop, including ragged rows (C*N*N not a multiple of 2048), more samples
+# than blocks, and the in-place mode of t2p_pc_run (conditioned positions pre-filled with x_init, never touched);
+# 64 x 5 x 128 x 128 is the bench shape
+@pytest.mark.parametrize("B,Cc,N,kind", [(2, 5, 32, "random"), (3, 8, 64, "length"), (64, 5, 16, "length"),
+                                          (5, 5, 6, "random"), (3, 3, 10, "length"), (2, 5, 128, "none"),
+                                          (64, 5, 128, "length"), (300, 5, 32, "length"), (2, 8, 256, "length")])
+@pytest.mark.parametrize("in_place", [False, True])
+def test_pc_steps_loop_layout(B, Cc, N, kind, in_place):
+    if in_place and kind == "none":
+        pytest.skip("no mask, nothing conditioned")
+    g = torch.Generator().manual_seed(16)
+    x = torch.randn(B, Cc, N, N, generator=g) * 10
+    h = torch.randn(B, Cc, N, N, generator=g)
+    labels = torch.randint(0, 50, (B,), generator=g)
+    sigmas = torch.tensor(np.exp(np.linspace(np.log(100.0), np.log(0.01), 50)))
+    G = torch.rand(B, generator=g) + 0.1
+    if kind == "random":
+        mask = torch.rand(B, Cc, N, N, generator=g) > 0.3
+    elif kind == "length":
+        mask = _length_mask(B, Cc, N, g, N // 3)
+    else:
+        mask = torch.ones(B, Cc, N, N, dtype=torch.bool)
+    x_init = torch.randn(B, Cc, N, N, generator=g)
+    seed, E = 77, Cc * N * N
+    L = _lib.lib()
+    dev = {k: v.cuda() for k, v in dict(x=x, h=h, labels=labels, sigmas=sigmas, G=G, x_init=x_init, mask=mask).items()}
+    mask_u8 = dev["mask"].contiguous().view(torch.uint8)
+
+    def noise(stream):
+        n = torch.empty(B, Cc, N, N, dtype=torch.float32, device="cuda")
+        _lib.check(L.t2p_philox_normal(C.c_uint64(seed), stream, 0, n.numel(), C.c_float(1.0), _lib.ptr(n), _st()))
+        return n
+
+    # reference math of _ref_steps on the device in float64 (same formulas; the CPU version is too slow at the bench shape)
+    score64 = dev["h"].double() / dev["sigmas"][dev["labels"]][:, None, None, None]
+    m = dev["mask"] if kind != "none" else torch.ones_like(dev["mask"])
+    grad_norm = torch.norm(score64.reshape(B, -1), dim=-1).mean()
+    nc, npred = noise(11), noise(12)
+    noise_norm = torch.norm(nc.reshape(B, -1), dim=-1).mean()
+    step = ((0.17 * noise_norm / grad_norm) ** 2 * 2 * torch.ones(B, device="cuda")).float()
+    xc_ref = dev["x"] + step[:, None, None, None] * score64 + torch.sqrt(step * 2)[:, None, None, None] * nc
+    xc_ref = torch.where(m, xc_ref, dev["x_init"].double()).float()
+    xm_ref = dev["x"] + (dev["G"][:, None, None, None] ** 2) * score64
+    xp_ref = torch.where(m, xm_ref + dev["G"][:, None, None, None] * npred, dev["x_init"].double()).float()
+    xm_ref = torch.where(m, xm_ref, dev["x_init"].double()).float()
+
+    ws = torch.empty(L.t2p_corrector_workspace_bytes(B, E) // 8, dtype=torch.float64, device="cuda")
+    def args(xbuf, stream):
+        a = _lib.StepArgs()
+        a.x, a.score, a.score_dtype, a.score_nhwc = xbuf.data_ptr(), dev["h"].data_ptr(), _lib.F32, 0
+        a.sigmas, a.labels, a.G = dev["sigmas"].data_ptr(), dev["labels"].data_ptr(), dev["G"].data_ptr()
+        a.snr = 0.17
+        if kind != "none":
+            a.mask, a.x_init = mask_u8.data_ptr(), dev["x_init"].data_ptr()
+            a.conditioned_in_place = 1 if in_place else 0
+        a.seed, a.stream_id, a.B, a.C, a.HW = seed, stream, B, Cc, N * N
+        a.workspace = ws.data_ptr()
+        return a
+
+    # in-place mode: the caller has applied the condition once (x, x_mean hold x_init where mask == 0); the
+    # conditioned entries of the sentinel buffers must come back untouched
+    start = torch.where(m, dev["x"], dev["x_init"]) if in_place else dev["x"]
+    xc = start.clone()
+    _lib.check(L.t2p_corrector_step(C.byref(args(xc, 11)), _st()))
+    xp = start.clone()
+    xmn = torch.full_like(xp, float("nan"))
+    if in_place:
+        xmn = torch.where(m, xmn, dev["x_init"])
+    a = args(xp, 12)
+    a.x_mean_out = xmn.data_ptr()
+    _lib.check(L.t2p_predictor_step(C.byref(a), _st()))
+    torch.cuda.synchronize()
+    for got, ref in ((xc, xc_ref), (xp, xp_ref), (xmn, xm_ref)):
+        assert torch.isfinite(got).all()
+        assert torch.equal(got[~m], dev["x_init"][~m])              # mask handling is bit-exact
+        assert rel_err(got, ref) < 2e-6
+    # run-to-run deterministic (fixed reduction order, no atomics)
+    xc2 = start.clone()
+    _lib.check(L.t2p_corrector_step(C.byref(args(xc2, 11)), _st()))
+    torch.cuda.synchronize()
+    assert torch.equal(xc, xc2)
+
+
 @pytest.mark.parametrize("B,H,W,cin,nout", [(2, 128, 128, 128, 5), (3, 32, 32, 64, 8), (1, 30, 48, 128, 5),
                                             (2, 64, 64, 256, 5), (1, 256, 256, 128, 5), (2, 4, 16, 64, 5),
                                             (1, 16, 32, 128, 8)])

@@ -26,7 +26,7 @@ class StepArgs(C.Structure):
                 ("alpha", C.c_void_p), ("probability_flow", C.c_int32), ("snr", C.c_float), ("mask", C.c_void_p),
                 ("x_init", C.c_void_p), ("x_mean_out", C.c_void_p), ("seed", C.c_uint64), ("stream_id", C.c_int64),
                 ("sample_offset", C.c_int64), ("B", C.c_int32), ("C", C.c_int32), ("HW", C.c_int32),
-                ("workspace", C.c_void_p)]
+                ("workspace", C.c_void_p), ("conditioned_in_place", C.c_int32), ("reserved", C.c_int32)]
 
 
 class RunArgs(C.Structure):

@@ -238,12 +238,12 @@ static PcStepArgs step_args(const t2p_step_args* a) {
   p.seed = a->seed; p.stream_base = a->stream_id; p.stream_mul = 0; p.iter_ptr = nullptr;
   p.sample_offset = a->sample_offset;
   p.B = a->B; p.C = a->C; p.HW = a->HW;
+  p.conditioned_in_place = a->conditioned_in_place;
   return p;
 }
 
 int64_t t2p_corrector_workspace_bytes(int B, int64_t elems_per_sample) {
-  (void)elems_per_sample;
-  return static_cast<int64_t>(sizeof(double)) * pc_corrector_workspace_doubles(B);
+  return static_cast<int64_t>(sizeof(double)) * pc_corrector_workspace_doubles(B, elems_per_sample);
 }
 
 int t2p_predictor_step(const t2p_step_args* a, void* stream) {
@@ -291,7 +291,7 @@ static void ensure_run_buffers(t2p_unet* u, int B, int K) {
     T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->G), sizeof(float) * B));
     T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->state), sizeof(long long) * 2));
     T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->h), sizeof(float) * B * E));
-    T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->partial), sizeof(double) * pc_corrector_workspace_doubles(B)));
+    T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->partial), sizeof(double) * pc_corrector_workspace_doubles(B, E)));
     u->run_B = B;
   }
   if (u->run_K < K) {
@@ -343,6 +343,14 @@ int t2p_pc_run(t2p_unet* u, const t2p_run_args* a, void* stream) {
   base.sample_offset = a->sample_offset;
   base.B = B; base.C = c.num_channels; base.HW = HW;
   base.partial = u->partial;
+  if (a->mask) {
+    // sampling.py:283-287 re-applies the condition after every half-step; x and x_mean take x_initial at the
+    // conditioned positions ONCE here and the step kernels leave those positions alone for the rest of the run
+    const long long n = static_cast<long long>(B) * c.num_channels * HW;
+    apply_mask(a->x, a->mask, a->x_init, n, st);
+    apply_mask(a->x_mean, a->mask, a->x_init, n, st);
+    base.conditioned_in_place = 1;
+  }
 
   auto iteration = [&]() {
     run_prep(u->state, u->label_table, u->g_table, B, u->labels, u->G, st);

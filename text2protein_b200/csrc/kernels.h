@@ -128,11 +128,12 @@ struct PcStepArgs {
   const long long* iter_ptr = nullptr;
   long long sample_offset = 0;
   int B = 0, C = 0, HW = 0;
-  double* partial = nullptr; // corrector only: pc_corrector_workspace_doubles(B) doubles
+  double* partial = nullptr; // corrector only: pc_corrector_workspace_doubles(B, C*HW) doubles
+  int conditioned_in_place = 0;  // caller guarantees x (and x_mean_out) already hold x_init where mask == 0
 };
 void pc_predictor_step(const PcStepArgs& a, cudaStream_t st);
 void pc_corrector_step(const PcStepArgs& a, cudaStream_t st);
-long long pc_corrector_workspace_doubles(int B);
+long long pc_corrector_workspace_doubles(int B, long long E);
 void philox_normal_fill(unsigned long long seed, unsigned long long stream, long long first_element, long long count,
                         float scale, float* out, cudaStream_t st);
 void philox_bits_fill(unsigned long long seed, unsigned long long stream, long long first_quad, long long quads,

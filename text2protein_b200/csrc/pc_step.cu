@@ -10,16 +10,18 @@
 // The arithmetic follows the reference's dtype promotions (score is float64): products with the
 // score run in double, noise terms in float, the state is rounded to float once per half-step.
 //
-// Work decomposition (both kernels): a sample is cut into rows of kThreads quads (4 consecutive elements, one
-// 16-byte access per tensor); the B * rows_per_sample rows are dealt out in contiguous, equal (+-1) ranges to a
-// single wave of resident blocks (2 x 512 threads per SM), so there is no partial second wave and no
-// per-element index arithmetic (the sample index is uniform per row).
+// Work decomposition (all kernels): a sample is cut into rows of kThreads quads (4 consecutive elements, one
+// 16-byte access per tensor).  A single wave of resident blocks (2 x 512 threads per SM) takes the rows
+// INTERLEAVED (block j: rows j, j + G, j + 2G, ...): a quad whose 4 positions are all conditioned takes x_initial
+// without its x / score loads and without Philox + Box-Muller, so with a length condition the cost of a row
+// depends on where it lies in its sample; contiguous row ranges left a third of the SMs idle (ncu: SM-active
+// cycles 64 % of elapsed), interleaving spreads every sample over all SMs.
 //
-// The corrector is a cooperative kernel.  Phase 1 generates the normals of the block's rows ONCE, keeps them in
-// shared memory (8 KB per row, up to 13 rows per block; rows beyond the cache are regenerated in phase 2),
-// accumulates sum(score^2) and sum(z^2) per (block, sample) into a partial slot (no atomics, no zeroing, fixed
-// order) and prefetches the block's x rows into L2; grid.sync(); every block folds the partials into the
-// batch-mean step size; phase 2 applies the update.  DRAM traffic is the algorithmic 12 B/element (+1 B mask).
+// The corrector is a cooperative kernel.  Phase 1 generates the normals of the block's rows ONCE and keeps them
+// in shared memory (8 KB per row; rows beyond the cache are regenerated in phase 2), writes sum(score^2) and
+// sum(z^2) of every row to a partial slot (warp shuffles in float, 16 warps summed in double: no atomics, fixed
+// order, independent of the grid size) and prefetches what phase 2 reads into L2; grid.sync(); every block folds
+// the row partials into the batch-mean step size; phase 2 applies the update.
 #include <cooperative_groups.h>
 
 #include "kernels.h"
@@ -31,8 +33,10 @@ namespace t2p {
 namespace {
 
 constexpr int kThreads = 512;       // threads per block = quads per row
-constexpr int kMaxCacheRows = 13;   // 13 x 8 KB of cached normals per block, two blocks per SM
-constexpr int kMaxBlocks = 4096;    // bound used to size the corrector's partial workspace
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxCacheRows = 13;   // direct corrector: 13 x 8 KB of cached normals per block, two blocks per SM
+constexpr int kMaxBlocks = 4096;
+constexpr int kSumChunk = 16;       // corrector phase 1: rows between two flushes of the per-row sums
 
 struct StepParams {
   float* x;
@@ -60,9 +64,10 @@ struct StepParams {
   int rps;                  // rows per sample, ceil(qps / kThreads)
   int rows;                 // B * rps
   int cache_rows;           // corrector: rows of normals a block keeps in shared memory
-  int prefetch;             // corrector: phase 1 prefetches the x rows of phase 2 into L2
+  int prefetch;             // corrector: phase 1 prefetches the operands of phase 2 into L2
   int skip_conditioned;     // fully conditioned quads copy x_initial without loading x / score or drawing noise
-  double* partial;          // corrector: [gridDim.x + B][2], slot = block + sample
+  int in_place;             // conditioned positions of x (and x_mean_out) already hold x_initial: such quads are not touched
+  double* partial;          // corrector: [rows][2] = sum (h / sigma)^2, sum z^2 of each row
 };
 
 __device__ __forceinline__ unsigned long long stream_of(const StepParams& p) {
@@ -70,16 +75,32 @@ __device__ __forceinline__ unsigned long long stream_of(const StepParams& p) {
   return static_cast<unsigned long long>(p.stream_base + it * p.stream_mul);
 }
 
-// contiguous row range of this block: [rows * j / G, rows * (j + 1) / G)
-__device__ __forceinline__ void block_rows(const StepParams& p, int& r0, int& r1) {
-  r0 = static_cast<int>(static_cast<long long>(p.rows) * blockIdx.x / gridDim.x);
-  r1 = static_cast<int>(static_cast<long long>(p.rows) * (blockIdx.x + 1) / gridDim.x);
-}
-
-// the block whose range holds row r (inverse of block_rows)
-__device__ __forceinline__ int block_of_row(const StepParams& p, int r) {
-  return static_cast<int>((static_cast<long long>(r + 1) * gridDim.x + p.rows - 1) / p.rows) - 1;
-}
+// walks the rows blockIdx.x, blockIdx.x + gridDim.x, ... of a block keeping (sample, row within the sample)
+// without a division per row; k counts the block's rows
+struct RowIter {
+  int r, b, rq, k, db, drq;
+  __device__ __forceinline__ explicit RowIter(const StepParams& p) {
+    r = blockIdx.x;
+    b = r / p.rps;
+    rq = r - b * p.rps;
+    k = 0;
+    db = gridDim.x / p.rps;
+    drq = gridDim.x - db * p.rps;
+  }
+  __device__ __forceinline__ bool done(const StepParams& p) const { return r >= p.rows; }
+  __device__ __forceinline__ void next(const StepParams& p) {
+    r += gridDim.x;
+    ++k;
+    b += db;
+    rq += drq;
+    if (rq >= p.rps) { rq -= p.rps; ++b; }
+  }
+  __device__ __forceinline__ int quad() const { return rq * kThreads + static_cast<int>(threadIdx.x); }  // within the sample
+  __device__ __forceinline__ bool valid(const StepParams& p) const { return r < p.rows && quad() < p.qps; }
+  __device__ __forceinline__ long long element(const StepParams& p) const {
+    return static_cast<long long>(b) * p.E + static_cast<long long>(quad()) * 4;
+  }
+};
 
 // RAW network output of 4 consecutive elements [e0, e0 + 4) of sample b as doubles; the 1 / sigma of the
 // reference's float64 `h / used_sigmas` is folded into the per-sample coefficient that multiplies it
@@ -134,55 +155,37 @@ __device__ __forceinline__ uchar4 load_mask4(const StepParams& p, long long gi0)
   return p.mask ? *reinterpret_cast<const uchar4*>(p.mask + gi0) : make_uchar4(1, 1, 1, 1);
 }
 
-// walks the rows [r0, r1) of a block keeping (sample, row within the sample) without a division per row
-struct RowIter {
-  int r, r1, b, rq;
-  __device__ __forceinline__ RowIter(const StepParams& p, int r0_, int r1_) : r(r0_), r1(r1_) {
-    b = r0_ / p.rps;
-    rq = r0_ - b * p.rps;
-  }
-  __device__ __forceinline__ bool done() const { return r >= r1; }
-  __device__ __forceinline__ void next(const StepParams& p) {
-    ++r;
-    if (++rq == p.rps) { rq = 0; ++b; }
-  }
-  __device__ __forceinline__ int quad() const { return rq * kThreads + static_cast<int>(threadIdx.x); }  // within the sample
-  __device__ __forceinline__ bool valid(const StepParams& p) const { return r < r1 && quad() < p.qps; }
-  __device__ __forceinline__ long long element(const StepParams& p) const {
-    return static_cast<long long>(b) * p.E + static_cast<long long>(quad()) * 4;
-  }
-};
-
-// The mask of a row is loaded one row ahead: a quad whose 4 positions are all conditioned (mask == 0) takes
-// x_initial whatever the update would be, so its x / score loads and its Philox + Box-Muller work are skipped
-// (with a length condition more than half of the quads, whole warps at a time: one image row of 128 residues is
-// one warp).  The result is bit-identical to computing the update and discarding it.
+// A quad whose 4 positions are all conditioned (mask == 0) takes x_initial whatever the update would be: its
+// x / score loads and its Philox + Box-Muller work are skipped (with a length condition more than half of the
+// quads, whole warps at a time: one image row of 128 residues is one warp).  Bit-identical to computing the
+// update and discarding it.  Inside t2p_pc_run the conditioned positions of x and x_mean hold x_initial from
+// the start of the run and nothing else writes them (in_place): there such a quad costs its 4 mask bytes.
 __device__ __forceinline__ bool all_conditioned(uchar4 m) { return !(m.x | m.y | m.z | m.w); }
 
 __device__ __forceinline__ void copy_initial4(const StepParams& p, long long gi0) {
+  if (p.in_place) return;
   const float4 xi = *reinterpret_cast<const float4*>(p.x_init + gi0);
   *reinterpret_cast<float4*>(p.x + gi0) = xi;
   if (p.x_mean_out) *reinterpret_cast<float4*>(p.x_mean_out + gi0) = xi;
 }
 
-// FAST: fp32 NCHW score, VE SDE (no drift), noise on -- the configuration of every shipped sampling config; the
-// generic instantiation keeps the fp64 / NHWC score, VP drift and probability-flow variants of the API.
+// ------------------------------------------------------------------------------------------------------
+// Direct-load kernels: every operand layout of the API (fp64 / NHWC score, VP drift, probability flow, any
+// C*N*N % 4 == 0).  FAST: fp32 NCHW score, VE SDE, noise on.  The mask of a row is loaded one row ahead.
 template <bool FAST>
 __global__ void __launch_bounds__(kThreads, 2) predictor_kernel(const StepParams p) {
-  int r0, r1;
-  block_rows(p, r0, r1);
   const unsigned long long stream = stream_of(p);
   int cur_b = -1;
   float G = 0.f, sa = 0.f;
   double coef = 0.0;  // G^2 (fp32, as G[:, None, None, None] ** 2) * drift_scale / sigma
-  RowIter it(p, r0, r1);
+  RowIter it(p);
   uchar4 m = it.valid(p) ? load_mask4(p, it.element(p)) : make_uchar4(1, 1, 1, 1);
-  while (!it.done()) {
+  while (!it.done(p)) {
     RowIter nx = it;
     nx.next(p);
     const uchar4 m_next = nx.valid(p) ? load_mask4(p, nx.element(p)) : make_uchar4(1, 1, 1, 1);
     const int b = it.b, ql = it.quad();
-    if (b != cur_b) {  // uniform: a block crosses a sample boundary at most every rps rows
+    if (b != cur_b) {  // uniform
       cur_b = b;
       G = p.G[b];
       coef = static_cast<double>(__fmul_rn(G, G)) * static_cast<double>(p.drift_scale) * inv_sigma_of(p, b);
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, 2) predictor_kernel(const StepParams
 }
 
 // block-wide sum of two doubles (result valid in thread 0); `red` is reused, hence the trailing barrier
-__device__ __forceinline__ void block_sum2(double& a, double& c, double (*red)[kThreads / 32]) {
+__device__ __forceinline__ void block_sum2(double& a, double& c, double (*red)[kWarps]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -227,103 +230,141 @@ __device__ __forceinline__ void block_sum2(double& a, double& c, double (*red)[k
   __syncthreads();
   if (threadIdx.x == 0) {
     a = 0.0; c = 0.0;
-    for (int w = 0; w < kThreads / 32; ++w) { a += red[0][w]; c += red[1][w]; }
+    for (int w = 0; w < kWarps; ++w) { a += red[0][w]; c += red[1][w]; }
   }
   __syncthreads();
+}
+
+// ---- corrector phase 1 bookkeeping: per-row sums.  Every warp reduces the (score^2, z^2) of its 32 quads with
+// float shuffles (the addends are floats: 4 squares summed per quad) into acc[row % kSumChunk][warp]; every
+// kSumChunk rows, and after the last one, the 16 warp values of each row are summed in double, scaled by
+// 1 / sigma^2 and written to the row's partial slot.
+struct RowSums {
+  float2 (*acc)[kWarps];
+  __device__ __forceinline__ void add(int k, float hh, float zz) const {  // all lanes of every warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      hh += __shfl_xor_sync(0xffffffffu, hh, o);
+      zz += __shfl_xor_sync(0xffffffffu, zz, o);
+    }
+    if ((threadIdx.x & 31) == 0) acc[k % kSumChunk][threadIdx.x >> 5] = make_float2(hh, zz);
+  }
+  // rows [k0, k1) of this block (k1 - k0 <= kSumChunk); all threads
+  __device__ __forceinline__ void flush(const StepParams& p, int k0, int k1) const {
+    __syncthreads();
+    for (int k = k0 + static_cast<int>(threadIdx.x); k < k1; k += kThreads) {
+      double sg = 0.0, sn = 0.0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) {
+        sg += static_cast<double>(acc[k % kSumChunk][w].x);
+        sn += static_cast<double>(acc[k % kSumChunk][w].y);
+      }
+      const int r = static_cast<int>(blockIdx.x) + k * static_cast<int>(gridDim.x);
+      const double inv = inv_sigma_of(p, r / p.rps);
+      p.partial[2 * static_cast<long long>(r)] = sg * inv * inv;  // sum (h / sigma)^2
+      p.partial[2 * static_cast<long long>(r) + 1] = sn;
+    }
+    __syncthreads();
+  }
+};
+
+__device__ __forceinline__ float sum_sq4(float a, float b, float c, float d) {
+  return __fmaf_rn(d, d, __fmaf_rn(c, c, __fmaf_rn(b, b, __fmul_rn(a, a))));
+}
+
+// step size (before alpha) from the batch-mean norms; every block recomputes it from the row partials: 8 lanes
+// per sample, fixed order
+__device__ __forceinline__ float batch_step_size(const StepParams& p, double (*red)[kWarps], float* step_sh) {
+  double gsum = 0.0;
+  float nsum = 0.f;
+  const int total = (p.B * 8 + kThreads - 1) / kThreads * kThreads;
+  for (int idx = threadIdx.x; idx < total; idx += kThreads) {
+    const int b = idx >> 3, part = idx & 7;
+    double a = 0.0, c = 0.0;
+    if (b < p.B) {
+      const double* row = p.partial + 2 * static_cast<long long>(b) * p.rps;
+      for (int j = part; j < p.rps; j += 8) {
+        a += row[2 * j];
+        c += row[2 * j + 1];
+      }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if (part == 0 && b < p.B) {
+      gsum += sqrt(a);                        // ||grad_b||  (float64)
+      nsum += static_cast<float>(sqrt(c));    // ||noise_b|| (float32 tensor in the reference)
+    }
+  }
+  double nsum_d = static_cast<double>(nsum);
+  block_sum2(gsum, nsum_d, red);
+  if (threadIdx.x == 0) {
+    const double grad_norm = gsum / p.B;
+    const float noise_norm = static_cast<float>(nsum_d) / static_cast<float>(p.B);
+    const float sn = __fmul_rn(p.snr, noise_norm);  // python float * fp32 0-dim tensor -> fp32
+    const double r = static_cast<double>(sn) / grad_norm;
+    *step_sh = static_cast<float>(r * r * 2.0);     // * alpha (fp32 [B]) demotes the 0-dim double
+  }
+  __syncthreads();
+  return *step_sh;
 }
 
 template <bool FAST>
 __global__ void __launch_bounds__(kThreads, 2) corrector_kernel(const StepParams p) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ float4 zcache[];  // [cache_rows][kThreads] normals of this block's first rows
-  __shared__ double red[2][kThreads / 32];
+  __shared__ double red[2][kWarps];
+  __shared__ float2 acc[kSumChunk][kWarps];
   __shared__ float step_sh;
   const unsigned long long stream = stream_of(p);
-  int r0, r1;
-  block_rows(p, r0, r1);
+  const RowSums sums{acc};
 
-  // ---- phase 1: normals (kept), partial squared norms of the RAW score and of the noise per (block, sample)
+  // ---- phase 1: normals (kept), squared norms of the RAW score and of the noise per row
   {
-    double sg = 0.0, sn = 0.0;
-    int cur_b = r0 < r1 ? r0 / p.rps : 0;
-    auto flush = [&](int b) {
-      block_sum2(sg, sn, red);
-      if (threadIdx.x == 0) {
-        const double inv = inv_sigma_of(p, b);
-        p.partial[2 * (blockIdx.x + b)] = sg * inv * inv;  // sum (h / sigma)^2
-        p.partial[2 * (blockIdx.x + b) + 1] = sn;
+    RowIter it(p);
+    int k0 = 0;
+    for (; !it.done(p); it.next(p)) {
+      const int b = it.b, ql = it.quad();
+      float hh = 0.f, zz = 0.f;
+      if (ql < p.qps) {
+        const long long gi0 = it.element(p);
+        double s[4];
+        load_score4<FAST>(p, b, static_cast<long long>(ql) * 4, s);
+        if (p.prefetch) {  // phase 2's first-touch operands: x (one 128-byte line per 8 threads) and the mask (per warp)
+          if ((threadIdx.x & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + gi0));
+          if ((threadIdx.x & 31) == 0 && p.mask) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.mask + gi0));
+        }
+        float z[4];
+        philox_normal4(p.seed, stream, static_cast<unsigned long long>((p.sample_offset + b) * p.qps + ql), z);
+        if (it.k < p.cache_rows) zcache[it.k * kThreads + threadIdx.x] = make_float4(z[0], z[1], z[2], z[3]);
+        if constexpr (FAST) {
+          hh = sum_sq4(static_cast<float>(s[0]), static_cast<float>(s[1]), static_cast<float>(s[2]), static_cast<float>(s[3]));
+        } else {
+          hh = static_cast<float>(s[0] * s[0] + s[1] * s[1] + s[2] * s[2] + s[3] * s[3]);
+        }
+        zz = sum_sq4(z[0], z[1], z[2], z[3]);
       }
-      sg = 0.0; sn = 0.0;
-    };
-    int b = cur_b, rq = r0 - b * p.rps;
-    for (int r = r0; r < r1; ++r, ++rq) {
-      if (rq == p.rps) { rq = 0; ++b; }
-      if (b != cur_b) { flush(cur_b); cur_b = b; }
-      const int ql = rq * kThreads + static_cast<int>(threadIdx.x);
-      if (ql >= p.qps) continue;
-      const long long gi0 = static_cast<long long>(b) * p.E + static_cast<long long>(ql) * 4;
-      double s[4];
-      load_score4<FAST>(p, b, static_cast<long long>(ql) * 4, s);
-      if (p.prefetch) {  // phase 2's first-touch operands: x (one 128-byte line per 8 threads) and the mask (per warp)
-        if ((threadIdx.x & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.x + gi0));
-        if ((threadIdx.x & 31) == 0 && p.mask) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.mask + gi0));
-      }
-      float z[4];
-      philox_normal4(p.seed, stream, static_cast<unsigned long long>((p.sample_offset + b) * p.qps + ql), z);
-      if (r - r0 < p.cache_rows) zcache[(r - r0) * kThreads + threadIdx.x] = make_float4(z[0], z[1], z[2], z[3]);
-      if constexpr (FAST) {
-        // squares of 4 elements summed in float (the inputs are floats), the running sums in double
-        const float h0 = static_cast<float>(s[0]), h1 = static_cast<float>(s[1]), h2 = static_cast<float>(s[2]),
-                    h3 = static_cast<float>(s[3]);
-        sg += static_cast<double>(__fmaf_rn(h3, h3, __fmaf_rn(h2, h2, __fmaf_rn(h1, h1, __fmul_rn(h0, h0)))));
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) sg += s[i] * s[i];
-      }
-      sn += static_cast<double>(__fmaf_rn(z[3], z[3], __fmaf_rn(z[2], z[2], __fmaf_rn(z[1], z[1], __fmul_rn(z[0], z[0])))));
+      sums.add(it.k, hh, zz);
+      if (it.k - k0 == kSumChunk - 1) { sums.flush(p, k0, it.k + 1); k0 = it.k + 1; }
     }
-    if (r0 < r1) flush(cur_b);
+    sums.flush(p, k0, it.k);
   }
   grid.sync();
-
-  // ---- step size from the batch-mean norms (every block recomputes it from the (block, sample) partials)
-  {
-    double gsum = 0.0, nsum_d = 0.0;
-    float nsum = 0.f;
-    for (int b = threadIdx.x; b < p.B; b += kThreads) {
-      const int j0 = block_of_row(p, b * p.rps), j1 = block_of_row(p, (b + 1) * p.rps - 1);
-      double a = 0.0, c = 0.0;
-      for (int j = j0; j <= j1; ++j) {
-        a += p.partial[2 * (j + b)];
-        c += p.partial[2 * (j + b) + 1];
-      }
-      gsum += sqrt(a);                        // ||grad_b||  (float64)
-      nsum += static_cast<float>(sqrt(c));    // ||noise_b|| (float32 tensor in the reference)
-    }
-    nsum_d = static_cast<double>(nsum);
-    block_sum2(gsum, nsum_d, red);
-    if (threadIdx.x == 0) {
-      const double grad_norm = gsum / p.B;
-      const float noise_norm = static_cast<float>(nsum_d) / static_cast<float>(p.B);
-      const float sn = __fmul_rn(p.snr, noise_norm);  // python float * fp32 0-dim tensor -> fp32
-      const double r = static_cast<double>(sn) / grad_norm;
-      step_sh = static_cast<float>(r * r * 2.0);      // * alpha (fp32 [B]) demotes the 0-dim double
-    }
-    __syncthreads();
-  }
-  const float step0 = step_sh;
+  const float step0 = batch_step_size(p, red, &step_sh);
 
   // ---- phase 2: apply
   int cur_b = -1;
   float nscale = 0.f;
   double coef = 0.0;  // step / sigma
-  RowIter it(p, r0, r1);
+  RowIter it(p);
   uchar4 m = it.valid(p) ? load_mask4(p, it.element(p)) : make_uchar4(1, 1, 1, 1);
-  while (!it.done()) {
+  while (!it.done(p)) {
     RowIter nx = it;
     nx.next(p);
     const uchar4 m_next = nx.valid(p) ? load_mask4(p, nx.element(p)) : make_uchar4(1, 1, 1, 1);
-    const int b = it.b, ql = it.quad(), slot = it.r - r0;
+    const int b = it.b, ql = it.quad();
     if (b != cur_b) {
       cur_b = b;
       const float step = p.alpha ? __fmul_rn(step0, p.alpha[b]) : step0;
@@ -339,8 +380,8 @@ __global__ void __launch_bounds__(kThreads, 2) corrector_kernel(const StepParams
         double s[4], xn[4], xm[4];
         load_score4<FAST>(p, b, static_cast<long long>(ql) * 4, s);
         float z[4];
-        if (slot < p.cache_rows) {
-          const float4 zv = zcache[slot * kThreads + threadIdx.x];
+        if (it.k < p.cache_rows) {
+          const float4 zv = zcache[it.k * kThreads + threadIdx.x];
           z[0] = zv.x; z[1] = zv.y; z[2] = zv.z; z[3] = zv.w;
         } else {
           philox_normal4(p.seed, stream, static_cast<unsigned long long>((p.sample_offset + b) * p.qps + ql), z);
@@ -423,6 +464,7 @@ StepParams to_params(const PcStepArgs& a) {
   if (a.sigmas) T2P_CHECK(a.labels != nullptr, "labels required with sigmas");
   if (a.mask) T2P_CHECK(a.x_init != nullptr, "x_init required with mask");
   p.partial = a.partial;
+  p.in_place = (a.mask != nullptr && a.conditioned_in_place) ? 1 : 0;
   static const bool no_skip = getenv("T2P_STEP_NOSKIP") != nullptr;  // A/B knob
   p.skip_conditioned = (a.mask != nullptr && !no_skip) ? 1 : 0;
   return p;
@@ -446,6 +488,8 @@ int resident_blocks(const void* fn, size_t smem) {
   return std::min(per_sm * num_sms(), kMaxBlocks);
 }
 
+constexpr size_t kRowBytes = sizeof(float4) * kThreads;
+
 }  // namespace
 
 void pc_predictor_step(const PcStepArgs& a, cudaStream_t st) {
@@ -462,17 +506,18 @@ void pc_predictor_step(const PcStepArgs& a, cudaStream_t st) {
   T2P_LAUNCH_CHECK();
 }
 
-// doubles of partial-sum workspace the corrector needs for a batch of B samples: one (score, noise) slot per
-// (block, sample) pair that occurs, indexed block + sample
-long long pc_corrector_workspace_doubles(int B) { return 2LL * (kMaxBlocks + static_cast<long long>(B)); }
+// doubles of partial-sum workspace the corrector needs: (score^2, noise^2) per row of kThreads quads
+long long pc_corrector_workspace_doubles(int B, long long E) { return 2LL * B * cdiv64(E / 4, kThreads); }
 
 void pc_corrector_step(const PcStepArgs& a, cudaStream_t st) {
   StepParams p = to_params(a);
   T2P_CHECK(a.partial != nullptr, "corrector needs the partial-sum workspace");
+  static const bool no_cache = getenv("T2P_STEP_NOCACHE") != nullptr;
+  static const bool no_prefetch = getenv("T2P_STEP_NOPREFETCH") != nullptr;
+  p.prefetch = no_prefetch ? 0 : 1;
   const bool fast = !p.score_nhwc && !p.score_f64;
   const void* fn = fast ? reinterpret_cast<const void*>(corrector_kernel<true>)
                         : reinterpret_cast<const void*>(corrector_kernel<false>);
-  constexpr size_t kRowBytes = sizeof(float4) * kThreads;
   static bool attr_set[2] = {false, false};
   if (!attr_set[fast]) {
     T2P_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxCacheRows * kRowBytes)));
@@ -480,11 +525,8 @@ void pc_corrector_step(const PcStepArgs& a, cudaStream_t st) {
     attr_set[fast] = true;
   }
   // shared-memory cache sized for the rows a block gets when two blocks per SM are resident
-  static const bool no_cache = getenv("T2P_STEP_NOCACHE") != nullptr;
-  static const bool no_prefetch = getenv("T2P_STEP_NOPREFETCH") != nullptr;
   const int want = static_cast<int>(cdiv64(p.rows, 2LL * num_sms()));
   p.cache_rows = no_cache ? 0 : std::min(want, kMaxCacheRows);
-  p.prefetch = no_prefetch ? 0 : 1;
   const size_t smem = p.cache_rows * kRowBytes;
   static int wave[2][kMaxCacheRows + 1] = {};
   if (!wave[fast][p.cache_rows]) wave[fast][p.cache_rows] = resident_blocks(fn, smem);

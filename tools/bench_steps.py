@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--N", type=int, default=128)
     ap.add_argument("--mask", default="length", choices=["length", "none", "ones"])
     ap.add_argument("--tag", default="")
+    ap.add_argument("--in-place", action="store_true", help="conditioned positions already hold x_init (as inside t2p_pc_run)")
     a = ap.parse_args()
     dev = "cuda"
     B, Cc, N = a.B, a.C, a.N
@@ -68,6 +69,7 @@ def main():
         s.G, s.snr = G.data_ptr(), 0.17
         if a.mask != "none":
             s.mask, s.x_init = mask_u8.data_ptr(), xi[i].data_ptr()
+            s.conditioned_in_place = 1 if a.in_place else 0
         s.x_mean_out = (xmean if xmean is not None else xm[i]).data_ptr() if pred else None
         s.seed, s.stream_id, s.sample_offset = 2024, 5, 0
         s.B, s.C, s.HW = B, Cc, N * N
@@ -115,7 +117,19 @@ def main():
             torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1) / (reps * sets))
         n = B * E
-        print(json.dumps({"tag": a.tag, "lib": os.path.basename(a.lib), "kernel": name, "B": B, "C": Cc, "N": N,
+        # bytes the update needs given the mask: a quad with a free position reads x, score, mask and writes x
+        # (+ x_mean); a fully conditioned quad costs its mask bytes in place, else x_init in and x (+ x_mean) out;
+        # the corrector reads the whole score once more for the norms (its second read hits L2)
+        if a.mask == "none":
+            need = n * (bytes_per - 1)
+        else:
+            q = mask.reshape(-1, 4).any(-1).float().mean().item()  # fraction of quads with a free position
+            pred = name == "predictor_kernel"
+            free_b = 17 if pred else 13
+            cond_b = (1 if a.in_place else (13 if pred else 9)) + (0 if pred else 4)
+            need = n * (q * free_b + (1 - q) * cond_b)
+        print(json.dumps({"tag": a.tag, "in_place": a.in_place, "mask_aware_gbs": round(need / (best * 1e-3) / 1e9, 1),
+                          "mask_aware_frac": round(need / (best * 1e-3) / 1e9 / 6553.0, 3), "lib": os.path.basename(a.lib), "kernel": name, "B": B, "C": Cc, "N": N,
                           "mask": a.mask, "free_frac": round(free_frac, 3), "us": round(best * 1e3, 2),
                           "nominal_gbs": round(n * bytes_per / (best * 1e-3) / 1e9, 1),
                           "frac_of_6553": round(n * bytes_per / (best * 1e-3) / 1e9 / 6553.0, 3)}))

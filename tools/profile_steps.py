@@ -28,6 +28,7 @@ for it in range(4):
         a.x, a.score, a.score_dtype, a.score_nhwc = x.data_ptr(), sc.data_ptr(), 0, 0
         a.G, a.snr = G.data_ptr(), 0.17
         a.mask, a.x_init = mask_u8.data_ptr(), xi.data_ptr()
+        a.conditioned_in_place = 1
         a.x_mean_out = xm.data_ptr() if pred else None
         a.seed, a.stream_id, a.sample_offset = 2024, 5, 0
         a.B, a.C, a.HW = B, Cc, N * N
