@@ -306,7 +306,8 @@ def _length_mask(B, Cc, N, g, lo):
 # 64 x 5 x 128 x 128 is the bench shape
 @pytest.mark.parametrize("B,Cc,N,kind", [(2, 5, 32, "random"), (3, 8, 64, "length"), (64, 5, 16, "length"),
                                           (5, 5, 6, "random"), (3, 3, 10, "length"), (2, 5, 128, "none"),
-                                          (64, 5, 128, "length"), (300, 5, 32, "length"), (2, 8, 256, "length")])
+                                          (64, 5, 128, "length"), (300, 5, 32, "length"), (2, 8, 256, "length"),
+                                          (1024, 5, 16, "length")])
 @pytest.mark.parametrize("in_place", [False, True])
 def test_pc_steps_loop_layout(B, Cc, N, kind, in_place):
     if in_place and kind == "none":
