@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--N", type=int, default=128)
     ap.add_argument("--mask", default="length", choices=["length", "none", "ones"])
     ap.add_argument("--tag", default="")
+    ap.add_argument("--no-mean", action="store_true", help="predictor without the x_mean output (13 B/element)")
     ap.add_argument("--in-place", action="store_true", help="conditioned positions already hold x_init (as inside t2p_pc_run)")
     a = ap.parse_args()
     dev = "cuda"
@@ -70,7 +71,7 @@ def main():
         if a.mask != "none":
             s.mask, s.x_init = mask_u8.data_ptr(), xi[i].data_ptr()
             s.conditioned_in_place = 1 if a.in_place else 0
-        s.x_mean_out = (xmean if xmean is not None else xm[i]).data_ptr() if pred else None
+        s.x_mean_out = (xmean if xmean is not None else xm[i]).data_ptr() if (pred and not a.no_mean) else None
         s.seed, s.stream_id, s.sample_offset = 2024, 5, 0
         s.B, s.C, s.HW = B, Cc, N * N
         s.workspace = ws.data_ptr()
