@@ -374,10 +374,16 @@ def test_pc_steps_loop_layout(B, Cc, N, kind, in_place):
     a.x_mean_out = xmn.data_ptr()
     _lib.check(L.t2p_predictor_step(C.byref(a), _st()))
     torch.cuda.synchronize()
-    for got, ref in ((xc, xc_ref), (xp, xp_ref), (xmn, xm_ref)):
+    for name, got, ref in (("corrector", xc, xc_ref), ("predictor", xp, xp_ref), ("x_mean", xmn, xm_ref)):
         assert torch.isfinite(got).all()
         assert torch.equal(got[~m], dev["x_init"][~m])              # mask handling is bit-exact
         assert rel_err(got, ref) < 2e-6
+        if name != "corrector" and m.any():
+            # the predictor update is the reference's float64 expression rounded once to float: the same float except
+            # where coef * h (the kernel folds G^2 / sigma into one double) rounds differently in the 53rd bit.  (The
+            # corrector's step size hangs on an fp32 norm whose last bit depends on the summation order, also in torch.)
+            differ = (got[m] != ref[m]).float().mean().item()
+            assert differ < 1e-5, differ
     # run-to-run deterministic (fixed reduction order, no atomics)
     xc2 = start.clone()
     _lib.check(L.t2p_corrector_step(C.byref(args(xc2, 11)), _st()))
