@@ -32,9 +32,18 @@ namespace cg = cooperative_groups;
 namespace t2p {
 namespace {
 
-constexpr int kThreads = 512;       // threads per block = quads per row
+#ifndef T2P_STEP_THREADS
+#define T2P_STEP_THREADS 512
+#endif
+#ifndef T2P_STEP_BLOCKS
+#define T2P_STEP_BLOCKS 2
+#endif
+constexpr int kThreads = T2P_STEP_THREADS;     // threads per block = quads per row
+constexpr int kBlocksPerSM = T2P_STEP_BLOCKS;  // resident blocks per SM the kernels are compiled for (register cap)
 constexpr int kWarps = kThreads / 32;
-constexpr int kMaxCacheRows = 13;   // direct corrector: 13 x 8 KB of cached normals per block, two blocks per SM
+// corrector: rows of cached normals per block (16 B per thread and row), kBlocksPerSM blocks sharing 227 KB with
+// their static shared memory and the 1 KB the system reserves per block
+constexpr int kMaxCacheRows = (227 * 1024 / kBlocksPerSM - 4096) / (16 * kThreads);
 constexpr int kMaxBlocks = 4096;
 constexpr int kSumChunk = 16;       // corrector phase 1: rows between two flushes of the per-row sums
 
@@ -173,7 +182,7 @@ __device__ __forceinline__ void copy_initial4(const StepParams& p, long long gi0
 // Direct-load kernels: every operand layout of the API (fp64 / NHWC score, VP drift, probability flow, any
 // C*N*N % 4 == 0).  FAST: fp32 NCHW score, VE SDE, noise on.  The mask of a row is loaded one row ahead.
 template <bool FAST>
-__global__ void __launch_bounds__(kThreads, 2) predictor_kernel(const StepParams p) {
+__global__ void __launch_bounds__(kThreads, kBlocksPerSM) predictor_kernel(const StepParams p) {
   const unsigned long long stream = stream_of(p);
   int cur_b = -1;
   float G = 0.f, sa = 0.f;
@@ -312,7 +321,7 @@ __device__ __forceinline__ float batch_step_size(const StepParams& p, double (*r
 }
 
 template <bool FAST>
-__global__ void __launch_bounds__(kThreads, 2) corrector_kernel(const StepParams p) {
+__global__ void __launch_bounds__(kThreads, kBlocksPerSM) corrector_kernel(const StepParams p) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ float4 zcache[];  // [cache_rows][kThreads] normals of this block's first rows
   __shared__ double red[2][kWarps];
@@ -525,7 +534,7 @@ void pc_corrector_step(const PcStepArgs& a, cudaStream_t st) {
     attr_set[fast] = true;
   }
   // shared-memory cache sized for the rows a block gets when two blocks per SM are resident
-  const int want = static_cast<int>(cdiv64(p.rows, 2LL * num_sms()));
+  const int want = static_cast<int>(cdiv64(p.rows, static_cast<long long>(kBlocksPerSM) * num_sms()));
   p.cache_rows = no_cache ? 0 : std::min(want, kMaxCacheRows);
   const size_t smem = p.cache_rows * kRowBytes;
   static int wave[2][kMaxCacheRows + 1] = {};
