@@ -194,9 +194,9 @@ def _step_kernel_roofline(dev, B, shape, L, mask_u8, hbm_gbs):
     G = torch.full((B,), 0.3, device=dev)
     ws = torch.empty(max(1, L.t2p_corrector_workspace_bytes(B, E) // 8), dtype=torch.float64, device=dev)
     free_quads = mask_u8.reshape(-1, 4).any(-1).float().mean().item()  # fraction of quads with a free position
-    out = {}
-    for name, fn, free_b, cond_b in (("predictor_kernel", L.t2p_predictor_step, 17, 1),
-                                     ("corrector_kernel", L.t2p_corrector_step, 13, 5)):
+    all_free = torch.ones_like(mask_u8)
+
+    def timed(fn, predictor, mask):
         args = []
         for i in range(sets):
             a = _lib.StepArgs()
@@ -204,9 +204,9 @@ def _step_kernel_roofline(dev, B, shape, L, mask_u8, hbm_gbs):
             a.score_dtype, a.score_nhwc = 0, 0
             a.G = G.data_ptr()
             a.snr = 0.17
-            a.mask, a.x_init = mask_u8.data_ptr(), xi[i].data_ptr()
+            a.mask, a.x_init = mask.data_ptr(), xi[i].data_ptr()
             a.conditioned_in_place = 1
-            a.x_mean_out = xm[i].data_ptr() if name == "predictor_kernel" else None
+            a.x_mean_out = xm[i].data_ptr() if predictor else None
             a.seed, a.stream_id, a.sample_offset = 2024, 5, 0
             a.B, a.C, a.HW = B, shape[1], shape[2] * shape[3]
             a.workspace = ws.data_ptr()
@@ -230,14 +230,26 @@ def _step_kernel_roofline(dev, B, shape, L, mask_u8, hbm_gbs):
             graph.replay()
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / (reps * sets)
+        return e0.elapsed_time(e1) / (reps * sets)
+
+    out = {}
+    for name, fn, free_b, cond_b in (("predictor_kernel", L.t2p_predictor_step, 17, 1),
+                                     ("corrector_kernel", L.t2p_corrector_step, 13, 5)):
+        ms = timed(fn, name == "predictor_kernel", mask_u8)
         nbytes = n * (free_quads * free_b + (1.0 - free_quads) * cond_b)
         gbs = nbytes / (ms * 1e-3) / 1e9
         out[name] = {"ms": ms, "algorithmic_bytes": nbytes, "achieved_gbs": gbs, "peak_gbs": hbm_gbs,
                      "frac": gbs / hbm_gbs, "bound": "hbm", "free_quad_fraction": free_quads,
-                     "unmasked_bytes": n * free_b,
                      "note": "graph-replayed launches back to back; inputs rotate over 8 sets (> L2); bytes count "
-                             "what the bench's length mask leaves to update (unmasked_bytes = every position free)"}
+                             "what the bench's length mask leaves to update; all_free = the same kernel with every "
+                             "position free (17 / 13 B per element)"}
+        try:  # the same kernel with nothing conditioned: the number comparable across rounds
+            ms_free = timed(fn, name == "predictor_kernel", all_free)
+            out[name]["all_free"] = {"ms": ms_free, "algorithmic_bytes": n * free_b,
+                                     "achieved_gbs": n * free_b / (ms_free * 1e-3) / 1e9,
+                                     "frac": n * free_b / (ms_free * 1e-3) / 1e9 / hbm_gbs}
+        except Exception as e:  # never lose the bench line to the extra measurement
+            out[name]["all_free"] = {"error": str(e)[:200]}
     return out
 
 
