@@ -321,10 +321,12 @@ int t2p_pc_run(t2p_unet* u, const t2p_run_args* a, void* stream) {
     t2p_unet* u; cudaStream_t user;
     ~Rejoin() {
       u->net->set_reuse_temb(false);  // also on the error path
+      u->net->set_uniform_labels(false);
       if (cudaEventRecord(u->ev_out, u->run_stream) == cudaSuccess) cudaStreamWaitEvent(user, u->ev_out, 0);
     }
   } rejoin{u, user};
   UNet& net = *u->net;
+  net.set_uniform_labels(true);  // run_prep gives every sample of an iteration the same label
   const UNetConfig& c = net.cfg();
   const int B = a->B, K = a->num_iters;
   const int HW = c.max_res_num * c.max_res_num;

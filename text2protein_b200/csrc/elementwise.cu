@@ -225,14 +225,28 @@ __global__ void scale_by_sigma_kernel(const float* __restrict__ h, const long lo
   out[idx] = static_cast<TO>(v);
 }
 
+// rows 1 .. B-1 of a [B][n] fp32 matrix take row 0
+__global__ void broadcast_row_kernel(float* __restrict__ buf, int n, long long total) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx < total) buf[n + idx] = buf[idx % n];
+}
+
 }  // namespace
+
+void broadcast_row_f32(float* buf, int n, int B, cudaStream_t st) {
+  if (B <= 1) return;
+  const long long total = static_cast<long long>(B - 1) * n;
+  broadcast_row_kernel<<<static_cast<unsigned>(cdiv64(total, 256)), 256, 0, st>>>(buf, n, total);
+  T2P_LAUNCH_CHECK();
+}
 
 void temb_mlp(const long long* labels, int B, int nf, const float* w0, const float* b0, const float* w1,
               const float* b1, float* out, cudaStream_t st) {
   const size_t smem = sizeof(float) * (nf + 4 * nf);
   // -(ln 10000 / (half - 1)) evaluated in double then rounded once, as Python does (layers.py:101-103)
   const float neg_coef = static_cast<float>(-(log(10000.0) / static_cast<double>(nf / 2 - 1)));
-  temb_mlp_kernel<<<dim3(B, 8), 256, smem, st>>>(labels, nf, neg_coef, w0, b0, w1, b1, out);
+  // a single sample (uniform labels) is latency-bound: more, thinner slices of the second layer
+  temb_mlp_kernel<<<dim3(B, B == 1 ? 32 : 8), 256, smem, st>>>(labels, nf, neg_coef, w0, b0, w1, b1, out);
   T2P_LAUNCH_CHECK();
 }
 

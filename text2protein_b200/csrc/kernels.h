@@ -98,6 +98,7 @@ void pack_matrix(const float* w, int rows, int cols, int transpose, int out_dtyp
                  long long ld = 0);
 void pack_identity(int n, long long ld, int out_dtype, void* out, cudaStream_t st);
 void add_vectors_f32(const float* a, const float* b, int n, float* out, cudaStream_t st);
+void broadcast_row_f32(float* buf, int n, int B, cudaStream_t st);  // rows 1..B-1 of [B][n] = row 0
 void convert_f32(const float* in, long long n, int out_dtype, void* out, cudaStream_t st);
 void nhwc_to_nchw_f32(const void* in, int dtype, int B, int HW, int C, float* out, cudaStream_t st);
 void nchw_f32_to_nhwc(const float* in, int B, int HW, int C, int cpad, int out_dtype, void* out, cudaStream_t st);

@@ -840,15 +840,17 @@ void UNet::forward_impl(const float* x, const long long* labels, float* h_out, i
     // sequence -- planned once per batch size -- does not depend on the flag)
     float* temb = static_cast<float*>(ln_->ws.alloc(sizeof(float) * static_cast<size_t>(B) * 4 * nf));
     const bool reuse = reuse_temb_ && temb_valid_B_ == B;
-    if (!reuse) launches_ += 2;
+    const int Bt = uniform_labels_ ? 1 : B;  // samples the path is evaluated for
+    if (!reuse) launches_ += 2 + (Bt < B ? 1 : 0);
     if (!dry_ && !reuse) {
       temb_valid_B_ = B;
-      temb_mlp(labels, B, nf, static_cast<const float*>(pre0_w_->data), static_cast<const float*>(pre0_b_->data),
+      temb_mlp(labels, Bt, nf, static_cast<const float*>(pre0_w_->data), static_cast<const float*>(pre0_b_->data),
                static_cast<const float*>(pre1_w_->data), static_cast<const float*>(pre1_b_->data), temb, ln_->st);
       ConvGemmArgs g;
-      g.a0 = temb; g.c0 = 4 * nf; g.B = 1; g.H = 1; g.W = B; g.ksize = 1;
+      g.a0 = temb; g.c0 = 4 * nf; g.B = 1; g.H = 1; g.W = Bt; g.ksize = 1;
       g.w = dense_all_.wp; g.N = temb_total_; g.bias = dense_all_.bp; g.out = ln_->temb_all; g.out_dtype = kF32;
       conv_gemm_simt(g, kF32, ln_->st);
+      if (Bt < B) broadcast_row_f32(ln_->temb_all, temb_total_, B, ln_->st);
     }
     ln_->ws.free(temb);
   }

@@ -151,6 +151,9 @@ class UNet {
   // true: the next forward passes may reuse the time-embedding biases of the previous one (same labels, same B);
   // the PC loop sets it for the predictor evaluation that follows a corrector evaluation at the same noise level
   void set_reuse_temb(bool on) { reuse_temb_ = on; }
+  // every sample carries the same noise label (the PC loop): the time-embedding path is evaluated for one sample
+  // and its rows replicated -- bit-identical to evaluating it per sample
+  void set_uniform_labels(bool on) { uniform_labels_ = on; }
   // Reference-shaped output: NCHW, divided by sigmas[labels] in double (ncsnpp.py:259-261), fp64 or fp32.
   void forward(const float* x, const long long* labels, void* out, int out_dtype, int B, cudaStream_t st);
   const double* sigmas() const { return static_cast<const double*>(sigmas_->data); }
@@ -240,6 +243,7 @@ class UNet {
   size_t temb_persist_bytes_ = 0;
   int temb_valid_B_ = 0;
   bool reuse_temb_ = false;
+  bool uniform_labels_ = false;
   float* h_scratch_ = nullptr;
   size_t h_scratch_bytes_ = 0;
 };
