@@ -78,3 +78,12 @@ def stream_corrector(i, j, n_steps):
 
 def stream_predictor(i, n_steps):
     return 1 + i * (n_steps + 1) + n_steps
+
+
+# update_fn calls made outside the native loop (generic path: user models / predictors / VPSDE) draw stream
+# GENERIC_BASE + n for the n-th call after the run's seed was set (text2protein_b200 sampling._Noise)
+GENERIC_BASE = 1 << 40
+
+
+def stream_generic(n):
+    return GENERIC_BASE + n

@@ -71,3 +71,24 @@ def synthetic_condition(cfg, batch, kinds, seed=77):
         r = (ar[None, :] >= start[:, None]) & (ar[None, :] < stop[:, None])
         cond["inpainting"] = {"coords_6d": coords, "mask_inpaint": r[:, :, None] | r[:, None, :]}
     return cond
+
+
+def fullsize_inputs(cfg, batch, ctx_len, seed=3, ctx_scale=0.02):
+    """CPU inputs of the BASELINE-size parity runs (tests/golden/make_golden_fullsize.py and
+    tests/test_gpu_fullsize.py draw exactly these; the golden files carry checksums of them)."""
+    g = torch.Generator().manual_seed(seed)
+    C, N = cfg.data.num_channels, cfg.data.max_res_num
+    x = torch.randn(batch, C, N, N, generator=g) * 5
+    labels = torch.randint(0, cfg.model.num_scales, (batch,), generator=g)
+    ctx = torch.randn(batch, ctx_len, cfg.model.context_dim, generator=g) * ctx_scale
+    return x, labels, ctx
+
+
+# BASELINE.json configurations pinned at full size: name -> (yaml, batch, context length)
+FULLSIZE_CASES = {
+    "cond_length_L77": ("cond_length.yml", 1, 77),
+    "cond_length_L256": ("cond_length.yml", 1, 256),
+    "cond_ss_inpainting": ("cond_ss_inpainting.yml", 1, 256),  # no_cond.yml builds the identical network (C = 8)
+    "test_config": ("test_config.yml", 1, 32),                 # as shipped: N = 256, nf = 256, attention at 32/16/8
+    "test_config_large": ("test_config_large.yml", 1, 512),    # N = 256, ch_mult [1,1,2,2,2,4], d_head = 128, L = 512
+}
