@@ -18,12 +18,19 @@
 extern "C" {
 #endif
 
-#define T2P_ABI_VERSION 1
+#define T2P_ABI_VERSION 2
 
 enum t2p_dtype { T2P_F32 = 0, T2P_BF16 = 1, T2P_F64 = 2, T2P_I64 = 3, T2P_U8 = 4 };
 
 const char* t2p_last_error(void);
 int t2p_abi_version(void);
+
+/* Layout of the argument structs as THIS library was compiled: `which` = 0 t2p_unet_cfg, 1 t2p_step_args,
+ * 2 t2p_run_args, 3 t2p_conv_args, 4 t2p_gemm_record.  t2p_sizeof returns sizeof (or -1); t2p_struct_layout fills
+ * the byte offset of every field in declaration order (up to `cap`) and returns the field count.  A binding checks
+ * both against its own declaration before the first call (tests/test_abi.py does, for the ctypes binding). */
+int t2p_sizeof(int which);
+int t2p_struct_layout(int which, int32_t* offsets, int cap);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Score network.  Replaces score_sde_pytorch/utils.py:4-9 get_model + models/ncsnpp.py:74-263 UNetModel. */
@@ -69,6 +76,11 @@ int t2p_unet_set_context(t2p_unet* u, const float* ctx, int B, int L, void* stre
  * out [B][C][N][N] in `out_dtype` (T2P_F64 reproduces the reference's promoted dtype). */
 int t2p_unet_forward(t2p_unet* u, const float* x, const int64_t* labels, void* out, int out_dtype, int B,
                      void* stream);
+/* Same with a FLOATING time conditioning (models/utils.py:151-152: the VP branch of get_score_fn passes
+ * labels = t * (N - 1)): ncsnpp.py:221-223 embeds the float value (`timesteps`, fp32 [B]) and uses its truncation
+ * (`labels`, = time_cond.long()) only for the sigma lookup. */
+int t2p_unet_forward_t(t2p_unet* u, const float* x, const int64_t* labels, const float* timesteps, void* out,
+                       int out_dtype, int B, void* stream);
 
 /* Debug taps: with debug on, every top-level block's output is kept as fp32 NCHW ("pre_conv",
  * "input_blocks.<i>", "mid_blocks", "out_blocks.<i>", "out"). */
@@ -108,9 +120,17 @@ typedef struct t2p_step_args {
   int64_t sample_offset;    /* global index of local sample 0 (batch sharding) */
   int32_t B, C, HW;
   double* workspace;        /* corrector: >= t2p_corrector_workspace_bytes(B, C*HW) bytes */
-  int32_t conditioned_in_place; /* caller guarantees that x (and x_mean_out) already hold x_init wherever mask == 0
+  int32_t conditioned_in_place; /* caller guarantees that x_out (and x_mean_out) already hold x_init wherever mask == 0
                                  * (true inside a sampling run after the first mask application, sampling.py:283-287
                                  * being idempotent there): fully conditioned quads are then not read or written */
+  int32_t symmetrize;       /* 0 (default) = the reference's update, bit for bit.  1: channels 0 and 1 (Cb-Cb distance
+                             * and omega, symmetric maps) of the new state and of x_mean are replaced by their symmetric
+                             * part 0.5 (u[i][j] + u[j][i]) -- in float64, before the single float rounding, so the
+                             * stored maps are exactly symmetric -- wherever (i, j) and (j, i) are both free.  The
+                             * reference has no such option (downstream takes np.triu, rosetta_min/utils.py:140,157).
+                             * Needs x_out != x and a square map (W * W == HW). */
+  float* x_out;             /* where the new state goes; NULL = x (in place) */
+  int32_t W;                /* map width (symmetrize only) */
   int32_t reserved;
 } t2p_step_args;
 
@@ -143,9 +163,28 @@ typedef struct t2p_run_args {
   int64_t sample_offset;
   int32_t B;
   int32_t use_graph;         /* 1: capture one iteration into a CUDA graph and replay it */
+  int32_t symmetrize;        /* see t2p_step_args.symmetrize; 0 = the reference's behaviour */
+  int32_t reserved;
+  struct t2p_peer_group* peers; /* NULL (default): the Langevin step size is this call's batch mean (every shard is an
+                             * independent reference run, sampling.py:193-195).  Else: the mean over the GLOBAL batch of
+                             * all ranks of the group -- a sharded run then equals one reference run of the whole batch */
 } t2p_run_args;
 
 int t2p_pc_run(t2p_unet* u, const t2p_run_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Opt-in global-batch step size for batch-sharded runs on one node: between the norm phase and
+ * the update phase of the fused corrector kernel every rank writes its two norm sums into the mailbox of every
+ * peer through NVLink peer memory and reads theirs -- no host round trip, no extra launch, graph-replayable.
+ * Set-up: every rank creates a mailbox and exports its CUDA IPC handle (T2P_IPC_HANDLE_BYTES bytes); the handles
+ * are exchanged by the host (torch.distributed.all_gather_object in text2protein_b200/distributed.py) and opened.
+ * All ranks must then make the same sequence of t2p_pc_run calls with their group. */
+#define T2P_IPC_HANDLE_BYTES 64
+typedef struct t2p_peer_group t2p_peer_group;
+int t2p_peer_mailbox_create(int world, void** mailbox, void* ipc_handle_out);
+int t2p_peer_group_open(void* own_mailbox, const void* ipc_handles, int world, int rank, int64_t global_batch,
+                        t2p_peer_group** out);
+void t2p_peer_group_close(t2p_peer_group* g);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Per-kernel entry points (unit-testable against their torch counterparts).  NHWC / token-major tensors. */

@@ -4,7 +4,8 @@ Follows score_sde_pytorch/sampling.py:157-289 and sde_lib.py:106-157,199-245 inc
 of the reference (the score arrives as float64, the update runs in float64 and is cast back with
 ``.float()`` after each mask application).  Noise is injected through ``noise_fn(stream, like)`` so that a
 run can be replayed with the exact normals the CUDA kernel generated.  Pinned against the imported reference
-by tests/test_oracle_golden.py.
+by tests/test_oracle_golden.py (VE runs with and without conditions, a VP run, and a K = 2 run of the real
+cond_length.yml network at N = 128).
 """
 import numpy as np
 import torch
@@ -38,6 +39,9 @@ class VPSDERef:
         self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
         self.sqrt_1m_alphas_cumprod = torch.sqrt(1.0 - self.alphas_cumprod)
 
+    def timestep(self, t):
+        return (t * (self.N - 1) / self.T).long()
+
 
 def build_condition(x, condition):
     """sampling.py:260-275: returns (x, conditional_mask[bool B,C,N,N]); dict order matters."""
@@ -58,18 +62,34 @@ def build_condition(x, condition):
     return x, cm
 
 
+def symmetrize_free(u, cm):
+    """The opt-in symmetrisation of the step kernels (NO reference counterpart; this function is its
+    specification): channels 0 and 1 of ``u`` take 0.5 (u[i][j] + u[j][i]) wherever (i, j) and (j, i) are both
+    free in ``cm``; everything else is left alone."""
+    out = u.clone()
+    both = cm[:, :2] & cm[:, :2].transpose(2, 3)
+    sym = 0.5 * (u[:, :2] + u[:, :2].transpose(2, 3))
+    out[:, :2] = torch.where(both, sym, u[:, :2])
+    return out
+
+
 @torch.no_grad()
 def pc_sampler_ref(sde, score_model, shape, snr, n_steps=1, probability_flow=False, denoise=True, eps=1e-5,
-                   condition=None, context=None, noise_fn=None, num_iters=None, x0=None):
+                   condition=None, context=None, noise_fn=None, num_iters=None, x0=None, symmetrize=False,
+                   generic_streams=False):
     """``score_model(x, labels, context) -> float64 [B,C,N,N]`` (e.g. oracle.unet_ref.unet_forward bound to a
     state_dict).  ``noise_fn(stream, like) -> tensor`` supplies every normal draw; ``num_iters`` truncates the
-    loop to the first K of sde.N iterations (bench / parity at small K).  VESDE only (every shipped config)."""
-    from .philox_ref import STREAM_PRIOR, stream_corrector, stream_predictor
+    loop to the first K of sde.N iterations (bench / parity at small K).  VESDERef (every shipped config) or
+    VPSDERef (sde_lib.py:106-157 + the VP branches of models/utils.py:139-156 and sampling.py:184-186).
+    ``generic_streams``: noise stream ids of the product's generic update_fn path (philox_ref.stream_generic)
+    instead of the native loop's.  ``symmetrize``: see symmetrize_free (product extension, default off)."""
+    from .philox_ref import STREAM_PRIOR, stream_corrector, stream_generic, stream_predictor
 
-    assert isinstance(sde, VESDERef)
+    vp = isinstance(sde, VPSDERef)
+    assert vp or isinstance(sde, VESDERef)
     B = shape[0]
     if x0 is None:
-        x = noise_fn(STREAM_PRIOR, torch.empty(shape)) * sde.sigma_max  # sde_lib.py:229-230
+        x = noise_fn(STREAM_PRIOR, torch.empty(shape)) * (1.0 if vp else sde.sigma_max)  # sde_lib.py:136-137,229-230
     else:
         x = x0.clone()
     timesteps = torch.linspace(sde.T, eps, sde.N)
@@ -77,28 +97,50 @@ def pc_sampler_ref(sde, score_model, shape, snr, n_steps=1, probability_flow=Fal
     x_initial = x.detach().clone()
     x_mean = x
     K = sde.N if num_iters is None else num_iters
+    draws = 0
+
+    def score_fn(x, vec_t):
+        if vp:  # models/utils.py:151-156: float time conditioning, score = -out / sqrt(1 - alpha_bar)
+            labels = vec_t * (sde.N - 1)
+            out = score_model(x, labels, context)
+            std = sde.sqrt_1m_alphas_cumprod[labels.long()]
+            return -out / std[:, None, None, None]
+        return score_model(x, sde.labels(vec_t.clone()), context)
+
     for i in range(K):
         vec_t = torch.ones(B) * timesteps[i]
-        labels = sde.labels(vec_t.clone())
         # ---- Langevin corrector, sampling.py:179-199 (alpha = 1 for VE)
-        alpha = torch.ones_like(vec_t)
+        alpha = sde.alphas[sde.timestep(vec_t)] if vp else torch.ones_like(vec_t)
         for j in range(n_steps):
-            grad = score_model(x, labels, context)
-            noise = noise_fn(stream_corrector(i, j, n_steps), x)
+            grad = score_fn(x, vec_t)
+            noise = noise_fn(stream_generic(draws) if generic_streams else stream_corrector(i, j, n_steps), x)
+            draws += 1
             grad_norm = torch.norm(grad.reshape(B, -1), dim=-1).mean()
             noise_norm = torch.norm(noise.reshape(B, -1), dim=-1).mean()
             step_size = (snr * noise_norm / grad_norm) ** 2 * 2 * alpha
             x_mean = x + step_size[:, None, None, None] * grad
             x = x_mean + torch.sqrt(step_size * 2)[:, None, None, None] * noise
+            if symmetrize:  # inner steps before the last run unconditioned (the mask is applied after the corrector)
+                free = cm if j == n_steps - 1 else torch.ones_like(cm)
+                x, x_mean = symmetrize_free(x, free), symmetrize_free(x_mean, free)
         x = torch.where(cm, x, x_initial).float()
-        # ---- reverse-diffusion predictor, sampling.py:162-167 + sde_lib.py:96-101,237-245 (f = 0 for VE)
-        G = sde.discretize_G(vec_t)
-        score = score_model(x, labels, context)
-        rev_f = torch.zeros_like(x) - G[:, None, None, None] ** 2 * score * (0.5 if probability_flow else 1.0)
+        # ---- reverse-diffusion predictor, sampling.py:162-167 + sde_lib.py:96-101 over :149-157 (VP) / :237-245 (VE)
+        score = score_fn(x, vec_t)
+        if vp:
+            ts = sde.timestep(vec_t)
+            f = torch.sqrt(sde.alphas[ts])[:, None, None, None] * x - x
+            G = torch.sqrt(sde.discrete_betas[ts])
+        else:
+            f = torch.zeros_like(x)
+            G = sde.discretize_G(vec_t)
+        rev_f = f - G[:, None, None, None] ** 2 * score * (0.5 if probability_flow else 1.0)
         rev_G = torch.zeros_like(G) if probability_flow else G
-        z = noise_fn(stream_predictor(i, n_steps), x)
+        z = noise_fn(stream_generic(draws) if generic_streams else stream_predictor(i, n_steps), x)
+        draws += 1
         x_mean = x - rev_f
         x = x_mean + rev_G[:, None, None, None] * z
+        if symmetrize:
+            x, x_mean = symmetrize_free(x, cm), symmetrize_free(x_mean, cm)
         x = torch.where(cm, x, x_initial).float()
     x_mean = torch.where(cm, x_mean, x_initial).float()
     return (x_mean if denoise else x), K * (n_steps + 1)

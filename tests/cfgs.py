@@ -92,3 +92,15 @@ FULLSIZE_CASES = {
     "test_config": ("test_config.yml", 1, 32),                 # as shipped: N = 256, nf = 256, attention at 32/16/8
     "test_config_large": ("test_config_large.yml", 1, 512),    # N = 256, ch_mult [1,1,2,2,2,4], d_head = 128, L = 512
 }
+
+
+def rsde_inputs():
+    """Inputs of the RSDE / SDE golden (tests/golden/rsde.npz)."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 2, 4, 4, generator=g)
+    t = torch.tensor([1.0, 0.43, 1e-3])
+    return x, t
+
+
+def analytic_score(x, t, context=None):
+    return torch.sin(x) * (1.0 + t)[:, None, None, None]

@@ -31,7 +31,8 @@ sys.path.insert(0, ROOT)
 
 import make_golden as mg  # noqa: E402  (puts /root/reference on sys.path and imports the reference modules)
 from oracle.philox_ref import STREAM_PRIOR, philox_normal, stream_corrector, stream_generic, stream_predictor  # noqa: E402
-from tests.cfgs import FULLSIZE_CASES, fullsize_inputs, synthetic_condition, synthetic_inputs, tiny_cfg  # noqa: E402
+from tests.cfgs import (FULLSIZE_CASES, analytic_score, fullsize_inputs, rsde_inputs, synthetic_condition,  # noqa: E402
+                        synthetic_inputs, tiny_cfg)
 
 ref_sampling, ref_sde, ref_ncsnpp = mg.ref_sampling, mg.ref_sde, mg.ref_ncsnpp
 
@@ -123,17 +124,6 @@ def sampler_vpsde(seed=2024, B=2, L=8):
     np.savez_compressed(os.path.join(HERE, "sampler_vpsde_tiny5.npz"), sample=sample.numpy(),
                         K=np.array(VP_ITERS), N=np.array(N))
     print("sampler_vpsde_tiny5 absmax", sample.abs().max().item(), "nfe", nfe)
-
-
-def rsde_inputs():
-    g = torch.Generator().manual_seed(5)
-    x = torch.randn(3, 2, 4, 4, generator=g)
-    t = torch.tensor([1.0, 0.43, 1e-3])
-    return x, t
-
-
-def analytic_score(x, t, context=None):
-    return torch.sin(x) * (1.0 + t)[:, None, None, None]
 
 
 def rsde():

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"libt2p.so does not export {n}"
         assert n in _lib.SIGNATURES, f"_lib.SIGNATURES lacks {n}"
-    assert lib.t2p_abi_version() == 1
+    assert lib.t2p_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_struct_layouts_match_header_field_counts():
@@ -41,15 +41,41 @@ def test_struct_layouts_match_header_field_counts():
         assert len(fields) == len(cls._fields_), (cname, len(fields), len(cls._fields_))
 
 
+def test_struct_sizes_and_field_offsets_match_the_compiled_library():
+    """sizeof and offsetof of every argument struct as compiled into libt2p.so against the ctypes mirrors: a
+    reordered or retyped field fails here (and at load time, _lib.check_layout)."""
+    lib = _lib.lib()
+    for which, cls in _lib.STRUCTS.items():
+        assert lib.t2p_sizeof(which) == C.sizeof(cls), cls.__name__
+        n = len(cls._fields_)
+        offs = (C.c_int32 * (n + 4))()
+        assert lib.t2p_struct_layout(which, offs, n + 4) == n, cls.__name__
+        assert [getattr(cls, f).offset for f, _ in cls._fields_] == list(offs[:n]), cls.__name__
+    assert lib.t2p_sizeof(99) == -1
+
+    class Drifted(C.Structure):  # the guard does catch a retyped field
+        _fields_ = [(f, (C.c_int64 if f == "snr" else t)) for f, t in _lib.RunArgs._fields_]
+
+    saved = _lib.STRUCTS[2]
+    _lib.STRUCTS[2] = Drifted
+    try:
+        with pytest.raises(_lib.NativeError):
+            _lib.check_layout(lib)
+    finally:
+        _lib.STRUCTS[2] = saved
+
+
 def _tree(name):
     with open(os.path.join(ROOT, "tests", "golden", f"param_tree_{name}.json")) as f:
         return json.load(f)
 
 
-@pytest.mark.parametrize("which", ["tiny5", "cond_length"])
+@pytest.mark.parametrize("which", ["tiny5", "cond_length", "cond_ss_inpainting", "no_cond", "test_config",
+                                   "test_config_large"])
 def test_parameter_tree_matches_reference(which):
+    """All five BASELINE configurations (705 / 705 / 705 / 1065 / 1415 state_dict keys) + the tiny test network."""
     from text2protein_b200.score_sde_pytorch.models.ncsnpp import UNetModel
-    cfg = tiny_cfg(5) if which == "tiny5" else load_config("cond_length", device="cpu")
+    cfg = tiny_cfg(5) if which == "tiny5" else load_config(which, device="cpu")
     tree = _tree(which)
     model = UNetModel(cfg)
     sd = model.state_dict()

@@ -56,9 +56,10 @@ def _check_masks(sample, cond):
         assert torch.equal(sample[keep], cond["inpainting"]["coords_6d"][keep])
 
 
-# K = 4 corrector+predictor iterations; after them |x| ~ 1e2..1e3, so 1e-4 relative = a few 1e-2 absolute
+# K = 4 corrector+predictor iterations; after them |x| ~ 1e2..1e3, so 1e-4 relative = a few 1e-2 absolute.  bf16: the
+# stated tolerance of the score network itself (2e-2); the measured deviation of the K-step maps is ~2e-3.
 @pytest.mark.parametrize("c,kinds", [(5, ["length"]), (8, ["length", "ss", "inpainting"]), (8, [])])
-@pytest.mark.parametrize("dtype,tol", [("fp32", 1e-4), ("bf16", 0.2)])
+@pytest.mark.parametrize("dtype,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
 def test_native_loop_matches_oracle(c, kinds, dtype, tol):
     cfg, model, sd = make_native(tiny_cfg(c), dtype)
     _, _, ctx = synthetic_inputs(cfg, 2, 8)

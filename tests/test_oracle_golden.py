@@ -108,3 +108,83 @@ def test_sampler_matches_reference(golden_dir, name, c, kinds):
     if "inpainting" in kinds:
         keep = ~cond["inpainting"]["mask_inpaint"][:, None].expand_as(sample)
         assert torch.equal(sample[keep], cond["inpainting"]["coords_6d"][keep])
+
+
+def test_vpsde_sampler_matches_reference(golden_dir):
+    """VPSDE through the oracle (float time conditioning, score = -out / sqrt(1 - alpha_bar), DDPM discretisation,
+    alpha-scaled Langevin step) against the reference's own pc_sampler run -- SURVEY row a9."""
+    g = np.load(os.path.join(golden_dir, "sampler_vpsde_tiny5.npz"))
+    N, K = int(g["N"]), int(g["K"])
+    cfg = tiny_cfg(5, num_scales=N)
+    sd = _tiny_sd(golden_dir, cfg)
+    _, _, ctx = synthetic_inputs(cfg, 2, 8)
+    cond = synthetic_condition(cfg, 2, ["length"])
+    sde = sampler_ref.VPSDERef(cfg.model.beta_min, cfg.model.beta_max, N)
+    model = lambda x, lab, cx: unet_ref.unet_forward(sd, cfg, x, lab, cx)
+    sample, nfe = sampler_ref.pc_sampler_ref(sde, model, (2, 5, 32, 32), cfg.sampling.snr, n_steps=1, eps=1e-3,
+                                             condition=cond, context=ctx, noise_fn=sampler_ref.philox_noise_fn(2024),
+                                             num_iters=K, generic_streams=True)
+    assert nfe == 2 * K and sample.dtype == torch.float32
+    np.testing.assert_allclose(sample.numpy(), g["sample"], rtol=1e-4, atol=1e-3)
+    assert torch.equal(sample[:, -1], cond["length"].float())
+
+
+def _full_sd(golden_dir, yaml_name, cfg):
+    tree = _tree(golden_dir, yaml_name[:-4])
+    return unet_ref.state_dict_from_tree(tree, cfg, 42)
+
+
+@pytest.mark.parametrize("case", ["cond_length_L77", "cond_ss_inpainting", "test_config_large"])
+def test_unet_matches_reference_at_baseline_size(golden_dir, case):
+    """The oracle at the real architectures (N = 128 nf = 128; C = 8; N = 256 with d_head = 128 and L = 512, 863 M
+    parameters) against the reference's output -- what the full-size GPU parity tests lean on."""
+    from tests.cfgs import FULLSIZE_CASES, fullsize_inputs
+    from text2protein_b200 import load_config
+    fname, B, L = FULLSIZE_CASES[case]
+    cfg = load_config(fname, device="cpu")
+    g = np.load(os.path.join(golden_dir, f"unet_full_{case}.npz"))
+    sd = _full_sd(golden_dir, fname, cfg)
+    x, labels, ctx = fullsize_inputs(cfg, B, L)
+    # the torch generator drew the same inputs and weights as on the machine that made the golden
+    np.testing.assert_allclose([x.double().sum().item(), ctx.double().sum().item(), float(labels.sum())],
+                               g["in_sums"], rtol=1e-12)
+    out = unet_ref.unet_forward(sd, cfg, x, labels, ctx)
+    ref = torch.from_numpy(g["out"]).double()
+    assert ((out - ref).abs().max() / ref.abs().max()).item() < 1e-5
+
+
+def test_sampler_matches_reference_at_baseline_size(golden_dir):
+    """K = 2 iterations of the reference pc_sampler on the real cond_length.yml network (B = 2, N = 128)."""
+    from tests.cfgs import fullsize_inputs
+    from text2protein_b200 import load_config
+    cfg = load_config("cond_length", device="cpu")
+    g = np.load(os.path.join(golden_dir, "sampler_full_cond_length.npz"))
+    K = int(g["K"])
+    sd = _full_sd(golden_dir, "cond_length.yml", cfg)
+    _, _, ctx = fullsize_inputs(cfg, 2, 77)
+    cond = synthetic_condition(cfg, 2, ["length"])
+    sde = sampler_ref.VESDERef(cfg.model.sigma_min, cfg.model.sigma_max, cfg.model.num_scales)
+    model = lambda x, lab, cx: unet_ref.unet_forward(sd, cfg, x, lab, cx)
+    sample, _ = sampler_ref.pc_sampler_ref(sde, model, (2, 5, 128, 128), cfg.sampling.snr, n_steps=1, eps=1e-5,
+                                           condition=cond, context=ctx, noise_fn=sampler_ref.philox_noise_fn(2024),
+                                           num_iters=K)
+    ref = torch.from_numpy(g["sample"])
+    assert ((sample - ref).abs().max() / ref.abs().max()).item() < 1e-5
+    assert torch.equal(sample[:, -1], cond["length"].float())
+
+
+def test_symmetrize_free_specification():
+    """The opt-in symmetrisation (product extension): exactly symmetric where both positions are free, untouched
+    elsewhere and in channels >= 2; a no-op on an already symmetric map."""
+    g = torch.Generator().manual_seed(0)
+    u = torch.randn(2, 5, 6, 6, generator=g, dtype=torch.float64)
+    cm = torch.ones(2, 5, 6, 6, dtype=torch.bool)
+    cm[:, :, 4:, :] = False
+    cm[:, :, :, 4:] = False
+    cm[0, 0, 1, 2] = False  # asymmetric hole: neither (1,2) nor (2,1) is symmetrised
+    s = sampler_ref.symmetrize_free(u, cm)
+    assert torch.equal(s[:, 2:], u[:, 2:])
+    assert torch.equal(s[:, :2][~cm[:, :2]], u[:, :2][~cm[:, :2]])
+    assert torch.equal(s[0, 0, 2, 1], u[0, 0, 2, 1]) and torch.equal(s[0, 0, 1, 2], u[0, 0, 1, 2])
+    assert torch.equal(s[1, :2, :4, :4], s[1, :2, :4, :4].transpose(1, 2))
+    assert torch.equal(sampler_ref.symmetrize_free(s, cm), s)

@@ -34,7 +34,19 @@ def _digest(paths):
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
+LIB_KNOBS = os.path.join(HERE, "libt2p_knobs.so")
+
+
+def build(force=False, verbose=False, knobs=False):
+    """``knobs=True`` builds libt2p_knobs.so with -DT2P_TIMING_KNOBS: the A/B and timing switches of tools/ are
+    environment variables that only that build reads (csrc/common.h env_knob)."""
+    if knobs:
+        return _build(force, verbose, LIB_KNOBS, os.path.join(os.path.dirname(HERE), "build", "obj_knobs"),
+                      ["-DT2P_TIMING_KNOBS"])
+    return _build(force, verbose, LIB, OBJ_DIR, [])
+
+
+def _build(force, verbose, LIB, OBJ_DIR, defines):
     os.makedirs(OBJ_DIR, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "t2p.h"))
@@ -51,7 +63,7 @@ def build(force=False, verbose=False):
         if not force and os.path.exists(obj) and os.path.exists(keyfile) and open(keyfile).read() == key:
             return obj
         flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
-        extra = ["-DT2P_HAVE_ATTENTION_MMA"] if "attention_mma.cu" in sources else []
+        extra = (["-DT2P_HAVE_ATTENTION_MMA"] if "attention_mma.cu" in sources else []) + defines
         cmd = [_nvcc()] + flags + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

@@ -26,14 +26,16 @@ class StepArgs(C.Structure):
                 ("alpha", C.c_void_p), ("probability_flow", C.c_int32), ("snr", C.c_float), ("mask", C.c_void_p),
                 ("x_init", C.c_void_p), ("x_mean_out", C.c_void_p), ("seed", C.c_uint64), ("stream_id", C.c_int64),
                 ("sample_offset", C.c_int64), ("B", C.c_int32), ("C", C.c_int32), ("HW", C.c_int32),
-                ("workspace", C.c_void_p), ("conditioned_in_place", C.c_int32), ("reserved", C.c_int32)]
+                ("workspace", C.c_void_p), ("conditioned_in_place", C.c_int32), ("symmetrize", C.c_int32),
+                ("x_out", C.c_void_p), ("W", C.c_int32), ("reserved", C.c_int32)]
 
 
 class RunArgs(C.Structure):
     _fields_ = [("x", C.c_void_p), ("x_mean", C.c_void_p), ("mask", C.c_void_p), ("x_init", C.c_void_p),
                 ("label_table", C.c_void_p), ("g_table", C.c_void_p), ("num_iters", C.c_int32),
                 ("n_steps", C.c_int32), ("snr", C.c_float), ("probability_flow", C.c_int32), ("seed", C.c_uint64),
-                ("sample_offset", C.c_int64), ("B", C.c_int32), ("use_graph", C.c_int32)]
+                ("sample_offset", C.c_int64), ("B", C.c_int32), ("use_graph", C.c_int32), ("symmetrize", C.c_int32),
+                ("reserved", C.c_int32), ("peers", C.c_void_p)]
 
 
 class ConvArgs(C.Structure):
@@ -50,10 +52,22 @@ class GemmRecord(C.Structure):
                 ("tensor_core", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("ms", C.c_float)]
 
 
+ABI_VERSION = 2
+IPC_HANDLE_BYTES = 64
+# `which` codes of t2p_sizeof / t2p_struct_layout
+STRUCTS = {0: UnetCfg, 1: StepArgs, 2: RunArgs, 3: ConvArgs, 4: GemmRecord}
+
 # name -> (restype, argtypes); must list every symbol include/t2p.h declares (tests/test_abi.py checks)
 SIGNATURES = {
     "t2p_last_error": (C.c_char_p, []),
     "t2p_abi_version": (C.c_int, []),
+    "t2p_sizeof": (C.c_int, [C.c_int]),
+    "t2p_struct_layout": (C.c_int, [C.c_int, C.POINTER(C.c_int32), C.c_int]),
+    "t2p_unet_forward_t": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                     C.c_void_p]),
+    "t2p_peer_mailbox_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.c_void_p]),
+    "t2p_peer_group_open": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
+    "t2p_peer_group_close": (None, [C.c_void_p]),
     "t2p_unet_create": (C.c_int, [C.POINTER(UnetCfg), C.POINTER(C.c_void_p)]),
     "t2p_unet_destroy": (None, [C.c_void_p]),
     "t2p_unet_num_params": (C.c_int, [C.c_void_p]),
@@ -110,6 +124,29 @@ class NativeError(RuntimeError):
     pass
 
 
+def check_layout(handle):
+    """sizeof and every field offset of the ctypes mirrors against the structs the library was compiled with."""
+    for which, cls in STRUCTS.items():
+        if handle.t2p_sizeof(which) != C.sizeof(cls):
+            raise NativeError(f"{cls.__name__}: sizeof {C.sizeof(cls)} here, {handle.t2p_sizeof(which)} in libt2p.so")
+        n = len(cls._fields_)
+        offs = (C.c_int32 * n)()
+        if handle.t2p_struct_layout(which, offs, n) != n:
+            raise NativeError(f"{cls.__name__}: field count differs from libt2p.so")
+        for (fname, _), off in zip(cls._fields_, offs):
+            if getattr(cls, fname).offset != off:
+                raise NativeError(f"{cls.__name__}.{fname}: offset {getattr(cls, fname).offset} here, {off} in libt2p.so")
+
+
+def use_library(path):
+    """Selects another build of the library (e.g. libt2p_knobs.so, the -DT2P_TIMING_KNOBS build that tools/ and
+    ``bench.py --lib knobs`` use) -- before the first native call."""
+    global LIB_PATH
+    if _lib is not None:
+        raise NativeError("the native library is already loaded")
+    LIB_PATH = path if os.path.isabs(path) else os.path.join(_HERE, path)
+
+
 def lib():
     """Loads libt2p.so once; raises (never falls back) when it is missing."""
     global _lib
@@ -122,8 +159,9 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.t2p_abi_version() != 1:
+        if handle.t2p_abi_version() != ABI_VERSION:
             raise NativeError("libt2p.so ABI version mismatch; rebuild")
+        check_layout(handle)
         _lib = handle
     return _lib
 
@@ -136,6 +174,13 @@ def check(rc):
 def current_stream():
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def device_of(t):
+    """Context manager making ``t``'s device current for the native calls inside it: the library launches on the
+    current device (its per-device kernel attributes and SM counts are keyed by cudaGetDevice)."""
+    import torch
+    return torch.cuda.device(t.device)
 
 
 def ptr(t):

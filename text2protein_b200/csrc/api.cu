@@ -1,5 +1,6 @@
 // extern "C" surface of libt2p.so (include/t2p.h): argument marshalling, error plumbing and the
 // graph-captured sampling loop.
+#include <cstddef>
 #include <cstring>
 #include <memory>
 
@@ -21,11 +22,24 @@ struct RunKey {
   unsigned long long seed;
   long long sample_offset;
   long long generation;
+  // every device buffer the captured iteration points into that the caller does not own: activation arena and
+  // time-embedding buffer of the network (resource_epoch), loop buffers of this handle (buf_epoch)
+  long long resource_epoch, buf_epoch;
+  int symmetrize;
+  const void* peers;
   bool operator==(const RunKey& o) const {
     return x == o.x && x_mean == o.x_mean && mask == o.mask && x_init == o.x_init && B == o.B &&
            n_steps == o.n_steps && snr == o.snr && pf == o.pf && seed == o.seed && sample_offset == o.sample_offset &&
-           generation == o.generation;
+           generation == o.generation && resource_epoch == o.resource_epoch && buf_epoch == o.buf_epoch &&
+           symmetrize == o.symmetrize && peers == o.peers;
   }
+};
+
+struct t2p_peer_group {
+  t2p::PeerGroup g;
+  void* opened[t2p::PeerGroup::kMaxWorld] = {};  // peer mappings to close (own mailbox excluded)
+  void* own = nullptr;
+  unsigned long long runs = 0;  // t2p_pc_run calls made with this group (all ranks make the same sequence)
 };
 
 struct t2p_unet {
@@ -34,6 +48,8 @@ struct t2p_unet {
   RunKey graph_key{};
   // sampling-loop state (device), sized lazily
   int run_B = 0, run_K = 0;
+  long long buf_epoch = 0;
+  float* x_alt = nullptr;  // second state buffer of an out-of-place (symmetrised) run
   long long* labels = nullptr;
   float* G = nullptr;
   long long* state = nullptr;
@@ -50,7 +66,7 @@ struct t2p_unet {
     if (ev_out) cudaEventDestroy(ev_out);
     for (void* p : {static_cast<void*>(labels), static_cast<void*>(G), static_cast<void*>(state),
                     static_cast<void*>(label_table), static_cast<void*>(g_table), static_cast<void*>(h),
-                    static_cast<void*>(partial)})
+                    static_cast<void*>(partial), static_cast<void*>(x_alt)})
       if (p) cudaFree(p);
   }
 };
@@ -76,6 +92,62 @@ extern "C" {
 
 const char* t2p_last_error(void) { return g_last_error.c_str(); }
 int t2p_abi_version(void) { return T2P_ABI_VERSION; }
+
+#define T2P_OFF(T, f) static_cast<int32_t>(offsetof(T, f))
+static std::vector<int32_t> struct_offsets(int which) {
+  switch (which) {
+    case 0: return {T2P_OFF(t2p_unet_cfg, num_channels), T2P_OFF(t2p_unet_cfg, max_res_num), T2P_OFF(t2p_unet_cfg, nf),
+                    T2P_OFF(t2p_unet_cfg, n_ch_mult), T2P_OFF(t2p_unet_cfg, ch_mult), T2P_OFF(t2p_unet_cfg, num_res_blocks),
+                    T2P_OFF(t2p_unet_cfg, n_attn_resolutions), T2P_OFF(t2p_unet_cfg, attn_resolutions),
+                    T2P_OFF(t2p_unet_cfg, n_heads), T2P_OFF(t2p_unet_cfg, context_dim), T2P_OFF(t2p_unet_cfg, num_scales),
+                    T2P_OFF(t2p_unet_cfg, scale_by_sigma), T2P_OFF(t2p_unet_cfg, compute_dtype)};
+    case 1: return {T2P_OFF(t2p_step_args, x), T2P_OFF(t2p_step_args, score), T2P_OFF(t2p_step_args, score_dtype),
+                    T2P_OFF(t2p_step_args, score_nhwc), T2P_OFF(t2p_step_args, sigmas), T2P_OFF(t2p_step_args, labels),
+                    T2P_OFF(t2p_step_args, G), T2P_OFF(t2p_step_args, sqrt_alpha), T2P_OFF(t2p_step_args, alpha),
+                    T2P_OFF(t2p_step_args, probability_flow), T2P_OFF(t2p_step_args, snr), T2P_OFF(t2p_step_args, mask),
+                    T2P_OFF(t2p_step_args, x_init), T2P_OFF(t2p_step_args, x_mean_out), T2P_OFF(t2p_step_args, seed),
+                    T2P_OFF(t2p_step_args, stream_id), T2P_OFF(t2p_step_args, sample_offset), T2P_OFF(t2p_step_args, B),
+                    T2P_OFF(t2p_step_args, C), T2P_OFF(t2p_step_args, HW), T2P_OFF(t2p_step_args, workspace),
+                    T2P_OFF(t2p_step_args, conditioned_in_place), T2P_OFF(t2p_step_args, symmetrize),
+                    T2P_OFF(t2p_step_args, x_out), T2P_OFF(t2p_step_args, W), T2P_OFF(t2p_step_args, reserved)};
+    case 2: return {T2P_OFF(t2p_run_args, x), T2P_OFF(t2p_run_args, x_mean), T2P_OFF(t2p_run_args, mask),
+                    T2P_OFF(t2p_run_args, x_init), T2P_OFF(t2p_run_args, label_table), T2P_OFF(t2p_run_args, g_table),
+                    T2P_OFF(t2p_run_args, num_iters), T2P_OFF(t2p_run_args, n_steps), T2P_OFF(t2p_run_args, snr),
+                    T2P_OFF(t2p_run_args, probability_flow), T2P_OFF(t2p_run_args, seed),
+                    T2P_OFF(t2p_run_args, sample_offset), T2P_OFF(t2p_run_args, B), T2P_OFF(t2p_run_args, use_graph),
+                    T2P_OFF(t2p_run_args, symmetrize), T2P_OFF(t2p_run_args, reserved), T2P_OFF(t2p_run_args, peers)};
+    case 3: return {T2P_OFF(t2p_conv_args, a0), T2P_OFF(t2p_conv_args, c0), T2P_OFF(t2p_conv_args, a1),
+                    T2P_OFF(t2p_conv_args, c1), T2P_OFF(t2p_conv_args, B), T2P_OFF(t2p_conv_args, H), T2P_OFF(t2p_conv_args, W),
+                    T2P_OFF(t2p_conv_args, ksize), T2P_OFF(t2p_conv_args, w), T2P_OFF(t2p_conv_args, N),
+                    T2P_OFF(t2p_conv_args, bias), T2P_OFF(t2p_conv_args, rowbias), T2P_OFF(t2p_conv_args, rowbias_ld),
+                    T2P_OFF(t2p_conv_args, residual), T2P_OFF(t2p_conv_args, res_up), T2P_OFF(t2p_conv_args, alpha),
+                    T2P_OFF(t2p_conv_args, out), T2P_OFF(t2p_conv_args, out_dtype), T2P_OFF(t2p_conv_args, in_dtype),
+                    T2P_OFF(t2p_conv_args, stat_part), T2P_OFF(t2p_conv_args, x0), T2P_OFF(t2p_conv_args, xc0),
+                    T2P_OFF(t2p_conv_args, x1), T2P_OFF(t2p_conv_args, xc1)};
+    case 4: return {T2P_OFF(t2p_gemm_record, M), T2P_OFF(t2p_gemm_record, N), T2P_OFF(t2p_gemm_record, K),
+                    T2P_OFF(t2p_gemm_record, ksize), T2P_OFF(t2p_gemm_record, tensor_core), T2P_OFF(t2p_gemm_record, H),
+                    T2P_OFF(t2p_gemm_record, W), T2P_OFF(t2p_gemm_record, ms)};
+  }
+  return {};
+}
+
+int t2p_sizeof(int which) {
+  switch (which) {
+    case 0: return static_cast<int>(sizeof(t2p_unet_cfg));
+    case 1: return static_cast<int>(sizeof(t2p_step_args));
+    case 2: return static_cast<int>(sizeof(t2p_run_args));
+    case 3: return static_cast<int>(sizeof(t2p_conv_args));
+    case 4: return static_cast<int>(sizeof(t2p_gemm_record));
+  }
+  return -1;
+}
+
+int t2p_struct_layout(int which, int32_t* offsets, int cap) {
+  const std::vector<int32_t> o = struct_offsets(which);
+  if (o.empty()) return -1;
+  for (size_t i = 0; i < o.size() && static_cast<int>(i) < cap; ++i) offsets[i] = o[i];
+  return static_cast<int>(o.size());
+}
 
 int t2p_unet_create(const t2p_unet_cfg* c, t2p_unet** out) {
   T2P_API_BEGIN
@@ -191,6 +263,14 @@ int t2p_unet_forward(t2p_unet* u, const float* x, const int64_t* labels, void* o
   T2P_API_END
 }
 
+int t2p_unet_forward_t(t2p_unet* u, const float* x, const int64_t* labels, const float* timesteps, void* out,
+                       int out_dtype, int B, void* stream) {
+  T2P_API_BEGIN
+  T2P_CHECK(u && x && labels && out && B > 0, "bad forward arguments");
+  u->net->forward(x, reinterpret_cast<const long long*>(labels), out, out_dtype, B, S(stream), timesteps);
+  T2P_API_END
+}
+
 int t2p_unet_set_debug(t2p_unet* u, int enable) {
   T2P_API_BEGIN
   u->net->set_debug(enable != 0);
@@ -239,6 +319,9 @@ static PcStepArgs step_args(const t2p_step_args* a) {
   p.sample_offset = a->sample_offset;
   p.B = a->B; p.C = a->C; p.HW = a->HW;
   p.conditioned_in_place = a->conditioned_in_place;
+  p.x_out = a->x_out;
+  p.symmetrize = a->symmetrize;
+  p.W = a->W;
   return p;
 }
 
@@ -277,10 +360,15 @@ int t2p_philox_bits(uint64_t seed, int64_t stream_id, int64_t first_quad, int64_
 }
 
 // ---------------------------------------------------------------------------------------------- run
-static void ensure_run_buffers(t2p_unet* u, int B, int K) {
+// Device buffers of the loop.  Whenever one of them moves, buf_epoch changes and with it the graph key: a captured
+// iteration holds raw pointers into them (the cache used to be keyed on the caller's buffers only, so a run with a
+// larger K could replay a graph pointing at freed label / G tables).
+static void ensure_run_buffers(t2p_unet* u, int B, int K, bool need_alt) {
   const UNetConfig& c = u->net->cfg();
   const long long E = static_cast<long long>(c.num_channels) * c.max_res_num * c.max_res_num;
   if (u->run_B != B) {
+    ++u->buf_epoch;
+    if (u->x_alt) { T2P_CUDA(cudaFree(u->x_alt)); u->x_alt = nullptr; }
     for (void** p : {reinterpret_cast<void**>(&u->labels), reinterpret_cast<void**>(&u->G),
                      reinterpret_cast<void**>(&u->state), reinterpret_cast<void**>(&u->h),
                      reinterpret_cast<void**>(&u->partial)}) {
@@ -289,17 +377,26 @@ static void ensure_run_buffers(t2p_unet* u, int B, int K) {
     }
     T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->labels), sizeof(long long) * B));
     T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->G), sizeof(float) * B));
-    T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->state), sizeof(long long) * 2));
+    T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->state), sizeof(long long) * 4));
     T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->h), sizeof(float) * B * E));
     T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->partial), sizeof(double) * pc_corrector_workspace_doubles(B, E)));
     u->run_B = B;
   }
+  if (need_alt && !u->x_alt) {
+    ++u->buf_epoch;
+    T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->x_alt), sizeof(float) * B * E));
+  }
   if (u->run_K < K) {
+    ++u->buf_epoch;
+    const int cap = std::max(K, c.num_scales);  // one allocation covers every run of the model's own schedule
     if (u->label_table) T2P_CUDA(cudaFree(u->label_table));
     if (u->g_table) T2P_CUDA(cudaFree(u->g_table));
-    T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->label_table), sizeof(long long) * K));
-    T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->g_table), sizeof(float) * K));
-    u->run_K = K;
+    u->label_table = nullptr;
+    u->g_table = nullptr;
+    u->run_K = 0;
+    T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->label_table), sizeof(long long) * cap));
+    T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&u->g_table), sizeof(float) * cap));
+    u->run_K = cap;
   }
 }
 
@@ -330,10 +427,16 @@ int t2p_pc_run(t2p_unet* u, const t2p_run_args* a, void* stream) {
   const UNetConfig& c = net.cfg();
   const int B = a->B, K = a->num_iters;
   const int HW = c.max_res_num * c.max_res_num;
-  ensure_run_buffers(u, B, K);
+  const bool sym = a->symmetrize != 0;
+  ensure_run_buffers(u, B, K, sym);
   T2P_CUDA(cudaMemcpyAsync(u->label_table, a->label_table, sizeof(long long) * K, cudaMemcpyHostToDevice, st));
   T2P_CUDA(cudaMemcpyAsync(u->g_table, a->g_table, sizeof(float) * K, cudaMemcpyHostToDevice, st));
-  T2P_CUDA(cudaMemsetAsync(u->state, 0, sizeof(long long) * 2, st));
+  // state: [0] iteration, [1] next iteration, [2] last iteration of THIS run (x_mean is stored there only),
+  // [3] first mailbox tag of this run.  Uploaded from a pageable host array: the copy is staged before the call returns.
+  t2p_peer_group* pg = a->peers;
+  if (pg) T2P_CHECK(pg->g.world > 1 && pg->g.global_batch >= B, "bad peer group");
+  const long long state0[4] = {0, 0, K - 1, pg ? static_cast<long long>(++pg->runs << 32) : 0};
+  T2P_CUDA(cudaMemcpyAsync(u->state, state0, sizeof(state0), cudaMemcpyHostToDevice, st));
 
   PcStepArgs base;
   base.x = a->x; base.score = u->h; base.score_dtype = kF32; base.score_nhwc = 0;
@@ -345,6 +448,10 @@ int t2p_pc_run(t2p_unet* u, const t2p_run_args* a, void* stream) {
   base.sample_offset = a->sample_offset;
   base.B = B; base.C = c.num_channels; base.HW = HW;
   base.partial = u->partial;
+  base.last_iter_ptr = u->state + 2;
+  base.symmetrize = sym ? 1 : 0;
+  base.W = c.max_res_num;
+  if (pg) { base.peers = &pg->g; base.tag_base_ptr = u->state + 3; }
   if (a->mask) {
     // sampling.py:283-287 re-applies the condition after every half-step; x and x_mean take x_initial at the
     // conditioned positions ONCE here and the step kernels leave those positions alone for the rest of the run
@@ -353,25 +460,48 @@ int t2p_pc_run(t2p_unet* u, const t2p_run_args* a, void* stream) {
     apply_mask(a->x_mean, a->mask, a->x_init, n, st);
     base.conditioned_in_place = 1;
   }
+  // Out-of-place (symmetrised) runs ping-pong between the caller's x and x_alt: the update of (i, j) reads the OLD
+  // state at (j, i).  Both buffers start conditioned; an iteration with an odd number of half-steps copies back.
+  float* cur = a->x;
+  float* alt = sym ? u->x_alt : nullptr;
+  if (sym)
+    T2P_CUDA(cudaMemcpyAsync(alt, a->x, sizeof(float) * static_cast<size_t>(B) * c.num_channels * HW,
+                             cudaMemcpyDeviceToDevice, st));
 
   auto iteration = [&]() {
     run_prep(u->state, u->label_table, u->g_table, B, u->labels, u->G, st);
     // every score evaluation of one iteration is at the same noise level: the time-embedding path (pre_blocks
     // MLP + 42 Dense_0 projections) is computed by the first one and reused by the rest
     net.set_reuse_temb(false);
+    float* xin = cur;
+    float* xout = sym ? alt : cur;
     for (int j = 0; j < a->n_steps; ++j) {  // Langevin corrector, sampling.py:188-197
-      net.forward_raw(a->x, u->labels, u->h, B, st);
+      net.forward_raw(xin, u->labels, u->h, B, st);
       net.set_reuse_temb(true);
       PcStepArgs s = base;
+      s.x = xin; s.x_out = xout;
       s.stream_base = 1 + j;
+      if (a->n_steps > 1 && a->mask) {
+        // the reference re-applies the condition after the WHOLE corrector update (sampling.py:282-283), not
+        // between its inner steps: the inner steps run unmasked (conditioned positions drift and are seen by the
+        // next score evaluation), the last one restores x_initial everywhere it is conditioned
+        if (j + 1 < a->n_steps) { s.mask = nullptr; s.x_init = nullptr; }
+        s.conditioned_in_place = 0;
+      }
       pc_corrector_step(s, st);
+      std::swap(xin, xout);
+      if (!sym) xout = xin;
     }
-    net.forward_raw(a->x, u->labels, u->h, B, st);  // reverse-diffusion predictor, sampling.py:162-167
+    net.forward_raw(xin, u->labels, u->h, B, st);  // reverse-diffusion predictor, sampling.py:162-167
     net.set_reuse_temb(false);
     PcStepArgs s = base;
+    s.x = xin; s.x_out = xout;
     s.stream_base = 1 + a->n_steps;
     s.x_mean_out = a->x_mean;
     pc_predictor_step(s, st);
+    if (sym && xout != cur)  // odd number of half-steps: bring the state back to the caller's buffer
+      T2P_CUDA(cudaMemcpyAsync(cur, xout, sizeof(float) * static_cast<size_t>(B) * c.num_channels * HW,
+                               cudaMemcpyDeviceToDevice, st));
   };
 
   if (!a->use_graph) {
@@ -381,12 +511,16 @@ int t2p_pc_run(t2p_unet* u, const t2p_run_args* a, void* stream) {
     // it for all K iterations.  On a miss, iteration 0 runs eagerly (sizes the workspace, builds TMA
     // descriptors, sets kernel attributes outside the capture), then iterations 1..K-1 replay the capture.
     RunKey key{a->x, a->x_mean, a->mask, a->x_init, a->B, a->n_steps, a->snr, a->probability_flow, a->seed,
-               a->sample_offset, net.generation()};
+               a->sample_offset, net.generation(), 0, u->buf_epoch, a->symmetrize, pg};
     int first = 0;
+    // (the network's resource epoch is compared AFTER the eager iteration of a miss would have grown its buffers;
+    // on a hit nothing can have moved since the capture, or the epochs would differ)
+    key.resource_epoch = net.resource_epoch();
     if (!u->graph_exec || !(key == u->graph_key)) {
       if (u->graph_exec) { cudaGraphExecDestroy(u->graph_exec); u->graph_exec = nullptr; }
       iteration();
       first = 1;
+      key.resource_epoch = net.resource_epoch();
       if (K > 1) {
         cudaGraph_t graph = nullptr;
         T2P_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
@@ -407,6 +541,54 @@ int t2p_pc_run(t2p_unet* u, const t2p_run_args* a, void* stream) {
     for (int i = first; i < K; ++i) T2P_CUDA(cudaGraphLaunch(u->graph_exec, st));
   }
   T2P_API_END
+}
+
+// ---------------------------------------------------------------------------------------------- peers
+int t2p_peer_mailbox_create(int world, void** mailbox, void* ipc_handle_out) {
+  T2P_API_BEGIN
+  T2P_CHECK(mailbox && ipc_handle_out && world > 1 && world <= PeerGroup::kMaxWorld, "bad mailbox arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == T2P_IPC_HANDLE_BYTES, "IPC handle size");
+  void* p = nullptr;
+  const size_t bytes = sizeof(unsigned long long) * 4 * 2 * PeerGroup::kMaxWorld;
+  T2P_CUDA(cudaMalloc(&p, bytes));
+  T2P_CUDA(cudaMemset(p, 0, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); T2P_CUDA(e); }
+  std::memcpy(ipc_handle_out, &h, sizeof(h));
+  *mailbox = p;
+  T2P_API_END
+}
+
+int t2p_peer_group_open(void* own_mailbox, const void* ipc_handles, int world, int rank, int64_t global_batch,
+                        t2p_peer_group** out) {
+  T2P_API_BEGIN
+  T2P_CHECK(own_mailbox && ipc_handles && out && world > 1 && world <= PeerGroup::kMaxWorld && rank >= 0 && rank < world &&
+            global_batch > 0, "bad peer group arguments");
+  auto g = std::make_unique<t2p_peer_group>();
+  g->g.world = world;
+  g->g.rank = rank;
+  g->g.global_batch = global_batch;
+  g->own = own_mailbox;
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { g->g.box[r] = static_cast<unsigned long long*>(own_mailbox); continue; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, static_cast<const char*>(ipc_handles) + static_cast<size_t>(r) * sizeof(h), sizeof(h));
+    void* p = nullptr;
+    T2P_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    g->opened[r] = p;
+    g->g.box[r] = static_cast<unsigned long long*>(p);
+  }
+  *out = g.release();
+  T2P_API_END
+}
+
+void t2p_peer_group_close(t2p_peer_group* g) {
+  if (!g) return;
+  for (void* p : g->opened)
+    if (p) cudaIpcCloseMemHandle(p);
+  if (g->own) cudaFree(g->own);
+  delete g;
 }
 
 // ---------------------------------------------------------------------------------------------- per-op

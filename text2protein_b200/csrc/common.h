@@ -47,6 +47,27 @@ void set_last_error(const std::string& m);
 
 #define T2P_LAUNCH_CHECK() T2P_CUDA(cudaGetLastError())
 
+// Timing / A-B knobs (T2P_DEBUG_SKIP, T2P_DEBUG_DUP, T2P_HALO, T2P_PDL, T2P_STEP_*, ...) are environment variables that
+// only a library compiled with -DT2P_TIMING_KNOBS reads (libt2p_knobs.so, built for tools/ and `bench.py --lib knobs`).
+// The shipped libt2p.so never looks at the environment: a stray variable cannot drop work from a timed region.
+inline int env_knob(const char* name, int dflt) {
+#ifdef T2P_TIMING_KNOBS
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+#else
+  (void)name;
+  return dflt;
+#endif
+}
+inline bool env_knob_set(const char* name) {
+#ifdef T2P_TIMING_KNOBS
+  return getenv(name) != nullptr;
+#else
+  (void)name;
+  return false;
+#endif
+}
+
 // ---- programmatic dependent launch (PDL).  A kernel launched through launch_pdl() may become resident while
 // its predecessor in the stream is still draining: it calls pdl_trigger() first (its own successor may be
 // scheduled once every CTA of this grid has started), runs its prologue (barrier init, TMEM allocation,
@@ -61,10 +82,7 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // CLS: kernel class bit tested against the T2P_PDL mask (1 tcgen05 GEMMs, 2 gn_finalize, 4 gn_apply, 8 everything else)
 template <int CLS = 8, typename... P, typename... A>
 inline void launch_pdl(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
-  static const bool on = [] {
-    const char* e = getenv("T2P_PDL");
-    return e && (atoi(e) & CLS) != 0;
-  }();
+  static const bool on = (env_knob("T2P_PDL", 0) & CLS) != 0;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;

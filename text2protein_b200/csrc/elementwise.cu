@@ -11,7 +11,8 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); 
 // One block per sample: sinusoidal embedding (layers.py:97-111) -> Linear(nf,4nf) -> Linear(4nf,4nf)
 // (no activation in between, ncsnpp.py:227-228) -> SiLU (every consumer applies act(temb) first,
 // layers.py:316).  fp32 throughout; output [B][4nf].
-__global__ void temb_mlp_kernel(const long long* __restrict__ labels, int nf, float neg_coef,
+__global__ void temb_mlp_kernel(const long long* __restrict__ labels, const float* __restrict__ timesteps, int nf,
+                                float neg_coef,
                                 const float* __restrict__ w0,
                                 const float* __restrict__ b0, const float* __restrict__ w1,
                                 const float* __restrict__ b1, float* __restrict__ out) {
@@ -20,7 +21,9 @@ __global__ void temb_mlp_kernel(const long long* __restrict__ labels, int nf, fl
   float* h0 = sm + nf;
   const int b = blockIdx.x;
   const int half = nf / 2;
-  const float t = static_cast<float>(labels[b]);
+  // the embedded value is the time conditioning itself (a float for VP models, layers.py:106); integer labels
+  // are converted like `timesteps.float()`
+  const float t = timesteps ? timesteps[b] : static_cast<float>(labels[b]);
   for (int i = threadIdx.x; i < half; i += blockDim.x) {
     const float f = expf(static_cast<float>(i) * neg_coef);
     const float a = t * f;
@@ -240,13 +243,13 @@ void broadcast_row_f32(float* buf, int n, int B, cudaStream_t st) {
   T2P_LAUNCH_CHECK();
 }
 
-void temb_mlp(const long long* labels, int B, int nf, const float* w0, const float* b0, const float* w1,
+void temb_mlp(const long long* labels, const float* timesteps, int B, int nf, const float* w0, const float* b0, const float* w1,
               const float* b1, float* out, cudaStream_t st) {
   const size_t smem = sizeof(float) * (nf + 4 * nf);
   // -(ln 10000 / (half - 1)) evaluated in double then rounded once, as Python does (layers.py:101-103)
   const float neg_coef = static_cast<float>(-(log(10000.0) / static_cast<double>(nf / 2 - 1)));
   // a single sample (uniform labels) is latency-bound: more, thinner slices of the second layer
-  temb_mlp_kernel<<<dim3(B, B == 1 ? 32 : 8), 256, smem, st>>>(labels, nf, neg_coef, w0, b0, w1, b1, out);
+  temb_mlp_kernel<<<dim3(B, B == 1 ? 32 : 8), 256, smem, st>>>(labels, timesteps, nf, neg_coef, w0, b0, w1, b1, out);
   T2P_LAUNCH_CHECK();
 }
 

@@ -1145,7 +1145,7 @@ Plan make_plan(const ConvGemmArgs& a) {
       pl.channel_major = true;
       pl.rows = pick;
       pixel_box(a, pick, pl.tw, pl.th, pl.tb);
-      static const bool halo_on = [] { const char* e = getenv("T2P_HALO"); return !e || atoi(e) != 0; }();
+      static const bool halo_on = env_knob("T2P_HALO", 1) != 0;
       pl.halo = halo_on && pick == 256 && a.ksize == 3 && a.W == 128 && a.H % 2 == 0;
       pl.stats_ok = want_stats && a.out_dtype == kBF16;
       return pl;

@@ -89,7 +89,8 @@ void attention_mma(const AttnArgs& a, cudaStream_t st);  // bf16 tensor cores
 bool attention_mma_supported(const AttnArgs& a);
 
 // ----------------------------------------------------------------------------- helpers
-void temb_mlp(const long long* labels, int B, int nf, const float* w0, const float* b0, const float* w1,
+// timesteps: optional fp32 [B] time conditioning to embed instead of float(labels)
+void temb_mlp(const long long* labels, const float* timesteps, int B, int nf, const float* w0, const float* b0, const float* w1,
               const float* b1, float* out, cudaStream_t st);
 // `ld` = row pitch of `out` in elements (0: dense); lets several K segments share one packed row
 void pack_conv_weight(const float* w, int cout, int cin, int k, int cin_pad, int out_dtype, void* out,
@@ -109,6 +110,7 @@ void scale_by_sigma(const float* h_nchw, const long long* labels, const double* 
                     int do_scale, int out_dtype, void* out, cudaStream_t st);
 
 // ----------------------------------------------------------------------------- PC sampler steps
+struct PeerGroup;
 struct PcStepArgs {
   float* x = nullptr;           // [B][C][HW] fp32 state, updated in place
   const void* score = nullptr;  // fp32 or fp64; NCHW or NHWC
@@ -130,7 +132,27 @@ struct PcStepArgs {
   long long sample_offset = 0;
   int B = 0, C = 0, HW = 0;
   double* partial = nullptr; // corrector only: pc_corrector_workspace_doubles(B, C*HW) doubles
-  int conditioned_in_place = 0;  // caller guarantees x (and x_mean_out) already hold x_init where mask == 0
+  int conditioned_in_place = 0;  // caller guarantees x_out (and x_mean_out) already hold x_init where mask == 0
+  float* x_out = nullptr;        // new state (nullptr: x, in place); must differ from x with `symmetrize`
+  // 1: channels 0 and 1 (Cb-Cb distance, omega: symmetric maps) of the new state and of x_mean take their
+  // symmetric part 0.5 (u[i][j] + u[j][i]) wherever both positions are free -- needs a square image (W * W == HW)
+  int symmetrize = 0;
+  int W = 0;
+  // x_mean_out is written only when *iter_ptr == *last_iter_ptr (the sampler returns the x_mean of its LAST
+  // predictor step, sampling.py:289); nullptr: always
+  const long long* last_iter_ptr = nullptr;
+  // Langevin step size over the GLOBAL batch of a sharded run: after the norm phase every rank writes
+  // its (sum_b ||grad_b||, sum_b ||noise_b||) into the mailbox of every peer over NVLink and waits for theirs
+  const PeerGroup* peers = nullptr;
+  const long long* tag_base_ptr = nullptr;  // device: tag of this run's first corrector step
+};
+
+// mailboxes of the ranks of one node, mapped into this process (cudaIpcOpenMemHandle); see pc_step.cu
+struct PeerGroup {
+  static constexpr int kMaxWorld = 16;
+  int world = 1, rank = 0;
+  long long global_batch = 0;
+  unsigned long long* box[kMaxWorld] = {};  // box[r]: mailbox of rank r, [2 parities][world] slots of 4 x u64
 };
 void pc_predictor_step(const PcStepArgs& a, cudaStream_t st);
 void pc_corrector_step(const PcStepArgs& a, cudaStream_t st);

@@ -75,8 +75,14 @@ struct StepParams {
   int cache_rows;           // corrector: rows of normals a block keeps in shared memory
   int prefetch;             // corrector: phase 1 prefetches the operands of phase 2 into L2
   int skip_conditioned;     // fully conditioned quads copy x_initial without loading x / score or drawing noise
-  int in_place;             // conditioned positions of x (and x_mean_out) already hold x_initial: such quads are not touched
+  int in_place;             // conditioned positions of x_out (and x_mean_out) already hold x_initial: such quads are not touched
   double* partial;          // corrector: [rows][2] = sum (h / sigma)^2, sum z^2 of each row
+  float* x_out;             // new state (== x unless the caller asked for an out-of-place step)
+  int symmetrize;           // channels 0, 1: symmetric part wherever (i, j) and (j, i) are both free (needs x_out != x)
+  int W;                    // image width (symmetrize: HW == W * W)
+  const long long* last_iter_ptr;  // x_mean_out is written only in iteration *last_iter_ptr (null: always)
+  PeerGroup peers;          // world > 1: the step size is the mean over the global batch (mailbox exchange)
+  const long long* tag_base_ptr;
 };
 
 __device__ __forceinline__ unsigned long long stream_of(const StepParams& p) {
@@ -142,7 +148,8 @@ __device__ __forceinline__ double inv_sigma_of(const StepParams& p, int b) {
 
 // rounds the 4 updated values once to float, applies the condition mask (bit-exact: masked-out positions take
 // x_initial) and stores x (and x_mean) as one 16-byte vector each
-__device__ __forceinline__ void finish4(const StepParams& p, long long gi0, uchar4 m, const double (&xn)[4], const double (&xm)[4]) {
+__device__ __forceinline__ void finish4(const StepParams& p, float* xmean, long long gi0, uchar4 m, const double (&xn)[4],
+                                        const double (&xm)[4]) {
   float xf[4], mf[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -156,8 +163,16 @@ __device__ __forceinline__ void finish4(const StepParams& p, long long gi0, ucha
     if (!m.z) { xf[2] = xi.z; mf[2] = xi.z; }
     if (!m.w) { xf[3] = xi.w; mf[3] = xi.w; }
   }
-  *reinterpret_cast<float4*>(p.x + gi0) = make_float4(xf[0], xf[1], xf[2], xf[3]);
-  if (p.x_mean_out) *reinterpret_cast<float4*>(p.x_mean_out + gi0) = make_float4(mf[0], mf[1], mf[2], mf[3]);
+  *reinterpret_cast<float4*>(p.x_out + gi0) = make_float4(xf[0], xf[1], xf[2], xf[3]);
+  if (xmean) *reinterpret_cast<float4*>(xmean + gi0) = make_float4(mf[0], mf[1], mf[2], mf[3]);
+}
+
+// x_mean destination of this launch: the sampler returns the x_mean of its last predictor step only
+// (sampling.py:289), so inside a run the store is skipped in every iteration but the last
+__device__ __forceinline__ float* xmean_of(const StepParams& p) {
+  if (!p.x_mean_out) return nullptr;
+  if (p.last_iter_ptr && p.iter_ptr && *p.iter_ptr != *p.last_iter_ptr) return nullptr;
+  return p.x_mean_out;
 }
 
 __device__ __forceinline__ uchar4 load_mask4(const StepParams& p, long long gi0) {
@@ -171,11 +186,73 @@ __device__ __forceinline__ uchar4 load_mask4(const StepParams& p, long long gi0)
 // the start of the run and nothing else writes them (in_place): there such a quad costs its 4 mask bytes.
 __device__ __forceinline__ bool all_conditioned(uchar4 m) { return !(m.x | m.y | m.z | m.w); }
 
-__device__ __forceinline__ void copy_initial4(const StepParams& p, long long gi0) {
+__device__ __forceinline__ void copy_initial4(const StepParams& p, float* xmean, long long gi0) {
   if (p.in_place) return;
   const float4 xi = *reinterpret_cast<const float4*>(p.x_init + gi0);
-  *reinterpret_cast<float4*>(p.x + gi0) = xi;
-  if (p.x_mean_out) *reinterpret_cast<float4*>(p.x_mean_out + gi0) = xi;
+  *reinterpret_cast<float4*>(p.x_out + gi0) = xi;
+  if (xmean) *reinterpret_cast<float4*>(xmean + gi0) = xi;
+}
+
+// ---- symmetrisation (opt-in; the reference has none: downstream takes np.triu, rosetta_min/utils.py:140,157).
+// The half-step is linear in (x, score, z) given the per-sample scalars, so the symmetric part of the updated map
+// is 0.5 (u[i][j] + u[j][i]) with u the float64 update; both positions evaluate the same commutative sum and
+// round it once, hence the stored channels 0 / 1 are EXACTLY symmetric.  A position is symmetrised only when it
+// and its transpose are both free (every condition builder of the reference produces symmetric masks).
+struct Upd { double xm, xn; };
+
+__device__ __forceinline__ double load_score1(const StepParams& p, int b, long long e) {
+  long long idx;
+  if (p.score_nhwc) {
+    const int c = static_cast<int>(e / p.HW);
+    const int pix = static_cast<int>(e - static_cast<long long>(c) * p.HW);
+    idx = (static_cast<long long>(b) * p.HW + pix) * p.C + c;
+  } else {
+    idx = static_cast<long long>(b) * p.E + e;
+  }
+  return p.score_f64 ? static_cast<const double*>(p.score)[idx]
+                     : static_cast<double>(static_cast<const float*>(p.score)[idx]);
+}
+
+// one element of the half-step: x_mean = fma(coef, score, x - f), x = x_mean + nscale * z (z == 0: no noise)
+__device__ __forceinline__ Upd update1(float x, double s, float z, double coef, float nscale, float sa, bool vp_drift,
+                                       bool noise) {
+  double base = static_cast<double>(x);
+  if (vp_drift) base -= static_cast<double>(__fsub_rn(__fmul_rn(sa, x), x));
+  Upd u;
+  u.xm = fma(coef, s, base);
+  u.xn = noise ? u.xm + static_cast<double>(__fmul_rn(nscale, z)) : u.xm;
+  return u;
+}
+
+// the update of the transposed partner (c, j, i) of element e = (c, i, j) of sample b, or false when the pair is
+// not to be symmetrised (channel >= 2, or the partner is conditioned)
+__device__ __forceinline__ bool partner_update(const StepParams& p, int b, long long e, unsigned long long stream,
+                                               double coef, float nscale, float sa, bool vp_drift, bool noise, Upd& u) {
+  const int c = static_cast<int>(e / p.HW);
+  if (c >= 2) return false;
+  const int pix = static_cast<int>(e - static_cast<long long>(c) * p.HW);
+  const int i = pix / p.W, j = pix - i * p.W;
+  const long long et = static_cast<long long>(c) * p.HW + static_cast<long long>(j) * p.W + i;
+  const long long gt = static_cast<long long>(b) * p.E + et;
+  if (p.mask && !p.mask[gt]) return false;
+  float z[4] = {0.f, 0.f, 0.f, 0.f};
+  if (noise) philox_normal4(p.seed, stream, static_cast<unsigned long long>((p.sample_offset + b) * p.qps + (et >> 2)), z);
+  u = update1(p.x[gt], load_score1(p, b, et), z[et & 3], coef, nscale, sa, vp_drift, noise);
+  return true;
+}
+
+__device__ __forceinline__ void symmetrize4(const StepParams& p, int b, long long e0, uchar4 m, unsigned long long stream,
+                                            double coef, float nscale, float sa, bool vp_drift, bool noise,
+                                            double (&xn)[4], double (&xm)[4]) {
+  const unsigned char mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    Upd t;
+    if (mm[i] && partner_update(p, b, e0 + i, stream, coef, nscale, sa, vp_drift, noise, t)) {
+      xm[i] = 0.5 * (xm[i] + t.xm);
+      xn[i] = 0.5 * (xn[i] + t.xn);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -184,6 +261,7 @@ __device__ __forceinline__ void copy_initial4(const StepParams& p, long long gi0
 template <bool FAST>
 __global__ void __launch_bounds__(kThreads, kBlocksPerSM) predictor_kernel(const StepParams p) {
   const unsigned long long stream = stream_of(p);
+  float* const xmean = xmean_of(p);
   int cur_b = -1;
   float G = 0.f, sa = 0.f;
   double coef = 0.0;  // G^2 (fp32, as G[:, None, None, None] ** 2) * drift_scale / sigma
@@ -203,23 +281,25 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) predictor_kernel(const
     if (ql < p.qps) {
       const long long gi0 = it.element(p);
       if (p.skip_conditioned && all_conditioned(m)) {
-        copy_initial4(p, gi0);
+        copy_initial4(p, xmean, gi0);
       } else {
         const float4 xv = *reinterpret_cast<const float4*>(p.x + gi0);
         double s[4], xn[4], xm[4];
         load_score4<FAST>(p, b, static_cast<long long>(ql) * 4, s);
         const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
         float z[4] = {0.f, 0.f, 0.f, 0.f};
-        if (FAST || p.add_noise)
+        const bool noise = FAST || p.add_noise;
+        if (noise)
           philox_normal4(p.seed, stream, static_cast<unsigned long long>((p.sample_offset + b) * p.qps + ql), z);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          double base = static_cast<double>(xs[i]);  // x - f; f == 0 for VE: exactly x + G^2 * score
-          if (!FAST && p.sqrt_alpha) base -= static_cast<double>(__fsub_rn(__fmul_rn(sa, xs[i]), xs[i]));
-          xm[i] = fma(coef, s[i], base);
-          xn[i] = (FAST || p.add_noise) ? xm[i] + static_cast<double>(__fmul_rn(G, z[i])) : xm[i];
+        for (int i = 0; i < 4; ++i) {  // x - f; f == 0 for VE: exactly x + G^2 * score
+          const Upd u = update1(xs[i], s[i], z[i], coef, G, sa, !FAST && p.sqrt_alpha != nullptr, noise);
+          xm[i] = u.xm;
+          xn[i] = u.xn;
         }
-        finish4(p, gi0, m, xn, xm);
+        if (!FAST && p.symmetrize)
+          symmetrize4(p, b, static_cast<long long>(ql) * 4, m, stream, coef, G, sa, p.sqrt_alpha != nullptr, noise, xn, xm);
+        finish4(p, xmean, gi0, m, xn, xm);
       }
     }
     m = m_next;
@@ -281,6 +361,64 @@ __device__ __forceinline__ float sum_sq4(float a, float b, float c, float d) {
   return __fmaf_rn(d, d, __fmaf_rn(c, c, __fmaf_rn(b, b, __fmul_rn(a, a))));
 }
 
+// ---- global-batch step size of a sharded run (opt-in).  Every rank owns a mailbox of
+// [2 parities][world] slots {sum ||grad||, sum ||noise||, tag, -} mapped into all peers of the node
+// (cudaIpcOpenMemHandle, NVLink).  Block 0 of rank r writes its sums into slot r of EVERY mailbox, payload first,
+// then the tag with release semantics at system scope; every block of every rank polls ITS OWN mailbox (local
+// memory) until all `world` tags equal this step's tag, and adds the payloads in rank order -- the same double
+// sums on every rank and in every block.  Tags are unique per corrector step of a run and per run (tag base from
+// the host), consecutive steps alternate slot parity, and a rank publishes step s + 2 only after it has seen every
+// peer's step s + 1 tag, which a peer writes after ALL its blocks have left step s (kernel boundary): a slot is
+// never overwritten before its readers are done with it.  The wait is bounded:
+// a peer that never shows up traps the kernel after ~20 s instead of hanging the device.
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ void exchange_sums(const StepParams& p, double& gsum, double& nsum) {  // one thread per block
+  const PeerGroup& g = p.peers;
+  const long long it = p.iter_ptr ? *p.iter_ptr : 0;
+  // index of this corrector step within the run: iteration * n_steps + inner step (stream_mul = n_steps + 1)
+  const unsigned long long step =
+      static_cast<unsigned long long>(p.stream_mul > 0 ? it * (p.stream_mul - 1) + (p.stream_base - 1) : p.stream_base);
+  const unsigned long long tag = static_cast<unsigned long long>(p.tag_base_ptr ? *p.tag_base_ptr : 0) + step + 1;
+  const int parity = static_cast<int>(step & 1);
+  if (blockIdx.x == 0) {
+    for (int r = 0; r < g.world; ++r) {
+      unsigned long long* slot = g.box[r] + (static_cast<size_t>(parity) * g.world + g.rank) * 4;
+      asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(slot), "d"(gsum) : "memory");
+      asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(slot + 1), "d"(nsum) : "memory");
+      st_release_sys(slot + 2, tag);
+    }
+  }
+  double gs = 0.0, ns = 0.0;
+  const unsigned long long t0 = global_timer_ns();
+  for (int r = 0; r < g.world; ++r) {
+    const unsigned long long* slot = g.box[g.rank] + (static_cast<size_t>(parity) * g.world + r) * 4;
+    while (ld_acquire_sys(slot + 2) != tag) {
+      if (global_timer_ns() - t0 > 20000000000ull) __trap();
+      __nanosleep(200);
+    }
+    double a, c;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(a) : "l"(slot) : "memory");
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(c) : "l"(slot + 1) : "memory");
+    gs += a;
+    ns += c;
+  }
+  gsum = gs;
+  nsum = ns;
+}
+
 // step size (before alpha) from the batch-mean norms; every block recomputes it from the row partials: 8 lanes
 // per sample, fixed order
 __device__ __forceinline__ float batch_step_size(const StepParams& p, double (*red)[kWarps], float* step_sh) {
@@ -310,8 +448,13 @@ __device__ __forceinline__ float batch_step_size(const StepParams& p, double (*r
   double nsum_d = static_cast<double>(nsum);
   block_sum2(gsum, nsum_d, red);
   if (threadIdx.x == 0) {
-    const double grad_norm = gsum / p.B;
-    const float noise_norm = static_cast<float>(nsum_d) / static_cast<float>(p.B);
+    long long nb = p.B;
+    if (p.peers.world > 1) {  // mean over the GLOBAL batch: the reference's torch.norm(...).mean() of an unsharded run
+      exchange_sums(p, gsum, nsum_d);
+      nb = p.peers.global_batch;
+    }
+    const double grad_norm = gsum / static_cast<double>(nb);
+    const float noise_norm = static_cast<float>(nsum_d) / static_cast<float>(nb);
     const float sn = __fmul_rn(p.snr, noise_norm);  // python float * fp32 0-dim tensor -> fp32
     const double r = static_cast<double>(sn) / grad_norm;
     *step_sh = static_cast<float>(r * r * 2.0);     // * alpha (fp32 [B]) demotes the 0-dim double
@@ -364,6 +507,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) corrector_kernel(const
   const float step0 = batch_step_size(p, red, &step_sh);
 
   // ---- phase 2: apply
+  float* const xmean = xmean_of(p);
   int cur_b = -1;
   float nscale = 0.f;
   double coef = 0.0;  // step / sigma
@@ -383,7 +527,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) corrector_kernel(const
     if (ql < p.qps) {
       const long long gi0 = it.element(p);
       if (p.skip_conditioned && all_conditioned(m)) {
-        copy_initial4(p, gi0);
+        copy_initial4(p, xmean, gi0);
       } else {
         const float4 xv = *reinterpret_cast<const float4*>(p.x + gi0);
         double s[4], xn[4], xm[4];
@@ -398,10 +542,13 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) corrector_kernel(const
         const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          xm[i] = fma(coef, s[i], static_cast<double>(xs[i]));
-          xn[i] = xm[i] + static_cast<double>(__fmul_rn(nscale, z[i]));
+          const Upd u = update1(xs[i], s[i], z[i], coef, nscale, 0.f, false, true);
+          xm[i] = u.xm;
+          xn[i] = u.xn;
         }
-        finish4(p, gi0, m, xn, xm);
+        if (!FAST && p.symmetrize)
+          symmetrize4(p, b, static_cast<long long>(ql) * 4, m, stream, coef, nscale, 0.f, false, true, xn, xm);
+        finish4(p, xmean, gi0, m, xn, xm);
       }
     }
     m = m_next;
@@ -474,8 +621,24 @@ StepParams to_params(const PcStepArgs& a) {
   if (a.mask) T2P_CHECK(a.x_init != nullptr, "x_init required with mask");
   p.partial = a.partial;
   p.in_place = (a.mask != nullptr && a.conditioned_in_place) ? 1 : 0;
-  static const bool no_skip = getenv("T2P_STEP_NOSKIP") != nullptr;  // A/B knob
+  static const bool no_skip = env_knob_set("T2P_STEP_NOSKIP");  // A/B knob (knob builds only)
   p.skip_conditioned = (a.mask != nullptr && !no_skip) ? 1 : 0;
+  p.x_out = a.x_out ? a.x_out : a.x;
+  T2P_CHECK((reinterpret_cast<uintptr_t>(p.x_out) & 15) == 0, "x_out must be 16-byte aligned");
+  p.symmetrize = a.symmetrize ? 1 : 0;
+  p.W = a.W;
+  if (p.symmetrize) {
+    T2P_CHECK(p.x_out != a.x, "symmetrize needs an out-of-place step (x_out != x): the update reads the transposed state");
+    T2P_CHECK(a.W > 0 && static_cast<long long>(a.W) * a.W == a.HW, "symmetrize needs a square map (W * W == HW)");
+  }
+  p.last_iter_ptr = a.last_iter_ptr;
+  if (a.peers && a.peers->world > 1) {
+    p.peers = *a.peers;
+    p.tag_base_ptr = a.tag_base_ptr;
+    T2P_CHECK(p.peers.world <= PeerGroup::kMaxWorld && p.peers.global_batch > 0, "bad peer group");
+  } else {
+    p.peers.world = 1;
+  }
   return p;
 }
 
@@ -504,7 +667,7 @@ constexpr size_t kRowBytes = sizeof(float4) * kThreads;
 void pc_predictor_step(const PcStepArgs& a, cudaStream_t st) {
   StepParams p = to_params(a);
   T2P_CHECK(a.G != nullptr, "predictor needs G");
-  const bool fast = !p.score_nhwc && !p.score_f64 && p.sqrt_alpha == nullptr && p.add_noise;
+  const bool fast = !p.score_nhwc && !p.score_f64 && p.sqrt_alpha == nullptr && p.add_noise && !p.symmetrize;
   static int wave[2] = {0, 0};
   if (!wave[fast])
     wave[fast] = resident_blocks(fast ? reinterpret_cast<const void*>(predictor_kernel<true>)
@@ -521,10 +684,10 @@ long long pc_corrector_workspace_doubles(int B, long long E) { return 2LL * B * 
 void pc_corrector_step(const PcStepArgs& a, cudaStream_t st) {
   StepParams p = to_params(a);
   T2P_CHECK(a.partial != nullptr, "corrector needs the partial-sum workspace");
-  static const bool no_cache = getenv("T2P_STEP_NOCACHE") != nullptr;
-  static const bool no_prefetch = getenv("T2P_STEP_NOPREFETCH") != nullptr;
+  static const bool no_cache = env_knob_set("T2P_STEP_NOCACHE");
+  static const bool no_prefetch = env_knob_set("T2P_STEP_NOPREFETCH");
   p.prefetch = no_prefetch ? 0 : 1;
-  const bool fast = !p.score_nhwc && !p.score_f64;
+  const bool fast = !p.score_nhwc && !p.score_f64 && !p.symmetrize;
   const void* fn = fast ? reinterpret_cast<const void*>(corrector_kernel<true>)
                         : reinterpret_cast<const void*>(corrector_kernel<false>);
   static bool attr_set[2] = {false, false};

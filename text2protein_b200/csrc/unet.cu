@@ -22,6 +22,7 @@ void Workspace::begin(bool dry) {
 }
 void Workspace::reserve(size_t bytes) {
   if (bytes <= cap_) return;
+  ++epoch_;  // the arena moves: every address handed out so far (and captured into a CUDA graph) is dead
   if (base_) T2P_CUDA(cudaFree(base_));
   base_ = nullptr;
   cap_ = 0;
@@ -426,17 +427,17 @@ void UNet::free_act(Act& a) {
   a = Act{};
 }
 
-// Timing experiments only (they break the numerics): T2P_DEBUG_SKIP is a mask of kernel classes that are NOT
+// Timing experiments only, compiled in with -DT2P_TIMING_KNOBS (see env_knob(), common.h; they break the numerics): T2P_DEBUG_SKIP is a mask of kernel classes that are NOT
 // launched -- 1 gn_finalize, 2 gn_apply, 4 attention, 8 LayerNorm + GEGLU, 16 final layer, 64 gn_stats (T2P_DEBUG_DUP also: 128 halo-shaped 3x3 GEMMs, 256 other 3x3 GEMMs, 512 1x1 / linear GEMMs) -- so that the
 // share of each class in the captured forward can be read off two bench runs (see also T2P_DEBUG_SKIP_ST).
 static int debug_skip() {
-  static const int m = [] { const char* e = std::getenv("T2P_DEBUG_SKIP"); return e ? std::atoi(e) : 0; }();
+  static const int m = env_knob("T2P_DEBUG_SKIP", 0);
   return m;
 }
 // T2P_DEBUG_DUP: same classes, launched TWICE (results unchanged) -- the honest way to time the classes whose
 // removal would turn the activations into NaNs (and NaN operands make every GEMM draw less power and run faster).
 static int debug_dup() {
-  static const int m = [] { const char* e = std::getenv("T2P_DEBUG_DUP"); return e ? std::atoi(e) : 0; }();
+  static const int m = env_knob("T2P_DEBUG_DUP", 0);
   return m;
 }
 
@@ -731,7 +732,7 @@ Act UNet::run_block(BlockM& blk, const Act& a0, const Act* a1, const std::string
     } else {
       // timing experiment only (breaks the numerics): T2P_DEBUG_SKIP_ST=1 drops the SpatialTransformer blocks so
       // that their share of the captured forward can be read off a bench run
-      static const bool skip_st = std::getenv("T2P_DEBUG_SKIP_ST") != nullptr;
+      static const bool skip_st = env_knob_set("T2P_DEBUG_SKIP_ST");
       if (skip_st) continue;
       next = run_st(*m.st, cur);
     }
@@ -819,7 +820,7 @@ void UNet::forward_impl(const float* x, const long long* labels, float* h_out, i
   const int N = cfg_.max_res_num, C = cfg_.num_channels, nf = cfg_.nf;
   ln_->seq = 0;
   {
-    static const bool on = [] { const char* e = getenv("T2P_SERPENTINE"); return !e || atoi(e) != 0; }();
+    static const bool on = env_knob("T2P_SERPENTINE", 1) != 0;
     serpentine_ = on;
   }
   // Time-embedding path (pre_blocks MLP + every ResBlock's Dense_0): a function of the labels only.  It lives in a
@@ -827,6 +828,7 @@ void UNet::forward_impl(const float* x, const long long* labels, float* h_out, i
   // predictor of one PC iteration) can ask for it to be reused.
   const size_t temb_bytes = sizeof(float) * static_cast<size_t>(B) * temb_total_;
   if (!dry_ && temb_bytes > temb_persist_bytes_) {
+    ++resource_epoch_;
     if (temb_persist_) T2P_CUDA(cudaFree(temb_persist_));
     temb_persist_ = nullptr;
     temb_persist_bytes_ = 0;
@@ -844,7 +846,7 @@ void UNet::forward_impl(const float* x, const long long* labels, float* h_out, i
     if (!reuse) launches_ += 2 + (Bt < B ? 1 : 0);
     if (!dry_ && !reuse) {
       temb_valid_B_ = B;
-      temb_mlp(labels, Bt, nf, static_cast<const float*>(pre0_w_->data), static_cast<const float*>(pre0_b_->data),
+      temb_mlp(labels, timesteps_, Bt, nf, static_cast<const float*>(pre0_w_->data), static_cast<const float*>(pre0_b_->data),
                static_cast<const float*>(pre1_w_->data), static_cast<const float*>(pre1_b_->data), temb, ln_->st);
       ConvGemmArgs g;
       g.a0 = temb; g.c0 = 4 * nf; g.B = 1; g.H = 1; g.W = Bt; g.ksize = 1;
@@ -906,7 +908,7 @@ void UNet::forward_impl(const float* x, const long long* labels, float* h_out, i
     h_owned = true;
   }
   T2P_CHECK(hs.empty(), "skip stack not drained");
-  static const bool fuse_out = [] { const char* e = getenv("T2P_FUSED_OUT"); return !e || atoi(e) != 0; }();
+  static const bool fuse_out = env_knob("T2P_FUSED_OUT", 1) != 0;
   if (fuse_out && cfg_.compute_dtype == kBF16 && final_conv_fused_supported(h.C, C, N, N)) {
     // out = Conv3x3(SiLU(GroupNorm(h))) in one pass over h (final_conv.cu): no normalised copy of the largest tensor
     float* affine = nullptr;
@@ -931,8 +933,10 @@ void UNet::forward_impl(const float* x, const long long* labels, float* h_out, i
   ln_->temb_all = nullptr;
 }
 
-void UNet::forward_raw(const float* x, const long long* labels, float* h_out, int B, cudaStream_t st) {
+void UNet::forward_raw(const float* x, const long long* labels, float* h_out, int B, cudaStream_t st,
+                       const float* timesteps) {
   T2P_CHECK(finalized_, "finalize() before forward()");
+  timesteps_ = timesteps;
   // (Measured and retired: two half-batches on two streams, so that the GEMMs of one half overlap the HBM-bound
   // normalisation / attention kernels of the other -- 26.99 vs 26.91 ms per PC iteration at cfg2, no gain at twice
   // the activation arena: both kernel kinds are bound by the same L2 / HBM path.)
@@ -951,7 +955,8 @@ void UNet::forward_raw(const float* x, const long long* labels, float* h_out, in
   forward_impl(x, labels, h_out, B);
 }
 
-void UNet::forward(const float* x, const long long* labels, void* out, int out_dtype, int B, cudaStream_t st) {
+void UNet::forward(const float* x, const long long* labels, void* out, int out_dtype, int B, cudaStream_t st,
+                   const float* timesteps) {
   const int N = cfg_.max_res_num, C = cfg_.num_channels;
   const size_t need = sizeof(float) * static_cast<size_t>(B) * N * N * C;
   if (need > h_scratch_bytes_) {
@@ -959,7 +964,7 @@ void UNet::forward(const float* x, const long long* labels, void* out, int out_d
     T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&h_scratch_), need));
     h_scratch_bytes_ = need;
   }
-  forward_raw(x, labels, h_scratch_, B, st);
+  forward_raw(x, labels, h_scratch_, B, st, timesteps);
   scale_by_sigma(h_scratch_, labels, sigmas(), B, N * N, C, cfg_.scale_by_sigma, out_dtype, out, st);
   if (debug_) {  // the final conv output is fp32 NCHW regardless of the compute dtype: the tap is a plain copy
     const int64_t n = static_cast<int64_t>(B) * C * N * N;

@@ -50,12 +50,14 @@ class Workspace {
   size_t peak() const { return peak_; }
   void reserve(size_t bytes);
   size_t capacity() const { return cap_; }
+  long long epoch() const { return epoch_; }  // bumped whenever the arena is re-allocated
 
  private:
   struct Block { size_t off, size; bool used; };
   std::vector<Block> blocks_;
   char* base_ = nullptr;
   size_t cap_ = 0, top_ = 0, peak_ = 0;
+  long long epoch_ = 0;
   bool dry_ = false;
 };
 
@@ -147,7 +149,9 @@ class UNet {
                           cudaStream_t st);
   // x: fp32 NCHW [B][C][N][N]; labels: int64 [B]; h_out: fp32 NCHW [B][C][N][N] un-scaled final conv
   // (what the fused PC-step kernels consume).  Returns through `h_out` only.
-  void forward_raw(const float* x, const long long* labels, float* h_out, int B, cudaStream_t st);
+  // timesteps: optional fp32 [B] time conditioning embedded instead of float(labels) (VP models, ncsnpp.py:221-223)
+  void forward_raw(const float* x, const long long* labels, float* h_out, int B, cudaStream_t st,
+                   const float* timesteps = nullptr);
   // true: the next forward passes may reuse the time-embedding biases of the previous one (same labels, same B);
   // the PC loop sets it for the predictor evaluation that follows a corrector evaluation at the same noise level
   void set_reuse_temb(bool on) { reuse_temb_ = on; }
@@ -155,7 +159,8 @@ class UNet {
   // and its rows replicated -- bit-identical to evaluating it per sample
   void set_uniform_labels(bool on) { uniform_labels_ = on; }
   // Reference-shaped output: NCHW, divided by sigmas[labels] in double (ncsnpp.py:259-261), fp64 or fp32.
-  void forward(const float* x, const long long* labels, void* out, int out_dtype, int B, cudaStream_t st);
+  void forward(const float* x, const long long* labels, void* out, int out_dtype, int B, cudaStream_t st,
+               const float* timesteps = nullptr);
   const double* sigmas() const { return static_cast<const double*>(sigmas_->data); }
   void set_debug(bool on) { debug_ = on; }
   // copies a recorded block output (fp32 NCHW) to dst; returns its shape
@@ -164,6 +169,9 @@ class UNet {
   void set_profile(bool on);
   int profile_records(GemmRecord* out, int cap);
   long long generation() const { return generation_; }  // bumped by finalize() / set_context()
+  // bumped whenever a device buffer a captured forward may point into (activation arena, time-embedding buffer)
+  // is re-allocated: a CUDA graph captured under another epoch must not be replayed
+  long long resource_epoch() const { return resource_epoch_ + lane_.ws.epoch(); }
   size_t workspace_bytes() const { return lane_.ws.capacity(); }
   long long launches_per_forward() const { return launches_; }
 
@@ -246,6 +254,8 @@ class UNet {
   bool uniform_labels_ = false;
   float* h_scratch_ = nullptr;
   size_t h_scratch_bytes_ = 0;
+  long long resource_epoch_ = 0;
+  const float* timesteps_ = nullptr;  // time conditioning of the forward being recorded (null: float(labels))
 };
 
 }  // namespace t2p

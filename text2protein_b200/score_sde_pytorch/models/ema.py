@@ -1,6 +1,13 @@
+# Modified from https://raw.githubusercontent.com/fadel/pytorch_ema/master/torch_ema/ema.py (MIT), as vendored by
+# the reference (szhan227/text2protein, score_sde_pytorch/models/ema.py); partially based on
+# https://github.com/tensorflow/tensorflow/blob/r1.13/tensorflow/python/training/moving_averages.py
 """Exponential moving average of parameters -- mirror of the reference ``score_sde_pytorch/models/ema.py``.
 Sampling copies the EMA shadow list into the model by POSITION (reference :51-61), which is why
-``UNetModel.parameters()`` keeps the reference's order."""
+``UNetModel.parameters()`` keeps the reference's order.
+
+``copy_to`` / ``restore`` write with ``Tensor.copy_`` under ``no_grad`` (the reference writes through ``.data``,
+which does NOT advance the tensor version counter): the native ``UNetModel`` notices a changed parameter through
+that counter and re-packs its kernel-layout weights before the next forward / sampling run."""
 import torch
 
 
@@ -25,15 +32,17 @@ class ExponentialMovingAverage:
 
     def copy_to(self, parameters):
         live = [p for p in parameters if p.requires_grad]
-        for shadow, p in zip(self.shadow_params, live):
-            p.data.copy_(shadow.data)
+        with torch.no_grad():
+            for shadow, p in zip(self.shadow_params, live):
+                p.copy_(shadow)
 
     def store(self, parameters):
         self.collected_params = [p.clone() for p in parameters]
 
     def restore(self, parameters):
-        for saved, p in zip(self.collected_params, parameters):
-            p.data.copy_(saved.data)
+        with torch.no_grad():
+            for saved, p in zip(self.collected_params, parameters):
+                p.copy_(saved)
 
     def state_dict(self):
         return dict(decay=self.decay, num_updates=self.num_updates, shadow_params=self.shadow_params)

@@ -98,6 +98,7 @@ class UNetModel(nn.Module):
         self._create_engine()
         self._build_tree()
         self._synced_version = None
+        self._synced_checksum = None
         self._ctx_key = None
         self.reset_parameters()
 
@@ -171,12 +172,24 @@ class UNetModel(nn.Module):
         ts = list(itertools.chain(self.parameters(), self.buffers()))
         return tuple(t._version for t in ts) + tuple(t.data_ptr() for t in ts)
 
-    def sync_weights(self, force=False):
+    def _weights_checksum(self):
+        """One multi-tensor reduction over all parameters (a few hundred microseconds): catches writers that bypass
+        the version counter (``p.data.copy_(...)``, the reference's own EMA idiom)."""
+        ps = [p.detach() for p in self.parameters()]
+        norms = torch._foreach_norm(ps)
+        return float(torch.stack(norms).double().sum().item())
+
+    def sync_weights(self, force=False, check_data=False):
         """Pushes the current parameters (e.g. after load_state_dict / ema.copy_to) to the engine and repacks
-        them into kernel layout.  Called automatically by forward when a parameter changed."""
+        them into kernel layout.  Called by ``forward`` and by the sampler; a change is detected through the
+        tensors' version counters and storage pointers, which every in-place torch op on the parameter advances
+        (``load_state_dict``, optimizers, this package's ``ExponentialMovingAverage``).  A write through ``p.data``
+        does not: the sampler therefore also compares a checksum of the values once per run (``check_data``);
+        around bare ``forward`` calls use ``sync_weights(force=True)`` after such a write."""
         ver = self._weights_version()
         if not force and ver == self._synced_version:
-            return
+            if not check_data or self._weights_checksum() == self._synced_checksum:
+                return
         L = _lib.lib()
         st = _lib.current_stream()
         keep = []
@@ -193,6 +206,7 @@ class UNetModel(nn.Module):
         _lib.check(L.t2p_unet_finalize(self._handle, st))
         torch.cuda.current_stream().synchronize()
         self._synced_version = ver
+        self._synced_checksum = self._weights_checksum()
         self._ctx_key = None
 
     def set_context(self, text_emb):
@@ -233,21 +247,25 @@ class UNetModel(nn.Module):
 
     @torch.no_grad()
     def forward(self, x, time_cond, text_emb=None):
-        """x [B,C,N,N] (any float dtype, cast to fp32 like ``x.float()``, reference :229), time_cond [B] integer
-        noise labels, text_emb [B,L,context_dim].  Returns float64 [B,C,N,N] = h / sigmas[time_cond]
-        (the reference's promoted dtype, :259-261)."""
+        """x [B,C,N,N] (any float dtype, cast to fp32 like ``x.float()``, reference :229), time_cond [B] noise
+        labels (integer for VE models; a float tensor -- the VP branch of get_score_fn passes t (N - 1) -- is embedded
+        as a float and truncated only for the sigma lookup, reference :221-223), text_emb [B,L,context_dim].
+        Returns float64 [B,C,N,N] = h / sigmas[time_cond.long()] (the reference's promoted dtype, :259-261)."""
         if not x.is_cuda:
             raise _lib.NativeError("UNetModel.forward needs CUDA tensors; there is no CPU path")
-        self.sync_weights()
-        self.set_context(text_emb)
-        xf = x.detach().to(torch.float32).contiguous()
-        labels = time_cond.detach().long().contiguous()
-        B = xf.shape[0]
-        if text_emb.shape[0] != B:
-            raise ValueError("context batch does not match x")
-        out = torch.empty(xf.shape, dtype=torch.float64, device=xf.device)
-        _lib.check(_lib.lib().t2p_unet_forward(self._handle, _lib.ptr(xf), _lib.ptr(labels), _lib.ptr(out),
-                                               _lib.F64, B, _lib.current_stream()))
+        with _lib.device_of(x):
+            self.sync_weights()
+            self.set_context(text_emb)
+            xf = x.detach().to(torch.float32).contiguous()
+            tc = time_cond.detach().to(xf.device)
+            labels = tc.long().contiguous()
+            timesteps = tc.to(torch.float32).contiguous() if tc.is_floating_point() else None
+            B = xf.shape[0]
+            if text_emb.shape[0] != B:
+                raise ValueError("context batch does not match x")
+            out = torch.empty(xf.shape, dtype=torch.float64, device=xf.device)
+            _lib.check(_lib.lib().t2p_unet_forward_t(self._handle, _lib.ptr(xf), _lib.ptr(labels), _lib.ptr(timesteps),
+                                                     _lib.ptr(out), _lib.F64, B, _lib.current_stream()))
         return out
 
     # ------------------------------------------------------------------ debugging aids

@@ -1,3 +1,18 @@
+# API surface and closed-form expressions follow score_sde_pytorch as vendored by the reference
+# (szhan227/text2protein, score_sde_pytorch/sampling.py):
+# Copyright 2020 The Google Research Authors.
+#
+# Licensed under the Apache License, Version 2.0 (the "License");
+# you may not use this file except in compliance with the License.
+# You may obtain a copy of the License at
+#
+#     http://www.apache.org/licenses/LICENSE-2.0
+#
+# Unless required by applicable law or agreed to in writing, software
+# distributed under the License is distributed on an "AS IS" BASIS,
+# WITHOUT WARRANTIES OR CONDITIONS OF ANY KIND, either express or implied.
+# See the License for the specific language governing permissions and
+# limitations under the License.
 """Predictor-corrector sampling -- drop-in for the reference ``score_sde_pytorch/sampling.py``.
 
 Same registries, classes and signatures (``get_sampling_fn``, ``get_pc_sampler``, ``ReverseDiffusionPredictor``,
@@ -60,7 +75,12 @@ def get_corrector(name):
 
 
 def get_sampling_fn(config, sde, shape, eps):
-    """Creates the sampling function from the config (reference :78-104)."""
+    """Creates the sampling function from the config (reference :78-104).  ``config.sampling.symmetrize``
+    (optional, default False = the reference's behaviour) turns on the symmetrisation of the distance / omega
+    maps inside the step kernels."""
+    extra = {}
+    if getattr(config.sampling, "symmetrize", False):
+        extra["symmetrize"] = True
     return get_pc_sampler(sde=sde,
                           shape=shape,
                           predictor=get_predictor(config.sampling.predictor.lower()),
@@ -70,7 +90,8 @@ def get_sampling_fn(config, sde, shape, eps):
                           probability_flow=config.sampling.probability_flow,
                           denoise=config.sampling.noise_removal,
                           eps=eps,
-                          device=config.device)
+                          device=config.device,
+                          **extra)
 
 
 # ---------------------------------------------------------------------------------------------- noise streams
@@ -78,6 +99,15 @@ class _Noise:
     """Seed / stream bookkeeping for update_fn calls made outside ``pc_sampler``."""
     seed = None
     counter = itertools.count(1 << 40)  # far from the stream ids a sampling run uses
+
+
+class _Run:
+    """State of the generic-path sampling run in progress: the stock update rules hand the condition mask (and the
+    symmetrisation switch) to the step kernel, whose result is then already conditioned -- the loop's own
+    ``torch.where`` (reference :283-287) becomes the idempotent re-application it is in the reference."""
+    mask_u8 = None
+    x_init = None
+    symmetrize = False
 
 
 def fresh_seed():
@@ -108,15 +138,18 @@ def philox_normal(shape, seed, stream, device, scale=1.0, sample_offset=0):
 
 # ---------------------------------------------------------------------------------------------- step kernels
 def _step_args(x, score, seed, stream, sample_offset=0):
+    """Arguments of one fused half-step.  Returns (args, new-state tensor, tensors to keep alive)."""
     if not x.is_cuda:
         raise _lib.NativeError("the fused PC-step kernels need CUDA tensors; there is no CPU path")
-    xs = x.detach().to(torch.float32).contiguous().clone()
+    xs = x.detach().to(torch.float32).contiguous()
     sc = score.detach()
     if sc.dtype not in (torch.float32, torch.float64):
         sc = sc.float()
     sc = sc.contiguous()
+    out = torch.empty_like(xs)  # the caller's x is never mutated
     a = _lib.StepArgs()
     a.x = xs.data_ptr()
+    a.x_out = out.data_ptr()
     a.score = sc.data_ptr()
     a.score_dtype = _lib.torch_dtype_code(sc.dtype)
     a.score_nhwc = 0
@@ -124,7 +157,15 @@ def _step_args(x, score, seed, stream, sample_offset=0):
     a.stream_id = stream
     a.sample_offset = sample_offset
     a.B, a.C, a.HW = xs.shape[0], xs.shape[1], xs.shape[2] * xs.shape[3]
-    return a, xs, sc
+    a.W = xs.shape[3]
+    keep = [xs, sc]
+    if _Run.mask_u8 is not None and _Run.mask_u8.shape == xs.shape:
+        a.mask, a.x_init = _Run.mask_u8.data_ptr(), _Run.x_init.data_ptr()
+    if _Run.symmetrize:
+        if xs.shape[2] != xs.shape[3]:
+            raise ValueError("symmetrize needs square maps")
+        a.symmetrize = 1
+    return a, out, keep
 
 
 class Predictor(abc.ABC):
@@ -169,22 +210,23 @@ class ReverseDiffusionPredictor(Predictor):
     def update_fn(self, x, t, context=None):
         score = self.score_fn(x, t, context)
         seed, stream = _next_stream()
-        a, xs, sc = _step_args(x, score, seed, stream)
-        if isinstance(self.sde, sde_lib.VESDE):
-            G = self.sde.discretize_G(t).to(torch.float32).contiguous()
-            keep = (G,)
-        else:
-            ts = self.sde.timestep(t)
-            G = torch.sqrt(self.sde.discrete_betas.to(x.device)[ts]).contiguous()
-            sa = torch.sqrt(self.sde.alphas.to(x.device)[ts]).contiguous()
-            a.sqrt_alpha = sa.data_ptr()
-            keep = (G, sa)
-        a.G = G.data_ptr()
-        a.probability_flow = 1 if self.probability_flow else 0
-        x_mean = torch.empty_like(xs)
-        a.x_mean_out = x_mean.data_ptr()
-        _lib.check(_lib.lib().t2p_predictor_step(C.byref(a), _lib.current_stream()))
-        del keep, sc
+        with _lib.device_of(x):
+            a, xs, keep = _step_args(x, score, seed, stream)
+            if isinstance(self.sde, sde_lib.VESDE):
+                G = self.sde.discretize_G(t).to(device=x.device, dtype=torch.float32).contiguous()
+            else:
+                ts = self.sde.timestep(t)
+                G = torch.sqrt(self.sde.discrete_betas.to(x.device)[ts]).contiguous()
+                sa = torch.sqrt(self.sde.alphas.to(x.device)[ts]).contiguous()
+                a.sqrt_alpha = sa.data_ptr()
+                keep.append(sa)
+            keep.append(G)
+            a.G = G.data_ptr()
+            a.probability_flow = 1 if self.probability_flow else 0
+            x_mean = torch.empty_like(xs)
+            a.x_mean_out = x_mean.data_ptr()
+            _lib.check(_lib.lib().t2p_predictor_step(C.byref(a), _lib.current_stream()))
+        del keep
         # the reference returns float64 here (the score is float64) and rounds with .float() right
         # after; the kernel rounds once at the end of the same float64 arithmetic.
         return xs.double(), x_mean.double()
@@ -209,16 +251,18 @@ class LangevinCorrector(Corrector):
         for _ in range(self.n_steps):
             grad = self.score_fn(x, t, context)
             seed, stream = _next_stream()
-            a, xs, sc = _step_args(x, grad, seed, stream)
-            a.snr = float(self.snr)
-            if alpha is not None:
-                a.alpha = alpha.data_ptr()
-            ws = torch.empty(max(1, _lib.lib().t2p_corrector_workspace_bytes(a.B, a.C * a.HW) // 8),
-                             dtype=torch.float64, device=xs.device)
-            a.workspace = ws.data_ptr()
-            xm = torch.empty_like(xs)
-            a.x_mean_out = xm.data_ptr()
-            _lib.check(_lib.lib().t2p_corrector_step(C.byref(a), _lib.current_stream()))
+            with _lib.device_of(x):
+                a, xs, keep = _step_args(x, grad, seed, stream)
+                a.snr = float(self.snr)
+                if alpha is not None:
+                    a.alpha = alpha.data_ptr()
+                ws = torch.empty(max(1, _lib.lib().t2p_corrector_workspace_bytes(a.B, a.C * a.HW) // 8),
+                                 dtype=torch.float64, device=xs.device)
+                a.workspace = ws.data_ptr()
+                xm = torch.empty_like(xs)
+                a.x_mean_out = xm.data_ptr()
+                _lib.check(_lib.lib().t2p_corrector_step(C.byref(a), _lib.current_stream()))
+            del keep
             x, x_mean = xs.double(), xm.double()
         return x, x_mean
 
@@ -270,11 +314,24 @@ def ve_tables(sde, eps, num_iters):
 
 
 def get_pc_sampler(sde, shape, predictor, corrector, snr, n_steps=1, probability_flow=False, denoise=True,
-                   eps=1e-3, device='cuda', *, seed=None, num_iters=None, sample_offset=0, use_graph=True):
-    """Creates a PC sampler (reference :213-291).  Keyword-only extras: ``seed`` (Philox seed; default: drawn
-    from torch's generator per call), ``num_iters`` (run only the first K of sde.N iterations -- benchmarks and
-    parity tests), ``sample_offset`` (global index of this shard's first sample: noise is keyed by GLOBAL
-    sample index, so results do not depend on how the batch is sharded over GPUs), ``use_graph``."""
+                   eps=1e-3, device='cuda', *, seed=None, num_iters=None, sample_offset=0, use_graph=True,
+                   symmetrize=False, sync_step_size=None):
+    """Creates a PC sampler (reference :213-291).  Keyword-only extras, all defaulting to the reference's behaviour:
+
+    ``seed``            Philox seed (default: drawn from torch's generator per call).
+    ``num_iters``       run only the first K of sde.N iterations (benchmarks and parity tests).
+    ``sample_offset``   global index of this shard's first sample.  The NOISE is keyed by global sample index, so
+                        every sample sees the same normals however the batch is sharded over GPUs; the samples
+                        themselves still depend on the sharding through the Langevin step size, which is a mean
+                        over the batch a call sees (reference :193-195) -- unless ``sync_step_size`` is given.
+    ``sync_step_size``  a ``text2protein_b200.distributed.StepSizeSync`` (one per rank, same node): the step size
+                        becomes the mean over the GLOBAL batch, exchanged inside the corrector kernel through
+                        NVLink peer memory, and an n-way sharded run equals one reference run of the whole batch.
+                        Native fast path only.
+    ``symmetrize``      the step kernels replace channels 0 and 1 (Cb-Cb distance, omega) of the state by their
+                        symmetric part after every half-step wherever (i, j) and (j, i) are both free.  False =
+                        bit-identical to the reference, which has no such option.
+    ``use_graph``       replay the iteration as a CUDA graph (fast path)."""
     predictor_update_fn = functools.partial(shared_predictor_update_fn, sde=sde, predictor=predictor,
                                             probability_flow=probability_flow)
     corrector_update_fn = functools.partial(shared_corrector_update_fn, sde=sde, corrector=corrector, snr=snr,
@@ -283,9 +340,13 @@ def get_pc_sampler(sde, shape, predictor, corrector, snr, n_steps=1, probability
 
     def pc_sampler(model, condition=None, context=None):
         """Returns (samples [B,C,N,N] float32 on ``device``, number of function evaluations)."""
-        with torch.no_grad():
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise _lib.NativeError("pc_sampler needs a CUDA device; there is no CPU path")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        with torch.no_grad(), torch.cuda.device(dev):
             run_seed = fresh_seed() if seed is None else int(seed)
-            dev = torch.device(device)
             # prior: N(0, sigma_max^2) for VE / N(0, 1) for VP (sde_lib.py:136-137,229-230), Philox stream 0
             prior_scale = float(sde.sigma_max) if isinstance(sde, sde_lib.VESDE) else 1.0
             x = philox_normal(tuple(shape), run_seed, 0, dev, scale=prior_scale, sample_offset=sample_offset)
@@ -295,9 +356,13 @@ def get_pc_sampler(sde, shape, predictor, corrector, snr, n_steps=1, probability
             net = _unwrap(model)
             fast = (isinstance(net, UNetModel) and type(sde) is sde_lib.VESDE
                     and predictor is ReverseDiffusionPredictor and corrector is LangevinCorrector)
+            if symmetrize and shape[2] != shape[3]:
+                raise ValueError("symmetrize needs square maps")
+            if sync_step_size is not None and not fast:
+                raise NotImplementedError("sync_step_size is implemented for the native fast path only")
             if fast:
                 labels, G = ve_tables(sde, eps, K)
-                net.sync_weights()
+                net.sync_weights(check_data=True)
                 net.set_context(context)
                 x = x.contiguous()
                 x_mean = torch.empty_like(x)
@@ -313,6 +378,9 @@ def get_pc_sampler(sde, shape, predictor, corrector, snr, n_steps=1, probability
                 a.sample_offset = sample_offset
                 a.B = x.shape[0]
                 a.use_graph = 1 if use_graph else 0
+                a.symmetrize = 1 if symmetrize else 0
+                if sync_step_size is not None:
+                    a.peers = sync_step_size.handle
                 _lib.check(_lib.lib().t2p_pc_run(net.native_handle, C.byref(a), _lib.current_stream()))
                 return (x_mean if denoise else x), K * (n_steps + 1)
 
@@ -320,13 +388,19 @@ def get_pc_sampler(sde, shape, predictor, corrector, snr, n_steps=1, probability
             set_noise_seed(run_seed)
             timesteps = torch.linspace(sde.T, eps, sde.N, device=dev)
             x_mean = x
-            for i in range(K):
-                t = timesteps[i]
-                vec_t = torch.ones(shape[0], device=t.device) * t
-                x, x_mean = corrector_update_fn(x, vec_t, model=model, context=context)
-                x = torch.where(conditional_mask, x, x_initial).float()
-                x, x_mean = predictor_update_fn(x, vec_t, model=model, context=context)
-                x = torch.where(conditional_mask, x, x_initial).float()
+            _Run.mask_u8 = conditional_mask.contiguous().view(torch.uint8)
+            _Run.x_init = x_initial.float().contiguous()
+            _Run.symmetrize = bool(symmetrize)
+            try:
+                for i in range(K):
+                    t = timesteps[i]
+                    vec_t = torch.ones(shape[0], device=t.device) * t
+                    x, x_mean = corrector_update_fn(x, vec_t, model=model, context=context)
+                    x = torch.where(conditional_mask, x, x_initial).float()
+                    x, x_mean = predictor_update_fn(x, vec_t, model=model, context=context)
+                    x = torch.where(conditional_mask, x, x_initial).float()
+            finally:
+                _Run.mask_u8, _Run.x_init, _Run.symmetrize = None, None, False
             x_mean = torch.where(conditional_mask, x_mean, x_initial).float()
             return (x_mean if denoise else x), K * (n_steps + 1)
 

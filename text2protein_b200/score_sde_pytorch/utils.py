@@ -1,3 +1,18 @@
+# API surface and closed-form expressions follow score_sde_pytorch as vendored by the reference
+# (szhan227/text2protein, score_sde_pytorch/utils.py):
+# Copyright 2020 The Google Research Authors.
+#
+# Licensed under the Apache License, Version 2.0 (the "License");
+# you may not use this file except in compliance with the License.
+# You may obtain a copy of the License at
+#
+#     http://www.apache.org/licenses/LICENSE-2.0
+#
+# Unless required by applicable law or agreed to in writing, software
+# distributed under the License is distributed on an "AS IS" BASIS,
+# WITHOUT WARRANTIES OR CONDITIONS OF ANY KIND, either express or implied.
+# See the License for the specific language governing permissions and
+# limitations under the License.
 """Config-driven model constructor and checkpoint IO -- mirror of the reference ``score_sde_pytorch/utils.py``."""
 import torch
 
