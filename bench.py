@@ -31,6 +31,8 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 METRIC = "6D maps/sec (N=128, full PC loop)"
+# algorithmic FLOPs of one map at cond_length.yml = 2 * num_scales * 137.9 GFLOP (K/V projections hoisted)
+FLOPS_PER_MAP = 551.7e12
 UNIT = "maps/s"
 WORKLOAD = "cond_length.yml N=128 C=5 B=64/GPU L=256 num_scales=2000 VESDE PC(langevin+reverse_diffusion)"
 CTX_LEN = 256
@@ -45,10 +47,10 @@ def _peaks():
     return 1590.0, 1400.0, 6650.0, "fallback"
 
 
-def _inputs(cfg, batch, seed=1234, sample_offset=0):
+def _inputs(cfg, batch, seed=1234, sample_offset=0, want_ctx=True):
     g = torch.Generator().manual_seed(seed + sample_offset)
     N = cfg.data.max_res_num
-    ctx = torch.randn(batch, CTX_LEN, cfg.model.context_dim, generator=g) * 0.02
+    ctx = torch.randn(batch, CTX_LEN, cfg.model.context_dim, generator=g) * 0.02 if want_ctx else None
     lengths = torch.randint(40, N + 1, (batch,), generator=g)
     ar = torch.arange(N)
     lmask = (ar[None, :, None] < lengths[:, None, None]) & (ar[None, None, :] < lengths[:, None, None])
@@ -114,14 +116,22 @@ def _oracle_setup(cfg, batch, seed_weights=42):
     return sde, model, shape, ctx, cond
 
 
-def _oracle_iterations(cfg, batch, iters):
+def _oracle_iterations(cfg, batch, iters, warm=1):
+    """Seconds for `iters` PC iterations of the oracle port; weights / inputs are built and one warm-up iteration
+    is run BEFORE the clock starts."""
     from oracle import sampler_ref
     sde, model, shape, ctx, cond = _oracle_setup(cfg, batch)
-    t0 = time.perf_counter()
-    sampler_ref.pc_sampler_ref(sde, model, shape, cfg.sampling.snr, n_steps=cfg.sampling.n_steps_each, eps=1e-5,
-                               condition=cond, context=ctx, noise_fn=sampler_ref.philox_noise_fn(2024),
-                               num_iters=iters)
-    return time.perf_counter() - t0
+
+    def go(k):
+        t0 = time.perf_counter()
+        sampler_ref.pc_sampler_ref(sde, model, shape, cfg.sampling.snr, n_steps=cfg.sampling.n_steps_each, eps=1e-5,
+                                   condition=cond, context=ctx, noise_fn=sampler_ref.philox_noise_fn(2024),
+                                   num_iters=k)
+        return time.perf_counter() - t0
+
+    if warm:
+        go(warm)
+    return go(iters)
 
 
 def run_reference(args, cfg):
@@ -290,6 +300,111 @@ def _gn_apply_roofline(dev, B, cfg, L, hbm_gbs):
                                      "note": f"[{B},{N},{N},{nf}] bf16, graph-replayed back to back over 3 buffer sets (> L2)"}}
 
 
+# ------------------------------------------------------------------------------------------------ extra runs
+def _time_loop(model, cfg, B, K, W, ctx_len, kinds, dev, sample_offset=0):
+    """ms per PC iteration (CUDA events on the launching stream) of t2p_pc_run at per-GPU batch B: device-resident
+    synthetic inputs, W warm-up iterations (eager + graph capture), K timed graph replays."""
+    from text2protein_b200 import _lib
+    from text2protein_b200.score_sde_pytorch import sampling, sde_lib
+    L = _lib.lib()
+    C_, N = cfg.data.num_channels, cfg.data.max_res_num
+    shape = (B, C_, N, N)
+    sde = sde_lib.VESDE(cfg.model.sigma_min, cfg.model.sigma_max, cfg.model.num_scales)
+    ctx = torch.randn(B, ctx_len, cfg.model.context_dim, device=dev) * 0.02
+    cond = {"length": _inputs(cfg, B, sample_offset=sample_offset, want_ctx=False)[1]["length"].to(dev)} \
+        if kinds == ["length"] else {}
+    x = sampling.philox_normal(shape, 2024, 0, dev, scale=float(sde.sigma_max), sample_offset=sample_offset)
+    x, cmask = sampling.apply_condition(x, cond)
+    x = x.contiguous()
+    x_init, x_mean = x.clone(), torch.empty_like(x)
+    mask_u8 = cmask.contiguous().view(torch.uint8)
+    model.set_context(ctx)
+    labels, G = sampling.ve_tables(sde, 1e-5, max(K, W, 1))
+
+    def run(k):
+        a = _lib.RunArgs()
+        a.x, a.x_mean, a.mask, a.x_init = x.data_ptr(), x_mean.data_ptr(), mask_u8.data_ptr(), x_init.data_ptr()
+        a.label_table, a.g_table = labels.data_ptr(), G.data_ptr()
+        a.num_iters, a.n_steps, a.snr, a.probability_flow = k, 1, float(cfg.sampling.snr), 0
+        a.seed, a.sample_offset, a.B, a.use_graph = 2024, sample_offset, B, 1
+        _lib.check(L.t2p_pc_run(model.native_handle, C.byref(a), _lib.current_stream()))
+
+    side = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(side):
+        run(max(W, 2))
+        side.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(side)
+        run(K)
+        e1.record(side)
+        side.synchronize()
+    assert torch.isfinite(x).all()
+    return e0.elapsed_time(e1) / K
+
+
+def _extra_runs(args, dev, world, rank, cfg2_model, cfg2):
+    """What BASELINE.json's configs 3-5 and the scaling question ask for beyond the headline line:
+    (i) strong scaling of a FIXED global batch of cond_length.yml (64 and 256 maps over the run's N GPUs),
+    (ii) test_config_large.yml with a global batch of 256 sharded over the N GPUs, (iii) the no_cond.yml sweep of
+    8 ... 1024 chains.  Every number is ms per PC iteration, max over ranks, and whole-job maps/s; the per-N
+    efficiency is for the reader (the driver) to form from the runs at N = 1, 2, 4, 8."""
+    import torch.distributed as dist
+    from text2protein_b200 import load_config
+    from text2protein_b200.score_sde_pytorch.models.ncsnpp import UNetModel
+    from text2protein_b200.synthetic import rerandomize_device_
+
+    def reduce_max(ms):
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    def row(name, cfg, model, total, ctx_len, kinds, K, note):
+        b = total // world
+        if b < 1:
+            return {"workload": name, "global_batch": total, "skipped": "fewer chains than GPUs"}
+        ms = reduce_max(_time_loop(model, cfg, b, K, 2, ctx_len, kinds, dev, sample_offset=rank * b))
+        ns = cfg.model.num_scales
+        return {"workload": name, "global_batch": b * world, "batch_per_gpu": b, "ms_per_iteration": ms,
+                "maps_per_s": b * world / (ms * 1e-3 * ns), "iterations_timed": K, "limiter": note(b)}
+
+    def gemm_or_launch(b):
+        return ("tensor-core GEMMs (power-capped)" if b >= 32 else
+                "launch-/latency-bound low-resolution tail: ~400 kernels per forward at a few microseconds each "
+                "regardless of the batch")
+
+    rows = []
+    for total in (64, 256):
+        rows.append(row("strong scaling: cond_length.yml, fixed global batch", cfg2, cfg2_model, total, CTX_LEN,
+                        ["length"], 6, gemm_or_launch))
+
+    def fresh(name):
+        cfg = load_config(name, device=f"cuda:{dev.index}")
+        cfg.model.compute_dtype = "bf16"
+        with torch.device(dev):
+            m = UNetModel(cfg)
+        rerandomize_device_(m.named_parameters(), 42)
+        m.sync_weights()
+        return cfg, m
+
+    if not args.no_cfg5:
+        cfg5, m5 = fresh("no_cond")
+        for total in (8, 64, 256, 1024):
+            if total // world > 1024:
+                continue
+            rows.append(row("no_cond.yml sweep (C=8, unconditional, context L=256)", cfg5, m5, total, CTX_LEN, [], 4,
+                            gemm_or_launch))
+        del m5
+        torch.cuda.empty_cache()
+    if not args.no_cfg4:
+        cfg4, m4 = fresh("test_config_large")
+        rows.append(row("test_config_large.yml N=256 nf=256 L=512, global batch 256 sharded", cfg4, m4, 256, 512, [], 3,
+                        lambda b: "tensor-core GEMMs; 22 attention pairs at T<=1024, d_head=128"))
+        del m4
+        torch.cuda.empty_cache()
+    return rows
+
+
 # ------------------------------------------------------------------------------------------------ native arm
 def run_native(args, cfg):
     import torch.distributed as dist
@@ -440,11 +555,16 @@ def run_native(args, cfg):
         shapes = [{"k": k[1], "M": k[2], "N": k[3], "K": k[4], "n": v[0] // reps, "ms_each": v[1] / v[0],
                    "tflops": v[2] / (v[1] / v[0] * 1e-3) / 1e12}
                   for k, v in sorted(groups.items(), key=lambda kv: -kv[1][1])[:16]]
-        roof = {"bound": "tensor", "achieved": achieved, "peak": peak_sust, "unit": "TFLOP/s",
-                "frac": achieved / peak_sust, "traffic": None,
+        per_gpu = value / world
+        roof = {"bound": "tensor", "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s",
+                "frac": achieved / peak_burst, "frac_of_sustained": achieved / peak_sust, "traffic": None,
+                # whole loop: maps/s per GPU x algorithmic FLOPs per map over the same peak
+                "loop_achieved": per_gpu * FLOPS_PER_MAP / 1e12, "loop_frac": per_gpu * FLOPS_PER_MAP / 1e12 / peak_burst,
+                "loop_frac_of_sustained": per_gpu * FLOPS_PER_MAP / 1e12 / peak_sust,
                 "kernel": f"{_gemm_kernel_name(key[1], key[2] // B, key[3])} k={key[1]} M={key[2]} N={key[3]} K={key[4]}",
                 "launches_per_forward": cnt // reps, "avg_launch_ms": avg_ms,
-                "flops_per_launch": fl, "peak_source": f"{src} sustained (burst {peak_burst})",
+                "flops_per_launch": fl,
+                "peak_source": f"{src}: burst {peak_burst} (per-launch event timing), sustained {peak_sust}",
                 "share_of_gemm_time": ms / reps / all_ms,
                 "gemm_ms_per_forward": all_ms, "tc_gemm_ms_per_forward": tc_ms,
                 "gemm_flops_per_forward": fwd_flops,
@@ -465,11 +585,28 @@ def run_native(args, cfg):
     if rank == 0 and not args.no_cpu_baseline:
         cores = os.cpu_count()
         torch.set_num_threads(cores)
-        iters = 2
+        iters = 6
         dt = _oracle_iterations(cfg, 1, iters)
         cpu_ms = dt / iters * 1e3
         cpu = {"value": 1 / (cpu_ms * 1e-3 * num_scales), "unit": UNIT, "cores": torch.get_num_threads(),
-               "kind": "port", "sample": f"B=1 map, {iters} PC iterations of {num_scales} (incl. setup), fp32 torch CPU"}
+               "kind": "port", "ms_per_step": cpu_ms,
+               "sample": f"B=1 map, {iters} PC iterations of {num_scales} after 1 warm-up iteration, set-up excluded, "
+                         "fp32 torch CPU"}
+    if world > 1 and not args.no_cpu_baseline:
+        # the other ranks sleep on the rendezvous store (a blocking socket wait) while rank 0 uses the host cores:
+        # an NCCL barrier here would spin one core per rank
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            store.set("t2p_cpu_baseline_done", "1")
+        else:
+            store.wait(["t2p_cpu_baseline_done"])
+
+    extra = None
+    if not args.no_extra:
+        try:
+            extra = _extra_runs(args, dev, world, rank, model, cfg)
+        except Exception as e:  # never lose the headline line to the extra measurements
+            extra = [{"error": repr(e)[:300]}]
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -481,7 +618,11 @@ def run_native(args, cfg):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms_step},
                 "gpu_launches": gpu_launches, "launches_per_forward": launches_fwd,
+                "score_net_forward_ms": (ms_step - sum(v["ms"] for k, v in (steps or {}).items()
+                                                       if k in ("predictor_kernel", "corrector_kernel"))) / 2,
                 "roofline": roof, "step_kernels": steps, "cpu_baseline": cpu, "clocks": clk,
+                "extra_runs": extra, "library": os.path.basename(_lib.LIB_PATH),
+                "env_t2p": {k: v for k, v in os.environ.items() if k.startswith("T2P_")},
                 "workspace_gb": L.t2p_unet_workspace_bytes(model.native_handle) / 1e9}
         _emit(line)
     if world > 1:
@@ -514,7 +655,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the strong-scaling / cfg4 / cfg5 runs")
+    ap.add_argument("--no-cfg4", action="store_true")
+    ap.add_argument("--no-cfg5", action="store_true")
+    ap.add_argument("--lib", default="default", choices=["default", "knobs"],
+                    help="knobs: libt2p_knobs.so (-DT2P_TIMING_KNOBS; reads the T2P_* A/B environment variables)")
     args = ap.parse_args()
+    if args.lib == "knobs":
+        from text2protein_b200 import _lib
+        _lib.use_library("libt2p_knobs.so")
     from text2protein_b200 import load_config
     cfg = load_config("cond_length", device="cpu")
     if args.impl == "reference":
