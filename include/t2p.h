@@ -229,7 +229,9 @@ int t2p_groupnorm_apply(const void* a0, int c0, const void* a1, int c1, int B, i
 int t2p_layernorm(const void* x, const float* gamma, const float* beta, int64_t M, int C, float eps, int dtype,
                   void* y, void* stream);                     /* attention.py:203-205 */
 int t2p_geglu(const void* z, int64_t M, int D, int dtype, void* out, void* stream); /* attention.py:42-44 */
-/* softmax(scale * q k^T) v on strided token-major views: layers.py:160-176, attention.py:170-193 */
+/* softmax(scale * q k^T) v on strided token-major views: layers.py:160-176, attention.py:170-193.
+ * use_tensor_cores: 0 = CUDA-core kernel (fp32 or bf16), 1 = bf16 mma.sync kernel, 2 = bf16 tcgen05 / TMEM / TMA kernel
+ * (what the engine runs for head dims 32, 64, 128 and multiples of 256). */
 int t2p_attention(const void* q, const void* k, const void* v, void* out, int B, int heads, int Tq, int Tk, int d,
                   int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, float scale, int dtype, int use_tensor_cores,
                   void* stream);

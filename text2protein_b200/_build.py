@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libt2p.so")
 OBJ_DIR = os.path.join(os.path.dirname(HERE), "build", "obj")
 
-SOURCES = ["api.cu", "unet.cu", "gemm_tc.cu", "gemm_simt.cu", "norm.cu", "attention.cu", "attention_mma.cu",
+SOURCES = ["api.cu", "unet.cu", "gemm_tc.cu", "gemm_simt.cu", "norm.cu", "attention.cu", "attention_mma.cu", "attention_tc.cu",
            "elementwise.cu", "pc_step.cu", "conditions.cu", "final_conv.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--use_fast_math=false"]

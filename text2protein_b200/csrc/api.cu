@@ -688,7 +688,10 @@ int t2p_attention(const void* q, const void* k, const void* v, void* out, int B,
   a.q = q; a.k = k; a.v = v; a.out = out;
   a.B = B; a.heads = heads; a.Tq = Tq; a.Tk = Tk; a.d = d;
   a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo; a.scale = scale;
-  if (use_tensor_cores) {
+  if (use_tensor_cores == 2) {
+    T2P_CHECK(dtype == T2P_BF16 && attention_tc_supported(a), "tcgen05 attention needs bf16 and a supported head dim");
+    attention_tc(a, S(stream));
+  } else if (use_tensor_cores) {
     T2P_CHECK(dtype == T2P_BF16 && attention_mma_supported(a), "tensor-core attention needs bf16 and a supported head dim");
     attention_mma(a, S(stream));
   } else {

@@ -85,8 +85,12 @@ struct AttnArgs {
   float scale = 1.f;
 };
 void attention_simt(const AttnArgs& a, int dtype, cudaStream_t st);
-void attention_mma(const AttnArgs& a, cudaStream_t st);  // bf16 tensor cores
+void attention_mma(const AttnArgs& a, cudaStream_t st);  // bf16 mma.sync kernel (head dims the tcgen05 kernel lacks)
 bool attention_mma_supported(const AttnArgs& a);
+// bf16 tcgen05 kernel (attention_tc.cu): scores and output accumulator in TMEM, operands by TMA; d in {32, 64, 128}
+// or a multiple of 256
+void attention_tc(const AttnArgs& a, cudaStream_t st);
+bool attention_tc_supported(const AttnArgs& a);
 
 // ----------------------------------------------------------------------------- helpers
 // timesteps: optional fp32 [B] time conditioning to embed instead of float(labels)

@@ -579,7 +579,9 @@ void UNet::attention(const void* q, const void* k, const void* v, void* out, int
   a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo; a.scale = scale;
   ++launches_;
   if (dry_ || (debug_skip() & 4)) return;
-  if (cfg_.compute_dtype == kBF16 && attention_mma_supported(a)) attention_mma(a, ln_->st);
+  static const bool tc_on = env_knob("T2P_ATTN_TC", 1) != 0;  // A/B knob (knob builds only)
+  if (cfg_.compute_dtype == kBF16 && tc_on && attention_tc_supported(a)) attention_tc(a, ln_->st);
+  else if (cfg_.compute_dtype == kBF16 && attention_mma_supported(a)) attention_mma(a, ln_->st);
   else attention_simt(a, cfg_.compute_dtype, ln_->st);
 }
 
