@@ -658,12 +658,13 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the strong-scaling / cfg4 / cfg5 runs")
     ap.add_argument("--no-cfg4", action="store_true")
     ap.add_argument("--no-cfg5", action="store_true")
-    ap.add_argument("--lib", default="default", choices=["default", "knobs"],
-                    help="knobs: libt2p_knobs.so (-DT2P_TIMING_KNOBS; reads the T2P_* A/B environment variables)")
+    ap.add_argument("--lib", default="default",
+                    help="default = libt2p.so; knobs = libt2p_knobs.so (-DT2P_TIMING_KNOBS build: reads the T2P_* A/B "
+                         "environment variables); or the file name of another build under text2protein_b200/")
     args = ap.parse_args()
-    if args.lib == "knobs":
+    if args.lib != "default":
         from text2protein_b200 import _lib
-        _lib.use_library("libt2p_knobs.so")
+        _lib.use_library("libt2p_knobs.so" if args.lib == "knobs" else args.lib)
     from text2protein_b200 import load_config
     cfg = load_config("cond_length", device="cpu")
     if args.impl == "reference":

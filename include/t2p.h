@@ -82,6 +82,12 @@ int t2p_unet_forward(t2p_unet* u, const float* x, const int64_t* labels, void* o
 int t2p_unet_forward_t(t2p_unet* u, const float* x, const int64_t* labels, const float* timesteps, void* out,
                        int out_dtype, int B, void* stream);
 
+/* Option, default off: apply GroupNorm + SiLU inside the operand path of the 3x3 convolutions on 128-pixel-wide
+ * images (the layers holding most of the FLOPs) instead of a separate pass over the activation -- h = act(GroupNorm(x)),
+ * layers.py:305,318, never reaches HBM.  Same results to bf16 rounding; measured break-even in time on
+ * cond_length.yml at B = 64 (profiles/r02_fused_gn_ab.txt), 1.1 GB less activation arena. */
+int t2p_unet_set_fused_groupnorm(t2p_unet* u, int enable);
+
 /* Debug taps: with debug on, every top-level block's output is kept as fp32 NCHW ("pre_conv",
  * "input_blocks.<i>", "mid_blocks", "out_blocks.<i>", "out"). */
 int t2p_unet_set_debug(t2p_unet* u, int enable);
@@ -206,11 +212,17 @@ typedef struct t2p_conv_args {
   const void* x0; int32_t xc0;     /* optional NHWC sources entering through the centre tap only: a 1x1 convolution */
   const void* x1; int32_t xc1;     /* over x0|x1 summed with the one over a0|a1 (ResnetBlockBigGANpp Conv_2 folded into
                                       Conv_1, layers.py:318-327); w rows are [k*k*(c0+c1) | xc0 | xc1].  bf16, N >= 128 */
+  const float* gn_scale;           /* optional: a0|a1 are RAW and the kernel feeds silu(x * gn_scale + gn_shift) to the tensor */
+  const float* gn_shift;           /* core (h = act(GroupNorm(x)), layers.py:305,318): per-(sample, channel) affine over the
+                                      concat, fp32 [B][c0+c1].  Only where t2p_conv2d_fuses_groupnorm(args) != 0 */
 } t2p_conv_args;
 int t2p_conv2d(const t2p_conv_args* a, void* stream);        /* nn.Conv2d / NIN / nn.Linear: layers.py:82-95,128-137 */
 /* Pixel-tile size T of the fused GroupNorm statistics t2p_conv2d would write for these arguments (H*W % T == 0),
  * or 0 when this launch cannot produce them (then stat_part must be NULL).  Host-only, no GPU work. */
 int t2p_conv2d_stat_tile(const t2p_conv_args* a);
+/* 1 when t2p_conv2d can apply GroupNorm + SiLU to its 3x3 sources itself for these arguments (3x3, 128-pixel-wide
+ * images, bf16, N >= 128: the halo kernel), else 0.  Host-only. */
+int t2p_conv2d_fuses_groupnorm(const t2p_conv_args* a);
 
 /* Last layer, ncsnpp.py:212-216,257: out fp32 NCHW [B][nout][H][W] = Conv3x3(SiLU(x * scale + shift)) + bias, with x the
  * raw bf16 NHWC activation [B][H][W][cin], scale / shift the per-(sample, channel) GroupNorm affine [B][cin] and w the

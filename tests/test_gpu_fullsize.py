@@ -15,7 +15,7 @@ import torch
 from oracle import sampler_ref, unet_ref
 from tests.cfgs import FULLSIZE_CASES, fullsize_inputs, synthetic_condition
 from tests.gpu_util import rel_err
-from text2protein_b200 import load_config
+from text2protein_b200 import _lib, load_config
 from text2protein_b200.synthetic import rerandomize_
 
 pytestmark = pytest.mark.gpu
@@ -163,3 +163,25 @@ def test_pc_iterations_keep_conditions_bit_exact_at_n128(name, kinds, B):
         assert torch.equal(s[fixed], cond["inpainting"]["coords_6d"][fixed])
     s2, _ = fn(model, dev_cond, ctx)
     assert torch.equal(s, s2.cpu())  # same seed -> same bits
+
+
+def test_fused_groupnorm_option_matches_reference_golden(golden_dir):
+    """The opt-in fused GroupNorm + SiLU convolutions (profiles/r02_fused_gn_ab.txt) against the reference's output at
+    cfg2 and at test_config (128-pixel-wide level with 256 / 512 / 768 channels, multi-tile CTAs)."""
+    for case in ("cond_length_L256", "test_config"):
+        fname, B, L = FULLSIZE_CASES[case]
+        g = np.load(os.path.join(golden_dir, f"unet_full_{case}.npz"))
+        cfg, m = _model(fname[:-4], "bf16")
+        x, labels, ctx = fullsize_inputs(cfg, B, L)
+        plain = m(x.cuda(), labels.cuda(), ctx.cuda())
+        n_plain = _lib.lib().t2p_unet_launches_per_forward(m.native_handle)
+        m.set_fused_groupnorm(True)
+        fused = m(x.cuda(), labels.cuda(), ctx.cuda())
+        assert _lib.lib().t2p_unet_launches_per_forward(m.native_handle) < n_plain  # apply launches are gone
+        ref = torch.from_numpy(g["out"]).double()
+        assert rel_err(fused, ref) < 2e-2 and rel_err(plain, ref) < 2e-2
+        assert rel_err(fused, plain) < 2e-2
+        m.set_fused_groupnorm(False)
+        assert torch.equal(m(x.cuda(), labels.cuda(), ctx.cuda()), plain)
+        del m
+        torch.cuda.empty_cache()

@@ -98,6 +98,73 @@ def test_conv2d_upsampled_residual_and_fused_stats(H, cin, cout):
     assert torch.allclose(tot[..., 1], (out * out).sum(dim=(2, 3)), rtol=1e-4, atol=1e-2)
 
 
+@pytest.mark.parametrize("B,H,c0,c1,xc0,cout,stats", [(2, 128, 128, 0, 0, 128, True), (3, 128, 128, 128, 0, 128, False),
+                                                      (2, 128, 64, 0, 64, 128, True), (16, 6, 64, 64, 128, 256, False),
+                                                      (5, 128, 128, 0, 128, 128, True), (1, 128, 512, 0, 512, 512, True),
+                                                      (1, 128, 256, 0, 256, 512, False), (2, 128, 512, 256, 768, 256, True)])
+def test_conv2d_fused_groupnorm_silu(B, H, c0, c1, xc0, cout, stats):
+    """Conv3x3(silu(GroupNorm-affine(cat(a0, a1)))) [+ folded 1x1 skip over RAW x0] with the normalisation applied
+    inside the halo kernel's operand path (packed-bf16 arithmetic) against torch on the same bf16 inputs, including
+    image borders (zero padding applies AFTER the activation), ragged tile counts and fused output statistics."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    W = 128
+    bf = lambda t: t.bfloat16().float()  # noqa: E731
+    a0 = bf(torch.randn(B, c0, H, W, device="cuda", generator=g) * 1.5 + 0.3)
+    a1 = bf(torch.randn(B, c1, H, W, device="cuda", generator=g)) if c1 else None
+    x0 = bf(torch.randn(B, xc0, H, W, device="cuda", generator=g)) if xc0 else None
+    ctot = c0 + c1
+    scale = 1.0 + 0.3 * torch.randn(B, ctot, device="cuda", generator=g)
+    shift = 0.5 * torch.randn(B, ctot, device="cuda", generator=g)
+    w1 = bf(torch.randn(cout, ctot, 3, 3, device="cuda", generator=g) / math.sqrt(9 * ctot))
+    w2 = bf(torch.randn(cout, xc0, 1, 1, device="cuda", generator=g) / math.sqrt(xc0)) if xc0 else None
+    bias = torch.randn(cout, device="cuda", generator=g)
+    x = a0 if a1 is None else torch.cat([a0, a1], 1)
+    hn = F.silu(x * scale[:, :, None, None] + shift[:, :, None, None])
+    ref = F.conv2d(hn, w1, bias, padding=1)
+    cols = [w1.permute(0, 2, 3, 1).reshape(cout, -1)]
+    if xc0:
+        ref = ref + F.conv2d(x0, w2)
+        cols.append(w2.reshape(cout, -1))
+    wp = torch.cat(cols, 1).bfloat16().contiguous()
+    A0 = nhwc(a0, torch.bfloat16)
+    A1 = nhwc(a1, torch.bfloat16) if a1 is not None else None
+    X0 = nhwc(x0, torch.bfloat16) if x0 is not None else None
+    out = torch.empty(B, H, W, cout, dtype=torch.bfloat16, device="cuda")
+    a = _lib.ConvArgs()
+    a.a0, a.c0 = A0.data_ptr(), c0
+    if A1 is not None:
+        a.a1, a.c1 = A1.data_ptr(), c1
+    a.B, a.H, a.W, a.ksize = B, H, W, 3
+    a.w, a.N, a.bias, a.alpha = wp.data_ptr(), cout, bias.data_ptr(), 1.0
+    if X0 is not None:
+        a.x0, a.xc0 = X0.data_ptr(), xc0
+    a.out, a.out_dtype, a.in_dtype = out.data_ptr(), _lib.BF16, _lib.BF16
+    L = _lib.lib()
+    assert L.t2p_conv2d_fuses_groupnorm(C.byref(a)) == 1
+    a.gn_scale, a.gn_shift = scale.data_ptr(), shift.data_ptr()
+    ss = None
+    if stats:
+        tile = L.t2p_conv2d_stat_tile(C.byref(a))
+        assert tile > 0
+        ss = torch.zeros(B * H * W // tile, cout, 2, device="cuda")
+        a.stat_part = ss.data_ptr()
+    _lib.check(L.t2p_conv2d(C.byref(a), _st()))
+    torch.cuda.synchronize()
+    got = nchw(out.float())
+    assert torch.isfinite(got).all()
+    assert rel_err(got, ref) < 1.5e-2
+    # border rows / columns exercise the zero padding of the ACTIVATION (silu(shift) != 0 would leak in otherwise)
+    assert rel_err(got[:, :, 0], ref[:, :, 0]) < 1.5e-2 and rel_err(got[:, :, :, -1], ref[:, :, :, -1]) < 1.5e-2
+    if stats:
+        tot = ss.reshape(B, -1, cout, 2).sum(dim=1)
+        assert torch.allclose(tot[..., 0], got.sum(dim=(2, 3)), rtol=1e-4, atol=1e-1)
+    # a launch that cannot fuse says so and refuses the arguments
+    b = _lib.ConvArgs()
+    b.a0, b.c0, b.B, b.H, b.W, b.ksize, b.w, b.N = A0.data_ptr(), c0, B, H, W, 1, wp.data_ptr(), cout
+    b.out, b.out_dtype, b.in_dtype = out.data_ptr(), _lib.BF16, _lib.BF16
+    assert L.t2p_conv2d_fuses_groupnorm(C.byref(b)) == 0
+
+
 @pytest.mark.parametrize("H,cin,xc0,xc1,cout", [(16, 64, 128, 64, 128), (32, 128, 128, 0, 128), (8, 64, 64, 0, 256),
                                                 (128, 64, 64, 64, 128)])
 def test_conv2d_folded_skip_path(H, cin, xc0, xc1, cout):

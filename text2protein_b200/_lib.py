@@ -44,7 +44,7 @@ class ConvArgs(C.Structure):
                 ("bias", C.c_void_p), ("rowbias", C.c_void_p), ("rowbias_ld", C.c_int32), ("residual", C.c_void_p),
                 ("res_up", C.c_int32), ("alpha", C.c_float), ("out", C.c_void_p), ("out_dtype", C.c_int32),
                 ("in_dtype", C.c_int32), ("stat_part", C.c_void_p), ("x0", C.c_void_p), ("xc0", C.c_int32),
-                ("x1", C.c_void_p), ("xc1", C.c_int32)]
+                ("x1", C.c_void_p), ("xc1", C.c_int32), ("gn_scale", C.c_void_p), ("gn_shift", C.c_void_p)]
 
 
 class GemmRecord(C.Structure):
@@ -79,6 +79,7 @@ SIGNATURES = {
     "t2p_unet_set_context": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "t2p_unet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "t2p_unet_set_debug": (C.c_int, [C.c_void_p, C.c_int]),
+    "t2p_unet_set_fused_groupnorm": (C.c_int, [C.c_void_p, C.c_int]),
     "t2p_unet_tap": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]),
     "t2p_unet_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "t2p_unet_profile_read": (C.c_int, [C.c_void_p, C.POINTER(GemmRecord), C.c_int]),
@@ -102,6 +103,7 @@ SIGNATURES = {
     "t2p_postprocess_6d": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "t2p_conv2d": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "t2p_conv2d_stat_tile": (C.c_int, [C.POINTER(ConvArgs)]),
+    "t2p_conv2d_fuses_groupnorm": (C.c_int, [C.POINTER(ConvArgs)]),
     "t2p_final_conv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                  C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "t2p_groupnorm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -123,7 +123,8 @@ static std::vector<int32_t> struct_offsets(int which) {
                     T2P_OFF(t2p_conv_args, residual), T2P_OFF(t2p_conv_args, res_up), T2P_OFF(t2p_conv_args, alpha),
                     T2P_OFF(t2p_conv_args, out), T2P_OFF(t2p_conv_args, out_dtype), T2P_OFF(t2p_conv_args, in_dtype),
                     T2P_OFF(t2p_conv_args, stat_part), T2P_OFF(t2p_conv_args, x0), T2P_OFF(t2p_conv_args, xc0),
-                    T2P_OFF(t2p_conv_args, x1), T2P_OFF(t2p_conv_args, xc1)};
+                    T2P_OFF(t2p_conv_args, x1), T2P_OFF(t2p_conv_args, xc1), T2P_OFF(t2p_conv_args, gn_scale),
+                    T2P_OFF(t2p_conv_args, gn_shift)};
     case 4: return {T2P_OFF(t2p_gemm_record, M), T2P_OFF(t2p_gemm_record, N), T2P_OFF(t2p_gemm_record, K),
                     T2P_OFF(t2p_gemm_record, ksize), T2P_OFF(t2p_gemm_record, tensor_core), T2P_OFF(t2p_gemm_record, H),
                     T2P_OFF(t2p_gemm_record, W), T2P_OFF(t2p_gemm_record, ms)};
@@ -268,6 +269,13 @@ int t2p_unet_forward_t(t2p_unet* u, const float* x, const int64_t* labels, const
   T2P_API_BEGIN
   T2P_CHECK(u && x && labels && out && B > 0, "bad forward arguments");
   u->net->forward(x, reinterpret_cast<const long long*>(labels), out, out_dtype, B, S(stream), timesteps);
+  T2P_API_END
+}
+
+int t2p_unet_set_fused_groupnorm(t2p_unet* u, int enable) {
+  T2P_API_BEGIN
+  T2P_CHECK(u != nullptr, "null handle");
+  u->net->set_fused_groupnorm(enable != 0);
   T2P_API_END
 }
 
@@ -601,7 +609,18 @@ static ConvGemmArgs conv_args_from_abi(const t2p_conv_args* a) {
   g.out = a->out; g.out_dtype = a->out_dtype;
   g.stat_part = a->stat_part;
   g.x0 = a->x0; g.xc0 = a->xc0; g.x1 = a->x1; g.xc1 = a->xc1;
+  g.gn_scale = a->gn_scale; g.gn_shift = a->gn_shift;
   return g;
+}
+
+int t2p_conv2d_fuses_groupnorm(const t2p_conv_args* a) {
+  try {
+    if (!a || a->in_dtype != T2P_BF16 || a->c0 % 64 != 0 || a->c1 % 64 != 0 || a->ksize != 3) return 0;
+    return conv_gemm_tc_fuses_gn(conv_args_from_abi(a)) ? 1 : 0;
+  } catch (const std::exception& e) {
+    set_last_error(e.what());
+    return 0;
+  }
 }
 
 int t2p_conv2d_stat_tile(const t2p_conv_args* a) {
@@ -620,6 +639,8 @@ int t2p_conv2d(const t2p_conv_args* a, void* stream) {
   ConvGemmArgs g = conv_args_from_abi(a);
   if (a->xc0 > 0 || a->xc1 > 0)
     T2P_CHECK(a->in_dtype == T2P_BF16 && a->c0 % 64 == 0 && a->c1 % 64 == 0, "centre-tap sources are tcgen05-only");
+  if (a->gn_scale || a->gn_shift)
+    T2P_CHECK(a->gn_scale && a->gn_shift && t2p_conv2d_fuses_groupnorm(a), "this launch cannot fuse GroupNorm");
   if (a->in_dtype == T2P_BF16 && a->c0 % 64 == 0 && a->c1 % 64 == 0) conv_gemm_tc(g, S(stream));
   else conv_gemm_simt(g, a->in_dtype, S(stream));
   T2P_API_END

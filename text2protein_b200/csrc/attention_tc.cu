@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(THREADS) attention_tc_kernel(const __grid_cons
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < nkb; ++j) {
       const int valid = min(BKEY, p.Tk - j * BKEY);  // keys of this block that exist (TMA zero-fills the rest)
-      ptx::mbar_wait(ptx::smem_u32(&sfull_bar), j & 1);
+      ptx::mbar_wait_warp(ptx::smem_u32(&sfull_bar), j & 1);
       ptx::tc_fence_after();
       // pass A: row maximum of the raw scores
       float mx = m;
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(THREADS) attention_tc_kernel(const __grid_cons
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&pfull_bar));
     }
     // epilogue: O / l -> bf16 -> global (rows beyond Tq exist only in the tile)
-    ptx::mbar_wait(ptx::smem_u32(&ofull_bar), 0);
+    ptx::mbar_wait_warp(ptx::smem_u32(&ofull_bar), 0);
     ptx::tc_fence_after();
     const float inv = 1.f / l;
     const int t = q0 + row;

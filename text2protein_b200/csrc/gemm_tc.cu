@@ -24,6 +24,17 @@ namespace t2p {
 
 namespace {
 
+// (A/B, r02_fused_gn_ab.txt: one polling lane + __syncwarp instead of 32 spinning lanes changed nothing measurable
+// for the plain kernels and made the fused one slower -- the spinning warps react faster.)
+#ifndef T2P_EPI_WARP_WAIT
+#define T2P_EPI_WARP_WAIT 0
+#endif
+#if T2P_EPI_WARP_WAIT
+#define T2P_EPI_WAIT(bar, parity) ptx::mbar_wait_warp(bar, parity)
+#else
+#define T2P_EPI_WAIT(bar, parity) ptx::mbar_wait(bar, parity)
+#endif
+
 constexpr int BM = 128;      // rows (pixels) per tile == UMMA M
 constexpr int BK = 64;       // bf16 elements per 128-byte swizzled row
 constexpr int UMMA_K = 16;   // K per tcgen05.mma for 16-bit inputs
@@ -59,6 +70,13 @@ struct TcParams {
   int n_tiles;       // tiles along N
   int num_tiles;     // m_tiles * n_tiles
   int reverse;       // walk the tiles from the last to the first (see ConvGemmArgs::reverse)
+  // fused-GroupNorm halo kernel: the 3x3 sources are RAW activations; act(x * scale + shift) is applied on the way
+  // into shared memory.  a0 / a1 global pointers and the per-(sample, channel) affine over the concat [B][c0 + c1]
+  const __nv_bfloat16* raw0;
+  const __nv_bfloat16* raw1;
+  const float* gn_scale;
+  const float* gn_shift;
+  int hf_debug;      // timing experiments (knob builds): 1 = copy without arithmetic, 2 = no global loads either
 };
 
 template <int BN>
@@ -368,7 +386,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_tc_kernel(const __gr
         const int w = rem - h * p.W;
         er.res_row = (static_cast<long long>(b) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
       }
-      ptx::mbar_wait(ptx::smem_u32(&tfull_bar[as]), aph);
+      T2P_EPI_WAIT(ptx::smem_u32(&tfull_bar[as]), aph);
       ptx::tc_fence_after();
       const uint32_t tbase = tmem_base + as * C::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
       auto release_acc = [&]() {
@@ -560,7 +578,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, uint32_t tmem_b
     eq.nw0 = (tt - pt * p.n_tiles) * 128 + q * 32;  // first channel of this warp
     eq.m0 = pt * PX;
     epi_begin_tile<RBVAR>(p, eq, lane);
-    ptx::mbar_wait(ptx::smem_u32(&tfull_bar[as]), aph);
+    T2P_EPI_WAIT(ptx::smem_u32(&tfull_bar[as]), aph);
     ptx::tc_fence_after();
     const uint32_t tbase = tmem_base + as * PX + (static_cast<uint32_t>(q * 32) << 16);
     auto release_acc = [&]() {
@@ -968,6 +986,306 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_tcH_kernel(const __g
   if (warp == 1) ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
+
+// =====================================================================================================
+// Halo kernel with GroupNorm-apply + SiLU fused into the operand path (ResnetBlockBigGANpp: h = act(GroupNorm(x))
+// feeding Conv_0 / Conv_1, layers.py:305,318).  The normalised copy of the activation -- one HBM write and one HBM
+// read of the largest tensors of the network per convolution -- never exists: eight extra warps fetch the RAW
+// pixels of each (kh, channel chunk) box with 16-byte global loads, apply y = silu(x * scale + shift) and store the
+// result straight into the 128-byte-swizzled tile the MMA warp reads (shared-memory traffic is what the TMA write of
+// the plain kernel was; the first attempt, r01_fused_gn_halo_ab.txt, rewrote TMA-staged tiles in place and paid a
+// read-modify-write of every box in a shared-memory pipe the UMMA operand reads already fill).  The arithmetic is
+// packed bf16: with the affine pre-halved, h = fma(x, s/2, b/2), silu(2h) = h * tanh(h) + h -- one HFMA2, one
+// MUFU.TANH (bf16x2), one HFMA2 per PAIR of elements.  The conv's zero padding applies to the activation, so halo
+// pixels outside the image are stored as zeros, not as silu(shift).  Weights, the folded skip path (centre tap,
+// raw) and residual k-blocks still arrive by TMA; both producers fill the same ring of pixel buffers in a fixed
+// global order.  The two groups of four transform warps take alternate buffers, so each has two MMA periods to
+// hide its load latency.
+struct CfgHF {
+  static constexpr int W_BYTES = CfgH::W_BYTES;
+  static constexpr int P_ROWPITCH = CfgH::P_ROWPITCH;
+  static constexpr int P_ROWS = 2 * P_ROWPITCH;          // pixel rows (128 B each) of a staged box
+  static constexpr int P_BYTES = CfgH::P_BYTES;
+  static constexpr int NP = 3;
+  static constexpr int NW = 6;
+  static constexpr int OUT_BYTES = CfgH::OUT_BYTES;
+  static constexpr int SMEM_BYTES = NP * P_BYTES + NW * W_BYTES + OUT_BYTES + 1024;
+  static constexpr int PX = 256;
+  static constexpr int TMEM_COLS = 2 * PX;
+#ifndef T2P_HF_GROUPS
+#define T2P_HF_GROUPS 3
+#endif
+  static constexpr int T_GROUPS = T2P_HF_GROUPS;         // transform groups of four warps, taking the buffers in turn
+  static constexpr int T_WARPS = 4 * T_GROUPS;
+  static constexpr int THREADS = NUM_THREADS + 32 * T_WARPS;
+};
+
+__device__ __forceinline__ uint32_t bf16x2_fma(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t bf16x2_tanh(uint32_t a) {
+  uint32_t d;
+  asm("tanh.approx.bf16x2 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+
+__global__ void __launch_bounds__(CfgHF::THREADS, 1) conv_gemm_tcHF_kernel(const __grid_constant__ TcParams p) {
+  using C = CfgHF;
+  constexpr int PX = C::PX;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t pfull_bar[C::NP], pempty_bar[C::NP];
+  __shared__ __align__(8) uint64_t wfull_bar[C::NW], wempty_bar[C::NW];
+  __shared__ __align__(8) uint64_t tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t pbase = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t wbase = pbase + C::NP * C::P_BYTES;
+  const uint32_t out_stage = wbase + C::NW * C::W_BYTES;
+
+  const int chunks = (p.c0 + p.c1) / BK;
+  const int x_chunks = (p.xc0 + p.xc1) / BK;
+  const int r_chunks = p.residual ? 2 : 0;
+  const int bufs_per_tile = 3 * chunks + x_chunks + r_chunks;  // pixel buffers per tile, in ring order
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::NP; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&pfull_bar[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&pempty_bar[s]), 1);
+    }
+    for (int s = 0; s < C::NW; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&wfull_bar[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&wempty_bar[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&tfull_bar[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&tempty_bar[s]), 4);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(ptx::smem_u32(&tmem_base_slot), C::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  const int hw = p.H * p.W;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer: weights + centre-tap / residual pixels
+    if (lane == 0) {
+      ptx::prefetch_tmap(&p.tm_w);
+      if (p.xc0 > 0) ptx::prefetch_tmap(&p.tm_x0);
+      if (p.xc1 > 0) ptx::prefetch_tmap(&p.tm_x1);
+      if (p.residual) {
+        ptx::prefetch_tmap(&p.tm_res);
+        ptx::prefetch_tmap(&p.tm_ident);
+      }
+      int ws = 0;
+      uint32_t wph = 0;
+      long long pseq = 0;  // global index of the next pixel buffer of this CTA
+      auto load_w = [&](const CUtensorMap* tm, int c0, int c1) {
+        ptx::mbar_wait(ptx::smem_u32(&wempty_bar[ws]), wph ^ 1);
+        const uint32_t fb = ptx::smem_u32(&wfull_bar[ws]);
+        ptx::mbar_arrive_expect_tx(fb, C::W_BYTES);
+        ptx::tma_load_4d(wbase + ws * C::W_BYTES, tm, fb, c0, c1, 0, 0);
+        if (++ws == C::NW) { ws = 0; wph ^= 1; }
+      };
+      auto load_p = [&](const CUtensorMap* tm, int ch, int h, int b) {
+        const int ps = static_cast<int>(pseq % C::NP);
+        const uint32_t pph = static_cast<uint32_t>((pseq / C::NP) & 1);
+        ptx::mbar_wait(ptx::smem_u32(&pempty_bar[ps]), pph ^ 1);
+        const uint32_t fb = ptx::smem_u32(&pfull_bar[ps]);
+        ptx::mbar_arrive_expect_tx(fb, PX * BK * 2);
+        ptx::tma_load_4d(pbase + ps * C::P_BYTES, tm, fb, ch, 0, h, b);
+        ++pseq;
+      };
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int tt = p.reverse ? p.num_tiles - 1 - t : t;
+        const int pt = tt / p.n_tiles;
+        const int m0 = pt * PX;
+        const int n0 = (tt - pt * p.n_tiles) * 128;
+        const int b0 = m0 / hw;
+        const int h0 = (m0 - b0 * hw) / p.W;
+        for (int kh = 0; kh < 3; ++kh)
+          for (int cc = 0; cc < chunks; ++cc)
+            for (int kw = 0; kw < 3; ++kw) load_w(&p.tm_w, ((kh * 3 + kw) * chunks + cc) * BK, n0);
+        pseq += 3 * chunks;  // filled by the transform warps
+        int kb = 9 * chunks;
+        for (int cc = 0; cc < x_chunks; ++cc, ++kb) {
+          const int ch = cc * BK;
+          if (ch < p.xc0) load_p(&p.tm_x0, ch, h0, b0);
+          else load_p(&p.tm_x1, ch - p.xc0, h0, b0);
+          load_w(&p.tm_w, kb * BK, n0);
+        }
+        for (int j = 0; j < r_chunks; ++j) {
+          load_p(&p.tm_res, n0 + j * BK, h0, b0);
+          load_w(&p.tm_ident, j * BK, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (as in conv_gemm_tcH_kernel)
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(128);
+      int ps = 0, ws = 0;
+      uint32_t pph = 0, wph = 0;
+      uint32_t tl = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tl) {
+        const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
+        ptx::mbar_wait(ptx::smem_u32(&tempty_bar[as]), aph ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + as * PX;
+        bool first = true;
+        auto mma_block = [&](uint32_t pbuf, int rowpitch, int shift) {
+          ptx::mbar_wait(ptx::smem_u32(&wfull_bar[ws]), wph);
+          ptx::tc_fence_after();
+          const uint64_t dw = ptx::umma_desc_k_sw128(wbase + ws * C::W_BYTES);
+          const uint64_t d0 = ptx::umma_desc_k_sw128(pbuf + shift * 128);
+          const uint64_t d1 = ptx::umma_desc_k_sw128(pbuf + (rowpitch + shift) * 128);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint32_t acc = (first && k == 0) ? 0u : 1u;
+            ptx::umma_bf16(tmem_acc, dw + 2 * k, d0 + 2 * k, idesc, acc);
+            ptx::umma_bf16(tmem_acc + 128, dw + 2 * k, d1 + 2 * k, idesc, acc);
+          }
+          first = false;
+          ptx::umma_commit(ptx::smem_u32(&wempty_bar[ws]));
+          if (++ws == C::NW) { ws = 0; wph ^= 1; }
+        };
+        for (int kc = 0; kc < 3 * chunks; ++kc) {
+          ptx::mbar_wait(ptx::smem_u32(&pfull_bar[ps]), pph);
+          ptx::tc_fence_after();
+          const uint32_t pbuf = pbase + ps * C::P_BYTES;
+          for (int kw = 0; kw < 3; ++kw) mma_block(pbuf, C::P_ROWPITCH, kw);
+          ptx::umma_commit(ptx::smem_u32(&pempty_bar[ps]));
+          if (++ps == C::NP) { ps = 0; pph ^= 1; }
+        }
+        for (int kc = 0; kc < x_chunks + r_chunks; ++kc) {
+          ptx::mbar_wait(ptx::smem_u32(&pfull_bar[ps]), pph);
+          ptx::tc_fence_after();
+          mma_block(pbase + ps * C::P_BYTES, 128, 0);
+          ptx::umma_commit(ptx::smem_u32(&pempty_bar[ps]));
+          if (++ps == C::NP) { ps = 0; pph ^= 1; }
+        }
+        ptx::umma_commit(ptx::smem_u32(&tfull_bar[as]));
+      }
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------------------ epilogue (warps 2..5): thread = channel
+    const int q = warp & 3;
+    epilogue_dispatch<PX, PX / 32>(p, tmem_base, tfull_bar, tempty_bar, out_stage + q * (2 * 32 * 32 * 2), q, 0, 1, 0, lane);
+  } else {
+    // ------------------------------------------------------------ transform warps (6..13)
+    const int grp = (warp - 6) >> 2;                       // groups of four warps
+    const int tg = static_cast<int>(threadIdx.x) - NUM_THREADS - grp * 128;  // 0..127 within the group
+    const int c = tg & 7;                                  // logical 16-byte chunk = channels 8 c .. 8 c + 7 of the slice
+    const int r0 = tg >> 3;                                // first pixel row of this thread; then every 16th
+    const int ctot = p.c0 + p.c1;
+    constexpr int PASSES = (C::P_ROWS + 15) / 16;          // 17
+    long long seq_base = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, seq_base += bufs_per_tile) {
+      const int tt = p.reverse ? p.num_tiles - 1 - t : t;
+      const int pt = tt / p.n_tiles;
+      const int m0 = pt * PX;
+      const int b0 = m0 / hw;
+      const int h0 = (m0 - b0 * hw) / p.W;
+      for (int idx = 0; idx < 3 * chunks; ++idx) {
+        const long long seq = seq_base + idx;
+        if (static_cast<int>(seq % C::T_GROUPS) != grp) continue;
+        const int kh = idx / chunks, cc = idx - kh * chunks;
+        const int ch = cc * BK;
+        // this thread's 8 channels: pre-halved affine as packed bf16 pairs
+        const float* sc = p.gn_scale + static_cast<long long>(b0) * ctot + ch + c * 8;
+        const float* sh = p.gn_shift + static_cast<long long>(b0) * ctot + ch + c * 8;
+        const __nv_bfloat16* src = (ch < p.c0) ? p.raw0 : p.raw1;
+        const int cs = (ch < p.c0) ? p.c0 : p.c1;
+        const int cof = ((ch < p.c0) ? ch : ch - p.c0) + c * 8;
+        // All loads of the box go out BEFORE the wait for a free buffer: they land in registers, so their latency
+        // overlaps the time the MMA warp still needs for the buffer being recycled.
+        uint4 v[PASSES];
+        unsigned okmask = 0;
+#pragma unroll
+        for (int i = 0; i < PASSES; ++i) {
+          const int pr = r0 + 16 * i;                          // pixel row of the box: rr * 130 + (px + 1)
+          const int rr = pr >= C::P_ROWPITCH ? 1 : 0;
+          const int px = pr - rr * C::P_ROWPITCH - 1;
+          const int hh = h0 + kh - 1 + rr;
+          const bool ok = pr < C::P_ROWS && px >= 0 && px < p.W && hh >= 0 && hh < p.H;
+          v[i] = make_uint4(0u, 0u, 0u, 0u);
+          if (ok) {
+            okmask |= 1u << i;
+            if (!(p.hf_debug & 2))
+              v[i] = __ldg(reinterpret_cast<const uint4*>(src + ((static_cast<long long>(b0) * p.H + hh) * p.W + px) * cs + cof));
+          }
+        }
+        const float4 sc4[2] = {__ldg(reinterpret_cast<const float4*>(sc)), __ldg(reinterpret_cast<const float4*>(sc) + 1)};
+        const float4 sh4[2] = {__ldg(reinterpret_cast<const float4*>(sh)), __ldg(reinterpret_cast<const float4*>(sh) + 1)};
+        const int ps = static_cast<int>(seq % C::NP);
+        const uint32_t pph = static_cast<uint32_t>((seq / C::NP) & 1);
+        ptx::mbar_wait_relaxed(ptx::smem_u32(&pempty_bar[ps]), pph ^ 1);
+        // (the affine is fetched AFTER the pixel loads went out and consumed only here: its latency overlaps theirs)
+        uint32_t hs[4], hb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          hs[i] = ptx::pack_bf16x2(0.5f * (i & 1 ? sc4[i >> 1].z : sc4[i >> 1].x),
+                                   0.5f * (i & 1 ? sc4[i >> 1].w : sc4[i >> 1].y));
+          hb[i] = ptx::pack_bf16x2(0.5f * (i & 1 ? sh4[i >> 1].z : sh4[i >> 1].x), 0.5f * (i & 1 ? sh4[i >> 1].w : sh4[i >> 1].y));
+        }
+        const uint32_t pbuf = pbase + ps * C::P_BYTES;
+        // arithmetic for ALL rows first (68 independent chains per thread: the MUFU / HFMA2 latencies overlap), then
+        // the stores -- interleaving them row by row put a volatile store between the chains and left each warp with
+        // the instruction-level parallelism of a single row (the transform then took ~3.5 us per box and starved the
+        // MMA warp: r02_fused_gn_ab.txt)
+#pragma unroll
+        for (int i = 0; i < PASSES; ++i) {
+          uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+          if (!(p.hf_debug & 1)) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t h = bf16x2_fma(w[k], hs[k], hb[k]);
+              w[k] = bf16x2_fma(h, bf16x2_tanh(h), h);
+            }
+          }
+          const bool on = (okmask >> i) & 1u;  // halo pixels outside the image stay zero: padding follows the activation
+          v[i] = make_uint4(on ? w[0] : 0u, on ? w[1] : 0u, on ? w[2] : 0u, on ? w[3] : 0u);
+        }
+#pragma unroll
+        for (int i = 0; i < PASSES; ++i) {
+          const int pr = r0 + 16 * i;
+          if (pr < C::P_ROWS) {
+            const uint32_t dst = pbuf + pr * 128 + ((c ^ (pr & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v[i].x), "r"(v[i].y), "r"(v[i].z),
+                         "r"(v[i].w)
+                         : "memory");
+          }
+        }
+        ptx::fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");  // the four warps of this group
+        if (tg == 0) ptx::mbar_arrive(ptx::smem_u32(&pfull_bar[ps]));
+      }
+      // The centre-tap / residual buffers that follow are filled by the TMA warp.  This group still WAITS for the
+      // release of the ones on its alternation: mbarrier waits are by phase parity, so a producer may never get two
+      // revolutions of the ring ahead of the consumer -- skipping over a long TMA-owned stretch straight to the next
+      // tile would let its next wait pass on a stale phase and overwrite a buffer the MMA warp has not read yet.
+      for (int idx = 3 * chunks; idx < bufs_per_tile; ++idx) {
+        const long long seq = seq_base + idx;
+        if (static_cast<int>(seq % C::T_GROUPS) != grp) continue;
+        ptx::mbar_wait_relaxed(ptx::smem_u32(&pempty_bar[seq % C::NP]), static_cast<uint32_t>((seq / C::NP) & 1) ^ 1);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
 // ------------------------------------------------------------------------------------ host side
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -1102,6 +1420,19 @@ void launch_h(TcParams& p, cudaStream_t st) {
   launch_pdl<1>(conv_gemm_tcH_kernel, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, st, p);
 }
 
+void launch_hf(TcParams& p, cudaStream_t st) {
+  using C = CfgHF;
+  static bool configured = false;
+  if (!configured) {
+    T2P_CUDA(cudaFuncSetAttribute(conv_gemm_tcHF_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    configured = true;
+  }
+  p.n_tiles = cdiv(p.N, 128);
+  p.num_tiles = cdiv(p.M, C::PX) * p.n_tiles;
+  const int grid = std::min(p.num_tiles, sm_count());
+  launch_pdl<1>(conv_gemm_tcHF_kernel, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, p);
+}
+
 // `rows` consecutive pixels (b, h, w raster order) as one TMA box (tw, th, tb) of the NHWC tensor
 bool pixel_box(const ConvGemmArgs& a, int rows, uint32_t& tw, uint32_t& th, uint32_t& tb) {
   if (a.ksize == 1) { tw = rows; th = 1; tb = 1; return true; }
@@ -1168,6 +1499,8 @@ Plan make_plan(const ConvGemmArgs& a) {
 }  // namespace
 
 bool conv_gemm_tc_channel_major(const ConvGemmArgs& a) { return make_plan(a).channel_major; }
+
+bool conv_gemm_tc_fuses_gn(const ConvGemmArgs& a) { return make_plan(a).halo; }
 
 int conv_gemm_tc_stat_tile(const ConvGemmArgs& a) {
   ConvGemmArgs q = a;
@@ -1259,6 +1592,16 @@ void conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
       uint64_t d[4] = {128, 128, 1, 1};
       uint32_t b[4] = {BK, 128, 1, 1};
       p.tm_ident = make_tmap_bf16(identity128(), d, b);
+    }
+    if (a.gn_scale) {
+      T2P_CHECK(pl.halo && a.gn_shift, "fused GroupNorm needs the halo kernel (ask conv_gemm_tc_fuses_gn first)");
+      p.raw0 = static_cast<const __nv_bfloat16*>(a.a0);
+      p.raw1 = static_cast<const __nv_bfloat16*>(a.a1);
+      p.gn_scale = a.gn_scale;
+      p.gn_shift = a.gn_shift;
+      p.hf_debug = env_knob("T2P_HF_DEBUG", 0);
+      launch_hf(p, st);
+      return;
     }
     if (pl.halo) {
       launch_h(p, st);

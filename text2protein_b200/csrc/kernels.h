@@ -43,6 +43,11 @@ struct ConvGemmArgs {
   // that each starts on the part of its input the previous kernel wrote last (still resident in the 126 MB L2).
   int reverse = 0;
   int out_nchw = 0;    // 1: store out as [B][N][H*W] (fp32 only; used by the final conv)
+  // GroupNorm-apply + SiLU fused into the operand path: a0 | a1 are RAW activations and the kernel feeds
+  // silu(x * gn_scale[b][c] + gn_shift[b][c]) (affine over the channel concat, [B][c0 + c1] fp32) to the tensor
+  // core.  Only where conv_gemm_tc_fuses_gn(args) says so (3x3 on 128-pixel-wide images: the halo kernel).
+  const float* gn_scale = nullptr;
+  const float* gn_shift = nullptr;
 };
 
 // bf16 tcgen05 / TMEM / TMA path (sm_100a).  A, W are bf16.
@@ -52,6 +57,8 @@ void conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st);
 int conv_gemm_tc_stat_tile(const ConvGemmArgs& a);
 // true when these arguments run on the channel-major kernel (the one that accepts x0 / x1)
 bool conv_gemm_tc_channel_major(const ConvGemmArgs& a);
+// true when this launch can apply GroupNorm + SiLU to its 3x3 sources itself (gn_scale / gn_shift)
+bool conv_gemm_tc_fuses_gn(const ConvGemmArgs& a);
 // fp32 or bf16 SIMT path (verification mode and tiny-channel edge layers). dtype of A and W.
 void conv_gemm_simt(const ConvGemmArgs& a, int in_dtype, cudaStream_t st);
 

@@ -50,6 +50,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Wait with back-off: for waiters that have slack (producers running ahead of their consumer).  Every poll of an
+// mbarrier is a shared-memory transaction; hundreds of threads polling back to back compete with the tensor core's
+// operand reads.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, unsigned ns = 128) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
+// Whole-warp wait: lane 0 polls, the other lanes park at the warp barrier (32 lanes spinning on try_wait -- plus the
+// clock read of the time-out check -- take issue slots from the warps that have work; ncu on the fused halo kernel
+// showed 4.7x the useful instruction count before this).  __syncwarp orders the lanes' later accesses after lane 0's
+// acquire.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
+
 // ---------------------------------------------------------------- TMA
 // 1-D bulk copy global -> shared (TMA without a tensor map): 16-byte aligned addresses, size a multiple of 16;
 // completion is signalled as `bytes` of transaction count on the mbarrier

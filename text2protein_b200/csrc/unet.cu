@@ -441,10 +441,34 @@ static int debug_dup() {
   return m;
 }
 
+// true when the tcgen05 launch for this convolution applies GroupNorm + SiLU to its 3x3 sources itself
+bool UNet::fuses_gn(const Linear& l, const Act& a0, const Act* a1) const {
+  // opt-in (set_fused_groupnorm): measured break-even on cfg2, profiles/r02_fused_gn_ab.txt.  T2P_FUSE_GN (knob
+  // builds) overrides the option for A/B runs.
+  static const int knob = env_knob("T2P_FUSE_GN", -1);
+  if (!(knob >= 0 ? knob != 0 : fuse_gn_)) return false;
+  if (cfg_.compute_dtype != kBF16 || l.force_f32 || l.ksize != 3) return false;
+  ConvGemmArgs g;
+  g.c0 = a0.C;
+  g.c1 = a1 ? a1->C : 0;
+  if (g.c0 % 64 || g.c1 % 64) return false;
+  g.B = a0.B; g.H = a0.H; g.W = a0.W;
+  g.ksize = l.ksize;
+  g.N = l.N;
+  g.rows_per_sample = a0.H * a0.W;
+  g.out_dtype = kBF16;
+  g.xc0 = l.xk;  // (only the total matters to the plan)
+  return conv_gemm_tc_fuses_gn(g);
+}
+
 void UNet::gemm(const Linear& l, const Act& a0, const Act* a1, Act& out, const float* rowbias, int rowbias_ld,
                 const void* residual, int res_up, float alpha, int out_dtype, int out_nchw, const Act* x0,
-                const Act* x1) {
+                const Act* x1, const float* gn_affine) {
   ConvGemmArgs g;
+  if (gn_affine) {
+    g.gn_scale = gn_affine;
+    g.gn_shift = gn_affine + static_cast<size_t>(a0.B) * (a0.C + (a1 ? a1->C : 0));
+  }
   g.a0 = a0.p; g.c0 = a0.C;
   if (a1) { g.a1 = a1->p; g.c1 = a1->C; }
   if (x0) { g.x0 = x0->p; g.xc0 = x0->C; }
@@ -483,6 +507,16 @@ void UNet::gemm(const Linear& l, const Act& a0, const Act* a1, Act& out, const f
   for (int rep = 0; rep < 1 + ((debug_dup() & cls) ? 1 : 0); ++rep) {
     if (tc) conv_gemm_tc(g, ln_->st);
     else conv_gemm_simt(g, l.force_f32 ? kF32 : cfg_.compute_dtype, ln_->st);
+  }
+  static const bool dbg_sync = env_knob_set("T2P_DEBUG_SYNC");  // knob builds: find the launch that faults
+  if (dbg_sync) {
+    cudaError_t e = cudaStreamSynchronize(ln_->st);
+    if (e != cudaSuccess) {
+      std::fprintf(stderr, "GEMM FAULT: B=%d H=%d W=%d c0=%d c1=%d xc0=%d xc1=%d N=%d k=%d fused=%d stats=%d rowbias=%d reverse=%d: %s\n",
+                   g.B, g.H, g.W, g.c0, g.c1, g.xc0, g.xc1, g.N, g.ksize, g.gn_scale ? 1 : 0, g.stat_part ? 1 : 0,
+                   g.rowbias ? 1 : 0, g.reverse, cudaGetErrorString(e));
+      T2P_CUDA(e);
+    }
   }
   if (profile_) {
     T2P_CUDA(cudaEventRecord(e1, ln_->st));
@@ -590,13 +624,36 @@ Act UNet::run_res(ResBlockM& m, const Act& a0, const Act* a1) {
   const int B = a0.B, H = a0.H, W = a0.W;
   const int OH = m.down ? H / 2 : (m.up ? H * 2 : H), OW = m.down ? W / 2 : (m.up ? W * 2 : W);
   const int mode = m.down ? 1 : (m.up ? 2 : 0);
-  Act h = new_act(B, OH, OW, m.in_ch, false);
   Act xr;  // resampled raw input: 2x2 mean (skip path of a down block) or, folded up block, nearest x2
   if (m.down || (m.up && m.folded)) xr = new_act(B, OH, OW, m.in_ch, false);
-  group_norm(m.gn0, a0, a1, 1, mode, h, xr.p ? &xr : nullptr);
   Act h1 = new_act(B, OH, OW, m.out_ch, true);
-  gemm(m.conv0, h, nullptr, h1, ln_->temb_all + m.temb_off, temb_total_, nullptr, 0, 1.f);
-  free_act(h);
+  if (mode == 0 && fuses_gn(m.conv0, a0, a1)) {
+    // h = act(GroupNorm_0(x)) is applied inside Conv_0's operand path: the normalised tensor is never written
+    float* affine = nullptr;
+    Act none;
+    group_norm(m.gn0, a0, a1, 1, 0, none, nullptr, &affine);
+    gemm(m.conv0, a0, a1, h1, ln_->temb_all + m.temb_off, temb_total_, nullptr, 0, 1.f, -1, 0, nullptr, nullptr, affine);
+    ln_->ws.free(affine);
+  } else {
+    Act h = new_act(B, OH, OW, m.in_ch, false);
+    group_norm(m.gn0, a0, a1, 1, mode, h, xr.p ? &xr : nullptr);
+    gemm(m.conv0, h, nullptr, h1, ln_->temb_all + m.temb_off, temb_total_, nullptr, 0, 1.f);
+    free_act(h);
+  }
+  if (m.folded && fuses_gn(m.conv1, h1, nullptr)) {
+    // same for act(GroupNorm_1(h1)) feeding Conv_1 (+ the folded skip path, which reads RAW x anyway)
+    float* affine = nullptr;
+    Act none;
+    group_norm(m.gn1, h1, nullptr, 1, 0, none, nullptr, &affine);
+    Act out = new_act(B, OH, OW, m.out_ch, true);
+    const Act* x0 = xr.p ? &xr : &a0;
+    const Act* x1 = xr.p ? nullptr : a1;
+    gemm(m.conv1, h1, nullptr, out, nullptr, 0, nullptr, 0, 0.70710678118654752f, -1, 0, x0, x1, affine);
+    ln_->ws.free(affine);
+    free_act(h1);
+    if (xr.p) free_act(xr);
+    return out;
+  }
   Act h2 = new_act(B, OH, OW, m.out_ch, false);
   group_norm(m.gn1, h1, nullptr, 1, 0, h2, nullptr);
   free_act(h1);

@@ -163,6 +163,11 @@ class UNet {
                const float* timesteps = nullptr);
   const double* sigmas() const { return static_cast<const double*>(sigmas_->data); }
   void set_debug(bool on) { debug_ = on; }
+  // GroupNorm-apply + SiLU inside the operand path of the 3x3 convolutions on 128-pixel-wide images (gemm_tc.cu,
+  // conv_gemm_tcHF_kernel) instead of a separate pass; changes the launch sequence, hence the plan and any captured graph
+  void set_fused_groupnorm(bool on) {
+    if (on != fuse_gn_) { fuse_gn_ = on; planned_B_ = -1; ++generation_; }
+  }
   // copies a recorded block output (fp32 NCHW) to dst; returns its shape
   bool tap(const std::string& name, float* dst, int64_t capacity, int64_t shape[4], cudaStream_t st);
   // profile mode: CUDA events around every implicit-GEMM launch of the following forward passes
@@ -193,7 +198,8 @@ class UNet {
   void free_act(Act& a);
   void gemm(const Linear& l, const Act& a0, const Act* a1, Act& out, const float* rowbias, int rowbias_ld,
             const void* residual, int res_up, float alpha, int out_dtype = -1, int out_nchw = 0,
-            const Act* x0 = nullptr, const Act* x1 = nullptr);
+            const Act* x0 = nullptr, const Act* x1 = nullptr, const float* gn_affine = nullptr);
+  bool fuses_gn(const Linear& l, const Act& a0, const Act* a1) const;
   void group_norm(const GroupNormP& g, const Act& a0, const Act* a1, int act, int mode, Act& out, Act* raw_out,
                   float** affine_out = nullptr);
   void attention(const void* q, const void* k, const void* v, void* out, int B, int heads, int Tq, int Tk, int d,
@@ -235,6 +241,7 @@ class UNet {
   Lane* ln_ = &lane_;
   bool dry_ = false;
   bool debug_ = false;
+  bool fuse_gn_ = false;
   bool profile_ = false;
   long long generation_ = 0;
   std::vector<GemmRecord> profile_log_;

@@ -96,6 +96,8 @@ class UNetModel(nn.Module):
         self.register_buffer('sigmas', torch.tensor(mutils.get_sigmas(config)))
         self._handle = C.c_void_p(0)
         self._create_engine()
+        if hasattr(config.model, "get") and config.model.get("fused_groupnorm", False):
+            self.set_fused_groupnorm(True)
         self._build_tree()
         self._synced_version = None
         self._synced_checksum = None
@@ -267,6 +269,12 @@ class UNetModel(nn.Module):
             _lib.check(_lib.lib().t2p_unet_forward_t(self._handle, _lib.ptr(xf), _lib.ptr(labels), _lib.ptr(timesteps),
                                                      _lib.ptr(out), _lib.F64, B, _lib.current_stream()))
         return out
+
+    def set_fused_groupnorm(self, on=True):
+        """Option (default off): GroupNorm + SiLU inside the 3x3 convolutions on 128-pixel-wide images instead of
+        a separate pass (include/t2p.h, t2p_unet_set_fused_groupnorm).  ``config.model.fused_groupnorm`` sets it
+        at construction."""
+        _lib.check(_lib.lib().t2p_unet_set_fused_groupnorm(self._handle, 1 if on else 0))
 
     # ------------------------------------------------------------------ debugging aids
     def set_debug(self, on=True):
