@@ -166,11 +166,11 @@ def test_pc_iterations_keep_conditions_bit_exact_at_n128(name, kinds, B):
 
 
 def test_fused_groupnorm_option_matches_reference_golden(golden_dir):
-    """The opt-in fused GroupNorm + SiLU convolutions (profiles/r02_fused_gn_ab.txt) against the reference's output at
-    cfg2 and at test_config (128-pixel-wide level with 256 / 512 / 768 channels, multi-tile CTAs)."""
-    for case in ("cond_length_L256", "test_config"):
-        fname, B, L = FULLSIZE_CASES[case]
-        g = np.load(os.path.join(golden_dir, f"unet_full_{case}.npz"))
+    """The opt-in fused GroupNorm + SiLU convolutions (profiles/r02_fused_gn_ab.txt): against the reference's output at
+    test_config (its 128-pixel-wide level has 256 / 512 / 768 input channels and multi-tile CTAs) and, at cfg2 with
+    B = 4 (at B = 1 the 128 x 128 level is too small for the halo kernel and nothing is fused), against the plain path."""
+    for case, B in (("test_config", 1), ("cond_length_L256", 4)):
+        fname, _, L = FULLSIZE_CASES[case]
         cfg, m = _model(fname[:-4], "bf16")
         x, labels, ctx = fullsize_inputs(cfg, B, L)
         plain = m(x.cuda(), labels.cuda(), ctx.cuda())
@@ -178,9 +178,11 @@ def test_fused_groupnorm_option_matches_reference_golden(golden_dir):
         m.set_fused_groupnorm(True)
         fused = m(x.cuda(), labels.cuda(), ctx.cuda())
         assert _lib.lib().t2p_unet_launches_per_forward(m.native_handle) < n_plain  # apply launches are gone
-        ref = torch.from_numpy(g["out"]).double()
-        assert rel_err(fused, ref) < 2e-2 and rel_err(plain, ref) < 2e-2
         assert rel_err(fused, plain) < 2e-2
+        if B == 1:
+            g = np.load(os.path.join(golden_dir, f"unet_full_{case}.npz"))
+            ref = torch.from_numpy(g["out"]).double()
+            assert rel_err(fused, ref) < 2e-2 and rel_err(plain, ref) < 2e-2
         m.set_fused_groupnorm(False)
         assert torch.equal(m(x.cuda(), labels.cuda(), ctx.cuda()), plain)
         del m
