@@ -8,8 +8,8 @@
 //   warp 0     TMA producer: per 128-key block the Q / K tiles in 64-channel slices (K loop of the score GEMM),
 //              then the V tile in two 64-key slices (K loop of the output GEMM), through one ring of stages
 //   warp 1     tcgen05.mma issuer (one elected thread) + TMEM allocation
-//   warps 2-5  softmax: thread = query row = TMEM lane.  Reads the fp32 scores with tcgen05.ld (twice: running
-//              maximum, then exponentials), rescales the O accumulator in TMEM when the maximum moved
+//   warps 2-5  softmax: thread = query row = TMEM lane.  Reads its 128 fp32 scores with four tcgen05.ld in flight
+//              (one wait), takes the running maximum, rescales the O accumulator in TMEM when the maximum moved
 //              (tcgen05.ld / tcgen05.st), writes P as bf16 into a 128-byte-swizzled K-major shared-memory tile
 //              (the A operand of the output GEMM) and finally normalises and stores O.
 // Operand layouts: Q, K and P are K-major (the reduction index is contiguous); V is consumed exactly as it lies
@@ -23,6 +23,7 @@
 // single-buffered; overlap comes from two CTAs per SM (TMEM: 128 score columns + DV <= 128 output columns each).
 #include <cuda.h>
 
+#include <algorithm>
 #include <mutex>
 #include <unordered_map>
 
@@ -42,6 +43,7 @@ struct AttnTcParams {
   long long ldo;
   int Tq, Tk, heads, d, dv_splits;
   float scale_log2;  // scale * log2(e)
+  int q_tiles, hy, items;  // work items = B x (heads * dv_splits) x q_tiles, query tile fastest
 };
 
 template <int D, int DV>
@@ -112,25 +114,30 @@ __device__ __forceinline__ void tma_load_3d_to(uint32_t dst, const CUtensorMap* 
 }
 
 template <int D, int DV>
-__global__ void __launch_bounds__(THREADS) attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
+__global__ void __launch_bounds__(THREADS, (BKEY + DV) <= 256 ? 2 : 1) attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
   using C = ACfg<D, DV>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[C::NS], empty_bar[C::NS];
-  __shared__ __align__(8) uint64_t sfull_bar, pfull_bar, ofull_bar;
+  __shared__ __align__(8) uint64_t sfull_bar, pfull_bar, ofull_bar, oempty_bar;
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ring = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t pbuf = ring + C::NS * C::STAGE;  // 1024-aligned: every stage size is a multiple of 1 KB
 
-  const int q0 = blockIdx.x * BQ;
-  const int head = blockIdx.y / p.dv_splits;
-  const int dvs = blockIdx.y - head * p.dv_splits;
-  const int b = blockIdx.z;
   const int nd = p.d / C::CH;                 // K-loop slices of the score GEMM
   const int nkb = (p.Tk + BKEY - 1) / BKEY;   // key blocks
-  const int qk_col0 = head * p.d;             // first channel of this head in the q / k views
-  const int v_col0 = head * p.d + dvs * DV;   // first value channel this CTA produces
+  // Persistent: the CTA walks work items blockIdx.x, + gridDim.x, ...; barriers, TMEM and the TMA ring live across
+  // items, so the producer prefetches the next item's first tiles while the softmax warps finish the current one,
+  // and the set-up (barrier init, TMEM allocation, descriptor prefetch) is paid once per CTA instead of per tile.
+  struct Item { int q0, b, qk_col0, v_col0; };
+  auto item_of = [&](int it) {
+    const int qt = it % p.q_tiles;
+    const int r = it / p.q_tiles;
+    const int hy = r % p.hy, b = r / p.hy;
+    const int head = hy / p.dv_splits, dvs = hy - head * p.dv_splits;
+    return Item{qt * BQ, b, head * p.d, head * p.d + dvs * DV};
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::NS; ++s) {
@@ -140,6 +147,7 @@ __global__ void __launch_bounds__(THREADS) attention_tc_kernel(const __grid_cons
     ptx::mbar_init(ptx::smem_u32(&sfull_bar), 1);
     ptx::mbar_init(ptx::smem_u32(&pfull_bar), 4);  // one arrival per softmax warp
     ptx::mbar_init(ptx::smem_u32(&ofull_bar), 1);
+    ptx::mbar_init(ptx::smem_u32(&oempty_bar), 4);  // the softmax warps have read O of the finished item
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -161,6 +169,9 @@ __global__ void __launch_bounds__(THREADS) attention_tc_kernel(const __grid_cons
       ptx::prefetch_tmap(&p.tm_v);
       int s = 0;
       uint32_t ph = 0;
+      for (int it = blockIdx.x; it < p.items; it += gridDim.x) {
+      const Item w = item_of(it);
+      const int q0 = w.q0, b = w.b, qk_col0 = w.qk_col0, v_col0 = w.v_col0;
       for (int j = 0; j < nkb; ++j) {
         for (int c = 0; c < nd; ++c) {  // Q slice (re-read per key block: it stays in L2) + K slice
           ptx::mbar_wait(ptx::smem_u32(&empty_bar[s]), ph ^ 1);
@@ -182,6 +193,7 @@ __global__ void __launch_bounds__(THREADS) attention_tc_kernel(const __grid_cons
           if (++s == C::NS) { s = 0; ph ^= 1; }
         }
       }
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -190,8 +202,10 @@ __global__ void __launch_bounds__(THREADS) attention_tc_kernel(const __grid_cons
       constexpr uint32_t idesc_o = idesc_bf16(DV, true);
       int s = 0;
       uint32_t ph = 0;
-      for (int j = 0; j < nkb; ++j) {
-        // S = Q K_j^T.  (For j > 0 the softmax warps have finished reading S of block j - 1: p_full below.)
+      uint32_t blk = 0, nit = 0;  // key blocks / items processed by this CTA (barrier phases)
+      for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++nit) {
+      for (int j = 0; j < nkb; ++j, ++blk) {
+        // S = Q K_j^T.  (The softmax warps have finished reading the previous S: p_full of the block before.)
         for (int c = 0; c < nd; ++c) {
           ptx::mbar_wait(ptx::smem_u32(&full_bar[s]), ph);
           ptx::tc_fence_after();
@@ -205,7 +219,8 @@ __global__ void __launch_bounds__(THREADS) attention_tc_kernel(const __grid_cons
         }
         ptx::umma_commit(ptx::smem_u32(&sfull_bar));
         // O += P_j V_j once the softmax warps have written P_j (and rescaled O)
-        ptx::mbar_wait(ptx::smem_u32(&pfull_bar), j & 1);
+        ptx::mbar_wait(ptx::smem_u32(&pfull_bar), blk & 1);
+        if (j == 0 && nit > 0) ptx::mbar_wait(ptx::smem_u32(&oempty_bar), (nit - 1) & 1);  // O of the last item was read
         ptx::tc_fence_after();
         for (int kc = 0; kc < 2; ++kc) {
           ptx::mbar_wait(ptx::smem_u32(&full_bar[s]), ph);
@@ -222,6 +237,7 @@ __global__ void __launch_bounds__(THREADS) attention_tc_kernel(const __grid_cons
         }
       }
       ptx::umma_commit(ptx::smem_u32(&ofull_bar));
+      }
     }
   } else {
     // ------------------------------------------------------------------ softmax / correction / epilogue
@@ -229,27 +245,33 @@ __global__ void __launch_bounds__(THREADS) attention_tc_kernel(const __grid_cons
     const int row = qd * 32 + lane;        // query row within the tile
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
     const float sl2 = p.scale_log2;
+    uint32_t blk = 0, nit = 0;
+    for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++nit) {
+    const Item w = item_of(it);
+    const int q0 = w.q0, b = w.b, v_col0 = w.v_col0;
     float m = -INFINITY, l = 0.f;
-    for (int j = 0; j < nkb; ++j) {
+    for (int j = 0; j < nkb; ++j, ++blk) {
       const int valid = min(BKEY, p.Tk - j * BKEY);  // keys of this block that exist (TMA zero-fills the rest)
-      ptx::mbar_wait_warp(ptx::smem_u32(&sfull_bar), j & 1);
+      ptx::mbar_wait_warp(ptx::smem_u32(&sfull_bar), blk & 1);
       ptx::tc_fence_after();
-      // pass A: row maximum of the raw scores
-      float mx = m;
-#pragma unroll 1
-      for (int c = 0; c < BKEY / 32; ++c) {
-        if (c * 32 >= valid) break;
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(tmem_s + lane_off + c * 32, r);
-        ptx::tmem_ld_wait();
-        if (c * 32 + 32 <= valid) {
+      // the whole score row (128 fp32) comes into registers with ONE wait: four tcgen05.ld in flight together
+      uint32_t r[4][32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-        } else {
+      for (int c = 0; c < 4; ++c) ptx::tmem_ld_32x32(tmem_s + lane_off + c * 32, r[c]);
+      ptx::tmem_ld_wait();
+      // row maximum of the raw scores (keys beyond Tk read as zero scores: masked out)
+      float mx = m;
+      if (valid == BKEY) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[c][i]));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
-        }
+            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[c][i]));
       }
       // correction of what has been accumulated so far (skipped by a warp none of whose rows moved)
       if (j > 0) {
@@ -258,41 +280,33 @@ __global__ void __launch_bounds__(THREADS) attention_tc_kernel(const __grid_cons
         if (__any_sync(0xffffffffu, mx > m)) {
 #pragma unroll 1
           for (int c = 0; c < DV / 32; ++c) {
-            uint32_t r[32];
-            ptx::tmem_ld_32x32(tmem_o + lane_off + c * 32, r);
+            uint32_t o[32];
+            ptx::tmem_ld_32x32(tmem_o + lane_off + c * 32, o);
             ptx::tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-            tmem_st_32x32(tmem_o + lane_off + c * 32, r);
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32(tmem_o + lane_off + c * 32, o);
           }
           tmem_st_wait();
         }
       }
       m = mx;
       const float moff = -m * sl2;
-      // pass B: P = exp2(s * sl2 - m * sl2) as bf16 into the swizzled K-major tile; row sum in fp32
+      // P = exp2(s * sl2 - m * sl2) as bf16 into the swizzled K-major tile; row sum in fp32
       const uint32_t prow = pbuf + row * 128;
-#pragma unroll 1
+#pragma unroll
       for (int c = 0; c < BKEY / 32; ++c) {
         uint32_t pk[16];
-        if (c * 32 < valid) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(tmem_s + lane_off + c * 32, r);
-          ptx::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float p0 = ex2(fmaf(__uint_as_float(r[i]), sl2, moff));
-            float p1 = ex2(fmaf(__uint_as_float(r[i + 1]), sl2, moff));
-            if (c * 32 + 32 > valid) {
-              if (c * 32 + i >= valid) p0 = 0.f;
-              if (c * 32 + i + 1 >= valid) p1 = 0.f;
-            }
-            l += p0 + p1;
-            pk[i >> 1] = ptx::pack_bf16x2(p0, p1);
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = ex2(fmaf(__uint_as_float(r[c][i]), sl2, moff));
+          float p1 = ex2(fmaf(__uint_as_float(r[c][i + 1]), sl2, moff));
+          if (valid != BKEY) {
+            if (c * 32 + i >= valid) p0 = 0.f;
+            if (c * 32 + i + 1 >= valid) p1 = 0.f;
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = 0u;
+          l += p0 + p1;
+          pk[i >> 1] = ptx::pack_bf16x2(p0, p1);
         }
         // columns [32 c, 32 c + 32) = 16-byte chunks 4 (c % 2) .. + 3 of the 64-key tile c / 2
         const uint32_t tile = prow + (c >> 1) * (BQ * 128);
@@ -310,7 +324,7 @@ __global__ void __launch_bounds__(THREADS) attention_tc_kernel(const __grid_cons
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&pfull_bar));
     }
     // epilogue: O / l -> bf16 -> global (rows beyond Tq exist only in the tile)
-    ptx::mbar_wait_warp(ptx::smem_u32(&ofull_bar), 0);
+    ptx::mbar_wait_warp(ptx::smem_u32(&ofull_bar), nit & 1);
     ptx::tc_fence_after();
     const float inv = 1.f / l;
     const int t = q0 + row;
@@ -331,6 +345,10 @@ __global__ void __launch_bounds__(THREADS) attention_tc_kernel(const __grid_cons
           *reinterpret_cast<uint4*>(orow + c * 32 + q4 * 8) = o;
         }
       }
+    }
+    ptx::tc_fence_before();  // every tcgen05.ld of O has completed: the next item may overwrite it
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&oempty_bar));
     }
   }
 
@@ -423,8 +441,15 @@ void launch(const AttnArgs& a, cudaStream_t st) {
   p.Tq = a.Tq; p.Tk = a.Tk; p.heads = a.heads; p.d = a.d;
   p.dv_splits = a.d / DV;
   p.scale_log2 = a.scale * 1.4426950408889634f;
-  dim3 grid(cdiv(a.Tq, BQ), a.heads * p.dv_splits, a.B);
-  attention_tc_kernel<D, DV><<<grid, THREADS, C::SMEM, st>>>(p);
+  p.q_tiles = cdiv(a.Tq, BQ);
+  p.hy = a.heads * p.dv_splits;
+  const long long items = static_cast<long long>(a.B) * p.hy * p.q_tiles;
+  T2P_CHECK(items < (1ll << 31), "attention problem too large");
+  p.items = static_cast<int>(items);
+  static int sms[64] = {};
+  if (dev < 64 && !sms[dev]) T2P_CUDA(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
+  const int resident = (dev < 64 ? sms[dev] : 148) * (C::TMEM_COLS == 256 ? 2 : 1);  // CTAs that fit at once
+  attention_tc_kernel<D, DV><<<std::min(p.items, resident), THREADS, C::SMEM, st>>>(p);
   T2P_LAUNCH_CHECK();
 }
 
@@ -435,7 +460,7 @@ bool attention_tc_supported(const AttnArgs& a) {
   const bool aligned = (a.ldq % 8 == 0) && (a.ldk % 8 == 0) && (a.ldv % 8 == 0) && (a.ldo % 8 == 0) &&
                        ((reinterpret_cast<uintptr_t>(a.q) | reinterpret_cast<uintptr_t>(a.k) |
                          reinterpret_cast<uintptr_t>(a.v) | reinterpret_cast<uintptr_t>(a.out)) % 16 == 0);
-  return dims && aligned && a.Tq > 0 && a.Tk > 0 && a.B <= 65535 && a.heads * (a.d > 256 ? a.d / 256 : 1) <= 65535;
+  return dims && aligned && a.Tq > 0 && a.Tk > 0;
 }
 
 void attention_tc(const AttnArgs& a, cudaStream_t st) {
