@@ -238,6 +238,11 @@ int t2p_groupnorm(const void* a0, int c0, const void* a1, int c1, int B, int H, 
  * This is the HBM-bound kernel the engine launches after the GEMM epilogue has produced the statistics. */
 int t2p_groupnorm_apply(const void* a0, int c0, const void* a1, int c1, int B, int H, int W, int dtype, const float* scale,
                         const float* shift, int silu, int resample_mode, void* out, void* raw_out, void* stream);
+/* The same GroupNorm [+ SiLU] (no resampling) as ONE launch for small tensors -- H*W <= 1024, (c0+c1) % 32 == 0,
+ * c0 % 32 == 0, groups of 4 / 8 / 16 / 32 channels: what the engine runs at 32 x 32 and below (statistics, finalize and
+ * apply of the other entry points are three launches there).  Fails for other shapes. */
+int t2p_groupnorm_small(const void* a0, int c0, const void* a1, int c1, int B, int H, int W, int dtype, int groups,
+                        float eps, const float* gamma, const float* beta, int silu, void* out, void* stream);
 int t2p_layernorm(const void* x, const float* gamma, const float* beta, int64_t M, int C, float eps, int dtype,
                   void* y, void* stream);                     /* attention.py:203-205 */
 int t2p_geglu(const void* z, int64_t M, int D, int dtype, void* out, void* stream); /* attention.py:42-44 */

@@ -688,6 +688,14 @@ int t2p_groupnorm(const void* a0, int c0, const void* a1, int c1, int B, int H, 
   T2P_API_END
 }
 
+int t2p_groupnorm_small(const void* a0, int c0, const void* a1, int c1, int B, int H, int W, int dtype, int groups,
+                        float eps, const float* gamma, const float* beta, int silu, void* out, void* stream) {
+  T2P_API_BEGIN
+  T2P_CHECK(a0 && gamma && beta && out && B > 0, "null argument");
+  gn_small(a0, c0, a1, c1, B, H * W, dtype, groups, eps, gamma, beta, silu, out, S(stream));
+  T2P_API_END
+}
+
 int t2p_layernorm(const void* x, const float* gamma, const float* beta, int64_t M, int C, float eps, int dtype,
                   void* y, void* stream) {
   T2P_API_BEGIN

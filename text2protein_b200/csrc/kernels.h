@@ -77,6 +77,10 @@ void gn_finalize(const float* part0, int nblk0, int c0, const float* part1, int 
 // (raw_out, optional, receives the upsampled raw input).
 void gn_apply(const void* a0, int c0, const void* a1, int c1, int B, int H, int W, int dtype, const float* scale,
               const float* shift, int act, int mode, void* out, void* raw_out, cudaStream_t st, int reverse = 0);
+// statistics + finalize + apply in ONE launch for small tensors (HW <= 1024, groups of 4 / 8 / 16 / 32 channels)
+bool gn_small_supported(int c0, int c1, int HW, int G);
+void gn_small(const void* a0, int c0, const void* a1, int c1, int B, int HW, int dtype, int G, float eps,
+              const float* gamma, const float* beta, int act, void* out, cudaStream_t st);
 void layernorm(const void* x, const float* gamma, const float* beta, long long M, int C, float eps, int dtype,
                void* y, cudaStream_t st);
 void geglu(const void* z, long long M, int D, int dtype, void* out, cudaStream_t st);

@@ -555,6 +555,17 @@ void UNet::group_norm(const GroupNormP& gn, const Act& a0, const Act* a1, int ac
   const int C = a0.C + (a1 ? a1->C : 0);
   T2P_CHECK(C == gn.C, "GroupNorm channel mismatch");
   const int B = a0.B, HW = a0.H * a0.W;
+  // small tensors (32 x 32 and below): statistics, finalize and apply in one launch, one pass over the data
+  // (largest H*W it is used for; A/B knob in knob builds.  At 32 x 32 the streaming apply kernel wins: a block that
+  // loads, reduces and only then stores does not overlap its reads with its writes -- profiles/r02_gn_small_ab.txt)
+  static const int small_max = env_knob("T2P_GN_SMALL", 256);
+  if (HW <= small_max && mode == 0 && !affine_out && gn_small_supported(a0.C, a1 ? a1->C : 0, HW, gn.G)) {
+    ++launches_;
+    if (!dry_ && !(debug_skip() & 2))
+      gn_small(a0.p, a0.C, a1 ? a1->p : nullptr, a1 ? a1->C : 0, B, HW, cfg_.compute_dtype, gn.G, 1e-6f,
+               static_cast<const float*>(gn.w->data), static_cast<const float*>(gn.b->data), act, out.p, ln_->st);
+    return;
+  }
   // statistics per source: taken from the producer's epilogue when it left them, else one reduction kernel
   const Act* src[2] = {&a0, a1};
   const float* part[2] = {nullptr, nullptr};

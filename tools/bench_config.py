@@ -1,5 +1,5 @@
 """PC-iteration time of any BASELINE configuration (device-resident, graph-replayed), for the tables in DESIGN.md.
-    python tools/bench_config.py <config> <batch> <ctx_len> [iters]"""
+    python tools/bench_config.py <config> <batch> <ctx_len> [iters] [library file, e.g. libt2p_knobs.so]"""
 import ctypes as C
 import json
 import os
@@ -14,6 +14,8 @@ from text2protein_b200.score_sde_pytorch import sampling, sde_lib  # noqa: E402
 from text2protein_b200.score_sde_pytorch.models.ncsnpp import UNetModel  # noqa: E402
 from text2protein_b200.synthetic import rerandomize_  # noqa: E402
 
+if len(sys.argv) > 5:
+    _lib.use_library(sys.argv[5])
 name, B, Lctx = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 K = int(sys.argv[4]) if len(sys.argv) > 4 else 6
 cfg = load_config(name, device="cuda")
