@@ -95,6 +95,22 @@ inline void launch_pdl(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem,
   cfg.numAttrs = on ? 1 : 0;
   T2P_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...));
 }
+
+// same with the programmatic-serialisation attribute decided per launch (size-dependent experiments)
+template <typename... P, typename... A>
+inline void launch_pdl_dyn(bool on, void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = on ? 1 : 0;
+  T2P_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...));
+}
 #endif
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }

@@ -1377,6 +1377,17 @@ int sm_count() {
   return n;
 }
 
+// Programmatic dependent launch, decided per launch.  On every tcgen05 GEMM it was slower (round 1, T2P_PDL bit 1);
+// on GEMM launches that leave SMs idle (fewer CTAs than SMs: the latency-bound layers at 16 x 16 and below) the next
+// kernel's set-up -- barrier init, TMEM allocation, descriptor prefetch -- runs under the tail of its predecessor:
+// neutral at 64 maps per GPU, -4.6 % per PC iteration at 8 (profiles/r02_gn_small_ab.txt).  T2P_PDL_SMALL (knob
+// builds) overrides the CTA threshold.
+bool pdl_for(int grid) {
+  static const bool all = (env_knob("T2P_PDL", 0) & 1) != 0;
+  static const int small = env_knob("T2P_PDL_SMALL", 147);
+  return all || grid <= small;
+}
+
 template <int BN>
 void launch(TcParams& p, cudaStream_t st) {
   using C = Cfg<BN>;
@@ -1389,7 +1400,7 @@ void launch(TcParams& p, cudaStream_t st) {
   p.n_tiles = cdiv(p.N, BN);
   p.num_tiles = cdiv(p.M, BM) * p.n_tiles;
   const int grid = std::min(p.num_tiles, sm_count());
-  launch_pdl<1>(conv_gemm_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, st, p);
+  launch_pdl_dyn(pdl_for(grid), conv_gemm_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, st, p);
 }
 
 template <int PX>
@@ -1404,7 +1415,7 @@ void launch_t(TcParams& p, cudaStream_t st) {
   p.n_tiles = cdiv(p.N, 128);
   p.num_tiles = cdiv(p.M, PX) * p.n_tiles;
   const int grid = std::min(p.num_tiles, sm_count());
-  launch_pdl<1>(conv_gemm_tcT_kernel<PX>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, p);
+  launch_pdl_dyn(pdl_for(grid), conv_gemm_tcT_kernel<PX>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, p);
 }
 
 void launch_h(TcParams& p, cudaStream_t st) {
