@@ -8,7 +8,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from oracle.philox_ref import philox_normal
-from text2protein_b200.distributed import gather_samples, shard_range
+from text2protein_b200.distributed import exchange_handles, gather_samples, shard_range
 
 
 def test_shard_ranges_cover_batch():
@@ -28,14 +28,21 @@ def _worker(rank, world, port, total, q):
     # what a rank's sampler draws: noise of ITS samples under the GLOBAL element indexing (sample_offset = a)
     local = torch.from_numpy(philox_normal(11, 3, a * per, (b - a) * per)).reshape(b - a, 5, 8, 8)
     full = gather_samples(local, total)
+    # the opaque per-rank handles of StepSizeSync travel in rank order, whatever the backend
+    handles = exchange_handles(bytes([rank]) * 64)
+    assert handles == b"".join(bytes([r]) * 64 for r in range(world))
     if rank == 0:
         q.put(full.numpy())
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_rank_gather_equals_single_process_noise():
-    total, world = 5, 2  # uneven shards: 3 + 2
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("total", [5, 6])  # uneven shards (3 + 2: padded gather) and equal shards (one all_gather_into_tensor)
+def test_two_rank_gather_equals_single_process_noise(total):
+    world = 2
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]

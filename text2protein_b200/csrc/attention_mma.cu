@@ -355,11 +355,10 @@ template <int D, int DV, int WARPS>
 void launch_pipe(const AttnArgs& a, cudaStream_t st) {
   constexpr int QROWS = WARPS * 16;
   constexpr size_t smem = sizeof(__nv_bfloat16) * (QROWS * (D + 8) + 2 * BN * (D + 8) + 2 * BN * (DV + 8));
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  if (first_use_on_device(configured)) {
     T2P_CUDA(cudaFuncSetAttribute(attention_pipe_kernel<D, DV, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
-    configured = true;
   }
   const Params p = make_params(a);
   dim3 grid(cdiv(a.Tq, QROWS), a.heads * (D / DV), a.B);

@@ -416,21 +416,12 @@ CUtensorMap view_map(const void* ptr, uint64_t cols, uint64_t rows, uint64_t bat
   return tm;
 }
 
-int cur_device() {
-  int dev = 0;
-  T2P_CUDA(cudaGetDevice(&dev));
-  return dev;
-}
-
 template <int D, int DV>
 void launch(const AttnArgs& a, cudaStream_t st) {
   using C = ACfg<D, DV>;
-  static bool configured[64] = {};
-  const int dev = cur_device();
-  if (dev < 64 && !configured[dev]) {
+  static bool configured[kMaxDevices] = {};
+  if (first_use_on_device(configured))
     T2P_CUDA(cudaFuncSetAttribute(attention_tc_kernel<D, DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    configured[dev] = true;
-  }
   AttnTcParams p{};
   const uint64_t width = static_cast<uint64_t>(a.heads) * a.d;
   p.tm_q = view_map(a.q, width, a.Tq, a.B, a.ldq, C::CH, 128);
@@ -446,9 +437,7 @@ void launch(const AttnArgs& a, cudaStream_t st) {
   const long long items = static_cast<long long>(a.B) * p.hy * p.q_tiles;
   T2P_CHECK(items < (1ll << 31), "attention problem too large");
   p.items = static_cast<int>(items);
-  static int sms[64] = {};
-  if (dev < 64 && !sms[dev]) T2P_CUDA(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
-  const int resident = (dev < 64 ? sms[dev] : 148) * (C::TMEM_COLS == 256 ? 2 : 1);  // CTAs that fit at once
+  const int resident = device_sm_count() * (C::TMEM_COLS == 256 ? 2 : 1);  // CTAs that fit at once
   attention_tc_kernel<D, DV><<<std::min(p.items, resident), THREADS, C::SMEM, st>>>(p);
   T2P_LAUNCH_CHECK();
 }

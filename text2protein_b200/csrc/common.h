@@ -113,6 +113,29 @@ inline void launch_pdl_dyn(bool on, void (*kernel)(P...), dim3 grid, dim3 block,
 }
 #endif
 
+// Kernel attributes (opt-in shared memory, carve-out), occupancy results and SM counts belong to a DEVICE: caches of
+// them are indexed by the current device, so a process that drives several GPUs configures each one.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  T2P_CUDA(cudaGetDevice(&dev));
+  T2P_CHECK(dev >= 0 && dev < kMaxDevices, "device index out of range");
+  return dev;
+}
+inline int device_sm_count() {
+  static int n[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!n[dev]) T2P_CUDA(cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev));
+  return n[dev];
+}
+// true exactly once per (call site's flag array, device)
+inline bool first_use_on_device(bool (&flags)[kMaxDevices]) {
+  const int dev = current_device();
+  if (flags[dev]) return false;
+  flags[dev] = true;
+  return true;
+}
+
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -207,11 +207,10 @@ template <int CIN, int TW, int ROWS>
 void fc_launch_rows(const FinalConvParams& p, cudaStream_t st) {
   constexpr size_t smem = sizeof(__nv_bfloat16) * ((ROWS + 2) * (TW + 2) * (FC_CH + 8) + 9 * 8 * (CIN + 8)) +
                           sizeof(float) * 2 * CIN;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  if (first_use_on_device(configured)) {
     T2P_CUDA(cudaFuncSetAttribute(final_conv_kernel<CIN, TW, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
-    configured = true;
   }
   dim3 grid(cdiv(p.H, ROWS), cdiv(p.W, TW), p.B);
   final_conv_kernel<CIN, TW, ROWS><<<grid, FC_THREADS, smem, st>>>(p);

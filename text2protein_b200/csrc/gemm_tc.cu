@@ -1355,27 +1355,19 @@ CUtensorMap make_tmap_bf16(const void* ptr, const uint64_t d[4], const uint32_t 
 }
 
 // 128 x 128 bf16 identity: the channel-major kernel adds the residual through two identity k-blocks
-const void* identity128() {
-  static void* dev = [] {
+const void* identity128() {  // one copy per device
+  static void* dev_ptr[kMaxDevices] = {};
+  void*& d = dev_ptr[current_device()];
+  if (!d) {
     std::vector<__nv_bfloat16> h(128 * 128, __float2bfloat16(0.f));
     for (int i = 0; i < 128; ++i) h[i * 128 + i] = __float2bfloat16(1.f);
-    void* d = nullptr;
     T2P_CUDA(cudaMalloc(&d, h.size() * 2));
     T2P_CUDA(cudaMemcpy(d, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
-    return d;
-  }();
-  return dev;
+  }
+  return d;
 }
 
-int sm_count() {
-  static int n = [] {
-    int dev = 0, v = 0;
-    T2P_CUDA(cudaGetDevice(&dev));
-    T2P_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
-    return v;
-  }();
-  return n;
-}
+int sm_count() { return device_sm_count(); }
 
 // Programmatic dependent launch, decided per launch.  On every tcgen05 GEMM it was slower (round 1, T2P_PDL bit 1);
 // on GEMM launches that leave SMs idle (fewer CTAs than SMs: the latency-bound layers at 16 x 16 and below) the next
@@ -1391,11 +1383,10 @@ bool pdl_for(int grid) {
 template <int BN>
 void launch(TcParams& p, cudaStream_t st) {
   using C = Cfg<BN>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  if (first_use_on_device(configured)) {
     T2P_CUDA(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   C::SMEM_BYTES));
-    configured = true;
   }
   p.n_tiles = cdiv(p.N, BN);
   p.num_tiles = cdiv(p.M, BM) * p.n_tiles;
@@ -1406,11 +1397,10 @@ void launch(TcParams& p, cudaStream_t st) {
 template <int PX>
 void launch_t(TcParams& p, cudaStream_t st) {
   using C = CfgT<PX>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  if (first_use_on_device(configured)) {
     T2P_CUDA(cudaFuncSetAttribute(conv_gemm_tcT_kernel<PX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   C::SMEM_BYTES));
-    configured = true;
   }
   p.n_tiles = cdiv(p.N, 128);
   p.num_tiles = cdiv(p.M, PX) * p.n_tiles;
@@ -1420,10 +1410,9 @@ void launch_t(TcParams& p, cudaStream_t st) {
 
 void launch_h(TcParams& p, cudaStream_t st) {
   using C = CfgH;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  if (first_use_on_device(configured)) {
     T2P_CUDA(cudaFuncSetAttribute(conv_gemm_tcH_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    configured = true;
   }
   p.n_tiles = cdiv(p.N, 128);
   p.num_tiles = cdiv(p.M, C::PX) * p.n_tiles;
@@ -1433,10 +1422,9 @@ void launch_h(TcParams& p, cudaStream_t st) {
 
 void launch_hf(TcParams& p, cudaStream_t st) {
   using C = CfgHF;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  if (first_use_on_device(configured)) {
     T2P_CUDA(cudaFuncSetAttribute(conv_gemm_tcHF_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    configured = true;
   }
   p.n_tiles = cdiv(p.N, 128);
   p.num_tiles = cdiv(p.M, C::PX) * p.n_tiles;

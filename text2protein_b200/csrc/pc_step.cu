@@ -642,15 +642,7 @@ StepParams to_params(const PcStepArgs& a) {
   return p;
 }
 
-int num_sms() {
-  static int n = [] {
-    int dev = 0, v = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    return v > 0 ? v : 148;
-  }();
-  return n;
-}
+int num_sms() { return device_sm_count(); }
 
 // resident blocks of `fn` over the whole device (one wave), at `smem` bytes of dynamic shared memory
 int resident_blocks(const void* fn, size_t smem) {
@@ -668,7 +660,8 @@ void pc_predictor_step(const PcStepArgs& a, cudaStream_t st) {
   StepParams p = to_params(a);
   T2P_CHECK(a.G != nullptr, "predictor needs G");
   const bool fast = !p.score_nhwc && !p.score_f64 && p.sqrt_alpha == nullptr && p.add_noise && !p.symmetrize;
-  static int wave[2] = {0, 0};
+  static int wave_dev[kMaxDevices][2] = {};
+  int (&wave)[2] = wave_dev[current_device()];
   if (!wave[fast])
     wave[fast] = resident_blocks(fast ? reinterpret_cast<const void*>(predictor_kernel<true>)
                                       : reinterpret_cast<const void*>(predictor_kernel<false>), 0);
@@ -690,7 +683,8 @@ void pc_corrector_step(const PcStepArgs& a, cudaStream_t st) {
   const bool fast = !p.score_nhwc && !p.score_f64 && !p.symmetrize;
   const void* fn = fast ? reinterpret_cast<const void*>(corrector_kernel<true>)
                         : reinterpret_cast<const void*>(corrector_kernel<false>);
-  static bool attr_set[2] = {false, false};
+  static bool attr_set_dev[kMaxDevices][2] = {};
+  bool (&attr_set)[2] = attr_set_dev[current_device()];
   if (!attr_set[fast]) {
     T2P_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxCacheRows * kRowBytes)));
     T2P_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -700,7 +694,8 @@ void pc_corrector_step(const PcStepArgs& a, cudaStream_t st) {
   const int want = static_cast<int>(cdiv64(p.rows, static_cast<long long>(kBlocksPerSM) * num_sms()));
   p.cache_rows = no_cache ? 0 : std::min(want, kMaxCacheRows);
   const size_t smem = p.cache_rows * kRowBytes;
-  static int wave[2][kMaxCacheRows + 1] = {};
+  static int wave_dev[kMaxDevices][2][kMaxCacheRows + 1] = {};
+  int (&wave)[2][kMaxCacheRows + 1] = wave_dev[current_device()];
   if (!wave[fast][p.cache_rows]) wave[fast][p.cache_rows] = resident_blocks(fn, smem);
   // cooperative launch: every block must be resident
   const int blocks = std::min(wave[fast][p.cache_rows], p.rows);
