@@ -818,14 +818,19 @@ struct CfgH {
   static constexpr int P_LOAD_BYTES = 2 * P_ROWPITCH * BK * 2;  // 33 280
   static constexpr int P_BYTES = 33 * 1024;              // buffer pitch (1 KB multiple)
   static constexpr int NP = 3;                           // pixel buffers
-  static constexpr int NW = 6;                           // weight buffers
-  static constexpr int OUT_BYTES = 4 * 2 * 32 * 32 * 2;
+#ifndef T2P_H_EPI_WARPS
+#define T2P_H_EPI_WARPS 4
+#endif
+  static constexpr int EPI_WARPS = T2P_H_EPI_WARPS;      // 4, or 8: two per TMEM lane quadrant, half a tile each
+  static constexpr int NW = EPI_WARPS == 8 ? 5 : 6;      // weight buffers (the staging of eight warps takes one)
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int OUT_BYTES = EPI_WARPS * 2 * 32 * 32 * 2;
   static constexpr int SMEM_BYTES = NP * P_BYTES + NW * W_BYTES + OUT_BYTES + 1024;
   static constexpr int PX = 256;
   static constexpr int TMEM_COLS = 2 * PX;
 };
 
-__global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_tcH_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(CfgH::THREADS, 1) conv_gemm_tcH_kernel(const __grid_constant__ TcParams p) {
   using C = CfgH;
   constexpr int PX = C::PX;
   pdl_trigger();
@@ -856,7 +861,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_tcH_kernel(const __g
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(ptx::smem_u32(&tfull_bar[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&tempty_bar[s]), 4);
+      ptx::mbar_init(ptx::smem_u32(&tempty_bar[s]), C::EPI_WARPS);
     }
     ptx::fence_mbar_init();
   }
@@ -978,7 +983,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_tcH_kernel(const __g
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..5): thread = channel
     const int q = warp & 3;
-    epilogue_dispatch<PX, PX / 32>(p, tmem_base, tfull_bar, tempty_bar, out_stage + q * (2 * 32 * 32 * 2), q, 0, 1, 0, lane);
+    if constexpr (C::EPI_WARPS == 8) {
+      const int half = (warp - 2) >> 2;
+      epilogue_dispatch<PX, PX / 64>(p, tmem_base, tfull_bar, tempty_bar, out_stage + (warp - 2) * (2 * 32 * 32 * 2), q,
+                                     half * (PX / 64), 2, half, lane);
+    } else {
+      epilogue_dispatch<PX, PX / 32>(p, tmem_base, tfull_bar, tempty_bar, out_stage + q * (2 * 32 * 32 * 2), q, 0, 1, 0, lane);
+    }
   }
 
   ptx::tc_fence_before();
@@ -1417,7 +1428,7 @@ void launch_h(TcParams& p, cudaStream_t st) {
   p.n_tiles = cdiv(p.N, 128);
   p.num_tiles = cdiv(p.M, C::PX) * p.n_tiles;
   const int grid = std::min(p.num_tiles, sm_count());
-  launch_pdl<1>(conv_gemm_tcH_kernel, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, st, p);
+  launch_pdl<1>(conv_gemm_tcH_kernel, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, p);
 }
 
 void launch_hf(TcParams& p, cudaStream_t st) {
@@ -1507,7 +1518,8 @@ int conv_gemm_tc_stat_tile(const ConvGemmArgs& a) {
   const Plan pl = make_plan(q);
   if (!pl.stats_ok) return 0;
   // the channel-major kernel's epilogue warps each own half a pixel tile; the halo kernel's own a whole one
-  return (pl.channel_major && !pl.halo) ? pl.rows / 2 : pl.rows;
+  if (pl.halo) return (CfgH::EPI_WARPS == 8 && !a.gn_scale) ? pl.rows / 2 : pl.rows;  // (the fused variant: four warps)
+  return pl.channel_major ? pl.rows / 2 : pl.rows;
 }
 
 void conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
