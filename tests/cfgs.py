@@ -104,3 +104,57 @@ def rsde_inputs():
 
 def analytic_score(x, t, context=None):
     return torch.sin(x) * (1.0 + t)[:, None, None, None]
+
+
+def synthetic_backbone(nres, seed):
+    """A self-avoiding-ish random-walk protein backbone: N, CA, C coordinates [nres, 3, 3] (Angstrom) with realistic
+    bond lengths, compact enough that many C-beta pairs fall inside and many outside the 20 A cut-off."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    ca = np.zeros((nres, 3))
+    d = rng.normal(size=3)
+    for i in range(1, nres):
+        d = d + 0.9 * rng.normal(size=3)
+        d /= np.linalg.norm(d)
+        ca[i] = ca[i - 1] + 3.8 * d
+    xyz = np.zeros((nres, 3, 3))
+    for i in range(nres):
+        u = rng.normal(size=3)
+        u /= np.linalg.norm(u)
+        v = rng.normal(size=3)
+        v -= v.dot(u) * u
+        v /= np.linalg.norm(v)
+        xyz[i, 1] = ca[i]
+        xyz[i, 0] = ca[i] + 1.46 * (-0.5 * u + 0.866 * v)   # N
+        xyz[i, 2] = ca[i] + 1.52 * (-0.5 * u - 0.866 * v)   # C
+    return xyz
+
+
+def write_pdb(path, xyz, chain="A", missing=(), extra_chain=True):
+    """Minimal PDB text of a backbone (fixed-column ATOM records), with optional missing atoms [(residue, atom name)],
+    a second chain, an alternate location and a water HETATM -- everything the reader must skip."""
+    names = ("N", "CA", "C")
+    lines, serial = [], 1
+    for i in range(xyz.shape[0]):
+        for j, a in enumerate(names):
+            if (i, a) in missing:
+                continue
+            x, y, z = xyz[i, j]
+            alt = "A" if (i == 2 and a == "CA") else " "
+            lines.append("ATOM  %5d %-4s%1s%3s %1s%4d    %8.3f%8.3f%8.3f  1.00  0.00" % (serial, " " + a, alt, "ALA", chain,
+                                                                                       i + 1, x, y, z))
+            serial += 1
+            if alt == "A":  # second alternate location of the same atom: ignored by the reader (first one wins)
+                lines.append("ATOM  %5d %-4s%1s%3s %1s%4d    %8.3f%8.3f%8.3f  0.50  0.00" % (serial, " " + a, "B", "ALA",
+                                                                                           chain, i + 1, x + 5, y, z))
+                serial += 1
+        lines.append("ATOM  %5d %-4s%1s%3s %1s%4d    %8.3f%8.3f%8.3f  1.00  0.00" % (serial, " O", " ", "ALA", chain, i + 1,
+                                                                                   0.0, 0.0, 0.0))
+        serial += 1
+    if extra_chain:
+        lines.append("ATOM  %5d %-4s%1s%3s %1s%4d    %8.3f%8.3f%8.3f  1.00  0.00" % (serial, " CA", " ", "GLY", "B", 1, 1.0, 2.0, 3.0))
+        lines.append("HETATM%5d %-4s%1s%3s %1s%4d    %8.3f%8.3f%8.3f  1.00  0.00" % (serial + 1, " O", " ", "HOH", chain, 900,
+                                                                                   9.0, 9.0, 9.0))
+    lines.append("END")
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")

@@ -188,5 +188,51 @@ def test_sampling_6d_driver_roundtrip(tmp_path):
     assert torch.equal(got[:, -1], mask.float().cpu())  # padding channel == length mask (min_res_num + 4 = 12)
 
 
+@pytest.mark.gpu
+def test_sampling_6d_driver_pdb_inpainting(tmp_path):
+    """``--pdb X.pdb --chain A --mask_info ...`` (sampling_6d.py:144-149, utils.py:108-137): the chain's own 6D map is
+    the inpainting source -- everything outside the rows / columns of the selected residues comes back bit-identical to
+    it, the padding channel equals the chain's length mask, the selected region moves."""
+    import yaml
+    from tests.cfgs import synthetic_backbone, write_pdb
+    from text2protein_b200 import sampling_6d
+    from text2protein_b200.pdb_conditions import map_from_pdb
+    from text2protein_b200.score_sde_pytorch.models.ema import ExponentialMovingAverage
+    from text2protein_b200.score_sde_pytorch.utils import get_model, save_checkpoint
+    cfg = with_device(tiny_cfg(5), "cuda")
+    cfg.data.min_res_num = 8
+    cfg.model.condition = ["length", "inpainting"]
+    cfg.model.compute_dtype = "fp32"
+    cfg_path = tmp_path / "tiny.yml"
+    cfg_path.write_text(yaml.safe_dump(eval(repr(dict_from(cfg)))))
+    torch.manual_seed(0)
+    model = get_model(cfg)
+    ema = ExponentialMovingAverage(model.parameters(), decay=cfg.model.ema_rate)
+    run = tmp_path / "training" / "tiny" / "run0" / "checkpoints"
+    run.mkdir(parents=True)
+    save_checkpoint(str(run / "best.pth"), dict(optimizer=sampling_6d._SamplingOptimizer(), model=model, ema=ema, step=1))
+    g = torch.Generator().manual_seed(2)
+    torch.save(torch.randn(50, cfg.model.context_dim, generator=g) * 0.3, tmp_path / "table.pt")
+    torch.save({"a": torch.randint(0, 50, (7,), generator=g), "b": torch.randint(0, 50, (7,), generator=g)}, tmp_path / "tok.pt")
+    nres = 20
+    write_pdb(str(tmp_path / "chain.pdb"), synthetic_backbone(nres, 4), chain="A")
+    written = sampling_6d.main([str(cfg_path), str(run / "best.pth"), "--batch_size", "2", "--tag", "p", "--pdb",
+                                str(tmp_path / "chain.pdb"), "--chain", "A", "--mask_info", "3:7,12", "--tokens",
+                                str(tmp_path / "tok.pt"), "--embed_table", str(tmp_path / "table.pt"), "--out_root",
+                                str(tmp_path), "--num_iters", "2", "--seed", "5"])
+    got = torch.cat([pkl.load(open(p_, "rb")) for p_ in written])
+    src, n = map_from_pdb(str(tmp_path / "chain.pdb"), "A", cfg)
+    assert n == nres and got.shape == (2, 5, 32, 32)
+    sel = torch.zeros(32, dtype=torch.bool)
+    sel[3:8] = True
+    sel[12] = True
+    free = sel[:, None] | sel[None, :]
+    for b in range(2):
+        assert torch.equal(got[b][:, ~free], src[:, ~free])          # outside the inpainted rows / columns: the chain
+        assert torch.equal(got[b, -1], src[-1])                       # padding channel == length mask of the chain
+        inside = free[:nres, :nres]
+        assert not torch.equal(got[b, 0, :nres, :nres][inside], src[0, :nres, :nres][inside])
+
+
 def dict_from(cfg):
     return {k: (dict_from(v) if isinstance(v, dict) else v) for k, v in cfg.items()}

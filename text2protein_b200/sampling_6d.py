@@ -1,7 +1,8 @@
 """Driver of the sampling path with the reference CLI (``sampling_6d.py``) and on-disk format.
 
     python -m text2protein_b200.sampling_6d CONFIG CHECKPOINT [--tag T] [--batch_size B] [--select_length True
-        --length_index I] [--mask_info 1:5,10:15 --coords coords.pt] [--tokens tokens.pt --embed_table table.pt]
+        --length_index I] [--pdb X.pdb --chain A --mask_info 1:5,10:15 | --coords coords.pt]
+        [--tokens tokens.pt --embed_table table.pt]
 
 writes ``sampling/coords_6d/<config stem>/<run dir>/<tag>/sampled_<id>.pkl`` = a pickled ``torch.Tensor`` of shape
 [1, C, N, N] per sample, exactly what the reference writes (sampling_6d.py:61,160-162) and what
@@ -92,8 +93,12 @@ def build_condition(args, config):
         return cond_utils.get_condition_from_lengths(config, [n_res] * args.batch_size, coords_6d=coords,
                                                      mask_info=args.mask_info)
     if args.pdb is not None:
-        raise NotImplementedError("--pdb needs the reference's biotite / ProteinDataset reader; export the chain's 6D "
-                                  "map with the reference and pass it with --coords")
+        # utils.py:108-137 get_conditions_from_pdb: the chain's own 6D map, replicated over the batch
+        from .pdb_conditions import map_from_pdb
+        coords, n_res = map_from_pdb(args.pdb, args.chain, config)
+        coords = coords[None].expand(args.batch_size, *coords.shape).contiguous()
+        return cond_utils.get_condition_from_lengths(config, [n_res] * args.batch_size, coords_6d=coords,
+                                                     mask_info=args.mask_info)
     return {}
 
 
