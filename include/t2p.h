@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define T2P_ABI_VERSION 2
+#define T2P_ABI_VERSION 3
 
 enum t2p_dtype { T2P_F32 = 0, T2P_BF16 = 1, T2P_F64 = 2, T2P_I64 = 3, T2P_U8 = 4 };
 
@@ -87,6 +87,12 @@ int t2p_unet_forward_t(t2p_unet* u, const float* x, const int64_t* labels, const
  * layers.py:305,318, never reaches HBM.  Same results to bf16 rounding; measured break-even in time on
  * cond_length.yml at B = 64 (profiles/r02_fused_gn_ab.txt), 1.1 GB less activation arena. */
 int t2p_unet_set_fused_groupnorm(t2p_unet* u, int enable);
+
+/* Option, default ON: a ResBlock's Conv_0 applies GroupNorm_1 + SiLU to its own output in its epilogue (per-sample
+ * statistics exchanged between the CTAs of the launch), h = act(GroupNorm_1(Conv_0(.) + temb)), layers.py:314-318 -- the
+ * raw Conv_0 output and the separate statistics / finalize / apply passes over it disappear wherever
+ * t2p_conv2d_normalises_output holds for the launch.  Off = the three-kernel sequence of rounds 1-2 (A/B, debugging). */
+int t2p_unet_set_epilogue_groupnorm(t2p_unet* u, int enable);
 
 /* Debug taps: with debug on, every top-level block's output is kept as fp32 NCHW ("pre_conv",
  * "input_blocks.<i>", "mid_blocks", "out_blocks.<i>", "out"). */
@@ -215,6 +221,10 @@ typedef struct t2p_conv_args {
   const float* gn_scale;           /* optional: a0|a1 are RAW and the kernel feeds silu(x * gn_scale + gn_shift) to the tensor */
   const float* gn_shift;           /* core (h = act(GroupNorm(x)), layers.py:305,318): per-(sample, channel) affine over the
                                       concat, fp32 [B][c0+c1].  Only where t2p_conv2d_fuses_groupnorm(args) != 0 */
+  const float* gno_gamma;          /* optional (ABI 3): the launch normalises its OWN output, out = silu(GroupNorm(conv + bias + */
+  const float* gno_beta;           /* rowbias)) with the CONSUMER's GroupNorm(gno_groups, N, gno_eps) weight / bias [N] -- h =   */
+  int32_t gno_groups;              /* act(GroupNorm_1(Conv_0(.) + temb)), layers.py:314-318, without the raw tensor ever reaching */
+  float gno_eps;                   /* HBM.  Only where t2p_conv2d_normalises_output(args) != 0; excludes stat_part / gn_scale    */
 } t2p_conv_args;
 int t2p_conv2d(const t2p_conv_args* a, void* stream);        /* nn.Conv2d / NIN / nn.Linear: layers.py:82-95,128-137 */
 /* Pixel-tile size T of the fused GroupNorm statistics t2p_conv2d would write for these arguments (H*W % T == 0),
@@ -223,6 +233,10 @@ int t2p_conv2d_stat_tile(const t2p_conv_args* a);
 /* 1 when t2p_conv2d can apply GroupNorm + SiLU to its 3x3 sources itself for these arguments (3x3, 128-pixel-wide
  * images, bf16, N >= 128: the halo kernel), else 0.  Host-only. */
 int t2p_conv2d_fuses_groupnorm(const t2p_conv_args* a);
+/* 1 when t2p_conv2d can apply GroupNorm(gno_groups) + SiLU to its own output for these arguments (channel-major tcgen05
+ * kernel: bf16, N % 128 == 0, groups of 4 / 8 / 16 / 32 channels, whole pixel tiles per sample, no residual, and few enough
+ * tiles per sample for the inter-CTA statistics exchange), else 0.  Host-only; reads gno_groups. */
+int t2p_conv2d_normalises_output(const t2p_conv_args* a);
 
 /* Last layer, ncsnpp.py:212-216,257: out fp32 NCHW [B][nout][H][W] = Conv3x3(SiLU(x * scale + shift)) + bias, with x the
  * raw bf16 NHWC activation [B][H][W][cin], scale / shift the per-(sample, channel) GroupNorm affine [B][cin] and w the

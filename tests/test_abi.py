@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"libt2p.so does not export {n}"
         assert n in _lib.SIGNATURES, f"_lib.SIGNATURES lacks {n}"
-    assert lib.t2p_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.t2p_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_struct_layouts_match_header_field_counts():

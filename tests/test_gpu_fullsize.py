@@ -189,6 +189,31 @@ def test_fused_groupnorm_option_matches_reference_golden(golden_dir):
         torch.cuda.empty_cache()
 
 
+def test_epilogue_groupnorm_option_matches_reference_golden(golden_dir):
+    """GroupNorm_1 + SiLU in Conv_0's epilogue (default on): with and without it the engine agrees with the reference's
+    golden output at cfg2 (B = 1) and test_config, the option removes launches, and at cfg2 with B = 5 (several waves of
+    tiles per launch at 128 x 128) the two sequences agree with each other sample by sample."""
+    for case, B in (("cond_length_L256", 1), ("test_config", 1), ("cond_length_L256", 5)):
+        fname, _, L = FULLSIZE_CASES[case]
+        cfg, m = _model(fname[:-4], "bf16")
+        x, labels, ctx = fullsize_inputs(cfg, B, L)
+        on = m(x.cuda(), labels.cuda(), ctx.cuda())
+        n_on = _lib.lib().t2p_unet_launches_per_forward(m.native_handle)
+        m.set_epilogue_groupnorm(False)
+        off = m(x.cuda(), labels.cuda(), ctx.cuda())
+        assert _lib.lib().t2p_unet_launches_per_forward(m.native_handle) > n_on
+        per = (on - off).flatten(1).abs().amax(1) / off.flatten(1).abs().amax(1)
+        assert per.max() < 2e-2, per
+        if B == 1:
+            g = np.load(os.path.join(golden_dir, f"unet_full_{case}.npz"))
+            ref = torch.from_numpy(g["out"]).double()
+            assert rel_err(on, ref) < 2e-2 and rel_err(off, ref) < 2e-2
+        m.set_epilogue_groupnorm(True)
+        assert torch.equal(m(x.cuda(), labels.cuda(), ctx.cuda()), on)  # deterministic, exchange words left clean
+        del m
+        torch.cuda.empty_cache()
+
+
 @pytest.mark.parametrize("name,kinds,C_", [("cond_ss_inpainting", ["length", "ss", "inpainting"], 8), ("no_cond", [], 8)])
 def test_sampler_iteration_matches_oracle_at_cfg3_and_cfg5(name, kinds, C_):
     """One full PC iteration (corrector + predictor) of the C = 8 networks at N = 128 -- the masked inpainting sampler

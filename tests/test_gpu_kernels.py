@@ -165,6 +165,62 @@ def test_conv2d_fused_groupnorm_silu(B, H, c0, c1, xc0, cout, stats):
     assert L.t2p_conv2d_fuses_groupnorm(C.byref(b)) == 0
 
 
+@pytest.mark.parametrize("B,H,cin,cout,k", [(3, 128, 128, 128, 3), (20, 128, 64, 128, 3), (2, 64, 128, 256, 3),
+                                            (5, 32, 256, 256, 3), (4, 16, 256, 256, 3), (2, 8, 128, 256, 3),
+                                            (37, 64, 64, 128, 3), (3, 32, 128, 128, 1), (64, 16, 64, 512, 3),
+                                            (6, 16, 128, 1024, 1)])
+def test_conv2d_normalises_its_own_output(B, H, cin, cout, k):
+    """silu(GroupNorm_1(Conv_0(h) + bias + temb)) (layers.py:314-318) from the convolution's own epilogue: per-sample
+    statistics are exchanged between the CTAs of the launch.  Against torch on the same bf16 operands; B = 20 / 37 / 64
+    put several waves of tiles through the persistent CTAs (samples that straddle two waves), and a second call on
+    fresh buffers checks that the exchange words were handed back zeroed."""
+    g = torch.Generator(device="cuda").manual_seed(21)
+    bf = lambda t: t.bfloat16().float()  # noqa: E731
+    groups = min(cout // 4, 32)
+    a0 = bf(torch.randn(B, cin, H, H, device="cuda", generator=g))
+    w = bf(torch.randn(cout, cin, k, k, device="cuda", generator=g) / math.sqrt(cin * k * k))
+    bias = torch.randn(cout, device="cuda", generator=g)
+    rowbias = torch.randn(B, cout + 5, device="cuda", generator=g)
+    gamma = 1.0 + 0.3 * torch.randn(cout, device="cuda", generator=g)
+    beta = 0.5 * torch.randn(cout, device="cuda", generator=g)
+    # per-sample scale so that the statistics differ from sample to sample
+    a0 = bf(a0 * (0.5 + torch.arange(B, device="cuda").float()[:, None, None, None] / B))
+    conv = F.conv2d(a0, w, bias, padding=k // 2) + rowbias[:, :cout, None, None]
+    ref = F.silu(F.group_norm(conv, groups, gamma, beta, eps=1e-6))
+    wp = w.permute(0, 2, 3, 1).contiguous().reshape(cout, -1).bfloat16().contiguous()
+    A0 = nhwc(a0, torch.bfloat16)
+    L = _lib.lib()
+    for rep in range(2):
+        out = torch.full((B, H, H, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+        a = _lib.ConvArgs()
+        a.a0, a.c0 = A0.data_ptr(), cin
+        a.B, a.H, a.W, a.ksize = B, H, H, k
+        a.w, a.N, a.bias, a.alpha = wp.data_ptr(), cout, bias.data_ptr(), 1.0
+        a.rowbias, a.rowbias_ld = rowbias.data_ptr(), rowbias.shape[1]
+        a.out, a.out_dtype, a.in_dtype = out.data_ptr(), _lib.BF16, _lib.BF16
+        a.gno_groups, a.gno_eps = groups, 1e-6
+        assert L.t2p_conv2d_normalises_output(C.byref(a)) == 1
+        a.gno_gamma, a.gno_beta = gamma.data_ptr(), beta.data_ptr()
+        _lib.check(L.t2p_conv2d(C.byref(a), _st()))
+        torch.cuda.synchronize()
+        got = nchw(out.float())
+        assert torch.isfinite(got).all()
+        assert rel_err(got, ref) < 1e-2
+        # every sample on its own: a statistic taken from the wrong sample would show here
+        per = (got - ref).flatten(1).abs().amax(1) / ref.flatten(1).abs().amax(1)
+        assert per.max() < 1.5e-2, per
+    # launches that cannot do it say so and refuse the arguments: odd group size, residual, too many tiles per sample
+    b = _lib.ConvArgs()
+    b.a0, b.c0, b.B, b.H, b.W, b.ksize, b.w, b.N = A0.data_ptr(), cin, B, H, H, k, wp.data_ptr(), cout
+    b.out, b.out_dtype, b.in_dtype = out.data_ptr(), _lib.BF16, _lib.BF16
+    b.gno_groups = 3
+    assert L.t2p_conv2d_normalises_output(C.byref(b)) == 0
+    b.gno_groups, b.residual = groups, out.data_ptr()
+    assert L.t2p_conv2d_normalises_output(C.byref(b)) == 0
+    b.gno_gamma, b.gno_beta = gamma.data_ptr(), beta.data_ptr()
+    assert L.t2p_conv2d(C.byref(b), _st()) != 0
+
+
 @pytest.mark.parametrize("H,cin,xc0,xc1,cout", [(16, 64, 128, 64, 128), (32, 128, 128, 0, 128), (8, 64, 64, 0, 256),
                                                 (128, 64, 64, 64, 128)])
 def test_conv2d_folded_skip_path(H, cin, xc0, xc1, cout):

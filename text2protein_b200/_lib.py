@@ -44,7 +44,8 @@ class ConvArgs(C.Structure):
                 ("bias", C.c_void_p), ("rowbias", C.c_void_p), ("rowbias_ld", C.c_int32), ("residual", C.c_void_p),
                 ("res_up", C.c_int32), ("alpha", C.c_float), ("out", C.c_void_p), ("out_dtype", C.c_int32),
                 ("in_dtype", C.c_int32), ("stat_part", C.c_void_p), ("x0", C.c_void_p), ("xc0", C.c_int32),
-                ("x1", C.c_void_p), ("xc1", C.c_int32), ("gn_scale", C.c_void_p), ("gn_shift", C.c_void_p)]
+                ("x1", C.c_void_p), ("xc1", C.c_int32), ("gn_scale", C.c_void_p), ("gn_shift", C.c_void_p),
+                ("gno_gamma", C.c_void_p), ("gno_beta", C.c_void_p), ("gno_groups", C.c_int32), ("gno_eps", C.c_float)]
 
 
 class GemmRecord(C.Structure):
@@ -52,7 +53,7 @@ class GemmRecord(C.Structure):
                 ("tensor_core", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("ms", C.c_float)]
 
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 IPC_HANDLE_BYTES = 64
 # `which` codes of t2p_sizeof / t2p_struct_layout
 STRUCTS = {0: UnetCfg, 1: StepArgs, 2: RunArgs, 3: ConvArgs, 4: GemmRecord}
@@ -80,6 +81,7 @@ SIGNATURES = {
     "t2p_unet_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "t2p_unet_set_debug": (C.c_int, [C.c_void_p, C.c_int]),
     "t2p_unet_set_fused_groupnorm": (C.c_int, [C.c_void_p, C.c_int]),
+    "t2p_unet_set_epilogue_groupnorm": (C.c_int, [C.c_void_p, C.c_int]),
     "t2p_unet_tap": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]),
     "t2p_unet_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "t2p_unet_profile_read": (C.c_int, [C.c_void_p, C.POINTER(GemmRecord), C.c_int]),
@@ -104,6 +106,7 @@ SIGNATURES = {
     "t2p_conv2d": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "t2p_conv2d_stat_tile": (C.c_int, [C.POINTER(ConvArgs)]),
     "t2p_conv2d_fuses_groupnorm": (C.c_int, [C.POINTER(ConvArgs)]),
+    "t2p_conv2d_normalises_output": (C.c_int, [C.POINTER(ConvArgs)]),
     "t2p_final_conv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                  C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "t2p_groupnorm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -124,7 +124,8 @@ static std::vector<int32_t> struct_offsets(int which) {
                     T2P_OFF(t2p_conv_args, out), T2P_OFF(t2p_conv_args, out_dtype), T2P_OFF(t2p_conv_args, in_dtype),
                     T2P_OFF(t2p_conv_args, stat_part), T2P_OFF(t2p_conv_args, x0), T2P_OFF(t2p_conv_args, xc0),
                     T2P_OFF(t2p_conv_args, x1), T2P_OFF(t2p_conv_args, xc1), T2P_OFF(t2p_conv_args, gn_scale),
-                    T2P_OFF(t2p_conv_args, gn_shift)};
+                    T2P_OFF(t2p_conv_args, gn_shift), T2P_OFF(t2p_conv_args, gno_gamma), T2P_OFF(t2p_conv_args, gno_beta),
+                    T2P_OFF(t2p_conv_args, gno_groups), T2P_OFF(t2p_conv_args, gno_eps)};
     case 4: return {T2P_OFF(t2p_gemm_record, M), T2P_OFF(t2p_gemm_record, N), T2P_OFF(t2p_gemm_record, K),
                     T2P_OFF(t2p_gemm_record, ksize), T2P_OFF(t2p_gemm_record, tensor_core), T2P_OFF(t2p_gemm_record, H),
                     T2P_OFF(t2p_gemm_record, W), T2P_OFF(t2p_gemm_record, ms)};
@@ -269,6 +270,13 @@ int t2p_unet_forward_t(t2p_unet* u, const float* x, const int64_t* labels, const
   T2P_API_BEGIN
   T2P_CHECK(u && x && labels && out && B > 0, "bad forward arguments");
   u->net->forward(x, reinterpret_cast<const long long*>(labels), out, out_dtype, B, S(stream), timesteps);
+  T2P_API_END
+}
+
+int t2p_unet_set_epilogue_groupnorm(t2p_unet* u, int enable) {
+  T2P_API_BEGIN
+  T2P_CHECK(u != nullptr, "null handle");
+  u->net->set_epilogue_groupnorm(enable != 0);
   T2P_API_END
 }
 
@@ -613,6 +621,16 @@ static ConvGemmArgs conv_args_from_abi(const t2p_conv_args* a) {
   return g;
 }
 
+int t2p_conv2d_normalises_output(const t2p_conv_args* a) {
+  try {
+    if (!a || a->in_dtype != T2P_BF16 || a->c0 % 64 != 0 || a->c1 % 64 != 0 || a->stat_part || a->gn_scale) return 0;
+    return conv_gemm_tc_gn_out_ok(conv_args_from_abi(a), a->gno_groups) ? 1 : 0;
+  } catch (const std::exception& e) {
+    set_last_error(e.what());
+    return 0;
+  }
+}
+
 int t2p_conv2d_fuses_groupnorm(const t2p_conv_args* a) {
   try {
     if (!a || a->in_dtype != T2P_BF16 || a->c0 % 64 != 0 || a->c1 % 64 != 0 || a->ksize != 3) return 0;
@@ -641,6 +659,29 @@ int t2p_conv2d(const t2p_conv_args* a, void* stream) {
     T2P_CHECK(a->in_dtype == T2P_BF16 && a->c0 % 64 == 0 && a->c1 % 64 == 0, "centre-tap sources are tcgen05-only");
   if (a->gn_scale || a->gn_shift)
     T2P_CHECK(a->gn_scale && a->gn_shift && t2p_conv2d_fuses_groupnorm(a), "this launch cannot fuse GroupNorm");
+  if (a->gno_gamma || a->gno_beta) {
+    // the launch normalises its own output: scratch for the statistics exchange lives for this call only (the engine
+    // keeps its own, unet.cu)
+    T2P_CHECK(a->gno_gamma && a->gno_beta && t2p_conv2d_normalises_output(a), "this launch cannot normalise its output");
+    g.gno_gamma = a->gno_gamma; g.gno_beta = a->gno_beta; g.gno_groups = a->gno_groups; g.gno_eps = a->gno_eps;
+    const size_t part_bytes = sizeof(float) * static_cast<size_t>(conv_gemm_tc_gn_out_part_floats(g, a->gno_groups));
+    const size_t flag_bytes = sizeof(int) * static_cast<size_t>(conv_gemm_tc_gn_out_flag_ints(g));
+    char* scratch = nullptr;
+    T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&scratch), part_bytes + flag_bytes));
+    g.gno_part = reinterpret_cast<float*>(scratch);
+    g.gno_flags = reinterpret_cast<int*>(scratch + part_bytes);
+    cudaError_t e = cudaMemsetAsync(g.gno_flags, 0, flag_bytes, S(stream));
+    try {
+      T2P_CUDA(e);
+      conv_gemm_tc(g, S(stream));
+      T2P_CUDA(cudaStreamSynchronize(S(stream)));
+    } catch (...) {
+      cudaFree(scratch);
+      throw;
+    }
+    T2P_CUDA(cudaFree(scratch));
+    return 0;
+  }
   if (a->in_dtype == T2P_BF16 && a->c0 % 64 == 0 && a->c1 % 64 == 0) conv_gemm_tc(g, S(stream));
   else conv_gemm_simt(g, a->in_dtype, S(stream));
   T2P_API_END

@@ -77,6 +77,16 @@ struct TcParams {
   const float* gn_scale;
   const float* gn_shift;
   int hf_debug;      // timing experiments (knob builds): 1 = copy without arithmetic, 2 = no global loads either
+  // GroupNorm + SiLU of the OUTPUT applied in the epilogue (see epilogue_role_gn): the consumer's GroupNorm
+  const float* gno_gamma;   // [N] or null (mode off)
+  const float* gno_beta;
+  int gno_cpg;              // channels per group: 4 or 8
+  float gno_eps;
+  float* gno_part;          // [sample][tile part][N / cpg][2] per-part {sum, sum of squares} of the groups
+  int* gno_flags;           // [2][sample * n_tiles * 4]: parts arrived, warps that left -- zero on entry, left zero on exit
+  int gno_parts;            // parts per sample and channel quadrant = pixel tiles per sample x epilogue warps per quadrant
+  int gno_slots;            // samples * n_tiles * 4
+  int gno_debug;            // timing experiments (knob builds): 1 = do not wait for the other parts, 2 = no pass 1, 4 = no fold loads
 };
 
 template <int BN>
@@ -626,10 +636,277 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, uint32_t tmem_b
   if (lane == 0) ptx::tma_store_wait_read<0>();  // smem must stay valid until the last store has read it
 }
 
+// ----------------------------------------------------------------------------------------------------------
+// GroupNorm + SiLU of the convolution's OUTPUT inside its own epilogue (ResnetBlockBigGANpp: h = act(GroupNorm_1(
+// Conv_0(.) + temb)), layers.py:314-318): the raw tensor, its statistics pass, gn_finalize and gn_apply disappear --
+// the tensor core kernel has HBM bandwidth to spare, the separate apply pass had nothing else to do.  The statistics of
+// a sample need ALL its pixel tiles, which other CTAs hold, so the epilogue runs in two passes over the accumulator
+// (tcgen05.ld does not consume it):
+//   pass 1  v = acc * alpha + bias (+ time-embedding bias), per-group sum / sum of squares of this warp's pixels and
+//           32 channels; lane 0 stores them to gno_part and adds 1 to the counter of its (sample, n tile, quadrant) slot
+//           with red.release.gpu (stores and release by the same thread: no fence, no round trip)
+//   wait    lane 0 polls the counter (ld.acquire.gpu, bounded) until every part of the slot has arrived
+//   fold    EVERY warp adds the parts of its groups itself: all loads in flight at once (L2), the same fixed order in
+//           every warp and every run (deterministic, bit-identical across the warps of a sample), in double
+//   pass 2  y = silu(v * scale + shift) -> bf16 -> stmatrix -> TMA store, as the plain epilogue.
+// The chain after the last pass 1 of a sample is one release, one acquire and one load deep; an earlier version (one
+// elected warp folds, publishes the affine, everyone else waits for it) was eight dependent L2 round trips deep and
+// doubled the time of the 128 x 128 convolutions.  While a warp waits, the MMA warp works on the next tile in the other
+// accumulator.  No deadlock: CTAs are all resident, take their tiles in index order, and a sample's tiles span fewer
+// consecutive indices than there are CTAs (checked on the host), so the tile a CTA must finish BEFORE one of sample s
+// always belongs to an earlier sample.  The two words of a slot (arrived, left) are returned to zero by the last warp
+// that leaves it.
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float silu_tanh_f(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
 template <int PX, int NCH>
+__device__ __forceinline__ void epilogue_role_gn(const TcParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
+                                                 uint64_t* tempty_bar, uint32_t obuf, int q, int cf, int part_mul,
+                                                 int part_add, int lane) {
+  uint32_t tl = 0;
+  uint32_t nstore = 0;
+  const int tps = p.rows_per_sample / PX;       // pixel tiles per sample
+  const int cpg = p.gno_cpg;
+  const int gpw = 32 / cpg;                     // groups per warp (32 channels): 8, 4, 2 or 1
+  const int ngroups = p.N / cpg;
+  int* const arrived = p.gno_flags;
+  int* const left = p.gno_flags + p.gno_slots;
+  const double inv_cnt = 1.0 / (static_cast<double>(p.rows_per_sample) * cpg);
+  for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tl) {
+    const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
+    const int tt = p.reverse ? p.num_tiles - 1 - t : t;
+    const int pt = tt / p.n_tiles;
+    const int nt = tt - pt * p.n_tiles;
+    const int nw0 = nt * 128 + q * 32;
+    const int m0 = pt * PX;
+    const int sample = m0 / p.rows_per_sample;
+    const int tile_in_sample = pt - sample * tps;
+    const int part = tile_in_sample * part_mul + part_add;
+    const int slot = (sample * p.n_tiles + nt) * 4 + q;
+    float bch[4], ga[4], be[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int n = nw0 + (lane >> 2) + 8 * k;
+      float b = p.bias ? __ldg(p.bias + n) : 0.f;
+      if (p.rowbias) b += __ldg(p.rowbias + static_cast<long long>(sample) * p.rowbias_ld + n);
+      bch[k] = b * p.alpha;
+      ga[k] = __ldg(p.gno_gamma + n);
+      be[k] = __ldg(p.gno_beta + n);
+    }
+    T2P_EPI_WAIT(ptx::smem_u32(&tfull_bar[as]), aph);
+    ptx::tc_fence_after();
+    const uint32_t tbase = tmem_base + as * PX + (static_cast<uint32_t>(q * 32) << 16);
+    auto load_chunk = [&](int c, uint32_t (&lo)[16], uint32_t (&hi)[16]) {
+      ptx::tmem_ld_16x256_x4(tbase + c * 32, lo);
+      ptx::tmem_ld_16x256_x4(tbase + (16u << 16) + c * 32, hi);
+    };
+    uint32_t lo0[16], hi0[16], lo1[16], hi1[16];
+    // ---- pass 1: statistics of v over this warp's pixels (thread slot k holds channel (lane >> 2) + 8 k)
+    float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};
+    auto add_chunk = [&](const uint32_t (&lo)[16], const uint32_t (&hi)[16]) {
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        const float v[4][2] = {{__uint_as_float(lo[4 * n]), __uint_as_float(lo[4 * n + 1])},
+                               {__uint_as_float(lo[4 * n + 2]), __uint_as_float(lo[4 * n + 3])},
+                               {__uint_as_float(hi[4 * n]), __uint_as_float(hi[4 * n + 1])},
+                               {__uint_as_float(hi[4 * n + 2]), __uint_as_float(hi[4 * n + 3])}};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float f0 = fmaf(v[k][0], p.alpha, bch[k]), f1 = fmaf(v[k][1], p.alpha, bch[k]);
+          ssum[k] += f0 + f1;
+          ssq[k] = fmaf(f0, f0, fmaf(f1, f1, ssq[k]));
+        }
+      }
+    };
+#ifdef T2P_TIMING_KNOBS
+    if (!(p.gno_debug & 2)) {
+#endif
+    load_chunk(cf, lo0, hi0);
+#pragma unroll 1
+    for (int i = 0; i < NCH; i += 2) {
+      ptx::tmem_ld_wait();
+      if (i + 1 < NCH) load_chunk(cf + i + 1, lo1, hi1);
+      add_chunk(lo0, hi0);
+      if (i + 1 < NCH) {
+        ptx::tmem_ld_wait();
+        if (i + 2 < NCH) load_chunk(cf + i + 2, lo0, hi0);
+        add_chunk(lo1, hi1);
+      }
+    }
+#ifdef T2P_TIMING_KNOBS
+    }
+#endif
+    // channel totals over the four lanes that share a channel, then the channels of a group: groups of 4 channels =
+    // lanes with equal (lane >> 4) of one slot, groups of 8 = all lanes of a slot, groups of 16 / 32 = two / four slots.
+    // Lane 0 ends up with every group of the warp's 32 channels.
+    float gsum[8], gsq[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int o = 1; o <= 8; o <<= 1) {
+        ssum[k] += __shfl_xor_sync(0xffffffffu, ssum[k], o);
+        ssq[k] += __shfl_xor_sync(0xffffffffu, ssq[k], o);
+      }
+      // lanes 0..15 hold the channels (lane >> 2) < 4 of slot k, lanes 16..31 the channels 4..7
+      const float os = __shfl_xor_sync(0xffffffffu, ssum[k], 16), oq = __shfl_xor_sync(0xffffffffu, ssq[k], 16);
+      gsum[2 * k] = ssum[k]; gsq[2 * k] = ssq[k];        // (as seen from lane 0: group 2k of 4 channels ...
+      gsum[2 * k + 1] = os;  gsq[2 * k + 1] = oq;        //  ... and group 2k + 1)
+    }
+    if (lane == 0) {
+      float* const dst = p.gno_part + ((static_cast<long long>(sample) * p.gno_parts + part) * ngroups + nw0 / cpg) * 2;
+      if (cpg == 4) {
+#pragma unroll
+        for (int g = 0; g < 8; g += 2)
+          __stcg(reinterpret_cast<float4*>(dst + 2 * g), make_float4(gsum[g], gsq[g], gsum[g + 1], gsq[g + 1]));
+      } else if (cpg == 8) {
+        __stcg(reinterpret_cast<float4*>(dst), make_float4(gsum[0] + gsum[1], gsq[0] + gsq[1], gsum[2] + gsum[3], gsq[2] + gsq[3]));
+        __stcg(reinterpret_cast<float4*>(dst + 4), make_float4(gsum[4] + gsum[5], gsq[4] + gsq[5], gsum[6] + gsum[7], gsq[6] + gsq[7]));
+      } else if (cpg == 16) {
+        __stcg(reinterpret_cast<float4*>(dst), make_float4((gsum[0] + gsum[1]) + (gsum[2] + gsum[3]), (gsq[0] + gsq[1]) + (gsq[2] + gsq[3]),
+                                                          (gsum[4] + gsum[5]) + (gsum[6] + gsum[7]), (gsq[4] + gsq[5]) + (gsq[6] + gsq[7])));
+      } else {
+        __stcg(reinterpret_cast<float2*>(dst), make_float2(((gsum[0] + gsum[1]) + (gsum[2] + gsum[3])) + ((gsum[4] + gsum[5]) + (gsum[6] + gsum[7])),
+                                                          ((gsq[0] + gsq[1]) + (gsq[2] + gsq[3])) + ((gsq[4] + gsq[5]) + (gsq[6] + gsq[7]))));
+      }
+      red_release_gpu_add(&arrived[slot], 1);
+      const long long t0 = clock64();
+      while (ld_acquire_gpu(&arrived[slot]) < p.gno_parts) {
+#ifdef T2P_TIMING_KNOBS
+        if (p.gno_debug & 1) break;
+#endif
+        if (clock64() - t0 > 4000000000LL) __trap();
+      }
+    }
+    __syncwarp();
+    // ---- fold: lane l adds the parts r = l / gpw, l / gpw + 32 / gpw, ... of group l % gpw (coalesced: the groups of a
+    // part are adjacent), a butterfly over the lanes of equal group completes the sum
+    float mean_g, rstd_g;
+    {
+      const int g = lane & (gpw - 1);
+      const int rstep = cpg;  // 32 / gpw
+      const float* src = p.gno_part + (static_cast<long long>(sample) * p.gno_parts * ngroups + nw0 / cpg + g) * 2;
+      const long long pitch = static_cast<long long>(ngroups) * 2;
+      double gs = 0.0, gq = 0.0;
+      int r = lane / gpw;
+#ifdef T2P_TIMING_KNOBS
+      if (p.gno_debug & 4) r = p.gno_parts;
+#endif
+      // sixteen loads in flight per lane (a 128 x 128 image: 64 parts x 8 groups = 16 per lane): with four, the fold was
+      // four dependent L2 round trips, 3 us per tile
+      for (; r < p.gno_parts; r += 16 * rstep) {
+        float2 v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int ri = r + i * rstep;
+          v[i] = ri < p.gno_parts ? __ldcg(reinterpret_cast<const float2*>(src + ri * pitch)) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          gs += static_cast<double>(v[i].x);
+          gq += static_cast<double>(v[i].y);
+        }
+      }
+      for (int o = gpw; o < 32; o <<= 1) {
+        gs += __shfl_xor_sync(0xffffffffu, gs, o);
+        gq += __shfl_xor_sync(0xffffffffu, gq, o);
+      }
+      const double mean = gs * inv_cnt;
+      const float var = static_cast<float>(fmax(gq * inv_cnt - mean * mean, 0.0));
+      mean_g = static_cast<float>(mean);
+      rstd_g = rsqrtf(var + p.gno_eps);
+    }
+    int left_ticket = 0;
+    if (lane == 0) left_ticket = atomicAdd(&left[slot], 1);  // (its result is looked at after pass 2)
+    float sc[4], sh[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int src_lane = ((lane >> 2) + 8 * k) / cpg;  // a lane that holds this channel's group
+      const float m = __shfl_sync(0xffffffffu, mean_g, src_lane), rs = __shfl_sync(0xffffffffu, rstd_g, src_lane);
+      sc[k] = rs * ga[k];
+      sh[k] = be[k] - m * sc[k];
+    }
+    // ---- pass 2: normalise, activate, store
+    auto release_acc = [&]() {
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[as]));
+    };
+    auto emit_chunk = [&](const uint32_t (&lo)[16], const uint32_t (&hi)[16], int c) {
+      const uint32_t buf = obuf + (nstore & 1) * (32 * 32 * 2);
+      if (lane == 0) ptx::tma_store_wait_read<1>();
+      __syncwarp();
+      uint32_t pk[4][4];
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        const float v[4][2] = {{__uint_as_float(lo[4 * n]), __uint_as_float(lo[4 * n + 1])},
+                               {__uint_as_float(lo[4 * n + 2]), __uint_as_float(lo[4 * n + 3])},
+                               {__uint_as_float(hi[4 * n]), __uint_as_float(hi[4 * n + 1])},
+                               {__uint_as_float(hi[4 * n + 2]), __uint_as_float(hi[4 * n + 3])}};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float y0 = fmaf(fmaf(v[k][0], p.alpha, bch[k]), sc[k], sh[k]);
+          const float y1 = fmaf(fmaf(v[k][1], p.alpha, bch[k]), sc[k], sh[k]);
+          pk[k][n] = ptx::pack_bf16x2(silu_tanh_f(y0), silu_tanh_f(y1));
+        }
+      }
+      const int mt = lane >> 3, row = lane & 7;
+      const uint32_t rowaddr = buf + (8 * (mt >> 1) + row) * 64;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+        for (int ph = 0; ph < 2; ++ph)
+          ptx::stmatrix_x4_trans(rowaddr + ph * (16 * 64) + ((((2 * hf + (mt & 1)) ^ (row >> 1)) & 3) << 4), pk[2 * hf][2 * ph],
+                                 pk[2 * hf + 1][2 * ph], pk[2 * hf][2 * ph + 1], pk[2 * hf + 1][2 * ph + 1]);
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && nw0 < p.N && m0 + c * 32 < p.M) {
+        ptx::tma_store_4d(&p.tm_out, buf, nw0, m0 + c * 32, 0, 0);
+        ptx::tma_store_commit();
+      }
+      ++nstore;
+    };
+    load_chunk(cf, lo0, hi0);
+#pragma unroll 1
+    for (int i = 0; i < NCH; i += 2) {
+      ptx::tmem_ld_wait();
+      if (i + 1 < NCH) load_chunk(cf + i + 1, lo1, hi1);
+      else release_acc();
+      emit_chunk(lo0, hi0, cf + i);
+      if (i + 1 < NCH) {
+        ptx::tmem_ld_wait();
+        if (i + 2 < NCH) load_chunk(cf + i + 2, lo0, hi0);
+        else release_acc();
+        emit_chunk(lo1, hi1, cf + i + 1);
+      }
+    }
+    if (lane == 0 && left_ticket == p.gno_parts - 1) {  // last warp to leave the slot hands it back zeroed
+      arrived[slot] = 0;
+      left[slot] = 0;
+    }
+  }
+  if (lane == 0) ptx::tma_store_wait_read<0>();
+}
+
+template <int PX, int NCH, bool GNO = true>
 __device__ __forceinline__ void epilogue_dispatch(const TcParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
                                                   uint64_t* tempty_bar, uint32_t obuf, int q, int cf, int stat_mul,
                                                   int stat_add, int lane) {
+  if (GNO && p.gno_gamma) {  // (part index = stat_mul * tile + stat_add: whole tiles, or the halves of the eight-warp layout)
+    epilogue_role_gn<PX, NCH>(p, tmem_base, tfull_bar, tempty_bar, obuf, q, cf, stat_mul, stat_add, lane);
+    return;
+  }
   const bool rbvar = p.rowbias != nullptr && (p.rows_per_sample % PX) != 0;
   const bool stats = p.stat_part != nullptr;
   if (rbvar) {
@@ -1190,7 +1467,7 @@ __global__ void __launch_bounds__(CfgHF::THREADS, 1) conv_gemm_tcHF_kernel(const
   } else if (warp < 6) {
     // ------------------------------------------------------------ epilogue (warps 2..5): thread = channel
     const int q = warp & 3;
-    epilogue_dispatch<PX, PX / 32>(p, tmem_base, tfull_bar, tempty_bar, out_stage + q * (2 * 32 * 32 * 2), q, 0, 1, 0, lane);
+    epilogue_dispatch<PX, PX / 32, false>(p, tmem_base, tfull_bar, tempty_bar, out_stage + q * (2 * 32 * 32 * 2), q, 0, 1, 0, lane);
   } else {
     // ------------------------------------------------------------ transform warps (6..13)
     const int grp = (warp - 6) >> 2;                       // groups of four warps
@@ -1385,6 +1662,23 @@ int sm_count() { return device_sm_count(); }
 // kernel's set-up -- barrier init, TMEM allocation, descriptor prefetch -- runs under the tail of its predecessor:
 // neutral at 64 maps per GPU, -4.6 % per PC iteration at 8 (profiles/r02_gn_small_ab.txt).  T2P_PDL_SMALL (knob
 // builds) overrides the CTA threshold.
+// Grid of a launch that normalises its own output (epilogue_role_gn).  A sample whose tiles lie in two consecutive waves
+// of the persistent CTAs holds the epilogue of its first-wave tiles back until the second wave's MMAs are done; with
+// short tiles (K <= ~1500: the tile takes no longer than pass 1 + exchange + pass 2) that lag is not absorbed by the
+// second accumulator and every wave pays it (measured: 128 x 128, K = 1152: 0.25 -> 0.38 ms).  Rounding the grid down to
+// a multiple of the tiles per sample keeps every sample inside one wave at the price of the idle SMs (13.5 % at 64
+// tiles per sample, 2.7 % at 16).
+int gno_grid(const TcParams& p, int px) {
+  const int grid = std::min(p.num_tiles, sm_count());
+  if (!p.gno_gamma) return grid;
+  const int span = (p.rows_per_sample / px) * p.n_tiles;
+  const int ktot = p.taps * (p.c0 + p.c1) + p.xc0 + p.xc1;
+  static const int mode = env_knob("T2P_GNO_ALIGN", 2);  // knob builds: 0 never, 1 always, 2 by tile length
+  const bool align = mode == 1 || (mode == 2 && ktot <= 1536);
+  if (!align || span > grid) return grid;
+  return grid / span * span;
+}
+
 bool pdl_for(int grid) {
   static const bool all = (env_knob("T2P_PDL", 0) & 1) != 0;
   static const int small = env_knob("T2P_PDL_SMALL", 147);
@@ -1415,7 +1709,7 @@ void launch_t(TcParams& p, cudaStream_t st) {
   }
   p.n_tiles = cdiv(p.N, 128);
   p.num_tiles = cdiv(p.M, PX) * p.n_tiles;
-  const int grid = std::min(p.num_tiles, sm_count());
+  const int grid = gno_grid(p, PX);
   launch_pdl_dyn(pdl_for(grid), conv_gemm_tcT_kernel<PX>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, p);
 }
 
@@ -1427,7 +1721,7 @@ void launch_h(TcParams& p, cudaStream_t st) {
   }
   p.n_tiles = cdiv(p.N, 128);
   p.num_tiles = cdiv(p.M, C::PX) * p.n_tiles;
-  const int grid = std::min(p.num_tiles, sm_count());
+  const int grid = gno_grid(p, C::PX);
   launch_pdl<1>(conv_gemm_tcH_kernel, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, p);
 }
 
@@ -1512,6 +1806,36 @@ bool conv_gemm_tc_channel_major(const ConvGemmArgs& a) { return make_plan(a).cha
 
 bool conv_gemm_tc_fuses_gn(const ConvGemmArgs& a) { return make_plan(a).halo; }
 
+// parts (statistic slices) per sample and channel quadrant: pixel tiles per sample x epilogue warps per quadrant
+static int gn_out_parts(const ConvGemmArgs& a, const Plan& pl) {
+  const int warps_per_quadrant = pl.halo ? (CfgH::EPI_WARPS == 8 ? 2 : 1) : 2;
+  return a.rows_per_sample / pl.rows * warps_per_quadrant;
+}
+
+bool conv_gemm_tc_gn_out_ok(const ConvGemmArgs& a, int groups) {
+  if (groups <= 0 || a.N % 128 != 0 || a.N % groups != 0) return false;
+  const int cpg = a.N / groups;
+  if (cpg != 4 && cpg != 8 && cpg != 16 && cpg != 32) return false;
+  if (a.out_dtype != kBF16 || a.out_nchw || a.residual || a.res_up || a.rows_per_sample <= 0) return false;
+  ConvGemmArgs q = a;
+  q.stat_part = nullptr;
+  const Plan pl = make_plan(q);
+  if (!pl.channel_major || a.rows_per_sample % pl.rows != 0) return false;
+  // deadlock freedom of the per-sample wait (see epilogue_role_gn): the tiles of one sample must span fewer
+  // consecutive tile indices than there are CTAs
+  const long long span = static_cast<long long>(a.rows_per_sample / pl.rows) * (a.N / 128);
+  return span <= sm_count();
+}
+
+long long conv_gemm_tc_gn_out_part_floats(const ConvGemmArgs& a, int groups) {
+  ConvGemmArgs q = a;
+  q.stat_part = nullptr;
+  const Plan pl = make_plan(q);
+  return 2LL * a.B * gn_out_parts(a, pl) * groups;
+}
+
+long long conv_gemm_tc_gn_out_flag_ints(const ConvGemmArgs& a) { return 2LL * a.B * cdiv(a.N, 128) * 4; }
+
 int conv_gemm_tc_stat_tile(const ConvGemmArgs& a) {
   ConvGemmArgs q = a;
   if (!q.stat_part) q.stat_part = reinterpret_cast<float*>(16);  // plan as if statistics were requested
@@ -1589,6 +1913,20 @@ void conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
     uint64_t d[4] = {static_cast<uint64_t>(taps) * ctot + a.xc0 + a.xc1, static_cast<uint64_t>(a.N), 1, 1};
     uint32_t b[4] = {BK, static_cast<uint32_t>(pl.channel_major ? 128 : pl.bn), 1, 1};
     p.tm_w = make_tmap_bf16(a.w, d, b);
+  }
+  if (a.gno_gamma) {
+    T2P_CHECK(conv_gemm_tc_gn_out_ok(a, a.gno_groups) && a.gno_beta && a.gno_part && a.gno_flags &&
+                  !a.stat_part && !a.gn_scale,
+              "this launch cannot normalise its own output (ask conv_gemm_tc_gn_out_ok first)");
+    p.gno_gamma = a.gno_gamma;
+    p.gno_beta = a.gno_beta;
+    p.gno_cpg = a.N / a.gno_groups;
+    p.gno_eps = a.gno_eps;
+    p.gno_part = a.gno_part;
+    p.gno_flags = a.gno_flags;
+    p.gno_parts = gn_out_parts(a, pl);
+    p.gno_slots = a.B * (a.N / 128) * 4;
+    p.gno_debug = env_knob("T2P_GNO_DEBUG", 0);
   }
   if (pl.channel_major) {
     {

@@ -48,6 +48,16 @@ struct ConvGemmArgs {
   // core.  Only where conv_gemm_tc_fuses_gn(args) says so (3x3 on 128-pixel-wide images: the halo kernel).
   const float* gn_scale = nullptr;
   const float* gn_shift = nullptr;
+  // GroupNorm + SiLU of the OUTPUT inside the epilogue: out = silu(GroupNorm(acc * alpha + bias + rowbias)) with the
+  // CONSUMER's parameters (ResBlock: GroupNorm_1 after Conv_0).  Only where conv_gemm_tc_gn_out_ok(args); scratch:
+  // gno_part >= conv_gemm_tc_gn_out_part_floats(args) floats, gno_flags conv_gemm_tc_gn_out_flag_ints(args) ints that are
+  // ZERO on entry (the kernel leaves them zero).
+  const float* gno_gamma = nullptr;
+  const float* gno_beta = nullptr;
+  int gno_groups = 0;
+  float gno_eps = 1e-6f;
+  float* gno_part = nullptr;
+  int* gno_flags = nullptr;
 };
 
 // bf16 tcgen05 / TMEM / TMA path (sm_100a).  A, W are bf16.
@@ -59,6 +69,11 @@ int conv_gemm_tc_stat_tile(const ConvGemmArgs& a);
 bool conv_gemm_tc_channel_major(const ConvGemmArgs& a);
 // true when this launch can apply GroupNorm + SiLU to its 3x3 sources itself (gn_scale / gn_shift)
 bool conv_gemm_tc_fuses_gn(const ConvGemmArgs& a);
+// true when this launch can normalise + activate its own output (gno_*): channel-major kernel, whole pixel tiles per
+// sample, N % 128 == 0, `groups` groups of 4 / 8 / 16 / 32 channels, and few enough tiles per sample for the inter-CTA wait
+bool conv_gemm_tc_gn_out_ok(const ConvGemmArgs& a, int groups);
+long long conv_gemm_tc_gn_out_part_floats(const ConvGemmArgs& a, int groups);
+long long conv_gemm_tc_gn_out_flag_ints(const ConvGemmArgs& a);  // size of gno_flags
 // fp32 or bf16 SIMT path (verification mode and tiny-channel edge layers). dtype of A and W.
 void conv_gemm_simt(const ConvGemmArgs& a, int in_dtype, cudaStream_t st);
 

@@ -325,6 +325,7 @@ UNet::~UNet() {
   if (ctx_buf_) cudaFree(ctx_buf_);
   if (h_scratch_) cudaFree(h_scratch_);
   if (temb_persist_) cudaFree(temb_persist_);
+  if (gno_flags_) cudaFree(gno_flags_);
 }
 
 void UNet::load(const std::string& name, const void* dev_ptr, const std::vector<int64_t>& shape, int dtype,
@@ -461,9 +462,24 @@ bool UNet::fuses_gn(const Linear& l, const Act& a0, const Act* a1) const {
   return conv_gemm_tc_fuses_gn(g);
 }
 
+// true when the tcgen05 launch of this convolution can apply the CONSUMER's GroupNorm + SiLU to its own output
+bool UNet::normalises_output(const Linear& l, const Act& a0, const GroupNormP& gn) const {
+  static const int knob = env_knob("T2P_GN_OUT", -1);  // knob builds: A/B override of the option
+  if (!(knob >= 0 ? knob != 0 : gn_out_)) return false;
+  if (cfg_.compute_dtype != kBF16 || l.force_f32 || a0.C % 64 || gn.C != l.N) return false;
+  ConvGemmArgs g;
+  g.c0 = a0.C;
+  g.B = a0.B; g.H = a0.H; g.W = a0.W;
+  g.ksize = l.ksize;
+  g.N = l.N;
+  g.rows_per_sample = a0.H * a0.W;
+  g.out_dtype = kBF16;
+  return conv_gemm_tc_gn_out_ok(g, gn.G);
+}
+
 void UNet::gemm(const Linear& l, const Act& a0, const Act* a1, Act& out, const float* rowbias, int rowbias_ld,
                 const void* residual, int res_up, float alpha, int out_dtype, int out_nchw, const Act* x0,
-                const Act* x1, const float* gn_affine) {
+                const Act* x1, const float* gn_affine, const GroupNormP* gn_out) {
   ConvGemmArgs g;
   if (gn_affine) {
     g.gn_scale = gn_affine;
@@ -495,8 +511,34 @@ void UNet::gemm(const Linear& l, const Act& a0, const Act* a1, Act& out, const f
       g.stat_part = out.spart;
     }
   }
+  void* gno_scratch = nullptr;
+  if (gn_out) {
+    T2P_CHECK(tc && !g.stat_part && !gn_affine, "epilogue GroupNorm on a launch that cannot carry it");
+    g.gno_gamma = static_cast<const float*>(gn_out->w->data);
+    g.gno_beta = static_cast<const float*>(gn_out->b->data);
+    g.gno_groups = gn_out->G;
+    g.gno_eps = 1e-6f;
+    const size_t part_bytes = sizeof(float) * static_cast<size_t>(conv_gemm_tc_gn_out_part_floats(g, gn_out->G));
+    gno_scratch = ln_->ws.alloc(part_bytes);
+    g.gno_part = static_cast<float*>(gno_scratch);
+    const size_t flag_bytes = sizeof(int) * static_cast<size_t>(conv_gemm_tc_gn_out_flag_ints(g));
+    if (!dry_ && flag_bytes > gno_flags_bytes_) {
+      ++resource_epoch_;
+      if (gno_flags_) T2P_CUDA(cudaFree(gno_flags_));
+      gno_flags_ = nullptr;
+      gno_flags_bytes_ = 0;
+      const size_t cap = std::max<size_t>(2 * flag_bytes, 1 << 16);
+      T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&gno_flags_), cap));
+      T2P_CUDA(cudaMemset(gno_flags_, 0, cap));  // (synchronous, outside any capture: allocation happens in eager runs)
+      gno_flags_bytes_ = cap;
+    }
+    g.gno_flags = gno_flags_;
+  }
   ++launches_;
-  if (dry_) return;
+  if (dry_) {
+    if (gno_scratch) ln_->ws.free(gno_scratch);
+    return;
+  }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (profile_) {
     T2P_CUDA(cudaEventCreate(&e0));
@@ -518,6 +560,7 @@ void UNet::gemm(const Linear& l, const Act& a0, const Act* a1, Act& out, const f
       T2P_CUDA(e);
     }
   }
+  if (gno_scratch) ln_->ws.free(gno_scratch);
   if (profile_) {
     T2P_CUDA(cudaEventRecord(e1, ln_->st));
     GemmRecord r;
@@ -637,6 +680,20 @@ Act UNet::run_res(ResBlockM& m, const Act& a0, const Act* a1) {
   const int mode = m.down ? 1 : (m.up ? 2 : 0);
   Act xr;  // resampled raw input: 2x2 mean (skip path of a down block) or, folded up block, nearest x2
   if (m.down || (m.up && m.folded)) xr = new_act(B, OH, OW, m.in_ch, false);
+  {
+    Act probe;
+    probe.B = B; probe.H = OH; probe.W = OW; probe.C = m.in_ch;
+    if (normalises_output(m.conv0, probe, m.gn1) && !(mode == 0 && fuses_gn(m.conv0, a0, a1))) {
+      // h2 = act(GroupNorm_1(Conv_0(h) + temb)) leaves Conv_0's epilogue normalised: the raw tensor never exists
+      Act h = new_act(B, OH, OW, m.in_ch, false);
+      group_norm(m.gn0, a0, a1, 1, mode, h, xr.p ? &xr : nullptr);
+      Act h2 = new_act(B, OH, OW, m.out_ch, false);
+      gemm(m.conv0, h, nullptr, h2, ln_->temb_all + m.temb_off, temb_total_, nullptr, 0, 1.f, -1, 0, nullptr, nullptr, nullptr,
+           &m.gn1);
+      free_act(h);
+      return finish_res(m, a0, a1, h2, xr);
+    }
+  }
   Act h1 = new_act(B, OH, OW, m.out_ch, true);
   if (mode == 0 && fuses_gn(m.conv0, a0, a1)) {
     // h = act(GroupNorm_0(x)) is applied inside Conv_0's operand path: the normalised tensor is never written
@@ -668,6 +725,13 @@ Act UNet::run_res(ResBlockM& m, const Act& a0, const Act* a1) {
   Act h2 = new_act(B, OH, OW, m.out_ch, false);
   group_norm(m.gn1, h1, nullptr, 1, 0, h2, nullptr);
   free_act(h1);
+  return finish_res(m, a0, a1, h2, xr);
+}
+
+// second half of the block: out = (Conv_1(h2) + skip(x)) / sqrt(2), layers.py:319-327.  Takes ownership of h2 and xr.
+Act UNet::finish_res(ResBlockM& m, const Act& a0, const Act* a1, Act& h2, Act& xr) {
+  const int B = a0.B, H = a0.H, W = a0.W;
+  const int OH = h2.H, OW = h2.W;
   if (m.folded) {
     // out = (Conv_1(h2) + skip(x)) / sqrt(2) as ONE GEMM: the skip's channels are extra K columns (centre tap)
     Act out = new_act(B, OH, OW, m.out_ch, true);

@@ -168,6 +168,11 @@ class UNet {
   void set_fused_groupnorm(bool on) {
     if (on != fuse_gn_) { fuse_gn_ = on; planned_B_ = -1; ++generation_; }
   }
+  // GroupNorm_1 + SiLU inside Conv_0's EPILOGUE (gemm_tc.cu, epilogue_role_gn): the raw Conv_0 output, its statistics
+  // pass, gn_finalize and gn_apply of every ResBlock whose Conv_0 qualifies disappear.  Changes the launch sequence.
+  void set_epilogue_groupnorm(bool on) {
+    if (on != gn_out_) { gn_out_ = on; planned_B_ = -1; ++generation_; }
+  }
   // copies a recorded block output (fp32 NCHW) to dst; returns its shape
   bool tap(const std::string& name, float* dst, int64_t capacity, int64_t shape[4], cudaStream_t st);
   // profile mode: CUDA events around every implicit-GEMM launch of the following forward passes
@@ -198,13 +203,16 @@ class UNet {
   void free_act(Act& a);
   void gemm(const Linear& l, const Act& a0, const Act* a1, Act& out, const float* rowbias, int rowbias_ld,
             const void* residual, int res_up, float alpha, int out_dtype = -1, int out_nchw = 0,
-            const Act* x0 = nullptr, const Act* x1 = nullptr, const float* gn_affine = nullptr);
+            const Act* x0 = nullptr, const Act* x1 = nullptr, const float* gn_affine = nullptr,
+            const GroupNormP* gn_out = nullptr);
   bool fuses_gn(const Linear& l, const Act& a0, const Act* a1) const;
+  bool normalises_output(const Linear& l, const Act& a0, const GroupNormP& gn) const;
   void group_norm(const GroupNormP& g, const Act& a0, const Act* a1, int act, int mode, Act& out, Act* raw_out,
                   float** affine_out = nullptr);
   void attention(const void* q, const void* k, const void* v, void* out, int B, int heads, int Tq, int Tk, int d,
                  long long ldq, long long ldk, long long ldv, long long ldo, float scale);
   Act run_res(ResBlockM& m, const Act& a0, const Act* a1);
+  Act finish_res(ResBlockM& m, const Act& a0, const Act* a1, Act& h2, Act& xr);
   Act run_attn(AttnBlockM& m, const Act& x);
   Act run_st(TransformerM& m, const Act& x);
   Act run_block(BlockM& blk, const Act& a0, const Act* a1, const std::string& tapname);
@@ -242,6 +250,9 @@ class UNet {
   bool dry_ = false;
   bool debug_ = false;
   bool fuse_gn_ = false;
+  bool gn_out_ = true;
+  int* gno_flags_ = nullptr;  // zeroed ticket / ready / done words of the epilogue-GroupNorm exchange (left zero by every launch)
+  size_t gno_flags_bytes_ = 0;
   bool profile_ = false;
   long long generation_ = 0;
   std::vector<GemmRecord> profile_log_;

@@ -98,6 +98,8 @@ class UNetModel(nn.Module):
         self._create_engine()
         if hasattr(config.model, "get") and config.model.get("fused_groupnorm", False):
             self.set_fused_groupnorm(True)
+        if hasattr(config.model, "get") and config.model.get("epilogue_groupnorm", None) is not None:
+            self.set_epilogue_groupnorm(bool(config.model.get("epilogue_groupnorm")))
         self._build_tree()
         self._synced_version = None
         self._synced_checksum = None
@@ -275,6 +277,12 @@ class UNetModel(nn.Module):
         a separate pass (include/t2p.h, t2p_unet_set_fused_groupnorm).  ``config.model.fused_groupnorm`` sets it
         at construction."""
         _lib.check(_lib.lib().t2p_unet_set_fused_groupnorm(self._handle, 1 if on else 0))
+
+    def set_epilogue_groupnorm(self, on=True):
+        """Option (default on): every ResBlock's Conv_0 applies GroupNorm_1 + SiLU to its own output in its epilogue
+        (include/t2p.h, t2p_unet_set_epilogue_groupnorm).  ``config.model.epilogue_groupnorm`` sets it at
+        construction."""
+        _lib.check(_lib.lib().t2p_unet_set_epilogue_groupnorm(self._handle, 1 if on else 0))
 
     # ------------------------------------------------------------------ debugging aids
     def set_debug(self, on=True):

@@ -1,5 +1,5 @@
 """PC-iteration time of any BASELINE configuration (device-resident, graph-replayed), for the tables in DESIGN.md.
-    python tools/bench_config.py <config> <batch> <ctx_len> [iters] [library file, e.g. libt2p_knobs.so]"""
+    python tools/bench_config.py <config> <batch> <ctx_len> [iters] [library file, e.g. libt2p_knobs.so | -] [gn_out=0|1]"""
 import ctypes as C
 import json
 import os
@@ -14,7 +14,8 @@ from text2protein_b200.score_sde_pytorch import sampling, sde_lib  # noqa: E402
 from text2protein_b200.score_sde_pytorch.models.ncsnpp import UNetModel  # noqa: E402
 from text2protein_b200.synthetic import rerandomize_  # noqa: E402
 
-if len(sys.argv) > 5:
+opts = dict(a.split("=", 1) for a in sys.argv[6:])
+if len(sys.argv) > 5 and sys.argv[5] != "-":
     _lib.use_library(sys.argv[5])
 name, B, Lctx = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 K = int(sys.argv[4]) if len(sys.argv) > 4 else 6
@@ -22,6 +23,8 @@ cfg = load_config(name, device="cuda")
 cfg.model.compute_dtype = "bf16"
 model = UNetModel(cfg).cuda()
 rerandomize_(model.named_parameters(), 42)
+if "gn_out" in opts:
+    model.set_epilogue_groupnorm(opts["gn_out"] != "0")
 Cc, N = cfg.data.num_channels, cfg.data.max_res_num
 kinds = [k for k in cfg.model.condition]
 cond = synthetic_condition(cfg, B, kinds)
@@ -61,4 +64,4 @@ ms = e0.elapsed_time(e1) / K
 print(json.dumps({"config": name, "B": B, "N": N, "C": Cc, "L": Lctx, "conditions": kinds, "ms_per_pc_iteration": ms,
                   "maps_per_s_at_num_scales": B / (ms * 1e-3 * cfg.model.num_scales),
                   "launches_per_forward": int(L.t2p_unet_launches_per_forward(model.native_handle)),
-                  "workspace_gb": L.t2p_unet_workspace_bytes(model.native_handle) / 1e9}))
+                  "workspace_gb": L.t2p_unet_workspace_bytes(model.native_handle) / 1e9, "opts": opts}))
