@@ -668,9 +668,10 @@ int t2p_conv2d(const t2p_conv_args* a, void* stream) {
     const size_t flag_bytes = sizeof(int) * static_cast<size_t>(conv_gemm_tc_gn_out_flag_ints(g));
     char* scratch = nullptr;
     T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&scratch), part_bytes + flag_bytes));
-    g.gno_part = reinterpret_cast<float*>(scratch);
+    g.gno_part = scratch;
     g.gno_flags = reinterpret_cast<int*>(scratch + part_bytes);
-    cudaError_t e = cudaMemsetAsync(g.gno_flags, 0, flag_bytes, S(stream));
+    cudaError_t e = cudaMemsetAsync(g.gno_part, 0xff, part_bytes, S(stream));
+    if (e == cudaSuccess) e = cudaMemsetAsync(g.gno_flags, 0, flag_bytes, S(stream));
     try {
       T2P_CUDA(e);
       conv_gemm_tc(g, S(stream));

@@ -82,10 +82,13 @@ struct TcParams {
   const float* gno_beta;
   int gno_cpg;              // channels per group: 4 or 8
   float gno_eps;
-  float* gno_part;          // [sample][tile part][N / cpg][2] per-part {sum, sum of squares} of the groups
-  int* gno_flags;           // [2][sample * n_tiles * 4]: parts arrived, warps that left -- zero on entry, left zero on exit
+  unsigned long long* gno_part;  // [sample][tile part][N / cpg] per-part {sum, sum of squares} of the groups as one word;
+                                 // all ones (sentinel) on entry, left so on exit
+  int* gno_flags;           // [sample * n_tiles * 4]: warps that left the slot -- zero on entry, left zero on exit
   int gno_parts;            // parts per sample and channel quadrant = pixel tiles per sample x epilogue warps per quadrant
   int gno_slots;            // samples * n_tiles * 4
+  long long* gno_trace;     // knob builds, T2P_GNO_TRACE: [cta][tile][16] clock64 stamps of the MMA warp and epilogue warp 2
+  int gno_trace_tiles;
   int gno_debug;            // timing experiments (knob builds): 1 = do not wait for the other parts, 2 = no pass 1, 4 = no fold loads
 };
 
@@ -643,27 +646,36 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, uint32_t tmem_b
 // a sample need ALL its pixel tiles, which other CTAs hold, so the epilogue runs in two passes over the accumulator
 // (tcgen05.ld does not consume it):
 //   pass 1  v = acc * alpha + bias (+ time-embedding bias), per-group sum / sum of squares of this warp's pixels and
-//           32 channels; lane 0 stores them to gno_part and adds 1 to the counter of its (sample, n tile, quadrant) slot
-//           with red.release.gpu (stores and release by the same thread: no fence, no round trip)
-//   wait    lane 0 polls the counter (ld.acquire.gpu, bounded) until every part of the slot has arrived
-//   fold    EVERY warp adds the parts of its groups itself: all loads in flight at once (L2), the same fixed order in
-//           every warp and every run (deterministic, bit-identical across the warps of a sample), in double
+//           32 channels; lane 0 stores each {sum, sum of squares} pair as ONE 64-bit word into gno_part
+//   fold    EVERY warp of the (sample, n tile, quadrant) slot reads all parts of its groups and adds them itself, in
+//           double and in the same fixed order in every warp and every run (deterministic; bit-identical across the
+//           warps of a sample).  The buffer is its own flag: its words hold a sentinel (all ones: a NaN no arithmetic
+//           produces) until written, and a lane simply re-reads the words that are still the sentinel (bounded wait,
+//           back-off).  No counter, no fence, no release / acquire pair: the chain after the last pass 1 of a sample
+//           is one store and one load deep.
 //   pass 2  y = silu(v * scale + shift) -> bf16 -> stmatrix -> TMA store, as the plain epilogue.
-// The chain after the last pass 1 of a sample is one release, one acquire and one load deep; an earlier version (one
-// elected warp folds, publishes the affine, everyone else waits for it) was eight dependent L2 round trips deep and
-// doubled the time of the 128 x 128 convolutions.  While a warp waits, the MMA warp works on the next tile in the other
-// accumulator.  No deadlock: CTAs are all resident, take their tiles in index order, and a sample's tiles span fewer
-// consecutive indices than there are CTAs (checked on the host), so the tile a CTA must finish BEFORE one of sample s
-// always belongs to an earlier sample.  The two words of a slot (arrived, left) are returned to zero by the last warp
-// that leaves it.
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+// Time line of the first versions (clock64 stamps, T2P_GNO_TRACE in knob builds; 128 x 128, K = 1152, MMA 13.3 k clocks
+// per tile): one elected warp folds and publishes the affine -- eight dependent L2 round trips, the convolutions took
+// twice as long; counter with red.release / ld.acquire, every warp folds -- release fence 1.8 k, poll 2.5 k, fold 4.8 k
+// (an L2 round trip is ~2 k clocks under this kernel's operand traffic), pass 1 1.6 k, pass 2 4.8 k: 16.2 k per tile,
+// epilogue-bound.
+// While a warp waits, the MMA warp works on the next tile in the other accumulator.  No deadlock: CTAs are all
+// resident, take their tiles in index order, and a sample's tiles span fewer consecutive indices than there are CTAs
+// (checked on the host), so the tile a CTA must finish BEFORE one of sample s always belongs to an earlier sample.
+// The last warp to leave a slot (one counter word per slot, off the critical path) writes the sentinel back and zeroes
+// the counter: gno_part and gno_flags enter and leave every launch in the same state.
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
-  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long pack_stat(float sum, float sq) {
+  return (static_cast<unsigned long long>(__float_as_uint(sq)) << 32) | __float_as_uint(sum);
+}
+constexpr unsigned long long kStatSentinel = ~0ull;
 __device__ __forceinline__ float silu_tanh_f(float x) {
   const float h = 0.5f * x;
   float t;
@@ -681,8 +693,7 @@ __device__ __forceinline__ void epilogue_role_gn(const TcParams& p, uint32_t tme
   const int cpg = p.gno_cpg;
   const int gpw = 32 / cpg;                     // groups per warp (32 channels): 8, 4, 2 or 1
   const int ngroups = p.N / cpg;
-  int* const arrived = p.gno_flags;
-  int* const left = p.gno_flags + p.gno_slots;
+  int* const left = p.gno_flags;
   const double inv_cnt = 1.0 / (static_cast<double>(p.rows_per_sample) * cpg);
   for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tl) {
     const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
@@ -705,8 +716,17 @@ __device__ __forceinline__ void epilogue_role_gn(const TcParams& p, uint32_t tme
       ga[k] = __ldg(p.gno_gamma + n);
       be[k] = __ldg(p.gno_beta + n);
     }
+#ifdef T2P_TIMING_KNOBS
+    long long* const trc = (p.gno_trace && q == 0 && part_add == 0 && static_cast<int>(tl) < p.gno_trace_tiles)
+                               ? p.gno_trace + (static_cast<long long>(blockIdx.x) * p.gno_trace_tiles + tl) * 16 : nullptr;
+#define T2P_STAMP(i) do { if (trc && lane == 0) trc[i] = clock64(); } while (0)
+#else
+#define T2P_STAMP(i) do { } while (0)
+#endif
+    T2P_STAMP(0);
     T2P_EPI_WAIT(ptx::smem_u32(&tfull_bar[as]), aph);
     ptx::tc_fence_after();
+    T2P_STAMP(1);
     const uint32_t tbase = tmem_base + as * PX + (static_cast<uint32_t>(q * 32) << 16);
     auto load_chunk = [&](int c, uint32_t (&lo)[16], uint32_t (&hi)[16]) {
       ptx::tmem_ld_16x256_x4(tbase + c * 32, lo);
@@ -764,60 +784,74 @@ __device__ __forceinline__ void epilogue_role_gn(const TcParams& p, uint32_t tme
       gsum[2 * k] = ssum[k]; gsq[2 * k] = ssq[k];        // (as seen from lane 0: group 2k of 4 channels ...
       gsum[2 * k + 1] = os;  gsq[2 * k + 1] = oq;        //  ... and group 2k + 1)
     }
+    T2P_STAMP(2);
+    unsigned long long* const slot_part =
+        p.gno_part + static_cast<long long>(sample) * p.gno_parts * ngroups + nw0 / cpg;  // + part * ngroups + group
     if (lane == 0) {
-      float* const dst = p.gno_part + ((static_cast<long long>(sample) * p.gno_parts + part) * ngroups + nw0 / cpg) * 2;
+      unsigned long long* const dst = slot_part + static_cast<long long>(part) * ngroups;
       if (cpg == 4) {
 #pragma unroll
-        for (int g = 0; g < 8; g += 2)
-          __stcg(reinterpret_cast<float4*>(dst + 2 * g), make_float4(gsum[g], gsq[g], gsum[g + 1], gsq[g + 1]));
+        for (int g = 0; g < 8; ++g) st_relaxed_gpu_u64(dst + g, pack_stat(gsum[g], gsq[g]));
       } else if (cpg == 8) {
-        __stcg(reinterpret_cast<float4*>(dst), make_float4(gsum[0] + gsum[1], gsq[0] + gsq[1], gsum[2] + gsum[3], gsq[2] + gsq[3]));
-        __stcg(reinterpret_cast<float4*>(dst + 4), make_float4(gsum[4] + gsum[5], gsq[4] + gsq[5], gsum[6] + gsum[7], gsq[6] + gsq[7]));
+#pragma unroll
+        for (int g = 0; g < 4; ++g) st_relaxed_gpu_u64(dst + g, pack_stat(gsum[2 * g] + gsum[2 * g + 1], gsq[2 * g] + gsq[2 * g + 1]));
       } else if (cpg == 16) {
-        __stcg(reinterpret_cast<float4*>(dst), make_float4((gsum[0] + gsum[1]) + (gsum[2] + gsum[3]), (gsq[0] + gsq[1]) + (gsq[2] + gsq[3]),
-                                                          (gsum[4] + gsum[5]) + (gsum[6] + gsum[7]), (gsq[4] + gsq[5]) + (gsq[6] + gsq[7])));
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+          st_relaxed_gpu_u64(dst + g, pack_stat((gsum[4 * g] + gsum[4 * g + 1]) + (gsum[4 * g + 2] + gsum[4 * g + 3]),
+                                                (gsq[4 * g] + gsq[4 * g + 1]) + (gsq[4 * g + 2] + gsq[4 * g + 3])));
       } else {
-        __stcg(reinterpret_cast<float2*>(dst), make_float2(((gsum[0] + gsum[1]) + (gsum[2] + gsum[3])) + ((gsum[4] + gsum[5]) + (gsum[6] + gsum[7])),
-                                                          ((gsq[0] + gsq[1]) + (gsq[2] + gsq[3])) + ((gsq[4] + gsq[5]) + (gsq[6] + gsq[7]))));
-      }
-      red_release_gpu_add(&arrived[slot], 1);
-      const long long t0 = clock64();
-      while (ld_acquire_gpu(&arrived[slot]) < p.gno_parts) {
-#ifdef T2P_TIMING_KNOBS
-        if (p.gno_debug & 1) break;
-#endif
-        if (clock64() - t0 > 4000000000LL) __trap();
+        st_relaxed_gpu_u64(dst, pack_stat(((gsum[0] + gsum[1]) + (gsum[2] + gsum[3])) + ((gsum[4] + gsum[5]) + (gsum[6] + gsum[7])),
+                                          ((gsq[0] + gsq[1]) + (gsq[2] + gsq[3])) + ((gsq[4] + gsq[5]) + (gsq[6] + gsq[7]))));
       }
     }
-    __syncwarp();
+    T2P_STAMP(3);
     // ---- fold: lane l adds the parts r = l / gpw, l / gpw + 32 / gpw, ... of group l % gpw (coalesced: the groups of a
-    // part are adjacent), a butterfly over the lanes of equal group completes the sum
+    // part are adjacent), sixteen loads in flight, re-reading what has not arrived yet; a butterfly over the lanes of
+    // equal group completes the sum
     float mean_g, rstd_g;
     {
       const int g = lane & (gpw - 1);
       const int rstep = cpg;  // 32 / gpw
-      const float* src = p.gno_part + (static_cast<long long>(sample) * p.gno_parts * ngroups + nw0 / cpg + g) * 2;
-      const long long pitch = static_cast<long long>(ngroups) * 2;
+      const unsigned long long* const src = slot_part + g;
       double gs = 0.0, gq = 0.0;
-      int r = lane / gpw;
-#ifdef T2P_TIMING_KNOBS
-      if (p.gno_debug & 4) r = p.gno_parts;
-#endif
-      // sixteen loads in flight per lane (a 128 x 128 image: 64 parts x 8 groups = 16 per lane): with four, the fold was
-      // four dependent L2 round trips, 3 us per tile
-      for (; r < p.gno_parts; r += 16 * rstep) {
-        float2 v[16];
+      for (int r = lane / gpw; r < p.gno_parts; r += 16 * rstep) {
+        unsigned long long v[16];
+        unsigned pending = 0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int ri = r + i * rstep;
-          v[i] = ri < p.gno_parts ? __ldcg(reinterpret_cast<const float2*>(src + ri * pitch)) : make_float2(0.f, 0.f);
+        for (int i = 0; i < 16; ++i)
+          if (r + i * rstep < p.gno_parts) pending |= 1u << i;
+#ifdef T2P_TIMING_KNOBS
+        if (p.gno_debug & 4) pending = 0;
+#endif
+        const unsigned mine = pending;
+        long long t0 = 0;
+        unsigned spins = 0;
+        while (true) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (pending & (1u << i)) v[i] = ld_relaxed_gpu_u64(src + static_cast<long long>(r + i * rstep) * ngroups);
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if ((pending & (1u << i)) && static_cast<unsigned>(v[i] >> 32) != 0xffffffffu) pending &= ~(1u << i);
+#ifdef T2P_TIMING_KNOBS
+          if (p.gno_debug & 1) pending = 0;
+#endif
+          if (!pending) break;
+          if (spins == 0) t0 = clock64();
+          else if (clock64() - t0 > 4000000000LL) __trap();
+          if (++spins > 2) __nanosleep(spins > 16 ? 400 : 100);  // a sample spread over two waves waits a whole tile
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          gs += static_cast<double>(v[i].x);
-          gq += static_cast<double>(v[i].y);
+          if (mine & (1u << i)) {
+            gs += static_cast<double>(__uint_as_float(static_cast<unsigned>(v[i])));
+            gq += static_cast<double>(__uint_as_float(static_cast<unsigned>(v[i] >> 32)));
+          }
         }
       }
+      __syncwarp();
+      T2P_STAMP(4);
       for (int o = gpw; o < 32; o <<= 1) {
         gs += __shfl_xor_sync(0xffffffffu, gs, o);
         gq += __shfl_xor_sync(0xffffffffu, gq, o);
@@ -838,10 +872,12 @@ __device__ __forceinline__ void epilogue_role_gn(const TcParams& p, uint32_t tme
       sh[k] = be[k] - m * sc[k];
     }
     // ---- pass 2: normalise, activate, store
+    T2P_STAMP(5);
     auto release_acc = [&]() {
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[as]));
+      T2P_STAMP(6);
     };
     auto emit_chunk = [&](const uint32_t (&lo)[16], const uint32_t (&hi)[16], int c) {
       const uint32_t buf = obuf + (nstore & 1) * (32 * 32 * 2);
@@ -891,9 +927,12 @@ __device__ __forceinline__ void epilogue_role_gn(const TcParams& p, uint32_t tme
         emit_chunk(lo1, hi1, cf + i + 1);
       }
     }
-    if (lane == 0 && left_ticket == p.gno_parts - 1) {  // last warp to leave the slot hands it back zeroed
-      arrived[slot] = 0;
-      left[slot] = 0;
+    T2P_STAMP(7);
+    left_ticket = __shfl_sync(0xffffffffu, left_ticket, 0);
+    if (left_ticket == p.gno_parts - 1) {  // last warp to leave the slot: every reader is done, hand it back as found
+      for (int i = lane; i < p.gno_parts * gpw; i += 32)
+        st_relaxed_gpu_u64(slot_part + static_cast<long long>(i / gpw) * ngroups + (i & (gpw - 1)), kStatSentinel);
+      if (lane == 0) left[slot] = 0;
     }
   }
   if (lane == 0) ptx::tma_store_wait_read<0>();
@@ -1089,16 +1128,14 @@ __global__ void __launch_bounds__(CfgT<PX>::THREADS, 1) conv_gemm_tcT_kernel(con
 // function of the absolute shared-memory address, so a row-shifted window of a swizzled tile is itself a valid
 // operand (probe: csrc/probe_shift.cu).  The L2 -> SMEM stream per (kh, chunk) drops from 3 x (16 + 32) KB to
 // 3 x 16 + 32.5 KB.  Pixels and weights run through separate TMA rings.
-struct CfgH {
+template <int EW>
+struct CfgHT {
   static constexpr int W_BYTES = 128 * BK * 2;           // 16 KB weight tile (128 channels x 64 k)
   static constexpr int P_ROWPITCH = 130;                 // pixels per staged image row (128 + halo)
   static constexpr int P_LOAD_BYTES = 2 * P_ROWPITCH * BK * 2;  // 33 280
   static constexpr int P_BYTES = 33 * 1024;              // buffer pitch (1 KB multiple)
   static constexpr int NP = 3;                           // pixel buffers
-#ifndef T2P_H_EPI_WARPS
-#define T2P_H_EPI_WARPS 4
-#endif
-  static constexpr int EPI_WARPS = T2P_H_EPI_WARPS;      // 4, or 8: two per TMEM lane quadrant, half a tile each
+  static constexpr int EPI_WARPS = EW;                   // 4, or 8: two per TMEM lane quadrant, half a tile each
   static constexpr int NW = EPI_WARPS == 8 ? 5 : 6;      // weight buffers (the staging of eight warps takes one)
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
   static constexpr int OUT_BYTES = EPI_WARPS * 2 * 32 * 32 * 2;
@@ -1106,9 +1143,18 @@ struct CfgH {
   static constexpr int PX = 256;
   static constexpr int TMEM_COLS = 2 * PX;
 };
+#ifndef T2P_H_EPI_WARPS
+#define T2P_H_EPI_WARPS 4
+#endif
+// The plain epilogue is fastest with four warps (eight measured slower: one weight buffer less).  The epilogue that
+// normalises its own output (epilogue_role_gn) is a long dependent chain per 32-pixel chunk with one MUFU per element
+// -- a single warp per scheduler exposes every latency of it -- and runs with eight.
+using CfgH = CfgHT<T2P_H_EPI_WARPS>;
+constexpr int kGnoEpiWarpsH = 4;
 
-__global__ void __launch_bounds__(CfgH::THREADS, 1) conv_gemm_tcH_kernel(const __grid_constant__ TcParams p) {
-  using C = CfgH;
+template <int EW>
+__global__ void __launch_bounds__(CfgHT<EW>::THREADS, 1) conv_gemm_tcH_kernel(const __grid_constant__ TcParams p) {
+  using C = CfgHT<EW>;
   constexpr int PX = C::PX;
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
@@ -1218,8 +1264,16 @@ __global__ void __launch_bounds__(CfgH::THREADS, 1) conv_gemm_tcH_kernel(const _
       uint32_t tl = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tl) {
         const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
+#ifdef T2P_TIMING_KNOBS
+        long long* const trc = (p.gno_trace && static_cast<int>(tl) < p.gno_trace_tiles)
+                                   ? p.gno_trace + (static_cast<long long>(blockIdx.x) * p.gno_trace_tiles + tl) * 16 : nullptr;
+        if (trc) trc[8] = clock64();
+#endif
         ptx::mbar_wait(ptx::smem_u32(&tempty_bar[as]), aph ^ 1);
         ptx::tc_fence_after();
+#ifdef T2P_TIMING_KNOBS
+        if (trc) trc[9] = clock64();
+#endif
         const uint32_t tmem_acc = tmem_base + as * PX;
         bool first = true;
         // one weight tile against the two image rows of a staged pixel buffer (row pitch / tap shift in pixels)
@@ -1255,6 +1309,9 @@ __global__ void __launch_bounds__(CfgH::THREADS, 1) conv_gemm_tcH_kernel(const _
           if (++ps == C::NP) { ps = 0; pph ^= 1; }
         }
         ptx::umma_commit(ptx::smem_u32(&tfull_bar[as]));
+#ifdef T2P_TIMING_KNOBS
+        if (trc) trc[10] = clock64();
+#endif
       }
     }
   } else {
@@ -1713,16 +1770,69 @@ void launch_t(TcParams& p, cudaStream_t st) {
   launch_pdl_dyn(pdl_for(grid), conv_gemm_tcT_kernel<PX>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, p);
 }
 
-void launch_h(TcParams& p, cudaStream_t st) {
-  using C = CfgH;
+template <int EW>
+void launch_h_ew(TcParams& p, cudaStream_t st) {
+  using C = CfgHT<EW>;
   static bool configured[kMaxDevices] = {};
   if (first_use_on_device(configured)) {
-    T2P_CUDA(cudaFuncSetAttribute(conv_gemm_tcH_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    T2P_CUDA(cudaFuncSetAttribute(conv_gemm_tcH_kernel<EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   }
   p.n_tiles = cdiv(p.N, 128);
   p.num_tiles = cdiv(p.M, C::PX) * p.n_tiles;
   const int grid = gno_grid(p, C::PX);
-  launch_pdl<1>(conv_gemm_tcH_kernel, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, p);
+#ifdef T2P_TIMING_KNOBS
+  // T2P_GNO_TRACE=1 (knob builds): clock64 time line of the MMA warp and of epilogue warp 2 of every CTA, printed per launch
+  static const bool trace = env_knob("T2P_GNO_TRACE", 0) != 0;
+  const int tt = 40;
+  if (trace && p.gno_gamma) {
+    static long long* buf = nullptr;
+    if (!buf) T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&buf), sizeof(long long) * 148 * tt * 16));
+    T2P_CUDA(cudaMemsetAsync(buf, 0, sizeof(long long) * 148 * tt * 16, st));
+    p.gno_trace = buf;
+    p.gno_trace_tiles = tt;
+  }
+#endif
+  launch_pdl<1>(conv_gemm_tcH_kernel<EW>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, p);
+#ifdef T2P_TIMING_KNOBS
+  if (trace && p.gno_gamma) {
+    T2P_CUDA(cudaStreamSynchronize(st));
+    std::vector<long long> h(148 * tt * 16);
+    T2P_CUDA(cudaMemcpy(h.data(), p.gno_trace, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
+    const int ktot = p.taps * (p.c0 + p.c1) + p.xc0 + p.xc1;
+    // phases (clocks), averaged over the CTAs' tiles 2.. (steady state)
+    const char* names[] = {"tfull wait", "pass 1", "store", "poll+fold", "butterfly+affine", "-", "pass 2 -> release", "release -> end",
+                           "epilogue total", "MMA: tempty wait", "MMA: issue", "tile period"};
+    double sum[12] = {};
+    long long cnt = 0;
+    for (int c = 0; c < grid; ++c) {
+      const int ntile = std::min(tt, (p.num_tiles - c + grid - 1) / grid);
+      for (int t = 2; t + 1 < ntile; ++t) {
+        const long long* e = &h[(static_cast<size_t>(c) * tt + t) * 16];
+        const long long* n = e + 16;
+        if (!e[0] || !e[7] || !n[8]) continue;
+        const double d[12] = {double(e[1] - e[0]), double(e[2] - e[1]), double(e[3] - e[2]), double(e[4] - e[3]), double(e[5] - e[4]) , 0.0,
+                              double(e[6] - e[5]), double(e[7] - e[6]), double(e[7] - e[1]), double(e[9] - e[8]), double(e[10] - e[9]),
+                              double(n[8] - e[8])};
+        for (int i = 0; i < 12; ++i) sum[i] += d[i];
+        ++cnt;
+      }
+    }
+    std::fprintf(stderr, "[gno trace] M=%d N=%d K=%d grid=%d tiles=%d samples=%lld:", p.M, p.N, ktot, grid, p.num_tiles, cnt);
+    for (int i = 0; i < 12; ++i)
+      if (i != 5) std::fprintf(stderr, " %s %.0f |", names[i], cnt ? sum[i] / cnt : 0.0);
+    std::fprintf(stderr, "\n");
+  }
+#endif
+}
+
+int gno_h_warps() {  // (knob builds: T2P_GNO_H_WARPS=4 for the A/B)
+  static const int v = env_knob("T2P_GNO_H_WARPS", kGnoEpiWarpsH);
+  return v == 4 ? 4 : 8;
+}
+
+void launch_h(TcParams& p, cudaStream_t st) {
+  if (p.gno_gamma && gno_h_warps() == 8) launch_h_ew<8>(p, st);
+  else launch_h_ew<CfgH::EPI_WARPS>(p, st);
 }
 
 void launch_hf(TcParams& p, cudaStream_t st) {
@@ -1808,7 +1918,7 @@ bool conv_gemm_tc_fuses_gn(const ConvGemmArgs& a) { return make_plan(a).halo; }
 
 // parts (statistic slices) per sample and channel quadrant: pixel tiles per sample x epilogue warps per quadrant
 static int gn_out_parts(const ConvGemmArgs& a, const Plan& pl) {
-  const int warps_per_quadrant = pl.halo ? (CfgH::EPI_WARPS == 8 ? 2 : 1) : 2;
+  const int warps_per_quadrant = pl.halo ? (gno_h_warps() == 8 ? 2 : (CfgH::EPI_WARPS == 8 ? 2 : 1)) : 2;
   return a.rows_per_sample / pl.rows * warps_per_quadrant;
 }
 
@@ -1834,7 +1944,7 @@ long long conv_gemm_tc_gn_out_part_floats(const ConvGemmArgs& a, int groups) {
   return 2LL * a.B * gn_out_parts(a, pl) * groups;
 }
 
-long long conv_gemm_tc_gn_out_flag_ints(const ConvGemmArgs& a) { return 2LL * a.B * cdiv(a.N, 128) * 4; }
+long long conv_gemm_tc_gn_out_flag_ints(const ConvGemmArgs& a) { return 1LL * a.B * cdiv(a.N, 128) * 4; }
 
 int conv_gemm_tc_stat_tile(const ConvGemmArgs& a) {
   ConvGemmArgs q = a;
@@ -1922,7 +2032,7 @@ void conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
     p.gno_beta = a.gno_beta;
     p.gno_cpg = a.N / a.gno_groups;
     p.gno_eps = a.gno_eps;
-    p.gno_part = a.gno_part;
+    p.gno_part = static_cast<unsigned long long*>(a.gno_part);
     p.gno_flags = a.gno_flags;
     p.gno_parts = gn_out_parts(a, pl);
     p.gno_slots = a.B * (a.N / 128) * 4;

@@ -49,14 +49,15 @@ struct ConvGemmArgs {
   const float* gn_scale = nullptr;
   const float* gn_shift = nullptr;
   // GroupNorm + SiLU of the OUTPUT inside the epilogue: out = silu(GroupNorm(acc * alpha + bias + rowbias)) with the
-  // CONSUMER's parameters (ResBlock: GroupNorm_1 after Conv_0).  Only where conv_gemm_tc_gn_out_ok(args); scratch:
-  // gno_part >= conv_gemm_tc_gn_out_part_floats(args) floats, gno_flags conv_gemm_tc_gn_out_flag_ints(args) ints that are
-  // ZERO on entry (the kernel leaves them zero).
+  // CONSUMER's parameters (ResBlock: GroupNorm_1 after Conv_0).  Only where conv_gemm_tc_gn_out_ok(args); scratch the
+  // CALLER keeps in a fixed state between launches: gno_part >= conv_gemm_tc_gn_out_part_floats(args) floats with every
+  // byte 0xff (the "not written yet" sentinel), gno_flags conv_gemm_tc_gn_out_flag_ints(args) ints that are zero; the
+  // kernel restores both before it ends.
   const float* gno_gamma = nullptr;
   const float* gno_beta = nullptr;
   int gno_groups = 0;
   float gno_eps = 1e-6f;
-  float* gno_part = nullptr;
+  void* gno_part = nullptr;
   int* gno_flags = nullptr;
 };
 

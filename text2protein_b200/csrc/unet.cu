@@ -326,6 +326,7 @@ UNet::~UNet() {
   if (h_scratch_) cudaFree(h_scratch_);
   if (temb_persist_) cudaFree(temb_persist_);
   if (gno_flags_) cudaFree(gno_flags_);
+  if (gno_part_) cudaFree(gno_part_);
 }
 
 void UNet::load(const std::string& name, const void* dev_ptr, const std::vector<int64_t>& shape, int dtype,
@@ -511,34 +512,35 @@ void UNet::gemm(const Linear& l, const Act& a0, const Act* a1, Act& out, const f
       g.stat_part = out.spart;
     }
   }
-  void* gno_scratch = nullptr;
   if (gn_out) {
     T2P_CHECK(tc && !g.stat_part && !gn_affine, "epilogue GroupNorm on a launch that cannot carry it");
     g.gno_gamma = static_cast<const float*>(gn_out->w->data);
     g.gno_beta = static_cast<const float*>(gn_out->b->data);
     g.gno_groups = gn_out->G;
     g.gno_eps = 1e-6f;
+    // statistics exchange buffer + one counter per slot, persistent: every launch finds them in their idle state (all
+    // ones / zero) and leaves them so
     const size_t part_bytes = sizeof(float) * static_cast<size_t>(conv_gemm_tc_gn_out_part_floats(g, gn_out->G));
-    gno_scratch = ln_->ws.alloc(part_bytes);
-    g.gno_part = static_cast<float*>(gno_scratch);
     const size_t flag_bytes = sizeof(int) * static_cast<size_t>(conv_gemm_tc_gn_out_flag_ints(g));
-    if (!dry_ && flag_bytes > gno_flags_bytes_) {
+    if (!dry_ && (flag_bytes > gno_flags_bytes_ || part_bytes > gno_part_bytes_)) {
       ++resource_epoch_;
+      T2P_CUDA(cudaStreamSynchronize(ln_->st));  // earlier launches of this forward may still be using the old buffers
       if (gno_flags_) T2P_CUDA(cudaFree(gno_flags_));
+      if (gno_part_) T2P_CUDA(cudaFree(gno_part_));
       gno_flags_ = nullptr;
-      gno_flags_bytes_ = 0;
-      const size_t cap = std::max<size_t>(2 * flag_bytes, 1 << 16);
-      T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&gno_flags_), cap));
-      T2P_CUDA(cudaMemset(gno_flags_, 0, cap));  // (synchronous, outside any capture: allocation happens in eager runs)
-      gno_flags_bytes_ = cap;
+      gno_part_ = nullptr;
+      gno_flags_bytes_ = std::max<size_t>({2 * flag_bytes, gno_flags_bytes_, size_t(1) << 16});
+      gno_part_bytes_ = std::max<size_t>({part_bytes + part_bytes / 2, gno_part_bytes_, size_t(1) << 20});
+      T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&gno_flags_), gno_flags_bytes_));
+      T2P_CUDA(cudaMalloc(&gno_part_, gno_part_bytes_));
+      T2P_CUDA(cudaMemset(gno_flags_, 0, gno_flags_bytes_));  // (synchronous, outside any capture: buffers grow in eager runs)
+      T2P_CUDA(cudaMemset(gno_part_, 0xff, gno_part_bytes_));
     }
+    g.gno_part = gno_part_;
     g.gno_flags = gno_flags_;
   }
   ++launches_;
-  if (dry_) {
-    if (gno_scratch) ln_->ws.free(gno_scratch);
-    return;
-  }
+  if (dry_) return;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (profile_) {
     T2P_CUDA(cudaEventCreate(&e0));
@@ -560,7 +562,6 @@ void UNet::gemm(const Linear& l, const Act& a0, const Act* a1, Act& out, const f
       T2P_CUDA(e);
     }
   }
-  if (gno_scratch) ln_->ws.free(gno_scratch);
   if (profile_) {
     T2P_CUDA(cudaEventRecord(e1, ln_->st));
     GemmRecord r;

@@ -251,8 +251,12 @@ class UNet {
   bool debug_ = false;
   bool fuse_gn_ = false;
   bool gn_out_ = true;
-  int* gno_flags_ = nullptr;  // zeroed ticket / ready / done words of the epilogue-GroupNorm exchange (left zero by every launch)
+  // statistics exchange of the epilogue GroupNorm (gemm_tc.cu, epilogue_role_gn): per-slot counters (idle: zero) and the
+  // per-part statistics (idle: all ones); every launch leaves them idle
+  int* gno_flags_ = nullptr;
   size_t gno_flags_bytes_ = 0;
+  void* gno_part_ = nullptr;
+  size_t gno_part_bytes_ = 0;
   bool profile_ = false;
   long long generation_ = 0;
   std::vector<GemmRecord> profile_log_;
