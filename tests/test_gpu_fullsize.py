@@ -172,6 +172,7 @@ def test_fused_groupnorm_option_matches_reference_golden(golden_dir):
     for case, B in (("test_config", 1), ("cond_length_L256", 4)):
         fname, _, L = FULLSIZE_CASES[case]
         cfg, m = _model(fname[:-4], "bf16")
+        m.set_epilogue_groupnorm(False)  # the option is measured against (and replaces) the separate apply passes
         x, labels, ctx = fullsize_inputs(cfg, B, L)
         plain = m(x.cuda(), labels.cuda(), ctx.cuda())
         n_plain = _lib.lib().t2p_unet_launches_per_forward(m.native_handle)

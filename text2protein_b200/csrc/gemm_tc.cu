@@ -87,9 +87,7 @@ struct TcParams {
   int* gno_flags;           // [sample * n_tiles * 4]: warps that left the slot -- zero on entry, left zero on exit
   int gno_parts;            // parts per sample and channel quadrant = pixel tiles per sample x epilogue warps per quadrant
   int gno_slots;            // samples * n_tiles * 4
-  long long* gno_trace;     // knob builds, T2P_GNO_TRACE: [cta][tile][16] clock64 stamps of the MMA warp and epilogue warp 2
-  int gno_trace_tiles;
-  int gno_debug;            // timing experiments (knob builds): 1 = do not wait for the other parts, 2 = no pass 1, 4 = no fold loads
+  int gno_debug;            // timing experiments (knob builds): 1 = fix-up warps do not touch the tile, 2 = nor wait for its stores
 };
 
 template <int BN>
@@ -480,6 +478,158 @@ struct CfgT {
   static constexpr int TMEM_COLS = 2 * PX;
 };
 
+// ----------------------------------------------------------------------------------------------------------
+// GroupNorm + SiLU of the convolution's OUTPUT by the convolution kernel itself (ResnetBlockBigGANpp: h = act(
+// GroupNorm_1(Conv_0(.) + temb)), layers.py:314-318): the separate statistics / gn_finalize / gn_apply passes over the
+// tensor disappear.  The statistics of a sample need ALL its pixel tiles, which other CTAs hold:
+//   publish  every epilogue warp reduces its pixels x 32 channels to per-group {sum, sum of squares} and lane 0 stores
+//            each pair as ONE 64-bit word into gno_part[sample][part][group]
+//   fold     every warp that needs the statistics of a (sample, n tile, quadrant) slot reads all parts of its groups and
+//            adds them itself, in double and in the same fixed order in every warp and every run (deterministic;
+//            bit-identical across the warps of a sample).  The buffer is its own flag: a word holds a sentinel (all
+//            ones: a NaN no arithmetic produces) until written, and a lane re-reads the words that are still the
+//            sentinel (bounded wait, back-off).  No counter, no fence, no release / acquire pair.
+//   leave    one counter word per slot, off the critical path: the last reader writes the sentinel back and zeroes the
+//            counter -- gno_part and gno_flags enter and leave every launch in the same state.
+// Two ways to use them:
+//  * epilogue_role_gn (channel-major kernel, 64 x 64 images and below): two passes over the accumulator (tcgen05.ld does
+//    not consume it) -- statistics, publish, fold, then y = silu(v * scale + shift) -> bf16 -> TMA store.  The raw tensor
+//    never exists, but the accumulator is held while the warp waits for the other CTAs of its sample.
+//  * deferred (halo kernel, 128-pixel-wide images): the plain epilogue stores the RAW bf16 tile and publishes, the
+//    accumulator is released at once, and four extra warps (fixup_role) normalise each tile IN PLACE a tile or more
+//    later, out of L2.  Measured reason (profiles/r02_gn_out_epilogue_timeline.txt): with the two-pass form every wave
+//    of tiles waits for the slowest of the 64 CTAs of a sample -- tile period 1.40 x the mean MMA time whatever the
+//    protocol costs -- because one spare accumulator is all the slack TMEM has.
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long pack_stat(float sum, float sq) {
+  return (static_cast<unsigned long long>(__float_as_uint(sq)) << 32) | __float_as_uint(sum);
+}
+constexpr unsigned long long kStatSentinel = ~0ull;
+__device__ __forceinline__ float silu_tanh_f(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
+// geometry of one (sample, n tile, quadrant) slot of the exchange
+struct GnoSlot {
+  int cpg, gpw, ngroups;          // channels per group (4 / 8 / 16 / 32), groups per warp (32 channels), groups per sample
+  int slot;                       // (sample * n_tiles + nt) * 4 + q
+  unsigned long long* part;       // gno_part + (sample * parts * ngroups + first group of the warp): + part * ngroups + g
+};
+__device__ __forceinline__ GnoSlot gno_slot(const TcParams& p, int sample, int nt, int q) {
+  GnoSlot s;
+  s.cpg = p.gno_cpg;
+  s.gpw = 32 / s.cpg;
+  s.ngroups = p.N / s.cpg;
+  s.slot = (sample * p.n_tiles + nt) * 4 + q;
+  s.part = p.gno_part + static_cast<long long>(sample) * p.gno_parts * s.ngroups + (nt * 128 + q * 32) / s.cpg;
+  return s;
+}
+
+// publish: ssum / ssq = this lane's sums over its pixels of the channels (lane >> 2) + 8 k, k = 0..3 of the warp's 32.
+// Channel totals over the four lanes that share a channel, then the channels of a group: groups of 4 channels = lanes
+// with equal (lane >> 4) of one slot k, groups of 8 = all lanes of a slot, groups of 16 / 32 = two / four slots.
+__device__ __forceinline__ void gno_publish(const GnoSlot& gs, int part, float (&ssum)[4], float (&ssq)[4], int lane) {
+  float gsum[8], gsq[8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int o = 1; o <= 8; o <<= 1) {
+      ssum[k] += __shfl_xor_sync(0xffffffffu, ssum[k], o);
+      ssq[k] += __shfl_xor_sync(0xffffffffu, ssq[k], o);
+    }
+    // lanes 0..15 hold the channels (lane >> 2) < 4 of slot k, lanes 16..31 the channels 4..7
+    const float os = __shfl_xor_sync(0xffffffffu, ssum[k], 16), oq = __shfl_xor_sync(0xffffffffu, ssq[k], 16);
+    gsum[2 * k] = ssum[k]; gsq[2 * k] = ssq[k];        // (as seen from lane 0: group 2k of 4 channels ...
+    gsum[2 * k + 1] = os;  gsq[2 * k + 1] = oq;        //  ... and group 2k + 1)
+  }
+  if (lane != 0) return;
+  unsigned long long* const dst = gs.part + static_cast<long long>(part) * gs.ngroups;
+  if (gs.cpg == 4) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) st_relaxed_gpu_u64(dst + g, pack_stat(gsum[g], gsq[g]));
+  } else if (gs.cpg == 8) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) st_relaxed_gpu_u64(dst + g, pack_stat(gsum[2 * g] + gsum[2 * g + 1], gsq[2 * g] + gsq[2 * g + 1]));
+  } else if (gs.cpg == 16) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g)
+      st_relaxed_gpu_u64(dst + g, pack_stat((gsum[4 * g] + gsum[4 * g + 1]) + (gsum[4 * g + 2] + gsum[4 * g + 3]),
+                                            (gsq[4 * g] + gsq[4 * g + 1]) + (gsq[4 * g + 2] + gsq[4 * g + 3])));
+  } else {
+    st_relaxed_gpu_u64(dst, pack_stat(((gsum[0] + gsum[1]) + (gsum[2] + gsum[3])) + ((gsum[4] + gsum[5]) + (gsum[6] + gsum[7])),
+                                      ((gsq[0] + gsq[1]) + (gsq[2] + gsq[3])) + ((gsq[4] + gsq[5]) + (gsq[6] + gsq[7]))));
+  }
+}
+
+// fold (blocking): lane l adds the parts r = l / gpw, l / gpw + 32 / gpw, ... of group l % gpw (coalesced: the groups of
+// a part are adjacent), sixteen loads in flight, re-reading what has not arrived yet; a butterfly over the lanes of equal
+// group completes the sum.  On return lane g (g < gpw) -- and every lane congruent to it -- holds mean / rstd of group g.
+__device__ __forceinline__ void gno_fold(const TcParams& p, const GnoSlot& gs, int lane, float& mean_g, float& rstd_g) {
+  const int g = lane & (gs.gpw - 1);
+  const int rstep = gs.cpg;  // 32 / gpw
+  const unsigned long long* const src = gs.part + g;
+  double sum = 0.0, sq = 0.0;
+  for (int r = lane / gs.gpw; r < p.gno_parts; r += 16 * rstep) {
+    unsigned long long v[16];
+    unsigned pending = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (r + i * rstep < p.gno_parts) pending |= 1u << i;
+    const unsigned mine = pending;
+    long long t0 = 0;
+    unsigned spins = 0;
+    while (true) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (pending & (1u << i)) v[i] = ld_relaxed_gpu_u64(src + static_cast<long long>(r + i * rstep) * gs.ngroups);
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if ((pending & (1u << i)) && static_cast<unsigned>(v[i] >> 32) != 0xffffffffu) pending &= ~(1u << i);
+      if (!pending) break;
+      if (spins == 0) t0 = clock64();
+      else if (clock64() - t0 > 4000000000LL) __trap();
+      if (++spins > 2) __nanosleep(spins > 16 ? 400 : 100);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (mine & (1u << i)) {
+        sum += static_cast<double>(__uint_as_float(static_cast<unsigned>(v[i])));
+        sq += static_cast<double>(__uint_as_float(static_cast<unsigned>(v[i] >> 32)));
+      }
+    }
+  }
+  __syncwarp();
+  for (int o = gs.gpw; o < 32; o <<= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  }
+  const double inv_cnt = 1.0 / (static_cast<double>(p.rows_per_sample) * gs.cpg);
+  const double mean = sum * inv_cnt;
+  const float var = static_cast<float>(fmax(sq * inv_cnt - mean * mean, 0.0));
+  mean_g = static_cast<float>(mean);
+  rstd_g = rsqrtf(var + p.gno_eps);
+}
+
+// leave: `ticket` = what lane 0's atomicAdd(&gno_flags[slot], 1) returned (asked for right after the fold, looked at
+// here); `readers` warps read a slot.  The last one hands it back as it was found.
+__device__ __forceinline__ void gno_leave(const TcParams& p, const GnoSlot& gs, int ticket, int readers, int lane) {
+  ticket = __shfl_sync(0xffffffffu, ticket, 0);
+  if (ticket != readers - 1) return;
+  for (int i = lane; i < p.gno_parts * gs.gpw; i += 32)
+    st_relaxed_gpu_u64(gs.part + static_cast<long long>(i / gs.gpw) * gs.ngroups + (i & (gs.gpw - 1)), kStatSentinel);
+  if (lane == 0) p.gno_flags[gs.slot] = 0;
+}
+
 // Epilogue of the channel-major kernels.  The accumulator is read in the fragment layout of tcgen05.ld.16x256b:
 // thread t of a warp owns channels nw0 + t / 4 + 8 k (k = 0..3) and, in every group of 8 pixel columns, the two
 // adjacent pixels 2 (t % 4) + {0, 1} -- one packed bf16x2 conversion per pair, and a transposing stmatrix lays
@@ -577,13 +727,27 @@ __device__ __forceinline__ void epi_write_stats(const TcParams& p, EpiQ& eq, lon
 // One epilogue warp's loop over the CTA's tiles.  The warp drains TMEM lane quadrant q, pixel chunks
 // [cf, cf + NCH) of each PX-pixel accumulator (two accumulators, ping-pong), through its two staging buffers at
 // `obuf`; statistics tile index = stat_mul * pixel_tile + stat_add.
-template <int PX, int NCH, bool RBVAR, bool STATS>
+// GND (deferred GroupNorm of the output, see gno_publish): STATS without RBVAR; the statistics go to the exchange buffer
+// instead of stat_part, and the warp counts in the shared-memory word `ready_smem` the tiles whose stores have been
+// PERFORMED -- the fix-up warp of this quadrant (fixup_role) rewrites them in place.
+template <int PX, int NCH, bool RBVAR, bool STATS, bool GND = false>
 __device__ __forceinline__ void epilogue_role(const TcParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
                                               uint64_t* tempty_bar, uint32_t obuf, int q, int cf, int stat_mul,
-                                              int stat_add, int lane) {
+                                              int stat_add, int lane, uint32_t ready_smem = 0) {
   EpiQ eq;
   uint32_t tl = 0;
   uint32_t nstore = 0;
+  // `count` tiles have reached global memory: called after the stores of tile `count` have been ISSUED, it waits for
+  // everything but those (the previous tile's stores had a whole tile time to complete: waiting for the tile just stored
+  // instead cost the epilogue its overlap with the next accumulator)
+  auto publish_stored = [&](uint32_t count, bool last) {
+    if (lane == 0) {
+      if (last) ptx::tma_store_wait<0>();
+      else ptx::tma_store_wait<NCH>();
+      ptx::fence_proxy_async_global();
+      ptx::st_release_cta_shared(ready_smem, static_cast<int>(count));
+    }
+  };
   for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tl) {
     const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
     const int tt = p.reverse ? p.num_tiles - 1 - t : t;
@@ -634,55 +798,23 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, uint32_t tmem_b
         emit_chunk(lo1, hi1, cf + i + 1);
       }
     }
-    if (STATS) epi_write_stats(p, eq, static_cast<long long>(stat_mul) * pt + stat_add, lane);
+    if (GND) {
+      const int sample = eq.m0 / p.rows_per_sample;
+      const GnoSlot gs = gno_slot(p, sample, tt - pt * p.n_tiles, q);
+      gno_publish(gs, (pt - sample * (p.rows_per_sample / PX)) * stat_mul + stat_add, eq.ssum, eq.ssq, lane);
+      publish_stored(tl, false);
+    } else if (STATS) {
+      epi_write_stats(p, eq, static_cast<long long>(stat_mul) * pt + stat_add, lane);
+    }
   }
+  if (GND) publish_stored(tl, true);
   if (lane == 0) ptx::tma_store_wait_read<0>();  // smem must stay valid until the last store has read it
 }
 
-// ----------------------------------------------------------------------------------------------------------
-// GroupNorm + SiLU of the convolution's OUTPUT inside its own epilogue (ResnetBlockBigGANpp: h = act(GroupNorm_1(
-// Conv_0(.) + temb)), layers.py:314-318): the raw tensor, its statistics pass, gn_finalize and gn_apply disappear --
-// the tensor core kernel has HBM bandwidth to spare, the separate apply pass had nothing else to do.  The statistics of
-// a sample need ALL its pixel tiles, which other CTAs hold, so the epilogue runs in two passes over the accumulator
-// (tcgen05.ld does not consume it):
-//   pass 1  v = acc * alpha + bias (+ time-embedding bias), per-group sum / sum of squares of this warp's pixels and
-//           32 channels; lane 0 stores each {sum, sum of squares} pair as ONE 64-bit word into gno_part
-//   fold    EVERY warp of the (sample, n tile, quadrant) slot reads all parts of its groups and adds them itself, in
-//           double and in the same fixed order in every warp and every run (deterministic; bit-identical across the
-//           warps of a sample).  The buffer is its own flag: its words hold a sentinel (all ones: a NaN no arithmetic
-//           produces) until written, and a lane simply re-reads the words that are still the sentinel (bounded wait,
-//           back-off).  No counter, no fence, no release / acquire pair: the chain after the last pass 1 of a sample
-//           is one store and one load deep.
-//   pass 2  y = silu(v * scale + shift) -> bf16 -> stmatrix -> TMA store, as the plain epilogue.
-// Time line of the first versions (clock64 stamps, T2P_GNO_TRACE in knob builds; 128 x 128, K = 1152, MMA 13.3 k clocks
-// per tile): one elected warp folds and publishes the affine -- eight dependent L2 round trips, the convolutions took
-// twice as long; counter with red.release / ld.acquire, every warp folds -- release fence 1.8 k, poll 2.5 k, fold 4.8 k
-// (an L2 round trip is ~2 k clocks under this kernel's operand traffic), pass 1 1.6 k, pass 2 4.8 k: 16.2 k per tile,
-// epilogue-bound.
+// In-accumulator form (see the banner above gno_publish): one epilogue warp's loop over the CTA's tiles.
 // While a warp waits, the MMA warp works on the next tile in the other accumulator.  No deadlock: CTAs are all
 // resident, take their tiles in index order, and a sample's tiles span fewer consecutive indices than there are CTAs
 // (checked on the host), so the tile a CTA must finish BEFORE one of sample s always belongs to an earlier sample.
-// The last warp to leave a slot (one counter word per slot, off the critical path) writes the sentinel back and zeroes
-// the counter: gno_part and gno_flags enter and leave every launch in the same state.
-__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long pack_stat(float sum, float sq) {
-  return (static_cast<unsigned long long>(__float_as_uint(sq)) << 32) | __float_as_uint(sum);
-}
-constexpr unsigned long long kStatSentinel = ~0ull;
-__device__ __forceinline__ float silu_tanh_f(float x) {
-  const float h = 0.5f * x;
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
-  return fmaf(h, t, h);
-}
-
 template <int PX, int NCH>
 __device__ __forceinline__ void epilogue_role_gn(const TcParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
                                                  uint64_t* tempty_bar, uint32_t obuf, int q, int cf, int part_mul,
@@ -690,11 +822,6 @@ __device__ __forceinline__ void epilogue_role_gn(const TcParams& p, uint32_t tme
   uint32_t tl = 0;
   uint32_t nstore = 0;
   const int tps = p.rows_per_sample / PX;       // pixel tiles per sample
-  const int cpg = p.gno_cpg;
-  const int gpw = 32 / cpg;                     // groups per warp (32 channels): 8, 4, 2 or 1
-  const int ngroups = p.N / cpg;
-  int* const left = p.gno_flags;
-  const double inv_cnt = 1.0 / (static_cast<double>(p.rows_per_sample) * cpg);
   for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tl) {
     const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
     const int tt = p.reverse ? p.num_tiles - 1 - t : t;
@@ -703,9 +830,8 @@ __device__ __forceinline__ void epilogue_role_gn(const TcParams& p, uint32_t tme
     const int nw0 = nt * 128 + q * 32;
     const int m0 = pt * PX;
     const int sample = m0 / p.rows_per_sample;
-    const int tile_in_sample = pt - sample * tps;
-    const int part = tile_in_sample * part_mul + part_add;
-    const int slot = (sample * p.n_tiles + nt) * 4 + q;
+    const int part = (pt - sample * tps) * part_mul + part_add;
+    const GnoSlot gs = gno_slot(p, sample, nt, q);
     float bch[4], ga[4], be[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -716,17 +842,8 @@ __device__ __forceinline__ void epilogue_role_gn(const TcParams& p, uint32_t tme
       ga[k] = __ldg(p.gno_gamma + n);
       be[k] = __ldg(p.gno_beta + n);
     }
-#ifdef T2P_TIMING_KNOBS
-    long long* const trc = (p.gno_trace && q == 0 && part_add == 0 && static_cast<int>(tl) < p.gno_trace_tiles)
-                               ? p.gno_trace + (static_cast<long long>(blockIdx.x) * p.gno_trace_tiles + tl) * 16 : nullptr;
-#define T2P_STAMP(i) do { if (trc && lane == 0) trc[i] = clock64(); } while (0)
-#else
-#define T2P_STAMP(i) do { } while (0)
-#endif
-    T2P_STAMP(0);
     T2P_EPI_WAIT(ptx::smem_u32(&tfull_bar[as]), aph);
     ptx::tc_fence_after();
-    T2P_STAMP(1);
     const uint32_t tbase = tmem_base + as * PX + (static_cast<uint32_t>(q * 32) << 16);
     auto load_chunk = [&](int c, uint32_t (&lo)[16], uint32_t (&hi)[16]) {
       ptx::tmem_ld_16x256_x4(tbase + c * 32, lo);
@@ -750,9 +867,6 @@ __device__ __forceinline__ void epilogue_role_gn(const TcParams& p, uint32_t tme
         }
       }
     };
-#ifdef T2P_TIMING_KNOBS
-    if (!(p.gno_debug & 2)) {
-#endif
     load_chunk(cf, lo0, hi0);
 #pragma unroll 1
     for (int i = 0; i < NCH; i += 2) {
@@ -765,119 +879,24 @@ __device__ __forceinline__ void epilogue_role_gn(const TcParams& p, uint32_t tme
         add_chunk(lo1, hi1);
       }
     }
-#ifdef T2P_TIMING_KNOBS
-    }
-#endif
-    // channel totals over the four lanes that share a channel, then the channels of a group: groups of 4 channels =
-    // lanes with equal (lane >> 4) of one slot, groups of 8 = all lanes of a slot, groups of 16 / 32 = two / four slots.
-    // Lane 0 ends up with every group of the warp's 32 channels.
-    float gsum[8], gsq[8];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-#pragma unroll
-      for (int o = 1; o <= 8; o <<= 1) {
-        ssum[k] += __shfl_xor_sync(0xffffffffu, ssum[k], o);
-        ssq[k] += __shfl_xor_sync(0xffffffffu, ssq[k], o);
-      }
-      // lanes 0..15 hold the channels (lane >> 2) < 4 of slot k, lanes 16..31 the channels 4..7
-      const float os = __shfl_xor_sync(0xffffffffu, ssum[k], 16), oq = __shfl_xor_sync(0xffffffffu, ssq[k], 16);
-      gsum[2 * k] = ssum[k]; gsq[2 * k] = ssq[k];        // (as seen from lane 0: group 2k of 4 channels ...
-      gsum[2 * k + 1] = os;  gsq[2 * k + 1] = oq;        //  ... and group 2k + 1)
-    }
-    T2P_STAMP(2);
-    unsigned long long* const slot_part =
-        p.gno_part + static_cast<long long>(sample) * p.gno_parts * ngroups + nw0 / cpg;  // + part * ngroups + group
-    if (lane == 0) {
-      unsigned long long* const dst = slot_part + static_cast<long long>(part) * ngroups;
-      if (cpg == 4) {
-#pragma unroll
-        for (int g = 0; g < 8; ++g) st_relaxed_gpu_u64(dst + g, pack_stat(gsum[g], gsq[g]));
-      } else if (cpg == 8) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) st_relaxed_gpu_u64(dst + g, pack_stat(gsum[2 * g] + gsum[2 * g + 1], gsq[2 * g] + gsq[2 * g + 1]));
-      } else if (cpg == 16) {
-#pragma unroll
-        for (int g = 0; g < 2; ++g)
-          st_relaxed_gpu_u64(dst + g, pack_stat((gsum[4 * g] + gsum[4 * g + 1]) + (gsum[4 * g + 2] + gsum[4 * g + 3]),
-                                                (gsq[4 * g] + gsq[4 * g + 1]) + (gsq[4 * g + 2] + gsq[4 * g + 3])));
-      } else {
-        st_relaxed_gpu_u64(dst, pack_stat(((gsum[0] + gsum[1]) + (gsum[2] + gsum[3])) + ((gsum[4] + gsum[5]) + (gsum[6] + gsum[7])),
-                                          ((gsq[0] + gsq[1]) + (gsq[2] + gsq[3])) + ((gsq[4] + gsq[5]) + (gsq[6] + gsq[7]))));
-      }
-    }
-    T2P_STAMP(3);
-    // ---- fold: lane l adds the parts r = l / gpw, l / gpw + 32 / gpw, ... of group l % gpw (coalesced: the groups of a
-    // part are adjacent), sixteen loads in flight, re-reading what has not arrived yet; a butterfly over the lanes of
-    // equal group completes the sum
+    gno_publish(gs, part, ssum, ssq, lane);
     float mean_g, rstd_g;
-    {
-      const int g = lane & (gpw - 1);
-      const int rstep = cpg;  // 32 / gpw
-      const unsigned long long* const src = slot_part + g;
-      double gs = 0.0, gq = 0.0;
-      for (int r = lane / gpw; r < p.gno_parts; r += 16 * rstep) {
-        unsigned long long v[16];
-        unsigned pending = 0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (r + i * rstep < p.gno_parts) pending |= 1u << i;
-#ifdef T2P_TIMING_KNOBS
-        if (p.gno_debug & 4) pending = 0;
-#endif
-        const unsigned mine = pending;
-        long long t0 = 0;
-        unsigned spins = 0;
-        while (true) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (pending & (1u << i)) v[i] = ld_relaxed_gpu_u64(src + static_cast<long long>(r + i * rstep) * ngroups);
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if ((pending & (1u << i)) && static_cast<unsigned>(v[i] >> 32) != 0xffffffffu) pending &= ~(1u << i);
-#ifdef T2P_TIMING_KNOBS
-          if (p.gno_debug & 1) pending = 0;
-#endif
-          if (!pending) break;
-          if (spins == 0) t0 = clock64();
-          else if (clock64() - t0 > 4000000000LL) __trap();
-          if (++spins > 2) __nanosleep(spins > 16 ? 400 : 100);  // a sample spread over two waves waits a whole tile
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          if (mine & (1u << i)) {
-            gs += static_cast<double>(__uint_as_float(static_cast<unsigned>(v[i])));
-            gq += static_cast<double>(__uint_as_float(static_cast<unsigned>(v[i] >> 32)));
-          }
-        }
-      }
-      __syncwarp();
-      T2P_STAMP(4);
-      for (int o = gpw; o < 32; o <<= 1) {
-        gs += __shfl_xor_sync(0xffffffffu, gs, o);
-        gq += __shfl_xor_sync(0xffffffffu, gq, o);
-      }
-      const double mean = gs * inv_cnt;
-      const float var = static_cast<float>(fmax(gq * inv_cnt - mean * mean, 0.0));
-      mean_g = static_cast<float>(mean);
-      rstd_g = rsqrtf(var + p.gno_eps);
-    }
-    int left_ticket = 0;
-    if (lane == 0) left_ticket = atomicAdd(&left[slot], 1);  // (its result is looked at after pass 2)
+    gno_fold(p, gs, lane, mean_g, rstd_g);
+    int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(&p.gno_flags[gs.slot], 1);  // (its result is looked at after pass 2)
     float sc[4], sh[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int src_lane = ((lane >> 2) + 8 * k) / cpg;  // a lane that holds this channel's group
+      const int src_lane = ((lane >> 2) + 8 * k) / gs.cpg;  // a lane that holds this channel's group
       const float m = __shfl_sync(0xffffffffu, mean_g, src_lane), rs = __shfl_sync(0xffffffffu, rstd_g, src_lane);
       sc[k] = rs * ga[k];
       sh[k] = be[k] - m * sc[k];
     }
     // ---- pass 2: normalise, activate, store
-    T2P_STAMP(5);
     auto release_acc = [&]() {
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[as]));
-      T2P_STAMP(6);
     };
     auto emit_chunk = [&](const uint32_t (&lo)[16], const uint32_t (&hi)[16], int c) {
       const uint32_t buf = obuf + (nstore & 1) * (32 * 32 * 2);
@@ -927,22 +946,102 @@ __device__ __forceinline__ void epilogue_role_gn(const TcParams& p, uint32_t tme
         emit_chunk(lo1, hi1, cf + i + 1);
       }
     }
-    T2P_STAMP(7);
-    left_ticket = __shfl_sync(0xffffffffu, left_ticket, 0);
-    if (left_ticket == p.gno_parts - 1) {  // last warp to leave the slot: every reader is done, hand it back as found
-      for (int i = lane; i < p.gno_parts * gpw; i += 32)
-        st_relaxed_gpu_u64(slot_part + static_cast<long long>(i / gpw) * ngroups + (i & (gpw - 1)), kStatSentinel);
-      if (lane == 0) left[slot] = 0;
-    }
+    gno_leave(p, gs, ticket, p.gno_parts, lane);
   }
   if (lane == 0) ptx::tma_store_wait_read<0>();
 }
 
-template <int PX, int NCH, bool GNO = true>
+// Deferred form: one fix-up warp per TMEM lane quadrant q normalises, in place and out of L2, the 32 channels x PX pixels
+// that epilogue warp q stored raw (bf16) for each of the CTA's tiles.  `ready_smem`: the shared-memory word in which
+// that epilogue warp counts the tiles whose stores have been performed (it waits for its bulk groups before it takes
+// the next accumulator -- time it would spend waiting for the MMA anyway).  Lane = (pixel % 8, 8-channel slot): a warp
+// instruction moves 8 pixels x 64 bytes, eight 16-byte loads in flight per lane.
+template <int PX>
+__device__ __forceinline__ void fixup_role(const TcParams& p, uint32_t ready_smem, int q, int lane) {
+  const int tps = p.rows_per_sample / PX;
+  const int c8 = lane & 3;
+  uint32_t tl = 0;
+  for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tl) {
+    const int tt = p.reverse ? p.num_tiles - 1 - t : t;
+    const int pt = tt / p.n_tiles;
+    const int nt = tt - pt * p.n_tiles;
+    const int ch0 = nt * 128 + q * 32 + c8 * 8;
+    const int m0 = pt * PX;
+    const int sample = m0 / p.rows_per_sample;
+    const GnoSlot gs = gno_slot(p, sample, nt, q);
+    const float4 ga0 = __ldg(reinterpret_cast<const float4*>(p.gno_gamma + ch0)), ga1 = __ldg(reinterpret_cast<const float4*>(p.gno_gamma + ch0 + 4));
+    const float4 be0 = __ldg(reinterpret_cast<const float4*>(p.gno_beta + ch0)), be1 = __ldg(reinterpret_cast<const float4*>(p.gno_beta + ch0 + 4));
+    float mean_g, rstd_g;
+    gno_fold(p, gs, lane, mean_g, rstd_g);
+    int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(&p.gno_flags[gs.slot], 1);
+    // h = y / 2 = x * (scale / 2) + shift / 2;  silu(y) = h + h * tanh(h)
+    const float ga[8] = {ga0.x, ga0.y, ga0.z, ga0.w, ga1.x, ga1.y, ga1.z, ga1.w};
+    const float be[8] = {be0.x, be0.y, be0.z, be0.w, be1.x, be1.y, be1.z, be1.w};
+    float sc[8], sh[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int src_lane = (c8 * 8 + e) / gs.cpg;
+      const float m = __shfl_sync(0xffffffffu, mean_g, src_lane), rs = __shfl_sync(0xffffffffu, rstd_g, src_lane);
+      sc[e] = 0.5f * rs * ga[e];
+      sh[e] = 0.5f * be[e] - m * sc[e];
+    }
+#ifdef T2P_TIMING_KNOBS
+    if (p.gno_debug & 1) {
+      if (!(p.gno_debug & 2) && lane == 0) while (ptx::ld_acquire_cta_shared(ready_smem) <= static_cast<int>(tl)) __nanosleep(200);
+      __syncwarp();
+      gno_leave(p, gs, ticket, tps, lane);
+      continue;
+    }
+#endif
+    if (lane == 0) {  // the raw tile must have reached global memory
+      const long long t0 = clock64();
+      while (ptx::ld_acquire_cta_shared(ready_smem) <= static_cast<int>(tl)) {
+        __nanosleep(200);
+        if (clock64() - t0 > 4000000000LL) __trap();
+      }
+    }
+    __syncwarp();
+    char* const base = static_cast<char*>(p.out) + (static_cast<long long>(m0 + (lane >> 2)) * p.N + ch0) * 2;
+    const long long pitch = 8LL * p.N * 2;  // eight pixels on
+    // sixteen 16-byte loads per lane in flight (half of the warp's 16 KB slice): an L2 round trip is ~2 k clocks under
+    // this kernel's operand traffic; with eight in flight the four round trips per tile made the fix-up warps as slow as
+    // the MMA (all thirty-two do not fit the register file next to the other roles)
+    constexpr int NLD = 16;
+#pragma unroll 1
+    for (int i = 0; i < PX / 8; i += NLD) {
+      uint4 d[NLD];
+#pragma unroll
+      for (int b = 0; b < NLD; ++b) d[b] = __ldcg(reinterpret_cast<const uint4*>(base + (i + b) * pitch));
+#pragma unroll
+      for (int b = 0; b < NLD; ++b) {
+        uint32_t w[4] = {d[b].x, d[b].y, d[b].z, d[b].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float h0 = fmaf(__uint_as_float(w[j] << 16), sc[2 * j], sh[2 * j]);
+          const float h1 = fmaf(__uint_as_float(w[j] & 0xffff0000u), sc[2 * j + 1], sh[2 * j + 1]);
+          float t0, t1;
+          asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+          asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+          w[j] = ptx::pack_bf16x2(fmaf(h0, t0, h0), fmaf(h1, t1, h1));
+        }
+        __stcg(reinterpret_cast<uint4*>(base + (i + b) * pitch), make_uint4(w[0], w[1], w[2], w[3]));
+      }
+    }
+    gno_leave(p, gs, ticket, tps, lane);
+  }
+}
+
+// GNO: 0 = the kernel never normalises its output, 1 = in-accumulator form, 2 = deferred form (kernels with fix-up warps)
+template <int PX, int NCH, int GNO = 1>
 __device__ __forceinline__ void epilogue_dispatch(const TcParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
                                                   uint64_t* tempty_bar, uint32_t obuf, int q, int cf, int stat_mul,
-                                                  int stat_add, int lane) {
-  if (GNO && p.gno_gamma) {  // (part index = stat_mul * tile + stat_add: whole tiles, or the halves of the eight-warp layout)
+                                                  int stat_add, int lane, uint32_t ready_smem = 0) {
+  if (GNO == 2) {
+    epilogue_role<PX, NCH, false, true, true>(p, tmem_base, tfull_bar, tempty_bar, obuf, q, cf, stat_mul, stat_add, lane, ready_smem);
+    return;
+  }
+  if (GNO == 1 && p.gno_gamma) {  // (part index = stat_mul * tile + stat_add: whole tiles, or the halves of the eight-warp layout)
     epilogue_role_gn<PX, NCH>(p, tmem_base, tfull_bar, tempty_bar, obuf, q, cf, stat_mul, stat_add, lane);
     return;
   }
@@ -1128,7 +1227,7 @@ __global__ void __launch_bounds__(CfgT<PX>::THREADS, 1) conv_gemm_tcT_kernel(con
 // function of the absolute shared-memory address, so a row-shifted window of a swizzled tile is itself a valid
 // operand (probe: csrc/probe_shift.cu).  The L2 -> SMEM stream per (kh, chunk) drops from 3 x (16 + 32) KB to
 // 3 x 16 + 32.5 KB.  Pixels and weights run through separate TMA rings.
-template <int EW>
+template <int EW, bool GND = false>
 struct CfgHT {
   static constexpr int W_BYTES = 128 * BK * 2;           // 16 KB weight tile (128 channels x 64 k)
   static constexpr int P_ROWPITCH = 130;                 // pixels per staged image row (128 + halo)
@@ -1137,7 +1236,8 @@ struct CfgHT {
   static constexpr int NP = 3;                           // pixel buffers
   static constexpr int EPI_WARPS = EW;                   // 4, or 8: two per TMEM lane quadrant, half a tile each
   static constexpr int NW = EPI_WARPS == 8 ? 5 : 6;      // weight buffers (the staging of eight warps takes one)
-  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int FIX_WARPS = GND ? 4 : 0;          // deferred GroupNorm of the output: one fix-up warp per quadrant
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * FIX_WARPS;
   static constexpr int OUT_BYTES = EPI_WARPS * 2 * 32 * 32 * 2;
   static constexpr int SMEM_BYTES = NP * P_BYTES + NW * W_BYTES + OUT_BYTES + 1024;
   static constexpr int PX = 256;
@@ -1146,15 +1246,14 @@ struct CfgHT {
 #ifndef T2P_H_EPI_WARPS
 #define T2P_H_EPI_WARPS 4
 #endif
-// The plain epilogue is fastest with four warps (eight measured slower: one weight buffer less).  The epilogue that
-// normalises its own output (epilogue_role_gn) is a long dependent chain per 32-pixel chunk with one MUFU per element
-// -- a single warp per scheduler exposes every latency of it -- and runs with eight.
+// (the plain epilogue is fastest with four warps; eight measured slower: one weight buffer less)
 using CfgH = CfgHT<T2P_H_EPI_WARPS>;
-constexpr int kGnoEpiWarpsH = 4;
 
-template <int EW>
-__global__ void __launch_bounds__(CfgHT<EW>::THREADS, 1) conv_gemm_tcH_kernel(const __grid_constant__ TcParams p) {
-  using C = CfgHT<EW>;
+// GND: the launch normalises its own output in the deferred form (see gno_publish): four epilogue warps store the raw
+// tile and publish its statistics, four more warps rewrite it in place.
+template <int EW, bool GND>
+__global__ void __launch_bounds__(CfgHT<EW, GND>::THREADS, 1) conv_gemm_tcH_kernel(const __grid_constant__ TcParams p) {
+  using C = CfgHT<EW, GND>;
   constexpr int PX = C::PX;
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
@@ -1162,6 +1261,7 @@ __global__ void __launch_bounds__(CfgHT<EW>::THREADS, 1) conv_gemm_tcH_kernel(co
   __shared__ __align__(8) uint64_t wfull_bar[C::NW], wempty_bar[C::NW];
   __shared__ __align__(8) uint64_t tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ int stored_tiles[4];  // GND: per quadrant, tiles whose raw stores have been performed
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -1186,6 +1286,7 @@ __global__ void __launch_bounds__(CfgHT<EW>::THREADS, 1) conv_gemm_tcH_kernel(co
       ptx::mbar_init(ptx::smem_u32(&tfull_bar[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&tempty_bar[s]), C::EPI_WARPS);
     }
+    for (int s = 0; s < 4; ++s) stored_tiles[s] = 0;
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -1264,16 +1365,8 @@ __global__ void __launch_bounds__(CfgHT<EW>::THREADS, 1) conv_gemm_tcH_kernel(co
       uint32_t tl = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tl) {
         const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
-#ifdef T2P_TIMING_KNOBS
-        long long* const trc = (p.gno_trace && static_cast<int>(tl) < p.gno_trace_tiles)
-                                   ? p.gno_trace + (static_cast<long long>(blockIdx.x) * p.gno_trace_tiles + tl) * 16 : nullptr;
-        if (trc) trc[8] = clock64();
-#endif
         ptx::mbar_wait(ptx::smem_u32(&tempty_bar[as]), aph ^ 1);
         ptx::tc_fence_after();
-#ifdef T2P_TIMING_KNOBS
-        if (trc) trc[9] = clock64();
-#endif
         const uint32_t tmem_acc = tmem_base + as * PX;
         bool first = true;
         // one weight tile against the two image rows of a staged pixel buffer (row pitch / tap shift in pixels)
@@ -1309,21 +1402,26 @@ __global__ void __launch_bounds__(CfgHT<EW>::THREADS, 1) conv_gemm_tcH_kernel(co
           if (++ps == C::NP) { ps = 0; pph ^= 1; }
         }
         ptx::umma_commit(ptx::smem_u32(&tfull_bar[as]));
-#ifdef T2P_TIMING_KNOBS
-        if (trc) trc[10] = clock64();
-#endif
       }
     }
-  } else {
+  } else if (warp < 2 + C::EPI_WARPS) {
     // ------------------------------------------------------------ epilogue (warps 2..5): thread = channel
     const int q = warp & 3;
-    if constexpr (C::EPI_WARPS == 8) {
+    if constexpr (GND) {
+      static_assert(!GND || C::EPI_WARPS == 4, "deferred GroupNorm: one epilogue warp per quadrant");
+      epilogue_dispatch<PX, PX / 32, 2>(p, tmem_base, tfull_bar, tempty_bar, out_stage + q * (2 * 32 * 32 * 2), q, 0, 1, 0, lane,
+                                        ptx::smem_u32(&stored_tiles[q]));
+    } else if constexpr (C::EPI_WARPS == 8) {
       const int half = (warp - 2) >> 2;
-      epilogue_dispatch<PX, PX / 64>(p, tmem_base, tfull_bar, tempty_bar, out_stage + (warp - 2) * (2 * 32 * 32 * 2), q,
-                                     half * (PX / 64), 2, half, lane);
+      epilogue_dispatch<PX, PX / 64, 1>(p, tmem_base, tfull_bar, tempty_bar, out_stage + (warp - 2) * (2 * 32 * 32 * 2), q,
+                                        half * (PX / 64), 2, half, lane);
     } else {
-      epilogue_dispatch<PX, PX / 32>(p, tmem_base, tfull_bar, tempty_bar, out_stage + q * (2 * 32 * 32 * 2), q, 0, 1, 0, lane);
+      epilogue_dispatch<PX, PX / 32, 1>(p, tmem_base, tfull_bar, tempty_bar, out_stage + q * (2 * 32 * 32 * 2), q, 0, 1, 0, lane);
     }
+  } else {
+    // ------------------------------------------------------------ fix-up (GND; warps 6..9), quadrant = the epilogue warp's
+    const int q = warp & 3;
+    fixup_role<PX>(p, ptx::smem_u32(&stored_tiles[q]), q, lane);
   }
 
   ptx::tc_fence_before();
@@ -1524,7 +1622,7 @@ __global__ void __launch_bounds__(CfgHF::THREADS, 1) conv_gemm_tcHF_kernel(const
   } else if (warp < 6) {
     // ------------------------------------------------------------ epilogue (warps 2..5): thread = channel
     const int q = warp & 3;
-    epilogue_dispatch<PX, PX / 32, false>(p, tmem_base, tfull_bar, tempty_bar, out_stage + q * (2 * 32 * 32 * 2), q, 0, 1, 0, lane);
+    epilogue_dispatch<PX, PX / 32, 0>(p, tmem_base, tfull_bar, tempty_bar, out_stage + q * (2 * 32 * 32 * 2), q, 0, 1, 0, lane);
   } else {
     // ------------------------------------------------------------ transform warps (6..13)
     const int grp = (warp - 6) >> 2;                       // groups of four warps
@@ -1719,23 +1817,6 @@ int sm_count() { return device_sm_count(); }
 // kernel's set-up -- barrier init, TMEM allocation, descriptor prefetch -- runs under the tail of its predecessor:
 // neutral at 64 maps per GPU, -4.6 % per PC iteration at 8 (profiles/r02_gn_small_ab.txt).  T2P_PDL_SMALL (knob
 // builds) overrides the CTA threshold.
-// Grid of a launch that normalises its own output (epilogue_role_gn).  A sample whose tiles lie in two consecutive waves
-// of the persistent CTAs holds the epilogue of its first-wave tiles back until the second wave's MMAs are done; with
-// short tiles (K <= ~1500: the tile takes no longer than pass 1 + exchange + pass 2) that lag is not absorbed by the
-// second accumulator and every wave pays it (measured: 128 x 128, K = 1152: 0.25 -> 0.38 ms).  Rounding the grid down to
-// a multiple of the tiles per sample keeps every sample inside one wave at the price of the idle SMs (13.5 % at 64
-// tiles per sample, 2.7 % at 16).
-int gno_grid(const TcParams& p, int px) {
-  const int grid = std::min(p.num_tiles, sm_count());
-  if (!p.gno_gamma) return grid;
-  const int span = (p.rows_per_sample / px) * p.n_tiles;
-  const int ktot = p.taps * (p.c0 + p.c1) + p.xc0 + p.xc1;
-  static const int mode = env_knob("T2P_GNO_ALIGN", 2);  // knob builds: 0 never, 1 always, 2 by tile length
-  const bool align = mode == 1 || (mode == 2 && ktot <= 1536);
-  if (!align || span > grid) return grid;
-  return grid / span * span;
-}
-
 bool pdl_for(int grid) {
   static const bool all = (env_knob("T2P_PDL", 0) & 1) != 0;
   static const int small = env_knob("T2P_PDL_SMALL", 147);
@@ -1766,73 +1847,37 @@ void launch_t(TcParams& p, cudaStream_t st) {
   }
   p.n_tiles = cdiv(p.N, 128);
   p.num_tiles = cdiv(p.M, PX) * p.n_tiles;
-  const int grid = gno_grid(p, PX);
+  const int grid = std::min(p.num_tiles, sm_count());
   launch_pdl_dyn(pdl_for(grid), conv_gemm_tcT_kernel<PX>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, p);
 }
 
-template <int EW>
+template <int EW, bool GND>
 void launch_h_ew(TcParams& p, cudaStream_t st) {
-  using C = CfgHT<EW>;
+  using C = CfgHT<EW, GND>;
   static bool configured[kMaxDevices] = {};
   if (first_use_on_device(configured)) {
-    T2P_CUDA(cudaFuncSetAttribute(conv_gemm_tcH_kernel<EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    T2P_CUDA(cudaFuncSetAttribute(conv_gemm_tcH_kernel<EW, GND>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   }
   p.n_tiles = cdiv(p.N, 128);
   p.num_tiles = cdiv(p.M, C::PX) * p.n_tiles;
-  const int grid = gno_grid(p, C::PX);
-#ifdef T2P_TIMING_KNOBS
-  // T2P_GNO_TRACE=1 (knob builds): clock64 time line of the MMA warp and of epilogue warp 2 of every CTA, printed per launch
-  static const bool trace = env_knob("T2P_GNO_TRACE", 0) != 0;
-  const int tt = 40;
-  if (trace && p.gno_gamma) {
-    static long long* buf = nullptr;
-    if (!buf) T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&buf), sizeof(long long) * 148 * tt * 16));
-    T2P_CUDA(cudaMemsetAsync(buf, 0, sizeof(long long) * 148 * tt * 16, st));
-    p.gno_trace = buf;
-    p.gno_trace_tiles = tt;
-  }
-#endif
-  launch_pdl<1>(conv_gemm_tcH_kernel<EW>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, p);
-#ifdef T2P_TIMING_KNOBS
-  if (trace && p.gno_gamma) {
-    T2P_CUDA(cudaStreamSynchronize(st));
-    std::vector<long long> h(148 * tt * 16);
-    T2P_CUDA(cudaMemcpy(h.data(), p.gno_trace, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
-    const int ktot = p.taps * (p.c0 + p.c1) + p.xc0 + p.xc1;
-    // phases (clocks), averaged over the CTAs' tiles 2.. (steady state)
-    const char* names[] = {"tfull wait", "pass 1", "store", "poll+fold", "butterfly+affine", "-", "pass 2 -> release", "release -> end",
-                           "epilogue total", "MMA: tempty wait", "MMA: issue", "tile period"};
-    double sum[12] = {};
-    long long cnt = 0;
-    for (int c = 0; c < grid; ++c) {
-      const int ntile = std::min(tt, (p.num_tiles - c + grid - 1) / grid);
-      for (int t = 2; t + 1 < ntile; ++t) {
-        const long long* e = &h[(static_cast<size_t>(c) * tt + t) * 16];
-        const long long* n = e + 16;
-        if (!e[0] || !e[7] || !n[8]) continue;
-        const double d[12] = {double(e[1] - e[0]), double(e[2] - e[1]), double(e[3] - e[2]), double(e[4] - e[3]), double(e[5] - e[4]) , 0.0,
-                              double(e[6] - e[5]), double(e[7] - e[6]), double(e[7] - e[1]), double(e[9] - e[8]), double(e[10] - e[9]),
-                              double(n[8] - e[8])};
-        for (int i = 0; i < 12; ++i) sum[i] += d[i];
-        ++cnt;
-      }
-    }
-    std::fprintf(stderr, "[gno trace] M=%d N=%d K=%d grid=%d tiles=%d samples=%lld:", p.M, p.N, ktot, grid, p.num_tiles, cnt);
-    for (int i = 0; i < 12; ++i)
-      if (i != 5) std::fprintf(stderr, " %s %.0f |", names[i], cnt ? sum[i] / cnt : 0.0);
-    std::fprintf(stderr, "\n");
-  }
-#endif
+  const int grid = std::min(p.num_tiles, sm_count());
+  launch_pdl<1>(conv_gemm_tcH_kernel<EW, GND>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, p);
 }
 
-int gno_h_warps() {  // (knob builds: T2P_GNO_H_WARPS=4 for the A/B)
-  static const int v = env_knob("T2P_GNO_H_WARPS", kGnoEpiWarpsH);
-  return v == 4 ? 4 : 8;
+// Form of the output GroupNorm in the halo kernel.  Deferred (fix-up warps) when the CTAs work through several waves of
+// tiles: the in-accumulator form then pays the slowest CTA of a sample in every wave.  In-accumulator for launches of a
+// wave or two (small batches), where the deferred form's extra pass over the last tile is exposed.  Measured, cfg2,
+// ms per PC iteration (profiles/r02_gn_out_ab.txt): B = 64 off 22.95, deferred 22.36, in-accumulator 22.57; B = 8 off 6.29,
+// 6.23, 6.15.
+bool gno_h_deferred(long long num_tiles) {
+  static const int knob = env_knob("T2P_GNO_H_DEFER", -1);  // (knob builds: A/B)
+  if (knob >= 0) return knob != 0;
+  return num_tiles > 2LL * sm_count();
 }
 
 void launch_h(TcParams& p, cudaStream_t st) {
-  if (p.gno_gamma && gno_h_warps() == 8) launch_h_ew<8>(p, st);
-  else launch_h_ew<CfgH::EPI_WARPS>(p, st);
+  if (p.gno_gamma && gno_h_deferred(cdiv(p.M, CfgH::PX) * cdiv(p.N, 128))) launch_h_ew<4, true>(p, st);
+  else launch_h_ew<CfgH::EPI_WARPS, false>(p, st);
 }
 
 void launch_hf(TcParams& p, cudaStream_t st) {
@@ -1918,7 +1963,8 @@ bool conv_gemm_tc_fuses_gn(const ConvGemmArgs& a) { return make_plan(a).halo; }
 
 // parts (statistic slices) per sample and channel quadrant: pixel tiles per sample x epilogue warps per quadrant
 static int gn_out_parts(const ConvGemmArgs& a, const Plan& pl) {
-  const int warps_per_quadrant = pl.halo ? (gno_h_warps() == 8 ? 2 : (CfgH::EPI_WARPS == 8 ? 2 : 1)) : 2;
+  const long long tiles = cdiv64(static_cast<long long>(a.B) * a.H * a.W, pl.rows) * cdiv(a.N, 128);
+  const int warps_per_quadrant = pl.halo ? (CfgH::EPI_WARPS == 8 && !gno_h_deferred(tiles) ? 2 : 1) : 2;
   return a.rows_per_sample / pl.rows * warps_per_quadrant;
 }
 
@@ -1931,6 +1977,14 @@ bool conv_gemm_tc_gn_out_ok(const ConvGemmArgs& a, int groups) {
   q.stat_part = nullptr;
   const Plan pl = make_plan(q);
   if (!pl.channel_major || a.rows_per_sample % pl.rows != 0) return false;
+  {
+    // which launches normalise their output (knob builds: T2P_GNO_POLICY bit mask for the A/B): 1 = 128-pixel-wide images
+    // with K < 2304, 2 = with K >= 2304, 4 = 64 x 64 images, 8 = 32 x 32 and below
+    static const int policy = env_knob("T2P_GNO_POLICY", 15);
+    const int ktot = a.ksize * a.ksize * (a.c0 + a.c1) + a.xc0 + a.xc1;
+    const int cls = pl.halo ? (ktot < 2304 ? 1 : 2) : (a.rows_per_sample >= 4096 ? 4 : 8);
+    if (!(policy & cls)) return false;
+  }
   // deadlock freedom of the per-sample wait (see epilogue_role_gn): the tiles of one sample must span fewer
   // consecutive tile indices than there are CTAs
   const long long span = static_cast<long long>(a.rows_per_sample / pl.rows) * (a.N / 128);

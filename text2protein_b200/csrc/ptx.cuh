@@ -23,6 +23,18 @@ __device__ __forceinline__ void fence_mbar_init() {
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+__device__ __forceinline__ void fence_proxy_async_global() {
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+// a word in shared memory as a flag between warps of one CTA
+__device__ __forceinline__ void st_release_cta_shared(uint32_t addr, int v) {
+  asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_cta_shared(uint32_t addr) {
+  int v;
+  asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                : "memory");
@@ -123,6 +135,12 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+// wait until at most N of this thread's bulk groups are still incomplete (their global writes not yet performed)
+template <int N>
+__device__ __forceinline__ void tma_store_wait() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
 // ---------------------------------------------------------------- tcgen05 / TMEM
