@@ -82,6 +82,33 @@ def test_conv2d_matches_torch(dtype, tol, H, cin, cin1, cout, k):
     assert rel_err(out, ref) < tol
 
 
+@pytest.mark.parametrize("B,H,cin,cout,k", [(8, 4, 256, 256, 3), (64, 4, 512, 256, 3), (8, 16, 256, 256, 3), (3, 8, 256, 384, 3),
+                                            (1, 16, 512, 256, 3), (2, 4, 2048, 256, 1), (5, 2, 128, 200, 3)])
+def test_conv2d_split_k(B, H, cin, cout, k):
+    """Launches of few tiles and long K (the 16 x 16 ... 4 x 4 levels) share the k-blocks of a tile out over several CTAs
+    and the last arrival adds the fp32 partials in split order: against torch on the same bf16 operands, with the
+    per-sample bias changing inside a pixel tile (4 x 4 images), a residual through the identity k-blocks, a ragged
+    channel tile and fused statistics; two calls give the same bits (the sum does not depend on who arrives last)."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    bf = lambda t: t.bfloat16().float()  # noqa: E731
+    a0 = bf(torch.randn(B, cin, H, H, device="cuda", generator=g))
+    w = bf(torch.randn(cout, cin, k, k, device="cuda", generator=g) / math.sqrt(cin * k * k))
+    bias = torch.randn(cout, device="cuda", generator=g)
+    rowbias = torch.randn(B, cout + 3, device="cuda", generator=g)
+    res = bf(torch.randn(B, cout, H, H, device="cuda", generator=g))
+    ref = (F.conv2d(a0, w, bias, padding=k // 2) + rowbias[:, :cout, None, None] + res) * 0.70710678
+    stats = (H * H) % 32 == 0 and cout % 128 == 0
+    out, ss = _conv(a0, w, k, bias=bias, rowbias=rowbias, residual=res, alpha=0.70710678, in_dtype=torch.bfloat16, stats=stats)
+    assert rel_err(out, ref) < 1.5e-2
+    out2, ss2 = _conv(a0, w, k, bias=bias, rowbias=rowbias, residual=res, alpha=0.70710678, in_dtype=torch.bfloat16, stats=stats)
+    assert torch.equal(out, out2)
+    if stats:
+        tot = ss.sum(dim=1)
+        assert torch.allclose(tot[..., 0], out.sum(dim=(2, 3)), rtol=1e-4, atol=1e-2)
+        assert torch.allclose(tot[..., 1], (out * out).sum(dim=(2, 3)), rtol=1e-4, atol=1e-2)
+        assert torch.equal(ss, ss2)
+
+
 @pytest.mark.parametrize("H,cin,cout", [(16, 64, 64), (16, 64, 128), (32, 128, 256), (64, 64, 128)])
 def test_conv2d_upsampled_residual_and_fused_stats(H, cin, cout):
     g = torch.Generator(device="cuda").manual_seed(2)
@@ -168,7 +195,7 @@ def test_conv2d_fused_groupnorm_silu(B, H, c0, c1, xc0, cout, stats):
 @pytest.mark.parametrize("B,H,cin,cout,k", [(3, 128, 128, 128, 3), (20, 128, 64, 128, 3), (2, 64, 128, 256, 3),
                                             (5, 32, 256, 256, 3), (4, 16, 256, 256, 3), (2, 8, 128, 256, 3),
                                             (37, 64, 64, 128, 3), (3, 32, 128, 128, 1), (64, 16, 64, 512, 3),
-                                            (6, 16, 128, 1024, 1)])
+                                            (6, 16, 128, 1024, 1), (48, 32, 128, 256, 3), (40, 16, 128, 1024, 1)])
 def test_conv2d_normalises_its_own_output(B, H, cin, cout, k):
     """silu(GroupNorm_1(Conv_0(h) + bias + temb)) (layers.py:314-318) from the convolution's own epilogue: per-sample
     statistics are exchanged between the CTAs of the launch.  Against torch on the same bf16 operands; B = 20 / 37 / 64
@@ -199,7 +226,10 @@ def test_conv2d_normalises_its_own_output(B, H, cin, cout, k):
         a.rowbias, a.rowbias_ld = rowbias.data_ptr(), rowbias.shape[1]
         a.out, a.out_dtype, a.in_dtype = out.data_ptr(), _lib.BF16, _lib.BF16
         a.gno_groups, a.gno_eps = groups, 1e-6
-        assert L.t2p_conv2d_normalises_output(C.byref(a)) == 1
+        if L.t2p_conv2d_normalises_output(C.byref(a)) != 1:
+            # launches of few tiles split K over the idle SMs instead (and leave GroupNorm to the one-launch kernel)
+            assert B * H * H * ((cout + 127) // 128) <= 74 * 256
+            pytest.skip("this shape splits K")
         a.gno_gamma, a.gno_beta = gamma.data_ptr(), beta.data_ptr()
         _lib.check(L.t2p_conv2d(C.byref(a), _st()))
         torch.cuda.synchronize()

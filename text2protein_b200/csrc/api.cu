@@ -683,8 +683,32 @@ int t2p_conv2d(const t2p_conv_args* a, void* stream) {
     T2P_CUDA(cudaFree(scratch));
     return 0;
   }
-  if (a->in_dtype == T2P_BF16 && a->c0 % 64 == 0 && a->c1 % 64 == 0) conv_gemm_tc(g, S(stream));
-  else conv_gemm_simt(g, a->in_dtype, S(stream));
+  if (a->in_dtype == T2P_BF16 && a->c0 % 64 == 0 && a->c1 % 64 == 0) {
+    if (conv_gemm_tc_splits(g) > 1) {
+      // a launch of few tiles splits K over the idle SMs: partial accumulators + arrival counters for this call only
+      // (the engine keeps its own, unet.cu)
+      const size_t part_bytes = sizeof(float) * static_cast<size_t>(kSplitKPartFloats);
+      const size_t ticket_bytes = sizeof(int) * static_cast<size_t>(kSplitKTicketInts);
+      char* scratch = nullptr;
+      T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&scratch), part_bytes + ticket_bytes));
+      g.sk_part = reinterpret_cast<float*>(scratch);
+      g.sk_ticket = reinterpret_cast<int*>(scratch + part_bytes);
+      cudaError_t e = cudaMemsetAsync(g.sk_ticket, 0, ticket_bytes, S(stream));
+      try {
+        T2P_CUDA(e);
+        conv_gemm_tc(g, S(stream));
+        T2P_CUDA(cudaStreamSynchronize(S(stream)));
+      } catch (...) {
+        cudaFree(scratch);
+        throw;
+      }
+      T2P_CUDA(cudaFree(scratch));
+      return 0;
+    }
+    conv_gemm_tc(g, S(stream));
+  } else {
+    conv_gemm_simt(g, a->in_dtype, S(stream));
+  }
   T2P_API_END
 }
 

@@ -87,6 +87,10 @@ struct TcParams {
   int* gno_flags;           // [sample * n_tiles * 4]: warps that left the slot -- zero on entry, left zero on exit
   int gno_parts;            // parts per sample and channel quadrant = pixel tiles per sample x epilogue warps per quadrant
   int gno_slots;            // samples * n_tiles * 4
+  // split-K (channel-major kernel, launches of few tiles): the k-blocks of a tile are shared out over `splits` CTAs
+  int splits;               // >= 1
+  float* sk_part;           // [tile][split][128 channels][PX pixels] fp32 partial accumulators
+  int* sk_ticket;           // [tile][8 epilogue warps] arrivals -- zero on entry, left zero on exit
   int gno_debug;            // timing experiments (knob builds): 1 = fix-up warps do not touch the tile, 2 = nor wait for its stores
 };
 
@@ -811,6 +815,143 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, uint32_t tmem_b
   if (lane == 0) ptx::tma_store_wait_read<0>();  // smem must stay valid until the last store has read it
 }
 
+// ----------------------------------------------------------------------------------------------------------
+// Split-K epilogue (channel-major kernel).  The 3x3 convolutions at 16 x 16 and below have long K (2304-4608) and few
+// tiles: one CTA per tile walks 36-72 k-blocks at the latency of its own TMA ring (0.5 us per k-block, 19-30 us per
+// launch whatever the batch) while most SMs idle.  With `splits` > 1 a work item is (tile, K range) and consecutive CTAs
+// take the ranges of one tile.  Every epilogue warp dumps its 32 channels x pixels of the partial accumulator as fp32
+// ([128][PX] per item, 32-byte runs per four lanes), fences and takes a ticket for its (tile, warp) slot; the warp that
+// draws the last ticket adds the partials in split order 0, 1, ... -- its own included, read back like the others, so
+// the sum does not depend on who came last (deterministic) -- and runs the ordinary epilogue (bias, per-sample bias,
+// statistics, bf16, TMA store) on the sums.  Tickets are handed back zeroed.
+template <int PX, int NCH, bool RBVAR, bool STATS>
+__device__ __forceinline__ void epilogue_role_splitk(const TcParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
+                                                     uint64_t* tempty_bar, uint32_t obuf, int q, int cf, int stat_mul,
+                                                     int stat_add, int lane) {
+  EpiQ eq;
+  uint32_t tl = 0;
+  uint32_t nstore = 0;
+  const int S = p.splits;
+  const int num_items = p.num_tiles * S;
+  const int wslot = q + 4 * stat_add;  // (stat_add = which half of the pixel columns this warp drains)
+  // this thread's element (channel slot k, column group n, pixel pair) of a 32-pixel chunk inside a [128][PX] partial
+  const int frag_off = (q * 32 + (lane >> 2)) * PX + 2 * (lane & 3);
+  for (int it = blockIdx.x; it < num_items; it += gridDim.x, ++tl) {
+    const int t = it / S;
+    const int split = it - t * S;
+    const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
+    const int tt = p.reverse ? p.num_tiles - 1 - t : t;
+    const int pt = tt / p.n_tiles;
+    eq.nw0 = (tt - pt * p.n_tiles) * 128 + q * 32;
+    eq.m0 = pt * PX;
+    float* const tile_part = p.sk_part + static_cast<long long>(tt) * S * (128 * PX);
+    float* const mine = tile_part + static_cast<long long>(split) * (128 * PX) + frag_off;
+    T2P_EPI_WAIT(ptx::smem_u32(&tfull_bar[as]), aph);
+    ptx::tc_fence_after();
+    const uint32_t tbase = tmem_base + as * PX + (static_cast<uint32_t>(q * 32) << 16);
+    // ---- dump the partial accumulator
+#pragma unroll 1
+    for (int i = 0; i < NCH; ++i) {
+      uint32_t lo[16], hi[16];
+      ptx::tmem_ld_16x256_x4(tbase + (cf + i) * 32, lo);
+      ptx::tmem_ld_16x256_x4(tbase + (16u << 16) + (cf + i) * 32, hi);
+      ptx::tmem_ld_wait();
+      float* const dst = mine + (cf + i) * 32;
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        __stcg(reinterpret_cast<float2*>(dst + 8 * n), make_float2(__uint_as_float(lo[4 * n]), __uint_as_float(lo[4 * n + 1])));
+        __stcg(reinterpret_cast<float2*>(dst + 8 * PX + 8 * n), make_float2(__uint_as_float(lo[4 * n + 2]), __uint_as_float(lo[4 * n + 3])));
+        __stcg(reinterpret_cast<float2*>(dst + 16 * PX + 8 * n), make_float2(__uint_as_float(hi[4 * n]), __uint_as_float(hi[4 * n + 1])));
+        __stcg(reinterpret_cast<float2*>(dst + 24 * PX + 8 * n), make_float2(__uint_as_float(hi[4 * n + 2]), __uint_as_float(hi[4 * n + 3])));
+      }
+    }
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[as]));
+    __threadfence();
+    __syncwarp();
+    int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(&p.sk_ticket[tt * 8 + wslot], 1);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if (ticket != S - 1) continue;
+    // ---- last arrival for this (tile, warp): reduce and finish
+    __threadfence();
+    if (lane == 0) p.sk_ticket[tt * 8 + wslot] = 0;
+    epi_begin_tile<RBVAR>(p, eq, lane);
+#pragma unroll 1
+    for (int i = 0; i < NCH; ++i) {
+      const float* const src = tile_part + frag_off + (cf + i) * 32;
+      float acc[4][4][2];  // [k][n][pixel of the pair]
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) acc[k][n][0] = acc[k][n][1] = 0.f;
+#pragma unroll 1
+      for (int sp = 0; sp < S; sp += 2) {  // two partials (32 loads of 8 bytes per lane) in flight
+        float2 v[2][4][4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (sp + u < S) {
+            const float* const sb = src + static_cast<long long>(sp + u) * (128 * PX);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+              for (int n = 0; n < 4; ++n) v[u][k][n] = __ldcg(reinterpret_cast<const float2*>(sb + 8 * k * PX + 8 * n));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (sp + u < S) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+              for (int n = 0; n < 4; ++n) {
+                acc[k][n][0] += v[u][k][n].x;
+                acc[k][n][1] += v[u][k][n].y;
+              }
+          }
+        }
+      }
+      uint32_t lo[16], hi[16];
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        lo[4 * n] = __float_as_uint(acc[0][n][0]); lo[4 * n + 1] = __float_as_uint(acc[0][n][1]);
+        lo[4 * n + 2] = __float_as_uint(acc[1][n][0]); lo[4 * n + 3] = __float_as_uint(acc[1][n][1]);
+        hi[4 * n] = __float_as_uint(acc[2][n][0]); hi[4 * n + 1] = __float_as_uint(acc[2][n][1]);
+        hi[4 * n + 2] = __float_as_uint(acc[3][n][0]); hi[4 * n + 3] = __float_as_uint(acc[3][n][1]);
+      }
+      const uint32_t buf = obuf + (nstore & 1) * (32 * 32 * 2);
+      if (lane == 0) ptx::tma_store_wait_read<1>();
+      __syncwarp();
+      epilogue_chunk_q<RBVAR, STATS>(p, eq, lo, hi, eq.m0 + (cf + i) * 32, buf, lane);
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && eq.nw0 < p.N && eq.m0 + (cf + i) * 32 < p.M) {
+        ptx::tma_store_4d(&p.tm_out, buf, eq.nw0, eq.m0 + (cf + i) * 32, 0, 0);
+        ptx::tma_store_commit();
+      }
+      ++nstore;
+    }
+    if (STATS) epi_write_stats(p, eq, static_cast<long long>(stat_mul) * pt + stat_add, lane);
+  }
+  if (lane == 0) ptx::tma_store_wait_read<0>();
+}
+
+template <int PX, int NCH>
+__device__ __forceinline__ void epilogue_splitk_dispatch(const TcParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
+                                                         uint64_t* tempty_bar, uint32_t obuf, int q, int cf, int stat_mul,
+                                                         int stat_add, int lane) {
+  const bool rbvar = p.rowbias != nullptr && (p.rows_per_sample % PX) != 0;
+  const bool stats = p.stat_part != nullptr;
+  if (rbvar) {
+    if (stats) epilogue_role_splitk<PX, NCH, true, true>(p, tmem_base, tfull_bar, tempty_bar, obuf, q, cf, stat_mul, stat_add, lane);
+    else epilogue_role_splitk<PX, NCH, true, false>(p, tmem_base, tfull_bar, tempty_bar, obuf, q, cf, stat_mul, stat_add, lane);
+  } else {
+    if (stats) epilogue_role_splitk<PX, NCH, false, true>(p, tmem_base, tfull_bar, tempty_bar, obuf, q, cf, stat_mul, stat_add, lane);
+    else epilogue_role_splitk<PX, NCH, false, false>(p, tmem_base, tfull_bar, tempty_bar, obuf, q, cf, stat_mul, stat_add, lane);
+  }
+}
+
 // In-accumulator form (see the banner above gno_publish): one epilogue warp's loop over the CTA's tiles.
 // While a warp waits, the MMA warp works on the next tile in the other accumulator.  No deadlock: CTAs are all
 // resident, take their tiles in index order, and a sample's tiles span fewer consecutive indices than there are CTAs
@@ -1114,7 +1255,14 @@ __global__ void __launch_bounds__(CfgT<PX>::THREADS, 1) conv_gemm_tcT_kernel(con
       const int hw = p.H * p.W;
       int s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      // work item = (tile, K split): with p.splits > 1 the k-blocks of a tile are shared out over consecutive CTAs
+      const int S = p.splits;
+      const int num_items = p.num_tiles * S;
+      const int kb_taps = p.taps * chunks_per_tap;
+      for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
+        const int t = it / S;
+        const int split = it - t * S;
+        const int kb0 = split * num_kb / S, kb1 = (split + 1) * num_kb / S;
         const int tt = p.reverse ? p.num_tiles - 1 - t : t;
         const int pt = tt / p.n_tiles;
         const int m0 = pt * PX;
@@ -1126,53 +1274,38 @@ __global__ void __launch_bounds__(CfgT<PX>::THREADS, 1) conv_gemm_tcT_kernel(con
           h0 = rem / p.W;
           w0 = rem - h0 * p.W;
         }
-        int kb = 0;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int kh = (p.taps == 9) ? tap / 3 : 0;
-          const int kw = (p.taps == 9) ? tap - kh * 3 : 0;
-          for (int cc = 0; cc < chunks_per_tap; ++cc, ++kb) {
-            ptx::mbar_wait(ptx::smem_u32(&empty_bar[s]), ph ^ 1);
-            const uint32_t fb = ptx::smem_u32(&full_bar[s]);
-            ptx::mbar_arrive_expect_tx(fb, C::STAGE_BYTES);
-            const uint32_t sw = tiles + s * C::STAGE_BYTES;
-            const uint32_t sp = sw + C::W_BYTES;
-            const int ch = cc * BK;
-            ptx::tma_load_4d(sw, &p.tm_w, fb, kb * BK, n0, 0, 0);
-            if (ch < p.c0)
-              ptx::tma_load_4d(sp, &p.tm_a0, fb, ch, w0 + kw - pad, h0 + kh - pad, b0);
-            else
-              ptx::tma_load_4d(sp, &p.tm_a1, fb, ch - p.c0, w0 + kw - pad, h0 + kh - pad, b0);
-            if (++s == C::STAGES) { s = 0; ph ^= 1; }
-          }
-        }
-        // centre-tap-only sources (the skip path's 1x1 convolution folded into this GEMM)
-        for (int cc = 0; cc < x_chunks; ++cc, ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(ptx::smem_u32(&empty_bar[s]), ph ^ 1);
           const uint32_t fb = ptx::smem_u32(&full_bar[s]);
           ptx::mbar_arrive_expect_tx(fb, C::STAGE_BYTES);
           const uint32_t sw = tiles + s * C::STAGE_BYTES;
           const uint32_t sp = sw + C::W_BYTES;
-          const int ch = cc * BK;
-          ptx::tma_load_4d(sw, &p.tm_w, fb, kb * BK, n0, 0, 0);
-          if (ch < p.xc0)
-            ptx::tma_load_4d(sp, &p.tm_x0, fb, ch, w0, h0, b0);
-          else
-            ptx::tma_load_4d(sp, &p.tm_x1, fb, ch - p.xc0, w0, h0, b0);
-          if (++s == C::STAGES) { s = 0; ph ^= 1; }
-        }
-        if (p.residual) {
-          // residual[m][n0 .. n0 + 128) enters the accumulator through two identity k-blocks: exact in fp32,
-          // fetched by TMA like any operand, no epilogue loads
-          for (int j = 0; j < 2; ++j) {
-            ptx::mbar_wait(ptx::smem_u32(&empty_bar[s]), ph ^ 1);
-            const uint32_t fb = ptx::smem_u32(&full_bar[s]);
-            ptx::mbar_arrive_expect_tx(fb, C::STAGE_BYTES);
-            const uint32_t sw = tiles + s * C::STAGE_BYTES;
-            const uint32_t sp = sw + C::W_BYTES;
+          if (kb < kb_taps) {
+            const int tap = kb / chunks_per_tap;
+            const int ch = (kb - tap * chunks_per_tap) * BK;
+            const int kh = (p.taps == 9) ? tap / 3 : 0;
+            const int kw = (p.taps == 9) ? tap - kh * 3 : 0;
+            ptx::tma_load_4d(sw, &p.tm_w, fb, kb * BK, n0, 0, 0);
+            if (ch < p.c0)
+              ptx::tma_load_4d(sp, &p.tm_a0, fb, ch, w0 + kw - pad, h0 + kh - pad, b0);
+            else
+              ptx::tma_load_4d(sp, &p.tm_a1, fb, ch - p.c0, w0 + kw - pad, h0 + kh - pad, b0);
+          } else if (kb < kb_taps + x_chunks) {
+            // centre-tap-only sources (the skip path's 1x1 convolution folded into this GEMM)
+            const int ch = (kb - kb_taps) * BK;
+            ptx::tma_load_4d(sw, &p.tm_w, fb, kb * BK, n0, 0, 0);
+            if (ch < p.xc0)
+              ptx::tma_load_4d(sp, &p.tm_x0, fb, ch, w0, h0, b0);
+            else
+              ptx::tma_load_4d(sp, &p.tm_x1, fb, ch - p.xc0, w0, h0, b0);
+          } else {
+            // residual[m][n0 .. n0 + 128) enters the accumulator through two identity k-blocks: exact in fp32,
+            // fetched by TMA like any operand, no epilogue loads
+            const int j = kb - kb_taps - x_chunks;
             ptx::tma_load_4d(sw, &p.tm_ident, fb, j * BK, 0, 0, 0);
             ptx::tma_load_4d(sp, &p.tm_res, fb, n0 + j * BK, w0, h0, b0);
-            if (++s == C::STAGES) { s = 0; ph ^= 1; }
           }
+          if (++s == C::STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -1183,19 +1316,23 @@ __global__ void __launch_bounds__(CfgT<PX>::THREADS, 1) conv_gemm_tcT_kernel(con
       int s = 0;
       uint32_t ph = 0;
       uint32_t tl = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tl) {
+      const int S = p.splits;
+      const int num_items = p.num_tiles * S;
+      for (int it = blockIdx.x; it < num_items; it += gridDim.x, ++tl) {
+        const int split = it % S;
+        const int kb0 = split * num_kb / S, kb1 = (split + 1) * num_kb / S;
         const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
         ptx::mbar_wait(ptx::smem_u32(&tempty_bar[as]), aph ^ 1);
         ptx::tc_fence_after();
         const uint32_t tmem_acc = tmem_base + as * PX;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(ptx::smem_u32(&full_bar[s]), ph);
           ptx::tc_fence_after();
           const uint32_t sw = tiles + s * C::STAGE_BYTES;
           const uint64_t dw = ptx::umma_desc_k_sw128(sw);
           const uint64_t dp = ptx::umma_desc_k_sw128(sw + C::W_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) ptx::umma_bf16(tmem_acc, dw + 2 * k, dp + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < BK / UMMA_K; ++k) ptx::umma_bf16(tmem_acc, dw + 2 * k, dp + 2 * k, idesc, kb > kb0 || k != 0);
           ptx::umma_commit(ptx::smem_u32(&empty_bar[s]));
           if (++s == C::STAGES) { s = 0; ph ^= 1; }
         }
@@ -1210,8 +1347,12 @@ __global__ void __launch_bounds__(CfgT<PX>::THREADS, 1) conv_gemm_tcT_kernel(con
     const int half = (warp - 2) >> 2;
     constexpr int HC = PX / 64;  // 32-pixel chunks per warp (half of the tile)
     // this warp's two [32 px][32 ch] bf16 staging buffers; statistics tile = its half of the pixel tile: 2 * pt + half
-    epilogue_dispatch<PX, HC>(p, tmem_base, tfull_bar, tempty_bar, out_stage + (warp - 2) * (2 * 32 * 32 * 2), q,
-                              half * HC, 2, half, lane);
+    if (p.splits > 1)
+      epilogue_splitk_dispatch<PX, HC>(p, tmem_base, tfull_bar, tempty_bar, out_stage + (warp - 2) * (2 * 32 * 32 * 2), q,
+                                       half * HC, 2, half, lane);
+    else
+      epilogue_dispatch<PX, HC>(p, tmem_base, tfull_bar, tempty_bar, out_stage + (warp - 2) * (2 * 32 * 32 * 2), q,
+                                half * HC, 2, half, lane);
   }
 
   ptx::tc_fence_before();
@@ -1847,7 +1988,7 @@ void launch_t(TcParams& p, cudaStream_t st) {
   }
   p.n_tiles = cdiv(p.N, 128);
   p.num_tiles = cdiv(p.M, PX) * p.n_tiles;
-  const int grid = std::min(p.num_tiles, sm_count());
+  const int grid = std::min(p.num_tiles * p.splits, sm_count());
   launch_pdl_dyn(pdl_for(grid), conv_gemm_tcT_kernel<PX>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, p);
 }
 
@@ -1957,6 +2098,29 @@ Plan make_plan(const ConvGemmArgs& a) {
 
 }  // namespace
 
+// K splits of a channel-major launch with few tiles and long K (>= 32 k-blocks: the 3x3 convolutions at 16 x 16 and
+// below): as many as keep the (tile, split) items within one wave of CTAs, at least four k-blocks each, at most eight
+// (the last arrival adds the partials two at a time).  Measured (profiles/r02_splitk_ab.txt): such a kernel is mostly
+// fixed cost -- a 4-k-block launch takes 12 us under ncu, a 36-k-block one 20 us, 72 k-blocks 33 us -- so splitting
+// buys 3 us (K = 2304) to 13 us (K = 4608) per launch: -2.8 % per PC iteration at 8 maps per GPU, nothing at 64.
+static int plan_splits(const ConvGemmArgs& a, const Plan& pl) {
+  static const bool on = env_knob("T2P_SPLITK", 1) != 0;  // (knob builds: A/B)
+  if (!on || !pl.channel_major || pl.halo || a.gn_scale) return 1;
+  const long long tiles = cdiv64(static_cast<long long>(a.B) * a.H * a.W, pl.rows) * cdiv(a.N, 128);
+  const int num_kb = (a.ksize * a.ksize * (a.c0 + a.c1) + a.xc0 + a.xc1) / BK + (a.residual ? 2 : 0);
+  const long long cap = std::min<long long>(sm_count(), kSplitKMaxItems);
+  static const int min_kb = env_knob("T2P_SPLITK_MINKB", 32);  // (knob builds: A/B of the threshold)
+  if (tiles * 2 > cap || num_kb < min_kb) return 1;
+  const int s = static_cast<int>(std::min<long long>({8, cap / tiles, num_kb / 4}));
+  return s >= 2 ? s : 1;
+}
+
+int conv_gemm_tc_splits(const ConvGemmArgs& a) {
+  ConvGemmArgs q = a;
+  q.gno_gamma = nullptr;
+  return plan_splits(q, make_plan(q));
+}
+
 bool conv_gemm_tc_channel_major(const ConvGemmArgs& a) { return make_plan(a).channel_major; }
 
 bool conv_gemm_tc_fuses_gn(const ConvGemmArgs& a) { return make_plan(a).halo; }
@@ -1977,6 +2141,7 @@ bool conv_gemm_tc_gn_out_ok(const ConvGemmArgs& a, int groups) {
   q.stat_part = nullptr;
   const Plan pl = make_plan(q);
   if (!pl.channel_major || a.rows_per_sample % pl.rows != 0) return false;
+  if (plan_splits(q, pl) > 1) return false;  // launches of few tiles split K instead (and keep the one-launch GroupNorm)
   {
     // which launches normalise their output (knob builds: T2P_GNO_POLICY bit mask for the A/B): 1 = 128-pixel-wide images
     // with K < 2304, 2 = with K >= 2304, 4 = 64 x 64 images, 8 = 32 x 32 and below
@@ -2091,6 +2256,12 @@ void conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
     p.gno_parts = gn_out_parts(a, pl);
     p.gno_slots = a.B * (a.N / 128) * 4;
     p.gno_debug = env_knob("T2P_GNO_DEBUG", 0);
+  }
+  p.splits = 1;
+  if (a.sk_part && a.sk_ticket && !a.gno_gamma) {
+    p.splits = plan_splits(a, pl);
+    p.sk_part = a.sk_part;
+    p.sk_ticket = a.sk_ticket;
   }
   if (pl.channel_major) {
     {

@@ -53,6 +53,11 @@ struct ConvGemmArgs {
   // CALLER keeps in a fixed state between launches: gno_part >= conv_gemm_tc_gn_out_part_floats(args) floats with every
   // byte 0xff (the "not written yet" sentinel), gno_flags conv_gemm_tc_gn_out_flag_ints(args) ints that are zero; the
   // kernel restores both before it ends.
+  // Split-K scratch (channel-major tcgen05 kernel, launches of few tiles; see conv_gemm_tc_splits): fp32 partial
+  // accumulators, kSplitKPartFloats floats, and kSplitKTicketInts arrival counters that are ZERO between launches.
+  // Without them the launch does not split.
+  float* sk_part = nullptr;
+  int* sk_ticket = nullptr;
   const float* gno_gamma = nullptr;
   const float* gno_beta = nullptr;
   int gno_groups = 0;
@@ -75,6 +80,11 @@ bool conv_gemm_tc_fuses_gn(const ConvGemmArgs& a);
 bool conv_gemm_tc_gn_out_ok(const ConvGemmArgs& a, int groups);
 long long conv_gemm_tc_gn_out_part_floats(const ConvGemmArgs& a, int groups);
 long long conv_gemm_tc_gn_out_flag_ints(const ConvGemmArgs& a);  // size of gno_flags
+// K splits conv_gemm_tc uses for these arguments when given the split-K scratch (1 = none).  Host-only.
+int conv_gemm_tc_splits(const ConvGemmArgs& a);
+constexpr long long kSplitKMaxItems = 160;                                // (tile, split) work items of a split launch
+constexpr long long kSplitKPartFloats = kSplitKMaxItems * 128 * 256;      // [item][128 channels][<= 256 pixels]
+constexpr long long kSplitKTicketInts = kSplitKMaxItems * 8;              // [tile][8 epilogue warps]
 // fp32 or bf16 SIMT path (verification mode and tiny-channel edge layers). dtype of A and W.
 void conv_gemm_simt(const ConvGemmArgs& a, int in_dtype, cudaStream_t st);
 

@@ -327,6 +327,8 @@ UNet::~UNet() {
   if (temb_persist_) cudaFree(temb_persist_);
   if (gno_flags_) cudaFree(gno_flags_);
   if (gno_part_) cudaFree(gno_part_);
+  if (sk_part_) cudaFree(sk_part_);
+  if (sk_ticket_) cudaFree(sk_ticket_);
 }
 
 void UNet::load(const std::string& name, const void* dev_ptr, const std::vector<int64_t>& shape, int dtype,
@@ -538,6 +540,16 @@ void UNet::gemm(const Linear& l, const Act& a0, const Act* a1, Act& out, const f
     }
     g.gno_part = gno_part_;
     g.gno_flags = gno_flags_;
+  }
+  if (tc && !gn_out && !dry_) {
+    if (!sk_part_) {  // once per engine (first eager forward): 21 MB
+      T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&sk_part_), sizeof(float) * kSplitKPartFloats));
+      T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&sk_ticket_), sizeof(int) * kSplitKTicketInts));
+      T2P_CUDA(cudaMemset(sk_ticket_, 0, sizeof(int) * kSplitKTicketInts));
+      ++resource_epoch_;
+    }
+    g.sk_part = sk_part_;
+    g.sk_ticket = sk_ticket_;
   }
   ++launches_;
   if (dry_) return;

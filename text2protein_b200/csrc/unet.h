@@ -257,6 +257,9 @@ class UNet {
   size_t gno_flags_bytes_ = 0;
   void* gno_part_ = nullptr;
   size_t gno_part_bytes_ = 0;
+  // split-K scratch of the channel-major GEMM (launches of few tiles): partial accumulators, arrival counters (idle: zero)
+  float* sk_part_ = nullptr;
+  int* sk_ticket_ = nullptr;
   bool profile_ = false;
   long long generation_ = 0;
   std::vector<GemmRecord> profile_log_;

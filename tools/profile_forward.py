@@ -10,6 +10,10 @@ from text2protein_b200.synthetic import rerandomize_  # noqa: E402
 from text2protein_b200 import load_config  # noqa: E402
 from text2protein_b200.score_sde_pytorch.models.ncsnpp import UNetModel  # noqa: E402
 
+from text2protein_b200 import _lib  # noqa: E402
+
+if os.environ.get("T2P_LIB"):  # e.g. libt2p_knobs.so (the -DT2P_TIMING_KNOBS build, which reads the T2P_* A/B variables)
+    _lib.use_library(os.environ["T2P_LIB"])
 B = int(os.environ.get("T2P_B", "64"))
 cfg = load_config("cond_length", device="cuda")
 cfg.model.compute_dtype = "bf16"
