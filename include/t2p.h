@@ -101,7 +101,9 @@ int t2p_unet_tap(t2p_unet* u, const char* name, float* dst, int64_t capacity, in
 /* Profile mode: CUDA events around every implicit-GEMM launch of the following forward passes (eager only).
  * t2p_unet_profile_read synchronises, fills up to `cap` records and returns the number recorded (or -1). */
 typedef struct t2p_gemm_record {
-  int64_t M; int32_t N; int32_t K; int32_t ksize; int32_t tensor_core; int32_t H; int32_t W; float ms;
+  int64_t M; int32_t N; int32_t K; int32_t ksize;
+  int32_t tensor_core;  /* 0 = CUDA-core kernel, 1 = tcgen05 kernel, 2 = tcgen05 kernel that also applied GroupNorm + SiLU to its output */
+  int32_t H; int32_t W; float ms;
 } t2p_gemm_record;
 int t2p_unet_set_profile(t2p_unet* u, int enable);
 int t2p_unet_profile_read(t2p_unet* u, t2p_gemm_record* out, int cap);

@@ -577,7 +577,7 @@ void UNet::gemm(const Linear& l, const Act& a0, const Act* a1, Act& out, const f
   if (profile_) {
     T2P_CUDA(cudaEventRecord(e1, ln_->st));
     GemmRecord r;
-    r.M = a0.rows(); r.N = l.N; r.K = l.Kalg(); r.ksize = l.ksize; r.tc = tc ? 1 : 0;
+    r.M = a0.rows(); r.N = l.N; r.K = l.Kalg(); r.ksize = l.ksize; r.tc = tc ? (gn_out ? 2 : 1) : 0;
     r.H = a0.H; r.W = a0.W;
     r.e0 = e0; r.e1 = e1;
     profile_log_.push_back(r);
