@@ -195,7 +195,9 @@ def test_conv2d_fused_groupnorm_silu(B, H, c0, c1, xc0, cout, stats):
 @pytest.mark.parametrize("B,H,cin,cout,k", [(3, 128, 128, 128, 3), (20, 128, 64, 128, 3), (2, 64, 128, 256, 3),
                                             (5, 32, 256, 256, 3), (4, 16, 256, 256, 3), (2, 8, 128, 256, 3),
                                             (37, 64, 64, 128, 3), (3, 32, 128, 128, 1), (64, 16, 64, 512, 3),
-                                            (6, 16, 128, 1024, 1), (48, 32, 128, 256, 3), (40, 16, 128, 1024, 1)])
+                                            (6, 16, 128, 1024, 1), (48, 32, 128, 256, 3), (40, 16, 128, 1024, 1),
+                                            # deferred form with four channel tiles and groups of 16 (the N = 256 configs)
+                                            (2, 128, 64, 512, 3), (3, 128, 64, 256, 3)])
 def test_conv2d_normalises_its_own_output(B, H, cin, cout, k):
     """silu(GroupNorm_1(Conv_0(h) + bias + temb)) (layers.py:314-318) from the convolution's own epilogue: per-sample
     statistics are exchanged between the CTAs of the launch.  Against torch on the same bf16 operands; B = 20 / 37 / 64

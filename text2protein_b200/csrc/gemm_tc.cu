@@ -2153,7 +2153,9 @@ bool conv_gemm_tc_gn_out_ok(const ConvGemmArgs& a, int groups) {
   // deadlock freedom of the per-sample wait (see epilogue_role_gn): the tiles of one sample must span fewer
   // consecutive tile indices than there are CTAs
   const long long span = static_cast<long long>(a.rows_per_sample / pl.rows) * (a.N / 128);
-  return span <= sm_count();
+  if (span <= sm_count()) return true;
+  // (the deferred form never waits in an epilogue: any span will do)
+  return pl.halo && gno_h_deferred(cdiv64(static_cast<long long>(a.B) * a.H * a.W, pl.rows) * cdiv(a.N, 128));
 }
 
 long long conv_gemm_tc_gn_out_part_floats(const ConvGemmArgs& a, int groups) {
