@@ -87,12 +87,27 @@ struct TcParams {
   int* gno_flags;           // [sample * n_tiles * 4]: warps that left the slot -- zero on entry, left zero on exit
   int gno_parts;            // parts per sample and channel quadrant = pixel tiles per sample x epilogue warps per quadrant
   int gno_slots;            // samples * n_tiles * 4
+  const char* pf_ptr;       // optional L2 prefetch (the next GEMM's weights), multiple of 16 bytes
+  long long pf_bytes;
   // split-K (channel-major kernel, launches of few tiles): the k-blocks of a tile are shared out over `splits` CTAs
   int splits;               // >= 1
   float* sk_part;           // [tile][split][128 channels][PX pixels] fp32 partial accumulators
   int* sk_ticket;           // [tile][8 epilogue warps] arrivals -- zero on entry, left zero on exit
   int gno_debug;            // timing experiments (knob builds): 1 = fix-up warps do not touch the tile, 2 = nor wait for its stores
 };
+
+// The grid asks the L2 for [pf_ptr, pf_ptr + pf_bytes) in 4 KB pieces, one warp per CTA, before the kernel waits for its
+// predecessor (the range does not depend on it).
+__device__ __forceinline__ void prefetch_l2_range(const TcParams& p, int lane) {
+  if (!p.pf_ptr) return;
+  constexpr long long kChunk = 4096;
+  const long long chunks = (p.pf_bytes + kChunk - 1) / kChunk;
+  for (long long c = blockIdx.x + static_cast<long long>(gridDim.x) * lane; c < chunks; c += static_cast<long long>(gridDim.x) * 32) {
+    const long long off = c * kChunk;
+    const long long n = p.pf_bytes - off < kChunk ? p.pf_bytes - off : kChunk;
+    ptx::bulk_prefetch_l2(p.pf_ptr + off, static_cast<uint32_t>(n));
+  }
+}
 
 template <int BN>
 struct Cfg {
@@ -284,6 +299,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_tc_kernel(const __gr
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  if (warp == 2) prefetch_l2_range(p, lane);
   pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
 
   if (warp == 0) {
@@ -1237,6 +1253,7 @@ __global__ void __launch_bounds__(CfgT<PX>::THREADS, 1) conv_gemm_tcT_kernel(con
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  if (warp == 2) prefetch_l2_range(p, lane);
   pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
 
   if (warp == 0) {
@@ -1438,6 +1455,7 @@ __global__ void __launch_bounds__(CfgHT<EW, GND>::THREADS, 1) conv_gemm_tcH_kern
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  if (warp == 2) prefetch_l2_range(p, lane);
   pdl_wait();
 
   if (warp == 0) {
@@ -2259,6 +2277,8 @@ void conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
     p.gno_slots = a.B * (a.N / 128) * 4;
     p.gno_debug = env_knob("T2P_GNO_DEBUG", 0);
   }
+  p.pf_ptr = static_cast<const char*>(a.l2_prefetch);
+  p.pf_bytes = a.l2_prefetch ? (a.l2_prefetch_bytes & ~15LL) : 0;
   p.splits = 1;
   if (a.sk_part && a.sk_ticket && !a.gno_gamma) {
     p.splits = plan_splits(a, pl);

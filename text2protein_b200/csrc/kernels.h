@@ -58,6 +58,11 @@ struct ConvGemmArgs {
   // Without them the launch does not split.
   float* sk_part = nullptr;
   int* sk_ticket = nullptr;
+  // Optional: a device range the launch asks the L2 to fetch while it runs (tcgen05 kernels) -- the engine passes the
+  // NEXT GEMM's weights: at small batches a layer is a chain of k-blocks at the latency of its weight loads, and the
+  // 200 MB of weights do not survive in the 126 MB L2 from one forward to the next.
+  const void* l2_prefetch = nullptr;
+  long long l2_prefetch_bytes = 0;
   const float* gno_gamma = nullptr;
   const float* gno_beta = nullptr;
   int gno_groups = 0;

@@ -541,6 +541,20 @@ void UNet::gemm(const Linear& l, const Act& a0, const Act* a1, Act& out, const f
     g.gno_part = gno_part_;
     g.gno_flags = gno_flags_;
   }
+  {
+    static const bool pf_on = env_knob("T2P_L2_PREFETCH", 1) != 0;  // (knob builds: A/B)
+    const long long wbytes = static_cast<long long>(l.N) * l.Ktot() * (l.force_f32 ? 4 : static_cast<long long>(dtype_size(cfg_.compute_dtype)));
+    if (dry_) {
+      gemm_seq_.emplace_back(l.wp, wbytes);
+    } else {
+      const size_t i = gemm_idx_++;
+      if (tc && pf_on && !gemm_seq_.empty()) {
+        const auto& nxt = gemm_seq_[(i + 1) % gemm_seq_.size()];  // (the last launch fetches for the next forward's first)
+        g.l2_prefetch = nxt.first;
+        g.l2_prefetch_bytes = nxt.second;
+      }
+    }
+  }
   if (tc && !gn_out && !dry_) {
     if (!sk_part_) {  // once per engine (first eager forward): 21 MB
       T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&sk_part_), sizeof(float) * kSplitKPartFloats));
@@ -1023,6 +1037,10 @@ void UNet::forward_impl(const float* x, const long long* labels, float* h_out, i
       }
     }
     if (!dry_) {
+      if (!gemm_seq_.empty()) {  // (this launch is not in the sequence: it fetches for the first one that is)
+        g.l2_prefetch = gemm_seq_[0].first;
+        g.l2_prefetch_bytes = gemm_seq_[0].second;
+      }
       im2col3x3_nchw(x, B, C, N, N, first_kpad_, xa.p, ln_->st);
       conv_gemm_tc(g, ln_->st);
     }
@@ -1090,6 +1108,7 @@ void UNet::forward_raw(const float* x, const long long* labels, float* h_out, in
   if (planned_B_ != B) {
     // dry pass: same code path, no launches; sizes the arena for this batch
     dry_ = true;
+    gemm_seq_.clear();
     ln_->ws.begin(true);
     forward_impl(x, labels, h_out, B);
     dry_ = false;
@@ -1097,6 +1116,7 @@ void UNet::forward_raw(const float* x, const long long* labels, float* h_out, in
   }
   ln_->ws.reserve(ln_->ws.peak());
   launches_ = 0;
+  gemm_idx_ = 0;
   ln_->st = st;
   ln_->ws.begin(false);
   forward_impl(x, labels, h_out, B);

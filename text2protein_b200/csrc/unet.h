@@ -260,6 +260,10 @@ class UNet {
   // split-K scratch of the channel-major GEMM (launches of few tiles): partial accumulators, arrival counters (idle: zero)
   float* sk_part_ = nullptr;
   int* sk_ticket_ = nullptr;
+  // weights of the forward's GEMM launches in launch order (recorded by the dry pass): launch i asks the L2 for the
+  // weights of launch i + 1
+  std::vector<std::pair<const void*, long long>> gemm_seq_;
+  size_t gemm_idx_ = 0;
   bool profile_ = false;
   long long generation_ = 0;
   std::vector<GemmRecord> profile_log_;
