@@ -35,6 +35,11 @@ namespace {
 #define T2P_EPI_WAIT(bar, parity) ptx::mbar_wait(bar, parity)
 #endif
 
+#ifdef T2P_TIMING_KNOBS
+#define T2P_ESTAMP(i) do { if (p.trace && blockIdx.x == 0 && q == 0 && cf == 0 && tl == 0 && lane == 0) p.trace[i] = clock64(); } while (0)
+#else
+#define T2P_ESTAMP(i) do { } while (0)
+#endif
 constexpr int BM = 128;      // rows (pixels) per tile == UMMA M
 constexpr int BK = 64;       // bf16 elements per 128-byte swizzled row
 constexpr int UMMA_K = 16;   // K per tcgen05.mma for 16-bit inputs
@@ -87,6 +92,7 @@ struct TcParams {
   int* gno_flags;           // [sample * n_tiles * 4]: warps that left the slot -- zero on entry, left zero on exit
   int gno_parts;            // parts per sample and channel quadrant = pixel tiles per sample x epilogue warps per quadrant
   int gno_slots;            // samples * n_tiles * 4
+  long long* trace;         // knob builds, T2P_TRACE_T: clock64 stamps of CTA 0 of a channel-major launch
   const char* pf_ptr;       // optional L2 prefetch (the next GEMM's weights), multiple of 16 bytes
   long long pf_bytes;
   // split-K (channel-major kernel, launches of few tiles): the k-blocks of a tile are shared out over `splits` CTAs
@@ -777,6 +783,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, uint32_t tmem_b
     epi_begin_tile<RBVAR>(p, eq, lane);
     T2P_EPI_WAIT(ptx::smem_u32(&tfull_bar[as]), aph);
     ptx::tc_fence_after();
+    T2P_ESTAMP(6);
     const uint32_t tbase = tmem_base + as * PX + (static_cast<uint32_t>(q * 32) << 16);
     auto release_acc = [&]() {
       ptx::tc_fence_before();
@@ -826,6 +833,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, uint32_t tmem_b
     } else if (STATS) {
       epi_write_stats(p, eq, static_cast<long long>(stat_mul) * pt + stat_add, lane);
     }
+    T2P_ESTAMP(7);
   }
   if (GND) publish_stored(tl, true);
   if (lane == 0) ptx::tma_store_wait_read<0>();  // smem must stay valid until the last store has read it
@@ -1216,6 +1224,12 @@ __device__ __forceinline__ void epilogue_dispatch(const TcParams& p, uint32_t tm
 template <int PX>
 __global__ void __launch_bounds__(CfgT<PX>::THREADS, 1) conv_gemm_tcT_kernel(const __grid_constant__ TcParams p) {
   using C = CfgT<PX>;
+#ifdef T2P_TIMING_KNOBS
+#define T2P_TSTAMP(i) do { if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) p.trace[i] = clock64(); } while (0)
+#else
+#define T2P_TSTAMP(i) do { } while (0)
+#endif
+  if (threadIdx.x == 0) T2P_TSTAMP(0);
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[C::STAGES];
@@ -1254,7 +1268,9 @@ __global__ void __launch_bounds__(CfgT<PX>::THREADS, 1) conv_gemm_tcT_kernel(con
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
   if (warp == 2) prefetch_l2_range(p, lane);
-  pdl_wait();  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
+  if (threadIdx.x == 0) T2P_TSTAMP(1);
+  pdl_wait();
+  if (threadIdx.x == 0) T2P_TSTAMP(2);  // everything above overlapped the previous kernel's tail; its outputs are visible from here on
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -1345,6 +1361,8 @@ __global__ void __launch_bounds__(CfgT<PX>::THREADS, 1) conv_gemm_tcT_kernel(con
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(ptx::smem_u32(&full_bar[s]), ph);
           ptx::tc_fence_after();
+          if (tl == 0 && kb == kb0) T2P_TSTAMP(3);
+          if (tl == 0 && kb == kb1 - 1) T2P_TSTAMP(4);
           const uint32_t sw = tiles + s * C::STAGE_BYTES;
           const uint64_t dw = ptx::umma_desc_k_sw128(sw);
           const uint64_t dp = ptx::umma_desc_k_sw128(sw + C::W_BYTES);
@@ -1354,6 +1372,7 @@ __global__ void __launch_bounds__(CfgT<PX>::THREADS, 1) conv_gemm_tcT_kernel(con
           if (++s == C::STAGES) { s = 0; ph ^= 1; }
         }
         ptx::umma_commit(ptx::smem_u32(&tfull_bar[as]));
+        if (tl == 0) T2P_TSTAMP(5);
       }
     }
   } else {
@@ -1372,9 +1391,11 @@ __global__ void __launch_bounds__(CfgT<PX>::THREADS, 1) conv_gemm_tcT_kernel(con
                                 half * HC, 2, half, lane);
   }
 
+  if (warp == 2) T2P_TSTAMP(8);
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+  if (threadIdx.x == 0) T2P_TSTAMP(9);
 }
 
 // =====================================================================================================
@@ -2007,7 +2028,29 @@ void launch_t(TcParams& p, cudaStream_t st) {
   p.n_tiles = cdiv(p.N, 128);
   p.num_tiles = cdiv(p.M, PX) * p.n_tiles;
   const int grid = std::min(p.num_tiles * p.splits, sm_count());
+#ifdef T2P_TIMING_KNOBS
+  // T2P_TRACE_T=1 (knob builds): time line of CTA 0 of every launch of at most one wave, printed per launch
+  static const bool trace = env_knob("T2P_TRACE_T", 0) != 0;
+  static long long* tbuf = nullptr;
+  if (trace && p.num_tiles * p.splits <= sm_count()) {
+    if (!tbuf) T2P_CUDA(cudaMalloc(reinterpret_cast<void**>(&tbuf), 16 * sizeof(long long)));
+    T2P_CUDA(cudaMemsetAsync(tbuf, 0, 16 * sizeof(long long), st));
+    p.trace = tbuf;
+  }
+#endif
   launch_pdl_dyn(pdl_for(grid), conv_gemm_tcT_kernel<PX>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, p);
+#ifdef T2P_TIMING_KNOBS
+  if (p.trace) {
+    T2P_CUDA(cudaStreamSynchronize(st));
+    long long h[16];
+    T2P_CUDA(cudaMemcpy(h, p.trace, sizeof(h), cudaMemcpyDeviceToHost));
+    const int kb = (p.taps * (p.c0 + p.c1) + p.xc0 + p.xc1) / BK + (p.residual ? 2 : 0);
+    std::fprintf(stderr, "[tcT trace] PX=%d M=%d N=%d kb=%d splits=%d grid=%d stats=%d gno=%d | prologue %lld | pdl wait %lld | first data %lld | last data %lld | "
+                 "commit %lld | epilogue sees acc %lld | epilogue done %lld | stores read %lld | exit %lld (clocks from entry)\n",
+                 PX, p.M, p.N, kb, p.splits, grid, p.stat_part ? 1 : 0, p.gno_gamma ? 1 : 0, h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0],
+                 h[5] - h[0], h[6] - h[0], h[7] - h[0], h[8] - h[0], h[9] - h[0]);
+  }
+#endif
 }
 
 template <int EW, bool GND>
