@@ -115,6 +115,7 @@ __device__ __forceinline__ void tma_load_3d_to(uint32_t dst, const CUtensorMap* 
 
 template <int D, int DV>
 __global__ void __launch_bounds__(THREADS, (BKEY + DV) <= 256 ? 2 : 1) attention_tc_kernel(const __grid_constant__ AttnTcParams p) {
+  pdl_trigger();  // (a GEMM launched behind this kernel with programmatic serialisation may start its prologue)
   using C = ACfg<D, DV>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[C::NS], empty_bar[C::NS];

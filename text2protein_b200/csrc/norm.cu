@@ -376,6 +376,7 @@ __global__ void __launch_bounds__(256) gn_small_kernel(const T* __restrict__ a0,
                                                        T* __restrict__ out) {
   __shared__ float red[8][4][16];  // [warp][slot][8 sums | 8 sums of squares]
   __shared__ float stat[kGnsCS][2];  // per channel of the slice: scale, shift
+  pdl_trigger();  // (a GEMM launched behind this kernel with programmatic serialisation may start its prologue)
   const int ctot = c0 + c1;
   const int b = blockIdx.y;
   const int ch0 = blockIdx.x * kGnsCS;       // first channel of the slice (in the concat)
