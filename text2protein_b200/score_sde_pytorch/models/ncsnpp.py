@@ -134,6 +134,7 @@ class UNetModel(nn.Module):
         return out
 
     def _build_tree(self):
+        self._leaf_slots = []  # (module, parameter name) in the reference's parameter order: a flat walk for sync_weights
         for name, shape, dtype in self._engine_params():
             if name == "sigmas":
                 assert dtype == _lib.F64 and tuple(self.sigmas.shape) == shape
@@ -145,6 +146,7 @@ class UNetModel(nn.Module):
                     node.add_module(p, _Node())
                 node = node._modules[p]
             node.register_parameter(parts[-1], nn.Parameter(torch.empty(shape, dtype=torch.float32)))
+            self._leaf_slots.append((node, parts[-1]))
 
     def reset_parameters(self):
         """Random init in the spirit of the reference (DDPM fan_avg-uniform convs / dense, zero biases and
@@ -170,30 +172,54 @@ class UNetModel(nn.Module):
                     nn.init.kaiming_uniform_(p, a=math.sqrt(5))
 
     # ------------------------------------------------------------------ weights -> engine
+    def _param_tensors(self):
+        # the CURRENT parameter objects through the slots recorded at construction (same order as parameters()):
+        # nn.Module.parameters() walks ~350 submodules with a de-duplication set, 4-5 ms of every sampler call
+        return [m._parameters[n] for m, n in self._leaf_slots]
+
     def _weights_version(self):
-        # one walk over the parameter / buffer objects (no state_dict: building its prefixed key strings twice made
-        # this check 2 ms of every sampler call)
-        ts = list(itertools.chain(self.parameters(), self.buffers()))
+        ts = self._param_tensors() + [self.sigmas]
         return tuple(t._version for t in ts) + tuple(t.data_ptr() for t in ts)
 
-    def _weights_checksum(self):
+    def _weights_checksum_device(self):
         """One multi-tensor reduction over all parameters (a few hundred microseconds): catches writers that bypass
-        the version counter (``p.data.copy_(...)``, the reference's own EMA idiom)."""
-        ps = [p.detach() for p in self.parameters()]
-        norms = torch._foreach_norm(ps)
-        return float(torch.stack(norms).double().sum().item())
+        the version counter (``p.data.copy_(...)``, the reference's own EMA idiom).  A device scalar."""
+        norms = torch._foreach_norm([p.detach() for p in self._param_tensors()])
+        return torch.stack(norms).double().sum()
+
+    def _weights_checksum(self):
+        return float(self._weights_checksum_device().item())
 
     def sync_weights(self, force=False, check_data=False):
         """Pushes the current parameters (e.g. after load_state_dict / ema.copy_to) to the engine and repacks
         them into kernel layout.  Called by ``forward`` and by the sampler; a change is detected through the
         tensors' version counters and storage pointers, which every in-place torch op on the parameter advances
         (``load_state_dict``, optimizers, this package's ``ExponentialMovingAverage``).  A write through ``p.data``
-        does not: the sampler therefore also compares a checksum of the values once per run (``check_data``);
+        does not: the sampler therefore also compares a checksum of the values once per run (``check_data=True``: at
+        once, with a host wait; ``check_data="deferred"``: returns a callable the caller invokes AFTER launching its
+        work -- True means the weights had changed and the work must be redone after ``sync_weights(force=True)``);
         around bare ``forward`` calls use ``sync_weights(force=True)`` after such a write."""
         ver = self._weights_version()
         if not force and ver == self._synced_version:
-            if not check_data or self._weights_checksum() == self._synced_checksum:
-                return
+            if not check_data:
+                return None
+            if check_data == "deferred":
+                # the checksum is computed on the stream and read back asynchronously: the caller goes on launching
+                # its work and asks `stale()` afterwards (a host wait here would leave the GPU idle while the host
+                # prepares the run -- 6 ms of the 13 ms a sampler call costs on top of its iterations)
+                if getattr(self, "_chk_pin", None) is None:
+                    self._chk_pin = torch.empty(1, dtype=torch.float64).pin_memory()
+                self._chk_pin.copy_(self._weights_checksum_device().reshape(1), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                want, pin = self._synced_checksum, self._chk_pin
+
+                def stale():
+                    ev.synchronize()
+                    return float(pin[0]) != want
+                return stale
+            if self._weights_checksum() == self._synced_checksum:
+                return None
         L = _lib.lib()
         st = _lib.current_stream()
         keep = []
@@ -212,6 +238,7 @@ class UNetModel(nn.Module):
         self._synced_version = ver
         self._synced_checksum = self._weights_checksum()
         self._ctx_key = None
+        return None
 
     def set_context(self, text_emb):
         """Projects K|V of every cross-attention for this text context once (hoisted out of the loop).  ``text_emb``

@@ -362,7 +362,10 @@ def get_pc_sampler(sde, shape, predictor, corrector, snr, n_steps=1, probability
                 raise NotImplementedError("sync_step_size is implemented for the native fast path only")
             if fast:
                 labels, G = ve_tables(sde, eps, K)
-                net.sync_weights(check_data=True)
+                # weights written behind the version counters (p.data.copy_) are caught by a checksum that is read back
+                # while the run is already queued; if it differs, the weights are pushed and the run repeated.  (With
+                # a peer group every rank must make the same sequence of launches: checked up front there.)
+                stale = net.sync_weights(check_data=True if sync_step_size is not None else "deferred")
                 net.set_context(context)
                 x = x.contiguous()
                 x_mean = torch.empty_like(x)
@@ -382,6 +385,11 @@ def get_pc_sampler(sde, shape, predictor, corrector, snr, n_steps=1, probability
                 if sync_step_size is not None:
                     a.peers = sync_step_size.handle
                 _lib.check(_lib.lib().t2p_pc_run(net.native_handle, C.byref(a), _lib.current_stream()))
+                if stale is not None and stale():
+                    net.sync_weights(force=True)
+                    net.set_context(context)
+                    x.copy_(x_initial)
+                    _lib.check(_lib.lib().t2p_pc_run(net.native_handle, C.byref(a), _lib.current_stream()))
                 return (x_mean if denoise else x), K * (n_steps + 1)
 
             # generic path: reference loop structure, any model / registered update rule
