@@ -109,6 +109,35 @@ def test_conv2d_split_k(B, H, cin, cout, k):
         assert torch.equal(ss, ss2)
 
 
+@pytest.mark.parametrize("B,H,cin,cout,k", [(16, 32, 128, 256, 3), (8, 64, 64, 256, 3), (64, 16, 256, 256, 3), (256, 8, 64, 256, 1),
+                                            (12, 32, 64, 512, 3), (1024, 4, 128, 256, 3)])
+def test_conv2d_cta_pair(B, H, cin, cout, k):
+    """Layers of 256 output channels and more at >= 96 tiles run on CTA pairs (tcgen05.mma.cta_group::2: M = 256 over two
+    CTAs, each staging half of the 256-pixel tile): against torch on the same bf16 operands, with bias, per-sample bias,
+    a residual through the identity k-blocks (the follower's identity block is shifted by 128 columns) and statistics."""
+    g = torch.Generator(device="cuda").manual_seed(9)
+    bf = lambda t: t.bfloat16().float()  # noqa: E731
+    a0 = bf(torch.randn(B, cin, H, H, device="cuda", generator=g))
+    w = bf(torch.randn(cout, cin, k, k, device="cuda", generator=g) / math.sqrt(cin * k * k))
+    bias = torch.randn(cout, device="cuda", generator=g)
+    rowbias = torch.randn(B, cout + 1, device="cuda", generator=g)
+    res = bf(torch.randn(B, cout, H, H, device="cuda", generator=g))
+    ref = (F.conv2d(a0, w, bias, padding=k // 2) + rowbias[:, :cout, None, None] + res) * 0.70710678
+    stats = (H * H) % 128 == 0
+    out, ss = _conv(a0, w, k, bias=bias, rowbias=rowbias, residual=res, alpha=0.70710678, in_dtype=torch.bfloat16, stats=stats)
+    assert torch.isfinite(out).all()
+    per = (out - ref).flatten(1).abs().amax(1) / ref.flatten(1).abs().amax(1)
+    assert per.max() < 1.5e-2, per
+    # every 128-channel tile on its own: a swapped pair would show here
+    for c in range(0, cout, 128):
+        assert rel_err(out[:, c:c + 128], ref[:, c:c + 128]) < 1.5e-2
+    if stats:
+        tot = ss.sum(dim=1)
+        assert torch.allclose(tot[..., 0], out.sum(dim=(2, 3)), rtol=1e-4, atol=1e-2)
+    out2, _ = _conv(a0, w, k, bias=bias, rowbias=rowbias, residual=res, alpha=0.70710678, in_dtype=torch.bfloat16, stats=stats)
+    assert torch.equal(out, out2)
+
+
 @pytest.mark.parametrize("H,cin,cout", [(16, 64, 64), (16, 64, 128), (32, 128, 256), (64, 64, 128)])
 def test_conv2d_upsampled_residual_and_fused_stats(H, cin, cout):
     g = torch.Generator(device="cuda").manual_seed(2)

@@ -759,7 +759,8 @@ __device__ __forceinline__ void epi_write_stats(const TcParams& p, EpiQ& eq, lon
 template <int PX, int NCH, bool RBVAR, bool STATS, bool GND = false>
 __device__ __forceinline__ void epilogue_role(const TcParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
                                               uint64_t* tempty_bar, uint32_t obuf, int q, int cf, int stat_mul,
-                                              int stat_add, int lane, uint32_t ready_smem = 0) {
+                                              int stat_add, int lane, uint32_t ready_smem = 0, int acc_owner = -1) {
+  // acc_owner >= 0 (CTA-pair kernel): the accumulator is handed back on the mbarrier of that CTA of the cluster
   EpiQ eq;
   uint32_t tl = 0;
   uint32_t nstore = 0;
@@ -788,7 +789,10 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, uint32_t tmem_b
     auto release_acc = [&]() {
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[as]));
+      if (lane == 0) {
+        if (acc_owner < 0) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[as]));
+        else ptx::mbar_arrive_cluster(ptx::smem_u32(&tempty_bar[as]), static_cast<uint32_t>(acc_owner));
+      }
     };
     auto load_chunk = [&](int c, uint32_t (&lo)[16], uint32_t (&hi)[16]) {
       ptx::tmem_ld_16x256_x4(tbase + c * 32, lo);
@@ -983,7 +987,7 @@ __device__ __forceinline__ void epilogue_splitk_dispatch(const TcParams& p, uint
 template <int PX, int NCH>
 __device__ __forceinline__ void epilogue_role_gn(const TcParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
                                                  uint64_t* tempty_bar, uint32_t obuf, int q, int cf, int part_mul,
-                                                 int part_add, int lane) {
+                                                 int part_add, int lane, int acc_owner = -1) {
   uint32_t tl = 0;
   uint32_t nstore = 0;
   const int tps = p.rows_per_sample / PX;       // pixel tiles per sample
@@ -1061,7 +1065,10 @@ __device__ __forceinline__ void epilogue_role_gn(const TcParams& p, uint32_t tme
     auto release_acc = [&]() {
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[as]));
+      if (lane == 0) {
+        if (acc_owner < 0) ptx::mbar_arrive(ptx::smem_u32(&tempty_bar[as]));
+        else ptx::mbar_arrive_cluster(ptx::smem_u32(&tempty_bar[as]), static_cast<uint32_t>(acc_owner));
+      }
     };
     auto emit_chunk = [&](const uint32_t (&lo)[16], const uint32_t (&hi)[16], int c) {
       const uint32_t buf = obuf + (nstore & 1) * (32 * 32 * 2);
@@ -1201,23 +1208,23 @@ __device__ __forceinline__ void fixup_role(const TcParams& p, uint32_t ready_sme
 template <int PX, int NCH, int GNO = 1>
 __device__ __forceinline__ void epilogue_dispatch(const TcParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
                                                   uint64_t* tempty_bar, uint32_t obuf, int q, int cf, int stat_mul,
-                                                  int stat_add, int lane, uint32_t ready_smem = 0) {
+                                                  int stat_add, int lane, uint32_t ready_smem = 0, int acc_owner = -1) {
   if (GNO == 2) {
     epilogue_role<PX, NCH, false, true, true>(p, tmem_base, tfull_bar, tempty_bar, obuf, q, cf, stat_mul, stat_add, lane, ready_smem);
     return;
   }
   if (GNO == 1 && p.gno_gamma) {  // (part index = stat_mul * tile + stat_add: whole tiles, or the halves of the eight-warp layout)
-    epilogue_role_gn<PX, NCH>(p, tmem_base, tfull_bar, tempty_bar, obuf, q, cf, stat_mul, stat_add, lane);
+    epilogue_role_gn<PX, NCH>(p, tmem_base, tfull_bar, tempty_bar, obuf, q, cf, stat_mul, stat_add, lane, acc_owner);
     return;
   }
   const bool rbvar = p.rowbias != nullptr && (p.rows_per_sample % PX) != 0;
   const bool stats = p.stat_part != nullptr;
   if (rbvar) {
-    if (stats) epilogue_role<PX, NCH, true, true>(p, tmem_base, tfull_bar, tempty_bar, obuf, q, cf, stat_mul, stat_add, lane);
-    else epilogue_role<PX, NCH, true, false>(p, tmem_base, tfull_bar, tempty_bar, obuf, q, cf, stat_mul, stat_add, lane);
+    if (stats) epilogue_role<PX, NCH, true, true>(p, tmem_base, tfull_bar, tempty_bar, obuf, q, cf, stat_mul, stat_add, lane, 0, acc_owner);
+    else epilogue_role<PX, NCH, true, false>(p, tmem_base, tfull_bar, tempty_bar, obuf, q, cf, stat_mul, stat_add, lane, 0, acc_owner);
   } else {
-    if (stats) epilogue_role<PX, NCH, false, true>(p, tmem_base, tfull_bar, tempty_bar, obuf, q, cf, stat_mul, stat_add, lane);
-    else epilogue_role<PX, NCH, false, false>(p, tmem_base, tfull_bar, tempty_bar, obuf, q, cf, stat_mul, stat_add, lane);
+    if (stats) epilogue_role<PX, NCH, false, true>(p, tmem_base, tfull_bar, tempty_bar, obuf, q, cf, stat_mul, stat_add, lane, 0, acc_owner);
+    else epilogue_role<PX, NCH, false, false>(p, tmem_base, tfull_bar, tempty_bar, obuf, q, cf, stat_mul, stat_add, lane, 0, acc_owner);
   }
 }
 
@@ -1396,6 +1403,185 @@ __global__ void __launch_bounds__(CfgT<PX>::THREADS, 1) conv_gemm_tcT_kernel(con
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
   if (threadIdx.x == 0) T2P_TSTAMP(9);
+}
+
+// =====================================================================================================
+// CTA-pair variant of the channel-major kernel (tcgen05.mma.cta_group::2) for layers of 256 output channels and more:
+// the two CTAs of a cluster work on ONE 256-pixel tile and TWO adjacent 128-channel tiles.  Each holds its own 128 rows of
+// the weight matrix (A, M = 256 over the pair) and HALF of the pixel tile (B, N = 256: 128 pixels each); the leader's MMA
+// reads both halves.  Per CTA and k-block 16 + 16 KB come in from L2 instead of 16 + 32: the channel-major kernel is
+// bound by what one SM takes from L2 (profiles/r02_tcT_trace_B8.txt), not by the tensor core.
+//   * barriers: `full` lives in the leader (both CTAs' TMA loads count their bytes there: cta_group::2 loads with the
+//     peer bit of the barrier address cleared; the leader arms it with the bytes of BOTH); `empty` and `tfull` exist in
+//     both CTAs and the leader's tcgen05.commit arrives on both (multicast); `tempty` lives in the leader and takes the
+//     epilogue warps of both CTAs (the follower's arrive remotely).
+//   * tile order: CTA b takes tiles b, b + grid, ...; with an even number of channel tiles and an even grid the CTAs
+//     2c and 2c + 1 always hold the same pixel tile and adjacent channel tiles.
+//   * residual k-blocks: the follower's identity block sits 128 columns further left (TMA fills what is outside with
+//     zeros), so each CTA adds the residual channels of its own rows.
+// Epilogue: each CTA drains its own 128 lanes of TMEM exactly as the one-CTA kernel does.
+struct CfgP {
+  static constexpr int PX = 256;
+  static constexpr int W_BYTES = 128 * BK * 2;
+  static constexpr int P_BYTES = (PX / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = W_BYTES + P_BYTES;  // per CTA
+  static constexpr int STAGES = 6;
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int OUT_BYTES = EPI_WARPS * 2 * 32 * 32 * 2;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_BYTES + 1024;
+  static constexpr int TMEM_COLS = 2 * PX;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CfgP::THREADS, 1)
+    conv_gemm_tcP_kernel(const __grid_constant__ TcParams p) {
+  using C = CfgP;
+  constexpr int PX = C::PX;
+  pdl_trigger();
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[C::STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[C::STAGES];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();  // 0 = leader of the pair
+  const uint32_t tiles = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t out_stage = tiles + C::STAGES * C::STAGE_BYTES;
+
+  const int ctot = p.c0 + p.c1;
+  const int chunks_per_tap = ctot / BK;
+  const int x_chunks = (p.xc0 + p.xc1) / BK;
+  const int num_kb = p.taps * chunks_per_tap + x_chunks + (p.residual ? 4 : 0);  // (residual: the pair's 256 channels)
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&full_bar[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&empty_bar[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&tfull_bar[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&tempty_bar[s]), 2 * C::EPI_WARPS);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_pair(ptx::smem_u32(&tmem_base_slot), C::TMEM_COLS);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();  // the peer's barriers are initialised before anything arrives on them
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+  if (warp == 2) prefetch_l2_range(p, lane);
+  pdl_wait();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      ptx::prefetch_tmap(&p.tm_a0);
+      ptx::prefetch_tmap(&p.tm_w);
+      if (p.c1 > 0) ptx::prefetch_tmap(&p.tm_a1);
+      if (p.residual) {
+        ptx::prefetch_tmap(&p.tm_res);
+        ptx::prefetch_tmap(&p.tm_ident);
+      }
+      if (p.xc0 > 0) ptx::prefetch_tmap(&p.tm_x0);
+      if (p.xc1 > 0) ptx::prefetch_tmap(&p.tm_x1);
+      const int pad = (p.taps == 9) ? 1 : 0;
+      const int hw = p.H * p.W;
+      const int kb_taps = p.taps * chunks_per_tap;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int tt = p.reverse ? p.num_tiles - 1 - t : t;
+        const int pt = tt / p.n_tiles;
+        const int n0 = (tt - pt * p.n_tiles) * 128;
+        const int m0 = pt * PX + static_cast<int>(rank) * (PX / 2);  // this CTA's half of the pixel tile
+        int b0 = 0, h0 = 0, w0 = m0;
+        if (!p.mode2d) {
+          b0 = m0 / hw;
+          const int rem = m0 - b0 * hw;
+          h0 = rem / p.W;
+          w0 = rem - h0 * p.W;
+        }
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(ptx::smem_u32(&empty_bar[s]), ph ^ 1);
+          const uint32_t fb = ptx::smem_u32(&full_bar[s]);
+          if (rank == 0) ptx::mbar_arrive_expect_tx(fb, 2 * C::STAGE_BYTES);  // the bytes of both CTAs land on the leader's barrier
+          const uint32_t sw = tiles + s * C::STAGE_BYTES;
+          const uint32_t sp = sw + C::W_BYTES;
+          if (kb < kb_taps) {
+            const int tap = kb / chunks_per_tap;
+            const int ch = (kb - tap * chunks_per_tap) * BK;
+            const int kh = (p.taps == 9) ? tap / 3 : 0;
+            const int kw = (p.taps == 9) ? tap - kh * 3 : 0;
+            ptx::tma_load_4d_pair(sw, &p.tm_w, fb, kb * BK, n0, 0, 0);
+            if (ch < p.c0)
+              ptx::tma_load_4d_pair(sp, &p.tm_a0, fb, ch, w0 + kw - pad, h0 + kh - pad, b0);
+            else
+              ptx::tma_load_4d_pair(sp, &p.tm_a1, fb, ch - p.c0, w0 + kw - pad, h0 + kh - pad, b0);
+          } else if (kb < kb_taps + x_chunks) {
+            const int ch = (kb - kb_taps) * BK;
+            ptx::tma_load_4d_pair(sw, &p.tm_w, fb, kb * BK, n0, 0, 0);
+            if (ch < p.xc0)
+              ptx::tma_load_4d_pair(sp, &p.tm_x0, fb, ch, w0, h0, b0);
+            else
+              ptx::tma_load_4d_pair(sp, &p.tm_x1, fb, ch - p.xc0, w0, h0, b0);
+          } else {
+            // residual of the pair's 256 channels through the identity: k-block j covers residual channels
+            // [c_lo + 64 j, + 64) with c_lo = the pair's first channel; this CTA's rows are channels n0 .. n0 + 127
+            const int j = kb - kb_taps - x_chunks;  // 0..3
+            const int c_lo = n0 - (n0 & 128);
+            ptx::tma_load_4d_pair(sw, &p.tm_ident, fb, c_lo + j * BK - n0, 0, 0, 0);
+            ptx::tma_load_4d_pair(sp, &p.tm_res, fb, c_lo + j * BK, w0, h0, b0);
+          }
+          if (++s == C::STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader only)
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16_m256(PX);
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t tl = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tl) {
+        const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
+        ptx::mbar_wait(ptx::smem_u32(&tempty_bar[as]), aph ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + as * PX;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(ptx::smem_u32(&full_bar[s]), ph);
+          ptx::tc_fence_after();
+          const uint32_t sw = tiles + s * C::STAGE_BYTES;
+          const uint64_t dw = ptx::umma_desc_k_sw128(sw);
+          const uint64_t dp = ptx::umma_desc_k_sw128(sw + C::W_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) ptx::umma_bf16_pair(tmem_acc, dw + 2 * k, dp + 2 * k, idesc, (kb | k) != 0);
+          ptx::umma_commit_pair(ptx::smem_u32(&empty_bar[s]));
+          if (++s == C::STAGES) { s = 0; ph ^= 1; }
+        }
+        ptx::umma_commit_pair(ptx::smem_u32(&tfull_bar[as]));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..9 of both CTAs)
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int HC = PX / 64;
+    epilogue_dispatch<PX, HC, 1>(p, tmem_base, tfull_bar, tempty_bar, out_stage + (warp - 2) * (2 * 32 * 32 * 2), q,
+                                 half * HC, 2, half, lane, 0, /*acc_owner=*/0);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();  // neither CTA leaves (or frees tensor memory) while the other may still reach into it
+  if (warp == 1) ptx::tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
 }
 
 // =====================================================================================================
@@ -2053,6 +2239,35 @@ void launch_t(TcParams& p, cudaStream_t st) {
 #endif
 }
 
+// CTA-pair kernel: grid = 2 x (clusters that fit the device at once), even number of tiles
+void launch_p(TcParams& p, cudaStream_t st) {
+  using C = CfgP;
+  static bool configured[kMaxDevices] = {};
+  static int max_clusters[kMaxDevices] = {};
+  const int dev = current_device();
+  if (first_use_on_device(configured)) {
+    T2P_CUDA(cudaFuncSetAttribute(conv_gemm_tcP_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * 74);
+    cfg.blockDim = dim3(C::THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    T2P_CUDA(cudaOccupancyMaxActiveClusters(&n, conv_gemm_tcP_kernel, &cfg));
+    max_clusters[dev] = std::max(1, n);
+  }
+  p.n_tiles = cdiv(p.N, 128);
+  p.num_tiles = cdiv(p.M, C::PX) * p.n_tiles;
+  const int grid = 2 * std::min(p.num_tiles / 2, max_clusters[dev]);
+  launch_pdl_dyn(pdl_for(grid), conv_gemm_tcP_kernel, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, p);
+}
+
 template <int EW, bool GND>
 void launch_h_ew(TcParams& p, cudaStream_t st) {
   using C = CfgHT<EW, GND>;
@@ -2276,8 +2491,22 @@ void conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
   if (a.rowbias) T2P_CHECK(a.rows_per_sample > 0, "rows_per_sample required");
   if (a.res_up) T2P_CHECK(a.ksize == 3 && (a.H % 2 == 0) && (a.W % 2 == 0), "res_up needs an even image");
 
-  const Plan pl = make_plan(a);
+  Plan pl = make_plan(a);
   if (a.xc0 > 0) T2P_CHECK(pl.channel_major, "centre-tap sources need the channel-major kernel (N >= 128, bf16 out)");
+  // CTA-pair kernel (conv_gemm_tcP_kernel): 256-pixel tiles of layers with a multiple of 256 output channels; each CTA
+  // stages HALF of the pixel tile, so the pixel boxes are those of a 128-pixel tile
+  bool pair = false;
+  {
+    static const bool pair_on = env_knob("T2P_PAIR", 1) != 0;  // (knob builds: A/B)
+    uint32_t tw, th, tb;
+    if (pair_on && pl.channel_major && !pl.halo && pl.rows == 256 && a.N % 256 == 0 && !a.gn_scale &&
+        M % 256 == 0 && M / 256 * (a.N / 128) >= 2 && pixel_box(a, 128, tw, th, tb) &&
+        !(a.sk_part && a.sk_ticket && plan_splits(a, pl) > 1)) {
+      pair = true;
+      pl.tw = tw; pl.th = th; pl.tb = tb;
+    }
+  }
+  const int box_rows = pair ? 128 : pl.rows;
   if (a.stat_part)
     T2P_CHECK(pl.stats_ok, "fused GroupNorm statistics need whole pixel tiles per sample and bf16 output "
                            "(ask conv_gemm_tc_stat_tile first)");
@@ -2285,7 +2514,7 @@ void conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
   auto amap = [&](const void* ptr, int c) {
     if (p.mode2d) {
       uint64_t d[4] = {static_cast<uint64_t>(c), static_cast<uint64_t>(M), 1, 1};
-      uint32_t b[4] = {BK, static_cast<uint32_t>(pl.rows), 1, 1};
+      uint32_t b[4] = {BK, static_cast<uint32_t>(box_rows), 1, 1};
       return make_tmap_bf16(ptr, d, b);
     }
     uint64_t d[4] = {static_cast<uint64_t>(c), static_cast<uint64_t>(a.W), static_cast<uint64_t>(a.H),
@@ -2354,6 +2583,10 @@ void conv_gemm_tc(const ConvGemmArgs& a, cudaStream_t st) {
     }
     if (pl.halo) {
       launch_h(p, st);
+      return;
+    }
+    if (pair) {
+      launch_p(p, st);
       return;
     }
     switch (pl.rows) {
