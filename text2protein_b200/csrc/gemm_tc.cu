@@ -1542,6 +1542,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CfgP::THREADS, 1)
           if (++s == C::STAGES) { s = 0; ph ^= 1; }
         }
       }
+      // Tail: the leader's commits arrive on THIS CTA's `empty` barriers asynchronously, and nothing else waits for the
+      // last ring-full of them.  A CTA must not exit (its shared memory handed to the next CTA) while an arrive from its
+      // peer is still under way: wait for every stage's last release before leaving.
+      for (int i = 0; i < C::STAGES; ++i) {
+        ptx::mbar_wait(ptx::smem_u32(&empty_bar[s]), ph ^ 1);
+        if (++s == C::STAGES) { s = 0; ph ^= 1; }
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader only)
